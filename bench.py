@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""
+bench.py -- BNMF-ARD Gibbs iterations/sec on the north-star configuration
+(BASELINE.json configs[2]: synthetic 20000 x 20000, 20 % observed, K = 50).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one Gibbs iteration exactly as bnmf_gibbs.py:148-172: K lambda_k
+draws, K U-column updates, K V-column updates, one tau draw, trace store.
+Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for how each number
+is measured.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+HYPER = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0}
+METRIC = "BNMF-ARD Gibbs iters/sec, 20k x 20k K=50"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--I", type=int, default=20000)
+    ap.add_argument("--J", type=int, default=20000)
+    ap.add_argument("--K", type=int, default=50)
+    ap.add_argument("--density", type=float, default=0.2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=1000, help="side of the CPU-baseline sample block")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- #
+# synthetic data: R = U* V*^T + N(0,1), U*,V* ~ Exp(1), M ~ Bernoulli(rho)
+# --------------------------------------------------------------------------- #
+def synth_device(I, J, K, density, device, seed=20250):
+    """Full R (float64) and M (uint8) on `device`; identical on every rank."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    Us = -torch.log(1.0 - torch.rand(I, K, generator=g, device=device, dtype=torch.float64))
+    Vs = -torch.log(1.0 - torch.rand(J, K, generator=g, device=device, dtype=torch.float64))
+    R = Us @ Vs.T
+    R += torch.randn(I, J, generator=g, device=device, dtype=torch.float64)
+    M = (torch.rand(I, J, generator=g, device=device, dtype=torch.float32) < density).to(torch.uint8)
+    # at least one observation per row and column (bnmf_gibbs.py:92-101 asserts it)
+    ri = torch.randint(0, J, (I,), generator=g, device=device)
+    M[torch.arange(I, device=device), ri] = 1
+    ci = torch.randint(0, I, (J,), generator=g, device=device)
+    M[ci, torch.arange(J, device=device)] = 1
+    return R, M
+
+
+def synth_host(I, J, K, density, seed=20250):
+    rng = np.random.default_rng(seed)
+    R = rng.exponential(1.0, (I, K)) @ rng.exponential(1.0, (J, K)).T + rng.standard_normal((I, J))
+    M = (rng.random((I, J), dtype=np.float32) < density)
+    M[np.arange(I), rng.integers(0, J, I)] = True
+    M[rng.integers(0, I, J), np.arange(J)] = True
+    return R, M.astype(np.float64)
+
+
+# --------------------------------------------------------------------------- #
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------- #
+def run_reference(args):
+    """CPU arm: the reference's own bnmf_gibbs (shimmed copy under oracle/_ref) --
+    or the numpy oracle port if the copy is absent -- on a bounded sample of the
+    workload: the top-left s x s block of the same synthetic matrix, one
+    iteration per step; iterations/sec are scaled by (s*s)/(I*J) because the
+    reference's cost per iteration is proportional to I*J."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_baseline(args, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {"metric": METRIC, "value": res["value"], "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "BNMF Gibbs+ARD %dx%d rho=%.2f K=%d" % (args.I, args.J, args.density, args.K)},
+            "cpu_baseline": res,
+            "e2e": {"value": res["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline(args, steps=1, warmup=0):
+    import contextlib
+    import io
+    s = min(args.cpu_sample, args.I, args.J)
+    R, M = synth_host(s, s, args.K, args.density)
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:  # noqa: BLE001
+        threads = os.cpu_count() or 1
+    import refimport
+    ref = refimport.load()
+    np.random.seed(0)
+    if ref is not None:
+        kind = "reference"
+        m = ref.bnmf_gibbs(R, M, args.K, True, HYPER)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.initialise("random")
+            if warmup:
+                m.run(warmup)
+            t0 = time.perf_counter()
+            m.run(steps)
+            dt = time.perf_counter() - t0
+    else:
+        import nmf_oracle as orc
+        kind = "port"
+        rng = np.random.default_rng(0)
+        U, V = rng.exponential(1.0, (s, args.K)), rng.exponential(1.0, (s, args.K))
+        lam = np.ones(args.K)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            orc.gibbs_replay_iteration(R, M, U, V, 1.0, lam, lam, np.abs(U), np.abs(V))
+        dt = time.perf_counter() - t0
+    scale = (s * s) / float(args.I * args.J)
+    return {"value": steps / dt * scale, "unit": "iterations/s", "cores": int(threads), "kind": kind,
+            "sample": "top-left %dx%d block of the same synthetic recipe, %d iteration(s) in %.1f s, "
+                      "it/s scaled by (s*s)/(I*J) (reference cost is proportional to I*J)" % (s, s, steps, dt),
+            "sample_it_per_s": steps / dt}
+
+
+# --------------------------------------------------------------------------- #
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bnmtf_ard_b200 import _dist, _lib
+    from bnmtf_ard_b200._engine import NMFEngine
+
+    I, J, K = args.I, args.J, args.K
+    R, M = synth_device(I, J, K, args.density, dev)
+    r0, r1, _ = _dist.shard_bounds(I, rank, world)
+    c0, c1, _ = _dist.shard_bounds(J, rank, world)
+    Rrow, Mrow = R[r0:r1].contiguous(), M[r0:r1].contiguous()
+    Rcol, Mcol = R[:, c0:c1].contiguous(), M[:, c0:c1].contiguous()
+    torch.cuda.synchronize()
+    os.environ["BNMTF_TIME_SWEEPS"] = "1" if world == 1 else "0"
+    eng = NMFEngine.from_device_blocks(I, J, K, Rrow.data_ptr(), Mrow.data_ptr(), Rcol.data_ptr(), Mcol.data_ptr(),
+                                       device=local)
+    del Rrow, Mrow, Rcol, Mcol
+    if rank != 0 or args.no_e2e:
+        del R, M
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # state: lambda_k = alpha0/beta0, U,V ~ Exp(lambda), tau = 1  (initialise('random'))
+    eng.set_hyper(True, **HYPER)
+    eng.set_scalars(1.0, np.ones(K))
+    eng.init_factors(_lib.GIBBS, True, 12345)
+
+    eng.run(_lib.GIBBS, args.warmup, seed=1, traces=False)
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    res = eng.run(_lib.GIBBS, args.steps, seed=2, traces=False)
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    dev_s = float(res["seconds"][-1])
+    t = torch.tensor([dev_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s = float(t.item())
+    launches = eng.launch_count() - launches0
+    sweeps = eng.sweep_times()
+    perf = eng.performances(res["stats"][-1])
+    info = eng.layout_info()
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        value = args.steps / dev_s
+        line = {"metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BNMF Gibbs+ARD %dx%d rho=%.2f K=%d (BASELINE configs[2])" % (I, J, args.density, K),
+                           "cache": "inputs (R packed: %.2f GB/GPU) exceed the 126 MB L2" % (
+                               (info["slots_U"] + info["slots_V"]) * 12 / 1e9),
+                           "layout": info, "wall_s": wall, "train_mse_last": perf["MSE"]},
+                "gpu_launches": launches, "clocks": sampler.summary()}
+        # roofline of the dominant kernel (row sweep): algorithmic DRAM bytes of OUR formulation
+        if sweeps["n_U"] > 0:
+            ms = (sweeps["ms_U"] + sweeps["ms_V"]) / (sweeps["n_U"] + sweeps["n_V"])
+            bytes_per_launch = 0.5 * (info["slots_U"] + info["slots_V"]) * 12.0 + (I + J) * K * 8 * 1.5
+            ach = bytes_per_launch / (ms * 1e-3) / 1e9
+            northstar_bytes = 2 * K * 16.125 * I * J
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                "traffic": None, "peak_source": peak_src, "kernel": "sweep_kernel",
+                                "kernel_ms": ms, "kernel_share_of_step": (sweeps["ms_U"] + sweeps["ms_V"]) / (1e3 * dev_s),
+                                "north_star_equiv_gbs": northstar_bytes * value / 1e9,
+                                "north_star_equiv_frac": northstar_bytes * value / 1e9 / peak}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,173 @@
+"""numpy <-> C-ABI adapter for one NMF model handle (include/bnmtf_b200.h)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _dist, _lib
+from ._lib import (F_MU, F_TAU, F_VALUE, F_VAR, NSTATS, SIDE_U, SIDE_V, check, dptr, f64)
+
+
+class NMFEngine(object):
+    """Owns a bnmtf_nmf_t.  R, M are the full I x J matrices (every rank passes the
+    same ones, like the reference constructors); this rank packs its row shard for
+    the U sweep and its column shard for the V sweep."""
+
+    def __init__(self, R, M, K, device=None):
+        lib = _lib.require_device()
+        self.lib = lib
+        self.I, self.J = R.shape
+        self.K = int(K)
+        self.device = _lib.current_device() if device is None else int(device)
+        self.rank, self.world = _dist.info()
+        r0, r1, rs = _dist.shard_bounds(self.I, self.rank, self.world)
+        c0, c1, cs = _dist.shard_bounds(self.J, self.rank, self.world)
+        R = f64(R)
+        M8 = np.ascontiguousarray(np.asarray(M) != 0, dtype=np.uint8)
+        h = C.c_void_p()
+        check(lib.bnmtf_nmf_create(C.byref(h), self.device, self.I, self.J, self.K, dptr(R),
+                                   M8.ctypes.data_as(C.POINTER(C.c_uint8)), r0, r1, rs, c0, c1, cs))
+        self.h = h
+        self._finish_setup()
+
+    @classmethod
+    def from_device_blocks(cls, I, J, K, Rrow_ptr, Mrow_ptr, Rcol_ptr, Mcol_ptr, device=None):
+        """Build from dense blocks already on the device (raw device addresses): rows
+        [r0,r1) x J and I x columns [c0,c1) of this rank's shards (see shard_bounds)."""
+        self = cls.__new__(cls)
+        lib = _lib.require_device()
+        self.lib = lib
+        self.I, self.J, self.K = int(I), int(J), int(K)
+        self.device = _lib.current_device() if device is None else int(device)
+        self.rank, self.world = _dist.info()
+        r0, r1, rs = _dist.shard_bounds(self.I, self.rank, self.world)
+        c0, c1, cs = _dist.shard_bounds(self.J, self.rank, self.world)
+        h = C.c_void_p()
+        check(lib.bnmtf_nmf_create_dev(C.byref(h), self.device, self.I, self.J, self.K,
+                                       C.c_void_p(Rrow_ptr), C.c_void_p(Mrow_ptr), C.c_void_p(Rcol_ptr),
+                                       C.c_void_p(Mcol_ptr), r0, r1, rs, c0, c1, cs))
+        self.h = h
+        self._finish_setup()
+        return self
+
+    def _finish_setup(self):
+        lib = self.lib
+        out = np.zeros(3)
+        check(lib.bnmtf_nmf_data_stats(self.h, dptr(out)))
+        tot = _dist.allreduce_sum(out[:2])
+        self.size_Omega = float(tot[0])
+        self.mean_R = float(tot[1] / tot[0]) if tot[0] > 0 else 0.0
+        check(lib.bnmtf_nmf_set_data_stats(self.h, self.size_Omega, self.mean_R))
+        check(lib.bnmtf_nmf_data_stats(self.h, dptr(out)))
+        self.ss_total = float(_dist.allreduce_sum(out[2:3])[0])
+        if self.world > 1:
+            ident = np.zeros(128, dtype=np.uint8)
+            if self.rank == 0:
+                check(lib.bnmtf_nccl_unique_id(ident.ctypes.data_as(C.POINTER(C.c_uint8))))
+            ident = np.frombuffer(_dist.broadcast_bytes(ident.tobytes(), src=0), dtype=np.uint8).copy()
+            check(lib.bnmtf_nmf_set_comm(self.h, self.rank, self.world, ident.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.bnmtf_nmf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # -- state ---------------------------------------------------------------
+    def n_of(self, side):
+        return self.I if side == SIDE_U else self.J
+
+    def set_hyper(self, ARD, alphatau, betatau, alpha0=1.0, beta0=1.0, lambdaU=None, lambdaV=None):
+        lu = None if lambdaU is None else f64(lambdaU, (self.I, self.K))
+        lv = None if lambdaV is None else f64(lambdaV, (self.J, self.K))
+        check(self.lib.bnmtf_nmf_set_hyper(self.h, int(bool(ARD)), float(alphatau), float(betatau), float(alpha0),
+                                           float(beta0), dptr(lu), dptr(lv)))
+
+    def set_factor(self, side, field, arr):
+        a = f64(arr, (self.n_of(side), self.K))
+        check(self.lib.bnmtf_nmf_set_factor(self.h, side, field, dptr(a)))
+
+    def get_factor(self, side, field):
+        out = np.empty((self.n_of(side), self.K))
+        check(self.lib.bnmtf_nmf_get_factor(self.h, side, field, dptr(out)))
+        return out
+
+    def set_scalars(self, tau, lambdak=None):
+        lk = None if lambdak is None else f64(lambdak, (self.K,))
+        check(self.lib.bnmtf_nmf_set_scalars(self.h, float(tau), dptr(lk)))
+
+    def get_scalars(self, want_lambdak=True):
+        tau = C.c_double()
+        lk = np.zeros(self.K) if want_lambdak else None
+        check(self.lib.bnmtf_nmf_get_scalars(self.h, C.byref(tau), dptr(lk)))
+        return tau.value, lk
+
+    def set_vb_scalars(self, exp_tau, exp_logtau, alpha_s, beta_s, alphak_s=None, betak_s=None, exp_lambdak=None,
+                       exp_loglambdak=None):
+        vecs = [None if v is None else f64(v, (self.K,)) for v in (alphak_s, betak_s, exp_lambdak, exp_loglambdak)]
+        check(self.lib.bnmtf_nmf_set_vb_scalars(self.h, float(exp_tau), float(exp_logtau), float(alpha_s),
+                                                float(beta_s), *[dptr(v) for v in vecs]))
+
+    def get_vb_scalars(self):
+        sc, ls = np.zeros(4), np.zeros((4, self.K))
+        check(self.lib.bnmtf_nmf_get_vb_scalars(self.h, dptr(sc), dptr(ls)))
+        return sc, ls
+
+    def init_factors(self, method, random, seed):
+        check(self.lib.bnmtf_nmf_init_factors(self.h, method, int(bool(random)), C.c_uint64(seed)))
+
+    # -- compute ---------------------------------------------------------------
+    def column_params(self, method, side, k):
+        n = self.n_of(side)
+        t, m = np.empty(n), np.empty(n)
+        check(self.lib.bnmtf_nmf_column_params(self.h, method, side, int(k), dptr(t), dptr(m)))
+        return t, m
+
+    def stats(self, method):
+        out = np.zeros(NSTATS)
+        check(self.lib.bnmtf_nmf_stats(self.h, method, dptr(out)))
+        return out
+
+    def run(self, method, iterations, seed=0, traces=True, want_lambdak=True):
+        it = int(iterations)
+        res = {
+            "all_U": np.zeros((it, self.I, self.K)) if traces else None,
+            "all_V": np.zeros((it, self.J, self.K)) if traces else None,
+            "all_lambdak": np.zeros((it, self.K)) if want_lambdak else None,
+            "stats": np.zeros((it, NSTATS)),
+            "seconds": np.zeros(it),
+        }
+        check(self.lib.bnmtf_nmf_run(self.h, method, it, C.c_uint64(seed), dptr(res["all_U"]), dptr(res["all_V"]),
+                                     dptr(res["all_lambdak"]), dptr(res["stats"]), dptr(res["seconds"])))
+        return res
+
+    def launch_count(self):
+        return int(self.lib.bnmtf_nmf_launch_count(self.h))
+
+    def layout_info(self):
+        out = np.zeros(8, dtype=np.int64)
+        check(self.lib.bnmtf_nmf_layout_info(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return dict(zip(["tpr_U", "npt_U", "tpr_V", "npt_V", "slots_U", "slots_V", "nnz_U", "nnz_V"], out.tolist()))
+
+    def sweep_times(self):
+        out = np.zeros(4)
+        check(self.lib.bnmtf_nmf_sweep_times(self.h, dptr(out)))
+        return {"ms_U": out[0], "ms_V": out[1], "n_U": int(out[2]), "n_V": int(out[3])}
+
+    # -- metrics from the per-iteration sufficient statistics ------------------
+    def performances(self, stats_row):
+        """MSE, R^2, Rp on Omega (bnmf_gibbs.py:252-270) from RSS, sum E and
+        sum (R-mean)E; algebraically identical to the reference's centred sums."""
+        rss, se, srce = stats_row[_lib.ST_RSS], stats_row[_lib.ST_SUM_E], stats_row[_lib.ST_SUM_RCE]
+        n, sst = self.size_Omega, self.ss_total
+        mse = rss / n
+        r2 = 1.0 - rss / sst if sst != 0.0 else np.inf
+        cov = sst - srce
+        var_pred = sst - 2.0 * srce + (rss - se * se / n)
+        with np.errstate(all="ignore"):
+            rp = cov / (np.sqrt(sst) * np.sqrt(var_pred))
+        return {"MSE": float(mse), "R^2": float(r2), "Rp": float(rp)}

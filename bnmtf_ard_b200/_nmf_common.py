@@ -1,0 +1,112 @@
+"""Shared host-side logic of the four NMF classes: constructor checks with the
+reference's exact messages, lazy engine creation, prediction metrics.  The
+state (U, V, tau, ...) lives in plain numpy attributes on the object and is
+host-authoritative between calls, exactly like the reference objects; every
+method that computes uploads what it needs and downloads its results."""
+import math
+
+import numpy
+
+from . import _lib
+from ._engine import NMFEngine
+
+ALL_METRICS = ['MSE', 'R^2', 'Rp']
+ALL_QUALITY = ['loglikelihood', 'BIC', 'AIC', 'MSE', 'ELBO']
+
+
+class NMFCommon(object):
+    verbose = True      # print one line per iteration like the reference (after the device loop)
+
+    def _setup_data(self, R, M, K):
+        ''' Constructor checks shared by all models (bnmf_gibbs.py:61-75). '''
+        self.R = numpy.array(R, dtype=float)
+        self.M = numpy.array(M, dtype=float)
+        self.K = K
+
+        assert len(self.R.shape) == 2, "Input matrix R is not a two-dimensional array, " \
+            "but instead %s-dimensional." % len(self.R.shape)
+        assert self.R.shape == self.M.shape, "Input matrix R is not of the same size as " \
+            "the indicator matrix M: %s and %s respectively." % (self.R.shape, self.M.shape)
+
+        (self.I, self.J) = self.R.shape
+        self.size_Omega = self.M.sum()
+        self.check_empty_rows_columns()
+        self._eng = None
+
+    def _setup_hyper(self, ARD, hyperparameters):
+        ''' Hyper-parameter handling of the Bayesian models (bnmf_gibbs.py:76-89). '''
+        self.ARD = ARD
+        self.alphatau, self.betatau = float(hyperparameters['alphatau']), float(hyperparameters['betatau'])
+        if self.ARD:
+            self.alpha0, self.beta0 = float(hyperparameters['alpha0']), float(hyperparameters['beta0'])
+        else:
+            self.lambdaU, self.lambdaV = numpy.array(hyperparameters['lambdaU']), numpy.array(hyperparameters['lambdaV'])
+            # Make lambdaU/V into a numpy array if they are a float
+            if self.lambdaU.shape == ():
+                self.lambdaU = self.lambdaU * numpy.ones((self.I, self.K))
+            if self.lambdaV.shape == ():
+                self.lambdaV = self.lambdaV * numpy.ones((self.J, self.K))
+
+            assert self.lambdaU.shape == (self.I, self.K), "Prior matrix lambdaU has the wrong shape: %s instead of (%s, %s)." % (self.lambdaU.shape, self.I, self.K)
+            assert self.lambdaV.shape == (self.J, self.K), "Prior matrix lambdaV has the wrong shape: %s instead of (%s, %s)." % (self.lambdaV.shape, self.J, self.K)
+
+    def check_empty_rows_columns(self):
+        ''' Raise an exception if an entire row or column is empty (bnmf_gibbs.py:92-101). '''
+        sums_columns = self.M.sum(axis=0)
+        sums_rows = self.M.sum(axis=1)
+        empty_rows = numpy.flatnonzero(sums_rows == 0)
+        assert empty_rows.size == 0, "Fully unobserved row in R, row %s." % (empty_rows[0] if empty_rows.size else -1)
+        empty_columns = numpy.flatnonzero(sums_columns == 0)
+        assert empty_columns.size == 0, "Fully unobserved column in R, column %s." % (empty_columns[0] if empty_columns.size else -1)
+
+    # -- engine ----------------------------------------------------------------
+    def _engine(self):
+        ''' The device handle, created on first use (packs R, M on the GPU). '''
+        if self._eng is None:
+            self._eng = NMFEngine(self.R, self.M, self.K)
+        return self._eng
+
+    def _upload_hyper(self, eng):
+        if getattr(self, 'ARD', True):
+            eng.set_hyper(True, getattr(self, 'alphatau', 1.), getattr(self, 'betatau', 1.),
+                          getattr(self, 'alpha0', 1.), getattr(self, 'beta0', 1.))
+        else:
+            eng.set_hyper(False, self.alphatau, self.betatau, 1., 1., self.lambdaU, self.lambdaV)
+
+    def _fill_performances(self, eng, stats):
+        for row in stats:
+            perf = eng.performances(row)
+            for metric in ALL_METRICS:
+                self.all_performances[metric].append(perf[metric])
+
+    # -- metrics (bnmf_gibbs.py:252-270; identical in all eight models) --------
+    def compute_MSE(self, M, R, R_pred):
+        ''' Return the MSE of predictions in R_pred, expected values in R, for the entries in M. '''
+        return (M * (R - R_pred)**2).sum() / float(M.sum())
+
+    def compute_R2(self, M, R, R_pred):
+        ''' Return the R^2 of predictions in R_pred, expected values in R, for the entries in M. '''
+        mean = (M * R).sum() / float(M.sum())
+        SS_total = float((M * (R - mean)**2).sum())
+        SS_res = float((M * (R - R_pred)**2).sum())
+        return 1. - SS_res / SS_total if SS_total != 0. else numpy.inf
+
+    def compute_Rp(self, M, R, R_pred):
+        ''' Return the Rp of predictions in R_pred, expected values in R, for the entries in M. '''
+        mean_real = (M * R).sum() / float(M.sum())
+        mean_pred = (M * R_pred).sum() / float(M.sum())
+        covariance = (M * (R - mean_real) * (R_pred - mean_pred)).sum()
+        variance_real = (M * (R - mean_real)**2).sum()
+        variance_pred = (M * (R_pred - mean_pred)**2).sum()
+        return covariance / float(math.sqrt(variance_real) * math.sqrt(variance_pred))
+
+    def _predict_from(self, M_pred, X, Y):
+        R_pred = numpy.dot(X, Y.T)
+        MSE = self.compute_MSE(M_pred, self.R, R_pred)
+        R2 = self.compute_R2(M_pred, self.R, R_pred)
+        Rp = self.compute_Rp(M_pred, self.R, R_pred)
+        return {'MSE': MSE, 'R^2': R2, 'Rp': Rp}
+
+
+def method_id(name):
+    return {'gibbs': _lib.GIBBS, 'icm': _lib.ICM, 'vb': _lib.VB, 'np': _lib.NP}[name]

@@ -1,0 +1,820 @@
+// Host side of the engine: model handle, packing of R/M, the iteration loop and
+// the C ABI declared in include/bnmtf_b200.h.  No torch types anywhere.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bnmtf_b200.h"
+#include "kernels.cuh"
+
+using namespace bnmtf;
+
+static thread_local std::string g_err;
+const char* bnmtf_last_error(void) { return g_err.c_str(); }
+int bnmtf_abi_version(void) { return 1; }
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      char buf_[512];                                                                                \
+      snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      g_err = buf_;                                                                                  \
+      return 1;                                                                                      \
+    }                                                                                                \
+  } while (0)
+
+#define FAIL(...)                                  \
+  do {                                             \
+    char buf_[512];                                \
+    snprintf(buf_, sizeof buf_, __VA_ARGS__);      \
+    g_err = buf_;                                  \
+    return 1;                                      \
+  } while (0)
+
+static inline int64_t roundup(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+int bnmtf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ---- NCCL, loaded lazily (only multi-GPU jobs need it) ------------------------
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllGather && CommDestroy && GetErrorString;
+  }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8;
+
+// one sweep direction: rows of this side are updated, columns index the other factor
+struct Side {
+  int64_t n_glob = 0, n_loc = 0, row0 = 0, n_shard = 0, n_padglob = 0;
+  int64_t m_glob = 0;
+  int64_t nslots = 0, nnz = 0;
+  int tpr = 32, npt = 2;
+  uint32_t padcol = 0;
+  double* vals = nullptr;
+  uint32_t* cols = nullptr;
+  int64_t* rowstart = nullptr;
+  double *val = nullptr, *var = nullptr, *mu = nullptr, *tau = nullptr;  // [n_padglob][K]
+  double* km = nullptr;  // [K][ld][2]
+  int64_t ld = 0;
+  double* lam_rm = nullptr;
+  double* rowstats = nullptr;  // [n_padglob][NRS]
+  double* trace[2] = {nullptr, nullptr};
+  int occ[4] = {0, 0, 0, 0};  // cached resident blocks/SM of the sweep kernel per method
+};
+}  // namespace
+
+struct bnmtf_nmf_s {
+  int device = 0;
+  int64_t I = 0, J = 0;
+  int K = 0;
+  Side s[2];
+  Hyper hyper{};
+  double rmean = 0.0;
+  double* scal = nullptr;      // [SC_COUNT]
+  double* colsum = nullptr;    // [2K]
+  double* lamstate = nullptr;  // [4K]
+  double* lamk = nullptr;      // [K]
+  double* stats_dev = nullptr; // [iters chunk][16]
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  int num_sms = 148;
+  int rank = 0, world = 1;
+  NcclComm comm = nullptr;
+  int64_t launches = 0;
+  bool time_sweeps = false;
+  double sweep_ms[2] = {0, 0};
+  int64_t sweep_n[2] = {0, 0};
+  int km_mode = -1;            // NV layout currently held by the km copies
+};
+
+// ---- packing -------------------------------------------------------------------
+static void choose_team(int64_t maxlen, int* tpr, int* npt) {
+  // entries per thread (register-resident residual) and threads per row team;
+  // 16 x 512 and 32 x 512 are the largest register-resident configurations
+  int n = maxlen > 256 ? 16 : maxlen > 128 ? 8 : maxlen > 64 ? 4 : 2;
+  int64_t t = roundup((maxlen + n - 1) / n, 32);
+  if (t < 32) t = 32;
+  if (t > 512) { n = 32; t = roundup((maxlen + n - 1) / n, 32); }
+  *tpr = (int)t;
+  *npt = n;
+}
+
+// pack a dense device block (n x m, row-major, leading dim ld) into padded rows
+static int pack_block(bnmtf_nmf_s* h, Side& sd, const double* R_dev, const uint8_t* M_dev, int64_t n, int64_t m, int64_t ld,
+                      uint32_t padcol) {
+  int* rowlen_dev = nullptr;
+  CK(cudaMalloc(&rowlen_dev, sizeof(int) * std::max<int64_t>(n, 1)));
+  if (n > 0) {
+    count_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, h->stream>>>(M_dev, n, m, ld, rowlen_dev);
+    h->launches++;
+  }
+  std::vector<int> rowlen(n);
+  CK(cudaMemcpyAsync(rowlen.data(), rowlen_dev, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  int64_t maxlen = 1, nnz = 0;
+  for (int64_t i = 0; i < n; ++i) { maxlen = std::max<int64_t>(maxlen, rowlen[i]); nnz += rowlen[i]; }
+  choose_team(maxlen, &sd.tpr, &sd.npt);
+  if ((int64_t)sd.tpr * sd.npt < maxlen || sd.tpr > 512)
+    FAIL("a row/column of R has %lld observed entries; this build supports at most 16384 per row", (long long)maxlen);
+  std::vector<int64_t> rowstart(n + 1);
+  rowstart[0] = 0;
+  for (int64_t i = 0; i < n; ++i) rowstart[i + 1] = rowstart[i] + roundup(rowlen[i], sd.tpr);
+  sd.nslots = rowstart[n];
+  sd.nnz = nnz;
+  sd.padcol = padcol;
+  CK(cudaMalloc(&sd.rowstart, sizeof(int64_t) * (n + 1)));
+  CK(cudaMalloc(&sd.vals, sizeof(double) * std::max<int64_t>(sd.nslots, 1)));
+  CK(cudaMalloc(&sd.cols, sizeof(uint32_t) * std::max<int64_t>(sd.nslots, 1)));
+  CK(cudaMemcpyAsync(sd.rowstart, rowstart.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, h->stream));
+  if (n > 0) {
+    pack_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, h->stream>>>(R_dev, M_dev, n, m, ld, sd.rowstart, padcol, sd.vals, sd.cols);
+    h->launches++;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaFree(rowlen_dev));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int alloc_side_state(bnmtf_nmf_s* h, Side& sd, int K) {
+  const size_t nb = sizeof(double) * sd.n_padglob * K;
+  CK(cudaMalloc(&sd.val, nb)); CK(cudaMalloc(&sd.var, nb)); CK(cudaMalloc(&sd.mu, nb)); CK(cudaMalloc(&sd.tau, nb));
+  CK(cudaMemsetAsync(sd.val, 0, nb, h->stream)); CK(cudaMemsetAsync(sd.var, 0, nb, h->stream));
+  CK(cudaMemsetAsync(sd.mu, 0, nb, h->stream)); CK(cudaMemsetAsync(sd.tau, 0, nb, h->stream));
+  sd.ld = roundup(std::max(sd.n_padglob, sd.n_glob + 1), 16);
+  CK(cudaMalloc(&sd.km, sizeof(double) * 2 * sd.ld * K));
+  CK(cudaMemsetAsync(sd.km, 0, sizeof(double) * 2 * sd.ld * K, h->stream));
+  CK(cudaMalloc(&sd.rowstats, sizeof(double) * sd.n_padglob * NRS));
+  CK(cudaMemsetAsync(sd.rowstats, 0, sizeof(double) * sd.n_padglob * NRS, h->stream));
+  return 0;
+}
+
+int bnmtf_nmf_create_dev(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, const double* Rrow_dev,
+                         const uint8_t* Mrow_dev, const double* Rcol_dev, const uint8_t* Mcol_dev, int64_t row0,
+                         int64_t row1, int64_t shard_rows, int64_t col0, int64_t col1, int64_t shard_cols) {
+  if (!out) FAIL("out is NULL");
+  *out = nullptr;
+  if (I <= 0 || J <= 0 || K <= 0) FAIL("bad shape I=%lld J=%lld K=%d", (long long)I, (long long)J, K);
+  if (I >= (int64_t)0xFFFFFFF0ll || J >= (int64_t)0xFFFFFFF0ll) FAIL("dimension too large for 32-bit column indices");
+  if (row0 < 0 || row1 < row0 || row1 > I || col0 < 0 || col1 < col0 || col1 > J) FAIL("bad shard bounds");
+  if (shard_rows < row1 - row0 || shard_cols < col1 - col0) FAIL("shard size smaller than the owned range");
+  CK(cudaSetDevice(device));
+  bnmtf_nmf_s* h = new bnmtf_nmf_s();
+  h->device = device; h->I = I; h->J = J; h->K = K;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    delete h;
+    FAIL("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  }
+  h->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  const char* ts = getenv("BNMTF_TIME_SWEEPS");
+  h->time_sweeps = ts && atoi(ts) != 0;
+
+  Side& su = h->s[BNMTF_SIDE_U];
+  Side& sv = h->s[BNMTF_SIDE_V];
+  su.n_glob = I; su.m_glob = J; su.row0 = row0; su.n_loc = row1 - row0; su.n_shard = shard_rows;
+  sv.n_glob = J; sv.m_glob = I; sv.row0 = col0; sv.n_loc = col1 - col0; sv.n_shard = shard_cols;
+  su.n_padglob = std::max(I, ((I + shard_rows - 1) / shard_rows) * shard_rows);
+  sv.n_padglob = std::max(J, ((J + shard_cols - 1) / shard_cols) * shard_cols);
+
+  // U side: rows [row0,row1) x J
+  if (pack_block(h, su, Rrow_dev, Mrow_dev, su.n_loc, J, J, (uint32_t)J)) { return 1; }
+  // V side: columns [col0,col1): transpose the I x Jloc block, then pack its rows
+  {
+    const int64_t jl = sv.n_loc;
+    double* Rt = nullptr; uint8_t* Mt = nullptr;
+    CK(cudaMalloc(&Rt, sizeof(double) * std::max<int64_t>(jl * I, 1)));
+    CK(cudaMalloc(&Mt, std::max<int64_t>(jl * I, 1)));
+    if (jl > 0) {
+      dim3 blk(32, 8), grd((unsigned)((jl + 31) / 32), (unsigned)((I + 31) / 32));
+      transpose_kernel<double><<<grd, blk, 0, h->stream>>>(Rcol_dev, I, jl, jl, Rt, I);
+      transpose_kernel<uint8_t><<<grd, blk, 0, h->stream>>>(Mcol_dev, I, jl, jl, Mt, I);
+      h->launches += 2;
+    }
+    int rc = pack_block(h, sv, Rt, Mt, jl, I, I, (uint32_t)I);
+    cudaFree(Rt); cudaFree(Mt);
+    if (rc) return 1;
+  }
+  if (alloc_side_state(h, su, K) || alloc_side_state(h, sv, K)) return 1;
+  CK(cudaMalloc(&h->scal, sizeof(double) * SC_COUNT));
+  CK(cudaMalloc(&h->colsum, sizeof(double) * 2 * K));
+  CK(cudaMalloc(&h->lamstate, sizeof(double) * 4 * K));
+  CK(cudaMalloc(&h->lamk, sizeof(double) * K));
+  CK(cudaMemsetAsync(h->scal, 0, sizeof(double) * SC_COUNT, h->stream));
+  CK(cudaMemsetAsync(h->colsum, 0, sizeof(double) * 2 * K, h->stream));
+  CK(cudaMemsetAsync(h->lamstate, 0, sizeof(double) * 4 * K, h->stream));
+  CK(cudaMemsetAsync(h->lamk, 0, sizeof(double) * K, h->stream));
+  h->hyper.ARD = 1; h->hyper.alphatau = h->hyper.betatau = h->hyper.alpha0 = h->hyper.beta0 = 1.0;
+  h->hyper.size_Omega = (double)su.nnz;
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return 0;
+}
+
+int bnmtf_nmf_create(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, const double* R, const uint8_t* M,
+                     int64_t row0, int64_t row1, int64_t shard_rows, int64_t col0, int64_t col1, int64_t shard_cols) {
+  if (!R || !M) FAIL("R or M is NULL");
+  if (I <= 0 || J <= 0) FAIL("bad shape");
+  CK(cudaSetDevice(device));
+  const int64_t nr = row1 - row0, nc = col1 - col0;
+  const bool full = (nr == I && nc == J);
+  double *Rrow = nullptr, *Rcol = nullptr;
+  uint8_t *Mrow = nullptr, *Mcol = nullptr;
+  CK(cudaMalloc(&Rrow, sizeof(double) * std::max<int64_t>(nr * J, 1)));
+  CK(cudaMalloc(&Mrow, std::max<int64_t>(nr * J, 1)));
+  if (nr > 0) {
+    CK(cudaMemcpy(Rrow, R + row0 * J, sizeof(double) * nr * J, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(Mrow, M + row0 * J, (size_t)nr * J, cudaMemcpyHostToDevice));
+  }
+  if (full) {
+    Rcol = Rrow; Mcol = Mrow;
+  } else {
+    CK(cudaMalloc(&Rcol, sizeof(double) * std::max<int64_t>(I * nc, 1)));
+    CK(cudaMalloc(&Mcol, std::max<int64_t>(I * nc, 1)));
+    if (nc > 0) {
+      CK(cudaMemcpy2D(Rcol, sizeof(double) * nc, R + col0, sizeof(double) * J, sizeof(double) * nc, I, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy2D(Mcol, nc, M + col0, J, nc, I, cudaMemcpyHostToDevice));
+    }
+  }
+  int rc = bnmtf_nmf_create_dev(out, device, I, J, K, Rrow, Mrow, Rcol, Mcol, row0, row1, shard_rows, col0, col1, shard_cols);
+  cudaFree(Rrow); cudaFree(Mrow);
+  if (!full) { cudaFree(Rcol); cudaFree(Mcol); }
+  return rc;
+}
+
+static void free_side(Side& sd) {
+  cudaFree(sd.vals); cudaFree(sd.cols); cudaFree(sd.rowstart);
+  cudaFree(sd.val); cudaFree(sd.var); cudaFree(sd.mu); cudaFree(sd.tau);
+  cudaFree(sd.km); cudaFree(sd.lam_rm); cudaFree(sd.rowstats);
+  cudaFree(sd.trace[0]); cudaFree(sd.trace[1]);
+}
+
+int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  free_side(h->s[0]); free_side(h->s[1]);
+  cudaFree(h->scal); cudaFree(h->colsum); cudaFree(h->lamstate); cudaFree(h->lamk); cudaFree(h->stats_dev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return 0;
+}
+
+int bnmtf_nmf_data_stats(bnmtf_nmf_t h, double* out) {
+  if (!h || !out) FAIL("NULL argument");
+  CK(cudaSetDevice(h->device));
+  Side& su = h->s[0];
+  const int nb = 256;
+  double* part = nullptr;
+  CK(cudaMalloc(&part, sizeof(double) * nb * 3));
+  data_stats_kernel<<<nb, 256, 0, h->stream>>>(su.vals, su.cols, su.nslots, su.padcol, h->rmean, part);
+  h->launches++;
+  std::vector<double> hp(nb * 3);
+  CK(cudaMemcpyAsync(hp.data(), part, sizeof(double) * nb * 3, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaFree(part));
+  out[0] = out[1] = out[2] = 0.0;
+  for (int b = 0; b < nb; ++b) { out[0] += hp[b * 3]; out[1] += hp[b * 3 + 1]; out[2] += hp[b * 3 + 2]; }
+  return 0;
+}
+
+int bnmtf_nmf_set_data_stats(bnmtf_nmf_t h, double size_Omega, double mean_R) {
+  if (!h) FAIL("NULL handle");
+  h->hyper.size_Omega = size_Omega;
+  h->rmean = mean_R;
+  return 0;
+}
+
+int bnmtf_nccl_unique_id(uint8_t* id128) {
+  if (!id128) FAIL("NULL argument");
+  if (!g_nccl.load()) FAIL("cannot load libnccl.so.2: %s", dlerror());
+  NcclUniqueId id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) FAIL("ncclGetUniqueId: %s", g_nccl.GetErrorString(rc));
+  memcpy(id128, id.internal, 128);
+  return 0;
+}
+
+int bnmtf_nmf_set_comm(bnmtf_nmf_t h, int rank, int world, const uint8_t* nccl_id128) {
+  if (!h) FAIL("NULL handle");
+  if (world <= 1) { h->rank = 0; h->world = 1; return 0; }
+  if (!nccl_id128) FAIL("NULL nccl id");
+  if (!g_nccl.load()) FAIL("cannot load libnccl.so.2: %s", dlerror());
+  CK(cudaSetDevice(h->device));
+  for (int sidx = 0; sidx < 2; ++sidx) {
+    const Side& sd = h->s[sidx];
+    if (sd.n_shard * world != sd.n_padglob) FAIL("shard size %lld x world %d != padded extent %lld", (long long)sd.n_shard, world, (long long)sd.n_padglob);
+    if (sd.row0 != sd.n_shard * rank) FAIL("rank %d does not own the shard starting at %lld", rank, (long long)sd.row0);
+  }
+  NcclUniqueId id;
+  memcpy(id.internal, nccl_id128, 128);
+  int rc = g_nccl.CommInitRank(&h->comm, world, id, rank);
+  if (rc != 0) FAIL("ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
+  h->rank = rank; h->world = world;
+  return 0;
+}
+
+int bnmtf_nmf_set_hyper(bnmtf_nmf_t h, int ARD, double alphatau, double betatau, double alpha0, double beta0,
+                        const double* lambdaU, const double* lambdaV) {
+  if (!h) FAIL("NULL handle");
+  CK(cudaSetDevice(h->device));
+  h->hyper.ARD = ARD; h->hyper.alphatau = alphatau; h->hyper.betatau = betatau;
+  h->hyper.alpha0 = alpha0; h->hyper.beta0 = beta0;
+  h->hyper.sumlog_lamU = h->hyper.sumlog_lamV = 0.0;
+  const double* src[2] = {lambdaU, lambdaV};
+  for (int sidx = 0; sidx < 2; ++sidx) {
+    Side& sd = h->s[sidx];
+    if (!ARD) {
+      if (!src[sidx]) FAIL("lambda%c is required when ARD is off", sidx ? 'V' : 'U');
+      if (!sd.lam_rm) CK(cudaMalloc(&sd.lam_rm, sizeof(double) * sd.n_glob * h->K));
+      CK(cudaMemcpy(sd.lam_rm, src[sidx], sizeof(double) * sd.n_glob * h->K, cudaMemcpyHostToDevice));
+      double sl = 0.0;
+      for (int64_t q = 0; q < sd.n_glob * h->K; ++q) sl += log(src[sidx][q]);
+      (sidx ? h->hyper.sumlog_lamV : h->hyper.sumlog_lamU) = sl;
+    }
+  }
+  return 0;
+}
+
+static double* field_ptr(Side& sd, int field) {
+  switch (field) {
+    case BNMTF_F_VALUE: return sd.val;
+    case BNMTF_F_VAR: return sd.var;
+    case BNMTF_F_MU: return sd.mu;
+    case BNMTF_F_TAU: return sd.tau;
+  }
+  return nullptr;
+}
+
+int bnmtf_nmf_set_factor(bnmtf_nmf_t h, int side, int field, const double* src) {
+  if (!h || !src || side < 0 || side > 1) FAIL("bad argument");
+  double* p = field_ptr(h->s[side], field);
+  if (!p) FAIL("bad field %d", field);
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(p, src, sizeof(double) * h->s[side].n_glob * h->K, cudaMemcpyHostToDevice));
+  h->km_mode = -1;
+  return 0;
+}
+
+int bnmtf_nmf_get_factor(bnmtf_nmf_t h, int side, int field, double* dst) {
+  if (!h || !dst || side < 0 || side > 1) FAIL("bad argument");
+  double* p = field_ptr(h->s[side], field);
+  if (!p) FAIL("bad field %d", field);
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(dst, p, sizeof(double) * h->s[side].n_glob * h->K, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bnmtf_nmf_set_scalars(bnmtf_nmf_t h, double tau, const double* lambdak) {
+  if (!h) FAIL("NULL handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(h->scal + SC_TAU, &tau, sizeof(double), cudaMemcpyHostToDevice));
+  if (lambdak) {
+    CK(cudaMemcpy(h->lamk, lambdak, sizeof(double) * h->K, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->lamstate + 2 * h->K, lambdak, sizeof(double) * h->K, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int bnmtf_nmf_get_scalars(bnmtf_nmf_t h, double* tau, double* lambdak) {
+  if (!h) FAIL("NULL handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (tau) CK(cudaMemcpy(tau, h->scal + SC_TAU, sizeof(double), cudaMemcpyDeviceToHost));
+  if (lambdak) CK(cudaMemcpy(lambdak, h->lamk, sizeof(double) * h->K, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bnmtf_nmf_set_vb_scalars(bnmtf_nmf_t h, double exp_tau, double exp_logtau, double alpha_s, double beta_s,
+                             const double* alphak_s, const double* betak_s, const double* exp_lambdak,
+                             const double* exp_loglambdak) {
+  if (!h) FAIL("NULL handle");
+  CK(cudaSetDevice(h->device));
+  double sc[SC_COUNT] = {0};
+  sc[SC_TAU] = exp_tau; sc[SC_LOGTAU] = exp_logtau; sc[SC_ALPHA_S] = alpha_s; sc[SC_BETA_S] = beta_s;
+  CK(cudaMemcpy(h->scal, sc, sizeof(sc), cudaMemcpyHostToDevice));
+  const double* src[4] = {alphak_s, betak_s, exp_lambdak, exp_loglambdak};
+  for (int f = 0; f < 4; ++f)
+    if (src[f]) CK(cudaMemcpy(h->lamstate + f * h->K, src[f], sizeof(double) * h->K, cudaMemcpyHostToDevice));
+  if (exp_lambdak) CK(cudaMemcpy(h->lamk, exp_lambdak, sizeof(double) * h->K, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int bnmtf_nmf_get_vb_scalars(bnmtf_nmf_t h, double* scal4, double* lamstate4K) {
+  if (!h) FAIL("NULL handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (scal4) CK(cudaMemcpy(scal4, h->scal, sizeof(double) * 4, cudaMemcpyDeviceToHost));
+  if (lamstate4K) CK(cudaMemcpy(lamstate4K, h->lamstate, sizeof(double) * 4 * h->K, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---- launches --------------------------------------------------------------------
+static int refresh_km(bnmtf_nmf_s* h, int side, int method) {
+  Side& sd = h->s[side];
+  dim3 blk(32, 8), grd((unsigned)((sd.ld + 31) / 32), (unsigned)((h->K + 31) / 32));
+  if (method == BNMTF_VB)
+    rm_to_km_kernel<2><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, h->K, sd.ld);
+  else
+    rm_to_km_kernel<1><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, h->K, sd.ld);
+  h->launches++;
+  return 0;
+}
+
+template <int NPT, int MODE>
+static int launch_sweep_t(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int* occ_cache) {
+  const int tpr = p.tpr;
+  const int teams = tpr >= 128 ? 1 : 128 / tpr;
+  const int block = tpr * teams;
+  const int nw = tpr / 32;
+  const size_t smem = sizeof(double) * teams * (4 * (size_t)p.K + 3 * nw + 2);
+  auto kern = sweep_kernel<NPT, MODE>;
+  if (*occ_cache == 0) {
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
+    if (occ < 1) FAIL("sweep kernel does not fit: block %d smem %zu", block, smem);
+    *occ_cache = occ;
+  }
+  int64_t need = ((int64_t)n_loc + teams - 1) / teams;
+  int grid = (int)std::min<int64_t>(need, (int64_t)(*occ_cache) * h->num_sms);
+  if (grid < 1) return 0;
+  kern<<<grid, block, smem, h->stream>>>(p);
+  h->launches++;
+  return 0;
+}
+
+template <int MODE>
+static int launch_sweep_m(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int npt, int* occ) {
+  switch (npt) {
+    case 2: return launch_sweep_t<2, MODE>(h, p, n_loc, occ);
+    case 4: return launch_sweep_t<4, MODE>(h, p, n_loc, occ);
+    case 8: return launch_sweep_t<8, MODE>(h, p, n_loc, occ);
+    case 16: return launch_sweep_t<16, MODE>(h, p, n_loc, occ);
+    case 32: return launch_sweep_t<32, MODE>(h, p, n_loc, occ);
+  }
+  FAIL("unsupported entries-per-thread %d", npt);
+}
+
+// side: which factor is updated.  single_k: see SweepParams.
+static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint64_t seed, uint32_t iteration,
+                        double* out_tau, double* out_mu, bool want_mu) {
+  Side& sd = h->s[side];
+  Side& other = h->s[1 - side];
+  SweepParams p{};
+  p.vals = sd.vals; p.cols = sd.cols; p.rowstart = sd.rowstart;
+  p.n_loc = (int)sd.n_loc; p.row0 = sd.row0; p.K = h->K; p.tpr = sd.tpr; p.padcol = sd.padcol;
+  p.Ykm = other.km; p.ldy = other.ld;
+  p.Xval = sd.val; p.Xvar = sd.var;
+  const bool mu_out = (method == BNMTF_VB) || want_mu;
+  p.Xmu = mu_out ? sd.mu : nullptr; p.Xtau = mu_out ? sd.tau : nullptr;
+  p.lam_rm = h->hyper.ARD ? nullptr : sd.lam_rm;
+  p.lamk = (h->hyper.ARD && method != BNMTF_NP) ? h->lamk : nullptr;
+  p.scal = h->scal;
+  p.out_tau = out_tau; p.out_mu = out_mu;
+  p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
+  p.rmean = h->rmean;
+  p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
+  p.single_k = single_k;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool timed = h->time_sweeps && single_k == -1;
+  if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
+  int rc;
+  switch (method) {
+    case BNMTF_GIBBS: rc = launch_sweep_m<M_GIBBS>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
+    case BNMTF_ICM: rc = launch_sweep_m<M_ICM>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
+    case BNMTF_VB: rc = launch_sweep_m<M_VB>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
+    case BNMTF_NP: rc = launch_sweep_m<M_NP>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
+    default: FAIL("unknown method %d", method);
+  }
+  if (timed) {
+    cudaEventRecord(e1, h->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    h->sweep_ms[side] += ms; h->sweep_n[side]++;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  return rc;
+}
+
+static int launch_lambda(bnmtf_nmf_s* h, int method, uint64_t seed, uint32_t iteration, int update) {
+  Side& su = h->s[0]; Side& sv = h->s[1];
+  const int K = h->K;
+#define LK(MODE)                                                                                                      \
+  lambda_kernel<MODE><<<K, 256, 0, h->stream>>>(su.km, su.ld, h->I, sv.km, sv.ld, h->J, K, h->hyper, h->colsum,       \
+                                                h->lamstate, h->lamk, seed, iteration, update)
+  switch (method) {
+    case BNMTF_GIBBS: LK(M_GIBBS); break;
+    case BNMTF_ICM: LK(M_ICM); break;
+    case BNMTF_VB: LK(M_VB); break;
+    default: return 0;
+  }
+#undef LK
+  h->launches++;
+  return 0;
+}
+
+static int launch_finalize(bnmtf_nmf_s* h, int method, double* stats_out, uint64_t seed, uint32_t iteration, int update) {
+  Side& su = h->s[0]; Side& sv = h->s[1];
+#define FK(MODE)                                                                                                    \
+  finalize_kernel<MODE><<<1, 1024, 0, h->stream>>>(su.rowstats, su.n_glob, sv.rowstats, sv.n_glob, h->K, h->hyper,   \
+                                                   h->colsum, h->lamstate, h->scal, stats_out, seed, iteration,     \
+                                                   update, h->I, h->J)
+  switch (method) {
+    case BNMTF_GIBBS: FK(M_GIBBS); break;
+    case BNMTF_ICM: FK(M_ICM); break;
+    case BNMTF_VB: FK(M_VB); break;
+    case BNMTF_NP: FK(M_NP); break;
+    default: FAIL("unknown method %d", method);
+  }
+#undef FK
+  h->launches++;
+  return 0;
+}
+
+// after a sweep on `side`: make every rank hold the whole factor (and row stats)
+static int allgather_side(bnmtf_nmf_s* h, int method, int side, bool stats) {
+  if (h->world <= 1) return 0;
+  Side& sd = h->s[side];
+  const size_t cnt = (size_t)sd.n_shard * h->K;
+  double* fields[4] = {sd.val, method == BNMTF_VB ? sd.var : nullptr, nullptr, nullptr};
+  for (double* f : fields) {
+    if (!f) continue;
+    int rc = g_nccl.AllGather(f + (size_t)sd.row0 * h->K, f, cnt, NCCL_FLOAT64, h->comm, h->stream);
+    if (rc != 0) FAIL("ncclAllGather: %s", g_nccl.GetErrorString(rc));
+  }
+  if (stats) {
+    int rc = g_nccl.AllGather(sd.rowstats + (size_t)sd.row0 * NRS, sd.rowstats, (size_t)sd.n_shard * NRS, NCCL_FLOAT64,
+                              h->comm, h->stream);
+    if (rc != 0) FAIL("ncclAllGather: %s", g_nccl.GetErrorString(rc));
+  }
+  return 0;
+}
+
+int bnmtf_nmf_init_factors(bnmtf_nmf_t h, int method, int random, uint64_t seed) {
+  if (!h) FAIL("NULL handle");
+  CK(cudaSetDevice(h->device));
+  for (int sidx = 0; sidx < 2; ++sidx) {
+    Side& sd = h->s[sidx];
+    const int64_t n = sd.n_glob * h->K;
+    double* dst = method == BNMTF_VB ? sd.mu : sd.val;
+    init_factor_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+        dst, sd.n_glob, h->K, h->hyper.ARD ? nullptr : sd.lam_rm, h->hyper.ARD ? h->lamk : nullptr, random, seed,
+        sidx == 0 ? RNG_INIT_U : RNG_INIT_V);
+    h->launches++;
+    if (method == BNMTF_VB) {
+      vb_init_moments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(sd.mu, sd.tau, sd.val, sd.var, n);
+      h->launches++;
+    }
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  h->km_mode = -1;
+  return 0;
+}
+
+int bnmtf_nmf_column_params(bnmtf_nmf_t h, int method, int side, int k, double* out_tau, double* out_mu) {
+  if (!h || !out_tau || !out_mu || side < 0 || side > 1) FAIL("bad argument");
+  if (k < 0 || k >= h->K) FAIL("k out of range");
+  if (h->world > 1) FAIL("column_params is single-GPU only");
+  CK(cudaSetDevice(h->device));
+  Side& sd = h->s[side];
+  double *dt = nullptr, *dm = nullptr;
+  CK(cudaMalloc(&dt, sizeof(double) * sd.n_glob));
+  CK(cudaMalloc(&dm, sizeof(double) * sd.n_glob));
+  refresh_km(h, 0, method); refresh_km(h, 1, method);
+  h->km_mode = method == BNMTF_VB ? 2 : 1;
+  if (launch_sweep(h, method, side, k, 0, 0, dt, dm, false)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out_tau, dt, sizeof(double) * sd.n_glob, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out_mu, dm, sizeof(double) * sd.n_glob, cudaMemcpyDeviceToHost));
+  cudaFree(dt); cudaFree(dm);
+  return 0;
+}
+
+int bnmtf_nmf_stats(bnmtf_nmf_t h, int method, double* out) {
+  if (!h || !out) FAIL("bad argument");
+  CK(cudaSetDevice(h->device));
+  refresh_km(h, 0, method); refresh_km(h, 1, method);
+  h->km_mode = method == BNMTF_VB ? 2 : 1;
+  if (method == BNMTF_VB && launch_sweep(h, method, 0, -2, 0, 0, nullptr, nullptr, false)) return 1;
+  if (method == BNMTF_VB && allgather_side(h, method, 0, true)) return 1;
+  if (launch_sweep(h, method, 1, -2, 0, 0, nullptr, nullptr, false)) return 1;
+  if (allgather_side(h, method, 1, true)) return 1;
+  if (launch_lambda(h, method, 0, 0, 0)) return 1;
+  double* sdev = nullptr;
+  CK(cudaMalloc(&sdev, sizeof(double) * BNMTF_NSTATS));
+  if (launch_finalize(h, method, sdev, 0, 0, 0)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, sdev, sizeof(double) * BNMTF_NSTATS, cudaMemcpyDeviceToHost));
+  cudaFree(sdev);
+  return 0;
+}
+
+// run(iterations): see include/bnmtf_b200.h
+int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, double* all_U, double* all_V,
+                  double* all_lambdak, double* iter_stats, double* iter_seconds) {
+  if (!h) FAIL("NULL handle");
+  if (iterations < 0) FAIL("negative iteration count");
+  if (method < 0 || method > 3) FAIL("unknown method %d", method);
+  CK(cudaSetDevice(h->device));
+  const int K = h->K;
+  Side& su = h->s[0]; Side& sv = h->s[1];
+  const int want_mu = getenv("BNMTF_TRACE_PARAMS") && atoi(getenv("BNMTF_TRACE_PARAMS")) != 0;
+  h->sweep_ms[0] = h->sweep_ms[1] = 0; h->sweep_n[0] = h->sweep_n[1] = 0;
+  if (iterations == 0) return 0;
+
+  // traces are staged on the device in chunks and copied out while the next chunk runs
+  const size_t per_it = sizeof(double) * ((size_t)su.n_glob + sv.n_glob) * K;
+  const bool tr = (all_U != nullptr) || (all_V != nullptr);
+  int chunk = iterations;
+  if (tr) chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)iterations, ((size_t)256 << 20) / std::max<size_t>(per_it, 1)));
+  if (tr) {
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(su.trace[b]); cudaFree(sv.trace[b]); su.trace[b] = sv.trace[b] = nullptr;
+      CK(cudaMalloc(&su.trace[b], sizeof(double) * su.n_glob * K * chunk));
+      CK(cudaMalloc(&sv.trace[b], sizeof(double) * sv.n_glob * K * chunk));
+    }
+  }
+  cudaFree(h->stats_dev); h->stats_dev = nullptr;
+  double* lam_trace = nullptr;
+  CK(cudaMalloc(&h->stats_dev, sizeof(double) * BNMTF_NSTATS * iterations));
+  CK(cudaMalloc(&lam_trace, sizeof(double) * K * iterations));
+  CK(cudaMemsetAsync(lam_trace, 0, sizeof(double) * K * iterations, h->stream));
+
+  std::vector<cudaEvent_t> ev(iterations + 1);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  cudaEvent_t chunk_done[2], chunk_copied[2];
+  for (int b = 0; b < 2; ++b) { CK(cudaEventCreate(&chunk_done[b])); CK(cudaEventCreate(&chunk_copied[b])); }
+
+  refresh_km(h, 0, method); refresh_km(h, 1, method);
+  h->km_mode = method == BNMTF_VB ? 2 : 1;
+  CK(cudaEventRecord(ev[0], h->stream));
+
+  auto copy_chunk = [&](int c) -> int {
+    const int b = c & 1;
+    const int it0 = c * chunk, n_it = std::min(chunk, iterations - it0);
+    CK(cudaStreamWaitEvent(h->copy_stream, chunk_done[b], 0));
+    if (all_U) CK(cudaMemcpyAsync(all_U + (size_t)it0 * su.n_glob * K, su.trace[b], sizeof(double) * su.n_glob * K * n_it, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (all_V) CK(cudaMemcpyAsync(all_V + (size_t)it0 * sv.n_glob * K, sv.trace[b], sizeof(double) * sv.n_glob * K * n_it, cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaEventRecord(chunk_copied[b], h->copy_stream));
+    return 0;
+  };
+
+  const int nchunks = (iterations + chunk - 1) / chunk;
+  for (int c = 0; c < nchunks; ++c) {
+    const int b = c & 1;
+    if (tr && c >= 2) CK(cudaStreamWaitEvent(h->stream, chunk_copied[b], 0));
+    const int it0 = c * chunk, it1 = std::min(iterations, it0 + chunk);
+    for (int it = it0; it < it1; ++it) {
+      // lambda_k (ARD)                                   bnmf_gibbs.py:149-152
+      if (launch_lambda(h, method, seed, (uint32_t)it, 1)) return 1;
+      if (h->hyper.ARD && method != BNMTF_NP)
+        CK(cudaMemcpyAsync(lam_trace + (size_t)it * K, h->lamk, sizeof(double) * K, cudaMemcpyDeviceToDevice, h->stream));
+      // U sweep                                           bnmf_gibbs.py:154-158
+      if (launch_sweep(h, method, 0, -1, seed, (uint32_t)it, nullptr, nullptr, want_mu)) return 1;
+      if (allgather_side(h, method, 0, method == BNMTF_VB)) return 1;
+      refresh_km(h, 0, method);
+      // V sweep                                           bnmf_gibbs.py:160-164
+      if (launch_sweep(h, method, 1, -1, seed, (uint32_t)it, nullptr, nullptr, want_mu)) return 1;
+      if (allgather_side(h, method, 1, true)) return 1;
+      refresh_km(h, 1, method);
+      // tau, statistics                                   bnmf_gibbs.py:166-167,175
+      if (method == BNMTF_VB && launch_lambda(h, method, seed, (uint32_t)it, 0)) return 1;
+      if (launch_finalize(h, method, h->stats_dev + (size_t)it * BNMTF_NSTATS, seed, (uint32_t)it, 1)) return 1;
+      if (tr) {
+        const int slot = it - it0;
+        CK(cudaMemcpyAsync(su.trace[b] + (size_t)slot * su.n_glob * K, su.val, sizeof(double) * su.n_glob * K, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(sv.trace[b] + (size_t)slot * sv.n_glob * K, sv.val, sizeof(double) * sv.n_glob * K, cudaMemcpyDeviceToDevice, h->stream));
+      }
+      CK(cudaEventRecord(ev[it + 1], h->stream));
+    }
+    if (tr) {
+      CK(cudaEventRecord(chunk_done[b], h->stream));
+      if (c >= 1 && copy_chunk(c - 1)) return 1;
+    }
+  }
+  if (tr && copy_chunk(nchunks - 1)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaStreamSynchronize(h->copy_stream));
+  CK(cudaGetLastError());
+  if (iter_stats) CK(cudaMemcpy(iter_stats, h->stats_dev, sizeof(double) * BNMTF_NSTATS * iterations, cudaMemcpyDeviceToHost));
+  if (all_lambdak) CK(cudaMemcpy(all_lambdak, lam_trace, sizeof(double) * K * iterations, cudaMemcpyDeviceToHost));
+  if (iter_seconds) {
+    for (int it = 0; it < iterations; ++it) {
+      float ms = 0; CK(cudaEventElapsedTime(&ms, ev[0], ev[it + 1]));
+      iter_seconds[it] = ms * 1e-3;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  for (int b = 0; b < 2; ++b) { cudaEventDestroy(chunk_done[b]); cudaEventDestroy(chunk_copied[b]); }
+  cudaFree(lam_trace);
+  return 0;
+}
+
+int64_t bnmtf_nmf_launch_count(bnmtf_nmf_t h) { return h ? h->launches : 0; }
+
+int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {
+  if (!h || !out8) FAIL("bad argument");
+  out8[0] = h->s[0].tpr; out8[1] = h->s[0].npt; out8[2] = h->s[1].tpr; out8[3] = h->s[1].npt;
+  out8[4] = h->s[0].nslots; out8[5] = h->s[1].nslots; out8[6] = h->s[0].nnz; out8[7] = h->s[1].nnz;
+  return 0;
+}
+
+int bnmtf_nmf_sweep_times(bnmtf_nmf_t h, double* out4) {
+  if (!h || !out4) FAIL("bad argument");
+  out4[0] = h->sweep_ms[0]; out4[1] = h->sweep_ms[1]; out4[2] = (double)h->sweep_n[0]; out4[3] = (double)h->sweep_n[1];
+  return 0;
+}
+
+// ---- distributions ---------------------------------------------------------------
+namespace {
+struct DevBuf {
+  double* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+};
+}  // namespace
+
+#define DIST_PROLOGUE(NIN)                                                                          \
+  if (n < 0) FAIL("negative n");                                                                    \
+  if (n == 0) return 0;                                                                             \
+  CK(cudaSetDevice(device));                                                                        \
+  DevBuf in[2], o[2];                                                                               \
+  for (int q = 0; q < NIN; ++q) CK(cudaMalloc(&in[q].p, sizeof(double) * n));                       \
+  for (int q = 0; q < 2; ++q) CK(cudaMalloc(&o[q].p, sizeof(double) * n));                          \
+  const unsigned grid = (unsigned)((n + 255) / 256)
+
+int bnmtf_tn_draw(int device, uint64_t seed, int64_t n, const double* mu, const double* tau, double* out) {
+  DIST_PROLOGUE(2);
+  CK(cudaMemcpy(in[0].p, mu, sizeof(double) * n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(in[1].p, tau, sizeof(double) * n, cudaMemcpyHostToDevice));
+  api_tn_draw_kernel<<<grid, 256>>>(in[0].p, in[1].p, o[0].p, n, seed);
+  CK(cudaDeviceSynchronize()); CK(cudaGetLastError());
+  CK(cudaMemcpy(out, o[0].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bnmtf_tn_moments(int device, int64_t n, const double* mu, const double* tau, double* exp_out, double* var_out) {
+  DIST_PROLOGUE(2);
+  CK(cudaMemcpy(in[0].p, mu, sizeof(double) * n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(in[1].p, tau, sizeof(double) * n, cudaMemcpyHostToDevice));
+  api_tn_moments_kernel<<<grid, 256>>>(in[0].p, in[1].p, o[0].p, o[1].p, n);
+  CK(cudaDeviceSynchronize()); CK(cudaGetLastError());
+  if (exp_out) CK(cudaMemcpy(exp_out, o[0].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  if (var_out) CK(cudaMemcpy(var_out, o[1].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bnmtf_gamma_draw(int device, uint64_t seed, int64_t n, const double* alpha, const double* beta, double* out) {
+  DIST_PROLOGUE(2);
+  CK(cudaMemcpy(in[0].p, alpha, sizeof(double) * n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(in[1].p, beta, sizeof(double) * n, cudaMemcpyHostToDevice));
+  api_gamma_draw_kernel<<<grid, 256>>>(in[0].p, in[1].p, o[0].p, n, seed);
+  CK(cudaDeviceSynchronize()); CK(cudaGetLastError());
+  CK(cudaMemcpy(out, o[0].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bnmtf_exp_draw(int device, uint64_t seed, int64_t n, const double* lambda, double* out) {
+  DIST_PROLOGUE(1);
+  CK(cudaMemcpy(in[0].p, lambda, sizeof(double) * n, cudaMemcpyHostToDevice));
+  api_exp_draw_kernel<<<grid, 256>>>(in[0].p, o[0].p, n, seed);
+  CK(cudaDeviceSynchronize()); CK(cudaGetLastError());
+  CK(cudaMemcpy(out, o[0].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}

@@ -1,0 +1,599 @@
+// Device kernels of the BNMF / NMF hot path (sm_100a).
+//
+// Formulation: the K column updates of one factor are
+// conditionally independent across rows (bnmf_gibbs.py:155-158: U[:,k] for all
+// rows given V; rows never interact), so a *row team* keeps the residual of one
+// row of R -- observed entries only -- in registers and runs all K column
+// updates before touching memory again.  The residual is recomputed from R at
+// the start of each sweep, so nothing but the factors is carried between
+// sweeps.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "rng.cuh"
+
+namespace bnmtf {
+
+enum { M_GIBBS = 0, M_ICM = 1, M_VB = 2, M_NP = 3 };
+
+// per-row statistics written by a sweep (deterministic: one writer per row)
+enum { RS_RSS = 0, RS_SUM_E = 1, RS_SUM_RCE = 2, RS_ESDVAR = 3, RS_ELBOQ = 4, RS_PRIOR = 5, RS_IDIV = 6, RS_SPARE = 7, NRS = 8 };
+
+constexpr double MINIMUM_TN = 0.1;  // nmf_icm.py:59
+
+struct SweepParams {
+  // packed observed entries of this side: rows padded to multiples of tpr
+  const double* __restrict__ vals;
+  const uint32_t* __restrict__ cols;
+  const int64_t* __restrict__ rowstart;  // [n_loc+1], slot offsets
+  int n_loc;                             // local rows
+  int64_t row0;                          // global index of local row 0
+  int K;
+  int tpr;                               // threads per row team (multiple of 32)
+  uint32_t padcol;                       // column index that reads 0 from Ykm
+  const double* __restrict__ Ykm;        // other factor, k-major [K][ldy][NV]
+  int64_t ldy;
+  double* Xval;                          // own factor, row-major [n_glob_pad][K]
+  double* Xvar;                          // VB
+  double* Xmu;                           // VB state / optional parity output
+  double* Xtau;                          // VB state / optional parity output
+  const double* __restrict__ lam_rm;     // [n_glob][K] or nullptr
+  const double* __restrict__ lamk;       // [K] (ARD) or nullptr
+  const double* __restrict__ scal;       // scal[0] = tau (exp_tau)
+  double* out_tau;                       // single_k >= 0: [n_glob] outputs
+  double* out_mu;
+  double* rowstats;                      // [n_loc][NRS] or nullptr
+  double rmean;
+  uint64_t seed;
+  uint32_t iteration;
+  uint32_t purpose;
+  int single_k;                          // >=0 one column, no state change; -1 sweep; -2 dry (stats only)
+};
+
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Team-wide sum of NR values, result valid on the team leader warp (all of its
+// lanes).  Fixed order => bitwise reproducible.  Non-leader warps only arrive.
+template <int NR>
+__device__ __forceinline__ void team_reduce_to_leader(double (&v)[NR], double* red, int nw, int wteam, int lane,
+                                                      int barA, int tpr) {
+#pragma unroll
+  for (int r = 0; r < NR; ++r) v[r] = warp_sum(v[r]);
+  if (nw == 1) return;
+  if (wteam != 0) {
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) red[wteam * NR + r] = v[r];
+    }
+    __syncwarp();
+    bar_arrive(barA, tpr);
+  } else {
+    bar_sync(barA, tpr);
+    for (int w = 1; w < nw; ++w) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) v[r] += red[w * NR + r];
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------
+// Row-fused K-column sweep.  One team of `tpr` threads per row; thread t owns the
+// entries t, t+tpr, ... of the row (coalesced loads), NPT of them at most.
+//   Gibbs : bnmf_gibbs.py:155-164 (tauU/muU :203-210, TN_vector_draw)
+//   ICM   : nmf_icm.py:155-167
+//   VB    : bnmf_vb.py:167-174 (update_U :251-255, update_exp_U :275-278)
+//   NP    : nmf_np.py:107-126
+// -----------------------------------------------------------------------------
+// HOLDV: keep the gathered column of the other factor in registers between the
+// accumulation and the rank-1 correction (2 gathers per entry and column instead
+// of 3); switched off for very long rows where the registers are needed for e[].
+template <int NPT>
+struct SweepCfg {
+  static constexpr int MAXT = NPT < 16 ? 128 : 512;
+  static constexpr bool HOLDV = NPT <= 16;
+};
+
+template <int NPT, int MODE>
+__global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepParams p) {
+  constexpr int NV = (MODE == M_VB) ? 2 : 1;
+  constexpr bool HOLDV = SweepCfg<NPT>::HOLDV;
+  extern __shared__ double smem[];
+  const int tpr = p.tpr, K = p.K;
+  const int teams = blockDim.x / tpr;
+  const int team = threadIdx.x / tpr;
+  const int t = threadIdx.x - team * tpr;
+  const int lane = threadIdx.x & 31;
+  const int wteam = t >> 5;
+  const int nw = tpr >> 5;
+  const int barA = 1 + 2 * team, barB = 2 + 2 * team;
+  const int team_stride = 4 * K + 3 * nw + 2;
+  double* xs = smem + (size_t)team * team_stride;  // [K] current values of the row
+  double* xvar = xs + K;                            // [K] VB variance
+  double* xmu = xvar + K;                           // [K] conditional mean
+  double* xtau = xmu + K;                           // [K] conditional precision
+  double* red = xtau + K;                           // [3*nw]
+  double* bc = red + 3 * nw;                        // [2]
+  const bool leader = (t == 0);
+  const bool dry = (p.single_k == -2);
+
+  for (int row = blockIdx.x * teams + team; row < p.n_loc; row += gridDim.x * teams) {
+    const int64_t grow = p.row0 + row;
+    const int64_t base = p.rowstart[row];
+    const int npt = (int)((p.rowstart[row + 1] - base) / tpr);
+
+    double e[NPT];  // residual (NP: prediction p)
+    double q[(MODE == M_NP) ? NPT : 1];  // NP: r
+    uint32_t c[NPT];
+#pragma unroll
+    for (int n = 0; n < NPT; ++n) {
+      if (n < npt) {
+        e[n] = p.vals[base + (int64_t)n * tpr + t];
+        c[n] = p.cols[base + (int64_t)n * tpr + t] * NV;
+      } else {
+        e[n] = 0.0;
+        c[n] = p.padcol * NV;
+      }
+      if (MODE == M_NP) { q[n] = e[n]; e[n] = 0.0; }
+    }
+    for (int kk = t; kk < K; kk += tpr) {
+      xs[kk] = p.Xval[grow * K + kk];
+      if (MODE == M_VB) {
+        xvar[kk] = p.Xvar[grow * K + kk];
+        xmu[kk] = p.Xmu[grow * K + kk];
+        xtau[kk] = p.Xtau[grow * K + kk];
+      }
+    }
+    if (nw == 1) __syncwarp(); else bar_sync(barB, tpr);
+
+    // ---- residual of the row from the current factors: e = r - sum_k x_k y_k
+    for (int k = 0; k < K; ++k) {
+      const double xk = xs[k];
+      const double* __restrict__ y = p.Ykm + (size_t)k * p.ldy * NV;
+#pragma unroll
+      for (int n = 0; n < NPT; ++n) {
+        if (MODE == M_NP) e[n] = fma(xk, __ldg(y + c[n]), e[n]);
+        else e[n] = fma(-xk, __ldg(y + c[n]), e[n]);
+      }
+    }
+
+    double acc_esd = 0.0, acc_q = 0.0, acc_prior = 0.0;  // leader only
+
+    const int k_begin = (p.single_k >= 0) ? p.single_k : 0;
+    const int k_end = (p.single_k >= 0) ? p.single_k + 1 : K;
+    // Gibbs/ICM/NP statistics need no column loop in dry mode
+    const bool skip_loop = dry && MODE != M_VB;
+    for (int k = k_begin; k < k_end && !skip_loop; ++k) {
+      const double* __restrict__ y = p.Ykm + (size_t)k * p.ldy * NV;
+      double v[HOLDV ? NPT : 1];
+      double s[3] = {0.0, 0.0, 0.0};  // [0]=sum y^2 (NP: num), [1]=sum (var+y^2) (NP: den), [2]=sum e*y
+#pragma unroll
+      for (int n = 0; n < NPT; ++n) {
+        double vn;
+        if (MODE == M_VB) {
+          const double2 yy = __ldg(reinterpret_cast<const double2*>(y + c[n]));
+          vn = yy.x;
+          s[1] += yy.y;
+        } else {
+          vn = __ldg(y + c[n]);
+        }
+        if (HOLDV) v[n] = vn;
+        if (MODE == M_NP) {
+          // padded slots (and only those) read y == 0 exactly; skip the 0/0
+          const double ratio = (c[n] != p.padcol) ? q[n] / e[n] : 0.0;
+          s[0] = fma(vn, ratio, s[0]);
+          s[1] += vn;
+        } else {
+          s[0] = fma(vn, vn, s[0]);
+          s[2] = fma(e[n], vn, s[2]);
+        }
+      }
+      if (MODE == M_NP) {
+        double r2[2] = {s[0], s[1]};
+        team_reduce_to_leader<2>(r2, red, nw, wteam, lane, barA, tpr);
+        s[0] = r2[0]; s[1] = r2[1];
+      } else {
+        team_reduce_to_leader<3>(s, red, nw, wteam, lane, barA, tpr);
+      }
+      if (leader) {
+        const double x_old = xs[k];
+        const double lam = p.lamk ? p.lamk[k] : (p.lam_rm ? p.lam_rm[grow * K + k] : 0.0);
+        const double tau = p.scal[0];
+        double x_new, cm = 0.0, ct = 0.0;
+        if (MODE == M_NP) {
+          x_new = x_old * s[0] / s[1];  // nmf_np.py:122
+          ct = s[1]; cm = x_new;
+        } else if (MODE == M_VB) {
+          ct = tau * s[1];                                   // bnmf_vb.py:254
+          cm = (-lam + tau * (s[2] + x_old * s[0])) / ct;    // bnmf_vb.py:255
+          double en, vn;
+          if (dry) { cm = xmu[k]; ct = xtau[k]; en = x_old; vn = xvar[k]; }
+          else tn_moments(cm, ct, en, vn);
+          x_new = en;
+          xvar[k] = vn;
+          acc_esd += (vn + en * en) * s[1] - (en * en) * s[0];
+          acc_q += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951))
+                   + 0.5 * ct * (vn + (en - cm) * (en - cm));
+          acc_prior += lam * en;
+        } else {
+          ct = tau * s[0];                                   // bnmf_gibbs.py:205
+          cm = (-lam + tau * (s[2] + x_old * s[0])) / ct;    // bnmf_gibbs.py:210
+          if (MODE == M_GIBBS) {
+            Rng rng(p.seed, p.purpose, (uint64_t)grow, (uint32_t)k, p.iteration);
+            x_new = tn_draw(cm, ct, rng);                    // bnmf_gibbs.py:158
+          } else {
+            x_new = fmax(fmax(0.0, cm), MINIMUM_TN);         // nmf_icm.py:159-160
+          }
+        }
+        if (p.single_k >= 0) {
+          p.out_tau[grow] = ct;
+          p.out_mu[grow] = cm;
+          x_new = x_old;
+        }
+        xmu[k] = cm; xtau[k] = ct;
+        bc[0] = x_new - x_old;
+        xs[k] = x_new;
+      }
+      if (nw == 1) __syncwarp(); else bar_sync(barB, tpr);
+      const double delta = bc[0];
+      if (delta != 0.0) {
+#pragma unroll
+        for (int n = 0; n < NPT; ++n) {
+          const double vn = HOLDV ? v[n] : __ldg(y + c[n]);
+          if (MODE == M_NP) e[n] = fma(delta, vn, e[n]);
+          else e[n] = fma(-delta, vn, e[n]);
+        }
+      }
+    }
+
+    // ---- per-row statistics from the final residual
+    if (p.rowstats != nullptr && p.single_k < 0) {
+      double st[3] = {0.0, 0.0, 0.0};
+      double idiv = 0.0;
+#pragma unroll
+      for (int n = 0; n < NPT; ++n) {
+        if (n < npt) {
+          const double r = (MODE == M_NP) ? q[n] : p.vals[base + (int64_t)n * tpr + t];
+          const double ee = (MODE == M_NP) ? (r - e[n]) : e[n];
+          const bool valid = (c[n] != p.padcol * NV);
+          if (valid) {
+            st[0] = fma(ee, ee, st[0]);
+            st[1] += ee;
+            st[2] = fma(r - p.rmean, ee, st[2]);
+            if (MODE == M_NP) idiv += r * log(r / e[n]) - r + e[n];  // nmf_np.py:160-163
+          }
+        }
+      }
+      team_reduce_to_leader<3>(st, red, nw, wteam, lane, barA, tpr);
+      if (nw > 1) bar_sync(barB, tpr);  // red[] reuse
+      if (MODE == M_NP) {
+        double r1[1] = {idiv};
+        team_reduce_to_leader<1>(r1, red, nw, wteam, lane, barA, tpr);
+        idiv = r1[0];
+      }
+      if (leader) {
+        double* rs = p.rowstats + (size_t)row * NRS;
+        rs[RS_RSS] = st[0]; rs[RS_SUM_E] = st[1]; rs[RS_SUM_RCE] = st[2];
+        rs[RS_ESDVAR] = acc_esd; rs[RS_ELBOQ] = acc_q; rs[RS_PRIOR] = acc_prior;
+        rs[RS_IDIV] = idiv; rs[RS_SPARE] = 0.0;
+      }
+    }
+    if (nw == 1) __syncwarp(); else bar_sync(barB, tpr);
+
+    // ---- write the row back (coalesced)
+    if (p.single_k == -1) {
+      for (int kk = t; kk < K; kk += tpr) {
+        p.Xval[grow * K + kk] = xs[kk];
+        if (MODE == M_VB) p.Xvar[grow * K + kk] = xvar[kk];
+        if (p.Xmu != nullptr) { p.Xmu[grow * K + kk] = xmu[kk]; p.Xtau[grow * K + kk] = xtau[kk]; }
+      }
+    }
+    if (nw == 1) __syncwarp(); else bar_sync(barB, tpr);
+  }
+}
+
+// -----------------------------------------------------------------------------
+// Row-major factor [n_pad][K]  ->  k-major gather layout [K][ld][NV], zero padded
+// for i >= n.  NV == 2 (VB): (exp, var + exp^2) pairs (bnmf_vb.py:254).
+// -----------------------------------------------------------------------------
+template <int NV>
+__global__ void rm_to_km_kernel(const double* __restrict__ Xval, const double* __restrict__ Xvar, double* __restrict__ Ykm,
+                                int64_t n, int K, int64_t ld) {
+  __shared__ double tile[32][33];
+  __shared__ double tile2[(NV == 2) ? 32 : 1][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t i = i0 + r;
+    const int k = k0 + threadIdx.x;
+    double a = 0.0, b = 0.0;
+    if (i < n && k < K) {
+      a = Xval[i * K + k];
+      if (NV == 2) { const double vv = Xvar[i * K + k]; b = vv + a * a; }
+    }
+    tile[r][threadIdx.x] = a;
+    if (NV == 2) tile2[r][threadIdx.x] = b;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r;
+    const int64_t i = i0 + threadIdx.x;
+    if (k < K && i < ld) {
+      if (NV == 2) {
+        double2 o = make_double2(tile[threadIdx.x][r], tile2[threadIdx.x][r]);
+        reinterpret_cast<double2*>(Ykm)[(size_t)k * ld + i] = o;
+      } else {
+        Ykm[(size_t)k * ld + i] = tile[threadIdx.x][r];
+      }
+    }
+  }
+}
+
+// deterministic block sum (fixed tree), blockDim.x <= 1024, result on all threads
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < nw; ++i) r += sh[i];
+  return r;
+}
+
+struct Hyper {
+  int ARD;
+  double alphatau, betatau, alpha0, beta0;
+  double size_Omega;        // global
+  double sumlog_lamU, sumlog_lamV;  // non-ARD VB ELBO constants
+};
+
+// device scalar block layout
+enum { SC_TAU = 0, SC_LOGTAU = 1, SC_ALPHA_S = 2, SC_BETA_S = 3, SC_COUNT = 8 };
+
+// -----------------------------------------------------------------------------
+// Start of an iteration: column sums of both factors and the lambda_k update.
+//   Gibbs: lambdak[k] ~ Gamma(alpha0+I+J, beta0+sum U_k+sum V_k) bnmf_gibbs.py:150-152,195-201
+//   ICM  : mode (alpha-1)/beta                                    nmf_icm.py:150-152
+//   VB   : alphak_s, betak_s, exp_lambdak, exp_loglambdak         bnmf_vb.py:157-160,246-249,270-273
+// One block per k.  colsum[2][K]; lamstate[4][K] = alphak_s, betak_s, exp_lambdak(lambdak), exp_loglambdak.
+// -----------------------------------------------------------------------------
+template <int MODE>
+__global__ void lambda_kernel(const double* __restrict__ Ukm, int64_t ldu, int64_t I, const double* __restrict__ Vkm,
+                              int64_t ldv, int64_t J, int K, Hyper h, double* colsum, double* lamstate, double* lamk,
+                              uint64_t seed, uint32_t iteration, int update) {
+  constexpr int NV = (MODE == M_VB) ? 2 : 1;
+  __shared__ double sh[32];
+  const int k = blockIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int64_t i = threadIdx.x; i < I; i += blockDim.x) a += Ukm[((size_t)k * ldu + i) * NV];
+  for (int64_t j = threadIdx.x; j < J; j += blockDim.x) b += Vkm[((size_t)k * ldv + j) * NV];
+  a = block_sum(a, sh);
+  b = block_sum(b, sh);
+  if (threadIdx.x == 0) {
+    colsum[k] = a;
+    colsum[K + k] = b;
+    if (h.ARD && update) {
+      const double alpha = h.alpha0 + (double)I + (double)J;
+      const double beta = h.beta0 + a + b;
+      double lam;
+      if (MODE == M_GIBBS) {
+        Rng rng(seed, RNG_LAMBDA, (uint64_t)k, 0u, iteration);
+        lam = gamma_draw(alpha, beta, rng);
+      } else if (MODE == M_ICM) {
+        lam = (alpha - 1.0) / beta;
+      } else {
+        lam = alpha / beta;
+        lamstate[0 * K + k] = alpha;
+        lamstate[1 * K + k] = beta;
+        lamstate[3 * K + k] = digamma(alpha) - log(beta);
+      }
+      lamstate[2 * K + k] = lam;
+      lamk[k] = lam;
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------
+// End of an iteration: deterministic reduction of the per-row statistics, the
+// tau update and (VB) the ELBO.  Single block.
+//   Gibbs: tau ~ Gamma(alphatau+|Omega|/2, betatau+RSS/2)  bnmf_gibbs.py:167,187-193
+//   ICM  : mode                                              nmf_icm.py:170
+//   VB   : update_tau/update_exp_tau/elbo                    bnmf_vb.py:176-180,191-244,265-268
+// stats_out[BNMTF_NSTATS] layout: see include/bnmtf_b200.h.
+// -----------------------------------------------------------------------------
+template <int MODE>
+__global__ void finalize_kernel(const double* __restrict__ rsU, int64_t nU, const double* __restrict__ rsV, int64_t nV,
+                                int K, Hyper h, const double* __restrict__ colsum, const double* __restrict__ lamstate,
+                                double* scal, double* stats_out, uint64_t seed, uint32_t iteration, int update,
+                                int64_t I, int64_t J) {
+  __shared__ double sh[32];
+  __shared__ double tot[2 * NRS];
+  for (int sidx = 0; sidx < 2; ++sidx) {
+    const double* rs = sidx == 0 ? rsU : rsV;
+    const int64_t n = sidx == 0 ? nU : nV;
+    for (int f = 0; f < NRS; ++f) {
+      double a = 0.0;
+      if (rs != nullptr)
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a += rs[i * NRS + f];
+      a = block_sum(a, sh);
+      if (threadIdx.x == 0) tot[sidx * NRS + f] = a;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  // residual statistics always come from the V-side sweep (last of the iteration)
+  const double rss = tot[NRS + RS_RSS], sum_e = tot[NRS + RS_SUM_E], sum_rce = tot[NRS + RS_SUM_RCE];
+  for (int i = 0; i < 16; ++i) stats_out[i] = 0.0;
+  stats_out[0] = rss; stats_out[1] = sum_e; stats_out[2] = sum_rce;
+  const double alpha_s = h.alphatau + h.size_Omega / 2.0;
+  double beta_s = h.betatau + 0.5 * rss;
+  double tau = scal[SC_TAU];
+  if (MODE == M_GIBBS) {
+    if (update) { Rng rng(seed, RNG_TAU, 0ull, 0u, iteration); tau = gamma_draw(alpha_s, beta_s, rng); }
+  } else if (MODE == M_ICM) {
+    if (update) tau = (alpha_s - 1.0) / beta_s;
+  } else if (MODE == M_VB) {
+    const double esd = rss + tot[NRS + RS_ESDVAR];   // bnmf_vb.py:241-244
+    beta_s = h.betatau + 0.5 * esd;
+    double exp_logtau = scal[SC_LOGTAU];
+    double a_s = scal[SC_ALPHA_S], b_s = scal[SC_BETA_S];
+    if (update) {
+      a_s = alpha_s; b_s = beta_s;
+      tau = a_s / b_s;
+      exp_logtau = digamma(a_s) - log(b_s);
+      scal[SC_LOGTAU] = exp_logtau; scal[SC_ALPHA_S] = a_s; scal[SC_BETA_S] = b_s;
+    }
+    const double log2pi = 1.8378770664093454836;
+    double elbo = h.size_Omega / 2.0 * (exp_logtau - log2pi) - tau / 2.0 * esd;
+    if (h.ARD) {
+      double s_loglam = 0.0, s_lam = 0.0, s_logexplam = 0.0, s_lamcol = 0.0, q_lam = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const double al = lamstate[0 * K + k], be = lamstate[1 * K + k], el = lamstate[2 * K + k], ell = lamstate[3 * K + k];
+        s_loglam += ell; s_lam += el; s_logexplam += log(el);
+        s_lamcol += el * (colsum[k] + colsum[K + k]);
+        q_lam += -al * log(be) + lgamma(al) - (al - 1.0) * ell + be * el;
+      }
+      elbo += h.alpha0 * log(h.beta0) - lgamma(h.alpha0) + (h.alpha0 - 1.0) * s_loglam - h.beta0 * s_lam;
+      elbo += ((double)I + (double)J) * s_logexplam - s_lamcol;
+      elbo += q_lam;
+    } else {
+      elbo += h.sumlog_lamU - tot[RS_PRIOR] + h.sumlog_lamV - tot[NRS + RS_PRIOR];
+    }
+    elbo += h.alphatau * log(h.betatau) - lgamma(h.alphatau) + (h.alphatau - 1.0) * exp_logtau - h.betatau * tau;
+    elbo += tot[RS_ELBOQ] + (double)I * K / 2.0 * log2pi + tot[NRS + RS_ELBOQ] + (double)J * K / 2.0 * log2pi;
+    elbo += -a_s * log(b_s) + lgamma(a_s) - (a_s - 1.0) * exp_logtau + b_s * tau;
+    stats_out[5] = esd; stats_out[6] = elbo; stats_out[8] = exp_logtau;
+  } else {
+    stats_out[7] = tot[NRS + RS_IDIV];
+  }
+  if (update) scal[SC_TAU] = tau;
+  stats_out[3] = tau; stats_out[4] = beta_s; stats_out[9] = alpha_s;
+}
+
+// ---- packing -----------------------------------------------------------------
+// observed entries per row of a dense mask block (n x m, row-major, ld)
+__global__ void count_rows_kernel(const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld, int* __restrict__ rowlen) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  int cnt = 0;
+  for (int64_t j = lane; j < m; j += 32) cnt += (M[row * ld + j] != 0);
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) rowlen[row] = cnt;
+}
+
+// compact one row per warp, in column order, then pad the tail of the row
+__global__ void pack_rows_kernel(const double* __restrict__ R, const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld,
+                                 const int64_t* __restrict__ rowstart, uint32_t padcol, double* __restrict__ vals,
+                                 uint32_t* __restrict__ cols) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  int64_t pos = rowstart[row];
+  const int64_t end = rowstart[row + 1];
+  for (int64_t j0 = 0; j0 < m; j0 += 32) {
+    const int64_t j = j0 + lane;
+    const bool obs = (j < m) && (M[row * ld + j] != 0);
+    const unsigned bal = __ballot_sync(0xffffffffu, obs);
+    if (obs) {
+      const int off = __popc(bal & ((1u << lane) - 1u));
+      vals[pos + off] = R[row * ld + j];
+      cols[pos + off] = (uint32_t)j;
+    }
+    pos += __popc(bal);
+  }
+  for (int64_t q = pos + lane; q < end; q += 32) { vals[q] = 0.0; cols[q] = padcol; }
+}
+
+// dense transpose of an n x m block (doubles and mask bytes)
+template <typename T>
+__global__ void transpose_kernel(const T* __restrict__ A, int64_t n, int64_t m, int64_t lda, T* __restrict__ B, int64_t ldb) {
+  __shared__ T tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t i = i0 + r, j = j0 + threadIdx.x;
+    if (i < n && j < m) tile[r][threadIdx.x] = A[i * lda + j];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t j = j0 + r, i = i0 + threadIdx.x;
+    if (i < n && j < m) B[j * ldb + i] = tile[threadIdx.x][r];
+  }
+}
+
+// sum of r and of (r-c)^2 over the packed values; padded slots are flagged by cols == padcol
+__global__ void data_stats_kernel(const double* __restrict__ vals, const uint32_t* __restrict__ cols, int64_t nslots,
+                                  uint32_t padcol, double center, double* __restrict__ partial) {
+  __shared__ double sh[32];
+  double a = 0.0, b = 0.0, cnt = 0.0;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nslots; q += (int64_t)gridDim.x * blockDim.x) {
+    if (cols[q] != padcol) { const double r = vals[q]; a += r; b += (r - center) * (r - center); cnt += 1.0; }
+  }
+  a = block_sum(a, sh); b = block_sum(b, sh); cnt = block_sum(cnt, sh);
+  if (threadIdx.x == 0) { partial[blockIdx.x * 3 + 0] = cnt; partial[blockIdx.x * 3 + 1] = a; partial[blockIdx.x * 3 + 2] = b; }
+}
+
+// ---- initialise(): Exp(rate lambda) draws or 1/lambda -----------------------
+__global__ void init_factor_kernel(double* __restrict__ X, int64_t n, int K, const double* __restrict__ lam_rm,
+                                   const double* __restrict__ lamk, int random, uint64_t seed, uint32_t purpose) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * K) return;
+  const int64_t i = idx / K;
+  const int k = (int)(idx - i * K);
+  const double lam = lamk ? lamk[k] : lam_rm[idx];
+  if (random) {
+    Rng rng(seed, purpose, (uint64_t)i, (uint32_t)k, 0u);
+    X[idx] = exp_draw(lam, rng);
+  } else {
+    X[idx] = 1.0 / lam;
+  }
+}
+
+// VB initialise: tau_X = 1, moments of TN(mu, 1)  (bnmf_vb.py:118-135)
+__global__ void vb_init_moments_kernel(const double* __restrict__ mu, double* __restrict__ tau, double* __restrict__ ex,
+                                       double* __restrict__ var, int64_t n) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  tau[idx] = 1.0;
+  double e, v;
+  tn_moments(mu[idx], 1.0, e, v);
+  ex[idx] = e; var[idx] = v;
+}
+
+// ---- distributions API kernels ------------------------------------------------
+__global__ void api_tn_draw_kernel(const double* mu, const double* tau, double* out, int64_t n, uint64_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Rng rng(seed, RNG_API, (uint64_t)i, 1u, 0u);
+  out[i] = tn_draw(mu[i], tau[i], rng);
+}
+__global__ void api_tn_moments_kernel(const double* mu, const double* tau, double* e, double* v, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  tn_moments(mu[i], tau[i], e[i], v[i]);
+}
+__global__ void api_gamma_draw_kernel(const double* alpha, const double* beta, double* out, int64_t n, uint64_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Rng rng(seed, RNG_API, (uint64_t)i, 2u, 0u);
+  out[i] = gamma_draw(alpha[i], beta[i], rng);
+}
+__global__ void api_exp_draw_kernel(const double* lambda, double* out, int64_t n, uint64_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Rng rng(seed, RNG_API, (uint64_t)i, 3u, 0u);
+  out[i] = exp_draw(lambda[i], rng);
+}
+
+}  // namespace bnmtf

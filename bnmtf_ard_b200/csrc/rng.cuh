@@ -1,0 +1,150 @@
+// Counter-based RNG (Philox4x32-10) and the device samplers / moments that
+// replace code/models/distributions/*.py of the reference.
+//
+// Distributional contract: the reference draws through numpy's
+// MT19937 and Chopin's table sampler (rtnorm.py); its stream cannot be matched,
+// so these are exact samplers of the same densities, KS-tested in
+// tests/test_gpu_distributions.py.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace bnmtf {
+
+// ---- Philox4x32-10 (Salmon et al. 2011) ------------------------------------
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#ifdef __CUDA_ARCH__
+  uint32_t hi0 = __umulhi(M0, c[0]), hi1 = __umulhi(M1, c[2]);
+#else
+  uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c[0]) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c[2]) >> 32);
+#endif
+  uint32_t lo0 = M0 * c[0], lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k[0], n2 = hi0 ^ c[3] ^ k[1];
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+  k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+}
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  uint32_t k[2] = {k0, k1};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) philox_round(c, k);
+}
+
+// Purposes (stream tags) -- part of the counter so that streams never collide.
+enum : uint32_t { RNG_TN_U = 1, RNG_TN_V = 2, RNG_LAMBDA = 3, RNG_TAU = 4, RNG_INIT_U = 5, RNG_INIT_V = 6, RNG_API = 7 };
+
+// One stream = (seed, purpose, index, k, iteration); successive calls bump a
+// draw counter.  Results depend only on these identifiers, never on the launch
+// geometry or on the number of GPUs.
+struct Rng {
+  uint32_t k0, k1;       // key = seed
+  uint32_t c0, c1, c2;   // index (row), k | purpose<<24, iteration
+  uint32_t draw;         // bumped per Philox call
+  uint32_t buf[4];
+  int have;              // 64-bit words left in buf (0..2)
+
+  __device__ __forceinline__ Rng(uint64_t seed, uint32_t purpose, uint64_t index, uint32_t k, uint32_t iteration)
+      : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), c0((uint32_t)index),
+        c1((k & 0xFFFFFFu) | (purpose << 24)), c2(iteration ^ ((uint32_t)(index >> 32) * 0x9E3779B1u)), draw(0), have(0) {}
+
+  __device__ __forceinline__ uint64_t next64() {
+    if (have == 0) {
+      uint32_t c[4] = {c0, c1, c2, draw++};
+      philox4x32_10(c, k0, k1);
+      buf[0] = c[0]; buf[1] = c[1]; buf[2] = c[2]; buf[3] = c[3];
+      have = 2;
+    }
+    --have;
+    return ((uint64_t)buf[2 * have + 1] << 32) | buf[2 * have];
+  }
+  // uniform on the open interval (0,1), 53 random bits
+  __device__ __forceinline__ double u01() { return ((double)(next64() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+  __device__ __forceinline__ double normal() { return normcdfinv(u01()); }
+};
+
+// ---- exponential_draw(lambda): Exp with RATE lambda (exponential.py:7-9) ----
+__device__ __forceinline__ double exp_draw(double lambda, Rng& rng) { return -log(rng.u01()) / lambda; }
+
+// ---- gamma_draw(alpha,beta): shape alpha, RATE beta (gamma.py:11-14) --------
+// Marsaglia & Tsang (2000); alpha < 1 boosted by U^(1/alpha).
+__device__ __noinline__ double gamma_draw(double alpha, double beta, Rng& rng) {
+  double boost = 1.0;
+  if (alpha < 1.0) { boost = pow(rng.u01(), 1.0 / alpha); alpha += 1.0; }
+  const double d = alpha - 1.0 / 3.0, c = rsqrt(9.0 * d);
+  for (int it = 0; it < 1000; ++it) {
+    double x = rng.normal();
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    double u = rng.u01();
+    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return boost * d * v / beta;
+  }
+  return boost * d / beta;  // unreachable in practice (acceptance > 0.95 per trial)
+}
+
+// ---- TN_draw(mu,tau): N(mu,1/tau) truncated to [0,inf) ----------------------
+// truncated_normal.py:37-44, truncated_normal_vector.py:37-50, rtnorm.py:16-218.
+// Semantics kept: tau == 0 -> 0; a draw that is negative / inf / NaN -> 0.
+// Method (exact for the target density p(x) ~ exp(-tau (x-mu)^2/2) 1[x>=0]):
+//   a = -mu sqrt(tau) is the standardised lower bound.
+//   a <= 4 : inverse CDF in the upper tail,  P(Z >= z) = u * P(Z >= a).
+//   a  > 4 : Robert (1995) translated-exponential rejection; the excess z - a
+//            is returned directly so that mu + sigma z never cancels.
+__device__ __noinline__ double tn_draw(double mu, double tau, Rng& rng) {
+  if (tau == 0.0) return 0.0;
+  const double sigma = 1.0 / sqrt(tau);
+  const double a = -mu / sigma;
+  double d;
+  if (!(a > 4.0)) {
+    const double q = 0.5 * erfc(a * 0.70710678118654752440);  // P(Z >= a)
+    const double z = -normcdfinv(rng.u01() * q);
+    d = mu + sigma * z;
+  } else {
+    const double alpha = 0.5 * (a + sqrt(a * a + 4.0));
+    double x = 0.0;
+    for (int it = 0; it < 1000; ++it) {
+      x = -log(rng.u01()) / alpha;             // z = a + x
+      const double t = (a + x) - alpha;
+      if (log(rng.u01()) <= -0.5 * t * t) break;
+    }
+    d = sigma * x;
+  }
+  return (d >= 0.0 && isfinite(d)) ? d : 0.0;
+}
+
+// ---- TN_vector_expectation / TN_vector_variance -----------------------------
+// truncated_normal_vector.py:53-73 (same operation order as the reference so
+// that the results agree to rounding): sigma = 1/sqrt(tau); x = -mu/sigma;
+// lambda(x) = pdf(x) / (0.5 erfc(x/sqrt2)); mean = mu + sigma lambda;
+// var = sigma^2 (1 - lambda (lambda - x)); if mu < -30 sigma: mean = 1/(|mu| tau),
+// var = mean^2; anything negative / inf / NaN -> 0.
+__device__ __noinline__ void tn_moments(double mu, double tau, double& e, double& v) {
+  const double sigma = 1.0 / sqrt(tau);
+  if (mu < -30.0 * sigma) {
+    e = 1.0 / (fabs(mu) * tau);
+    v = e * e;
+  } else {
+    const double x = -mu / sigma;
+    const double pdf = exp(-0.5 * x * x) / 2.5066282746310002;  // sqrt(2 pi)
+    const double lambdax = pdf / (0.5 * erfc(x / 1.4142135623730951));
+    e = mu + sigma * lambdax;
+    v = (sigma * sigma) * (1.0 - lambdax * (lambdax - x));
+  }
+  if (!(e >= 0.0 && isfinite(e))) e = 0.0;
+  if (!(v >= 0.0 && isfinite(v))) v = 0.0;
+}
+
+// digamma for x > 0 (scipy.special.psi in gamma.py:22-24): recurrence up to
+// x >= 10, then the asymptotic series (error < 1e-16 relative there).
+__device__ inline double digamma(double x) {
+  double r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  const double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0
+                   + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+  return r + log(x) - 0.5 / x + t;
+}
+
+}  // namespace bnmtf

@@ -1,0 +1,191 @@
+/*
+ * bnmtf_b200.h -- C ABI of the B200-native inference engine for the BNMF / NMF
+ * model family of ThomasBrouwer/BNMTF_ARD.
+ *
+ * The reference is pure Python and defines no FFI of its own: its boundary is
+ * the duck-typed class protocol of code/models (ctor, initialise, run, predict,
+ * plus the per-parameter methods its tests call).  The entry points below are
+ * what a ctypes binding of that protocol needs; each one cites the reference
+ * method it replaces (paths relative to the reference checkout).  The Python
+ * mirror of the class protocol lives in bnmtf_ard_b200/ and calls only these.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Pointers are HOST pointers unless the
+ *    parameter name ends in `_dev`.  Matrices are C-contiguous (row-major)
+ *    float64; masks are uint8 (0 = unobserved, non-zero = observed).
+ *  - Every function returns 0 on success, non-zero on failure;
+ *    bnmtf_last_error() returns a message for the calling thread.
+ *  - Calls are synchronous on return.  One handle is used from one thread.
+ *  - There is no CPU fallback: without a CUDA device every compute entry
+ *    point fails.
+ */
+#ifndef BNMTF_B200_H
+#define BNMTF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bnmtf_nmf_s* bnmtf_nmf_t;
+
+/* inference method (which reference class the handle behaves as) */
+enum {
+  BNMTF_GIBBS = 0, /* code/models/bnmf_gibbs.py */
+  BNMTF_ICM   = 1, /* code/models/nmf_icm.py    */
+  BNMTF_VB    = 2, /* code/models/bnmf_vb.py    */
+  BNMTF_NP    = 3  /* code/models/nmf_np.py     */
+};
+
+/* which factor: U (rows of R, I x K) or V (columns of R, J x K) */
+enum { BNMTF_SIDE_U = 0, BNMTF_SIDE_V = 1 };
+
+/* per-factor state arrays (n x K row-major).  VALUE is U/V for Gibbs, ICM, NP
+ * and exp_U/exp_V for VB. */
+enum { BNMTF_F_VALUE = 0, BNMTF_F_VAR = 1, BNMTF_F_MU = 2, BNMTF_F_TAU = 3 };
+
+/* number of float64 values written per iteration into `iter_stats` of
+ * bnmtf_nmf_run / per call of bnmtf_nmf_stats; see BNMTF_ST_* */
+#define BNMTF_NSTATS 16
+enum {
+  BNMTF_ST_RSS      = 0,  /* sum_Omega (R - X Y^T)^2            bnmf_gibbs.py:193        */
+  BNMTF_ST_SUM_E    = 1,  /* sum_Omega (R - X Y^T)                                      */
+  BNMTF_ST_SUM_RCE  = 2,  /* sum_Omega (R - mean_Omega R) * E    -> R^2, Rp (:252-270)   */
+  BNMTF_ST_TAU      = 3,  /* tau draw / mode, or exp_tau (VB)                           */
+  BNMTF_ST_BETA_S   = 4,  /* beta* of tau                        bnmf_gibbs.py:191-193   */
+  BNMTF_ST_ESD      = 5,  /* VB exp_square_diff                  bnmf_vb.py:241-244      */
+  BNMTF_ST_ELBO     = 6,  /* VB elbo()                           bnmf_vb.py:191-232      */
+  BNMTF_ST_IDIV     = 7,  /* NP compute_I_div()                  nmf_np.py:160-163       */
+  BNMTF_ST_LOGTAU   = 8,  /* VB exp_logtau                                              */
+  BNMTF_ST_ALPHA_S  = 9   /* alpha* of tau                                              */
+};
+
+const char* bnmtf_last_error(void);
+int bnmtf_device_count(void);
+/* ABI version of this library (bumped on any signature change). */
+int bnmtf_abi_version(void);
+
+/* ------------------------------------------------------------------------- *
+ * Model handle.  Replaces the data side of the constructors
+ * (bnmf_gibbs.py:61-101, bnmf_vb.py:55-96, nmf_icm.py:61-101, nmf_np.py:36-70):
+ * copies R/M to the device, packs the observed entries (bit-exact values,
+ * row-compressed for the U sweep and column-compressed for the V sweep) and
+ * computes size_Omega and mean_Omega(R).
+ *
+ * Sharding (one process per GPU): this rank owns rows [row0,row1) of R for the
+ * U sweep and columns [col0,col1) for the V sweep; `shard_rows`/`shard_cols`
+ * are the equal shard sizes used by every rank (ceil(I/P), ceil(J/P)).  For a
+ * single GPU pass row0=0,row1=I,col0=0,col1=J,shard_rows=I,shard_cols=J.
+ * R and M are the FULL I x J matrices.
+ * ------------------------------------------------------------------------- */
+int bnmtf_nmf_create(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K,
+                     const double* R, const uint8_t* M,
+                     int64_t row0, int64_t row1, int64_t shard_rows,
+                     int64_t col0, int64_t col1, int64_t shard_cols);
+
+/* Same, from dense blocks already resident on `device`:
+ *   Rrow_dev/Mrow_dev : rows [row0,row1) x all J columns, row-major
+ *   Rcol_dev/Mcol_dev : all I rows x columns [col0,col1), row-major (ld = col1-col0)
+ * The blocks are only read and may be freed after the call. */
+int bnmtf_nmf_create_dev(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K,
+                         const double* Rrow_dev, const uint8_t* Mrow_dev,
+                         const double* Rcol_dev, const uint8_t* Mcol_dev,
+                         int64_t row0, int64_t row1, int64_t shard_rows,
+                         int64_t col0, int64_t col1, int64_t shard_cols);
+
+int bnmtf_nmf_destroy(bnmtf_nmf_t h);
+
+/* size_Omega, sum_Omega R, sum_Omega (R-mean)^2 of the LOCAL row shard
+ * (bnmf_gibbs.py:74; compute_R2/compute_Rp :256-270).  out[3]. */
+int bnmtf_nmf_data_stats(bnmtf_nmf_t h, double* out);
+/* Global values after the wrapper has summed data_stats over ranks. */
+int bnmtf_nmf_set_data_stats(bnmtf_nmf_t h, double size_Omega, double mean_R);
+
+/* Join a multi-GPU job: `nccl_id` is the 128-byte ncclUniqueId created by rank
+ * 0 (bnmtf_nccl_unique_id) and distributed by the caller (torch.distributed).
+ * Loads libnccl lazily; not needed for world == 1. */
+int bnmtf_nccl_unique_id(uint8_t* id128);
+int bnmtf_nmf_set_comm(bnmtf_nmf_t h, int rank, int world, const uint8_t* nccl_id128);
+
+/* Hyper-parameters (bnmf_gibbs.py:76-89).  lambdaU (I x K) / lambdaV (J x K)
+ * are used when ARD == 0 and may be NULL when ARD != 0. */
+int bnmtf_nmf_set_hyper(bnmtf_nmf_t h, int ARD, double alphatau, double betatau,
+                        double alpha0, double beta0,
+                        const double* lambdaU, const double* lambdaV);
+
+/* Host-authoritative state: upload / download one factor array (n x K). */
+int bnmtf_nmf_set_factor(bnmtf_nmf_t h, int side, int field, const double* src);
+int bnmtf_nmf_get_factor(bnmtf_nmf_t h, int side, int field, double* dst);
+/* tau (exp_tau for VB) and lambdak / exp_lambdak (K values; NULL when not ARD). */
+int bnmtf_nmf_set_scalars(bnmtf_nmf_t h, double tau, const double* lambdak);
+int bnmtf_nmf_get_scalars(bnmtf_nmf_t h, double* tau, double* lambdak);
+
+/* VB variational parameters that are scalars / K-vectors (bnmf_vb.py:105-115,
+ * 236-249,265-273): exp_tau, exp_logtau, alpha_s, beta_s and alphak_s, betak_s,
+ * exp_lambdak, exp_loglambdak (each K values, NULL when not ARD).
+ * get: scal4 = {exp_tau, exp_logtau, alpha_s, beta_s}; lamstate4K = the four
+ * K-vectors back to back. */
+int bnmtf_nmf_set_vb_scalars(bnmtf_nmf_t h, double exp_tau, double exp_logtau, double alpha_s, double beta_s,
+                             const double* alphak_s, const double* betak_s,
+                             const double* exp_lambdak, const double* exp_loglambdak);
+int bnmtf_nmf_get_vb_scalars(bnmtf_nmf_t h, double* scal4, double* lamstate4K);
+
+/* initialise() draws (bnmf_gibbs.py:110-132, bnmf_vb.py:105-142): fills VALUE
+ * (MU for VB) of both factors with Exp(rate lambda) draws (random != 0) or
+ * 1/lambda, lambda = lambdak (ARD) or lambdaU/V. */
+int bnmtf_nmf_init_factors(bnmtf_nmf_t h, int method, int random, uint64_t seed);
+
+/* Single-column conditionals from the CURRENT state, nothing is modified:
+ *   Gibbs/ICM: tauU(k), muU(tauUk,k) / tauV(k), muV(tauVk,k)  bnmf_gibbs.py:203-219
+ *   VB       : tau_U[:,k], mu_U[:,k] of update_U(k)/update_V(k) bnmf_vb.py:251-261
+ *   NP       : out_mu = the updated column of update_U(k)/update_V(k)
+ *              (nmf_np.py:120-126), out_tau = its denominator.
+ * out_tau/out_mu have n = I (side U) or J (side V) entries.  Single-GPU only. */
+int bnmtf_nmf_column_params(bnmtf_nmf_t h, int method, int side, int k,
+                            double* out_tau, double* out_mu);
+
+/* Residual statistics of the CURRENT state into out[BNMTF_NSTATS]:
+ * RSS / sums for beta_s(), predict_while_running(), exp_square_diff(), elbo(),
+ * compute_I_div().  Nothing is modified. */
+int bnmtf_nmf_stats(bnmtf_nmf_t h, int method, double* out);
+
+/* run(iterations)  (bnmf_gibbs.py:135-183, nmf_icm.py:135-186,
+ * bnmf_vb.py:145-188, nmf_np.py:97-117), starting from the state on the
+ * handle.  Trace pointers may be NULL:
+ *   all_U   [iterations][I][K], all_V [iterations][J][K]   (Gibbs/ICM draws)
+ *   all_lambdak [iterations][K]                             (ARD)
+ *   iter_stats  [iterations][BNMTF_NSTATS]
+ *   iter_seconds[iterations]  cumulative device-side seconds (all_times)
+ * `seed` keys the Philox streams (Gibbs only). */
+int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed,
+                  double* all_U, double* all_V, double* all_lambdak,
+                  double* iter_stats, double* iter_seconds);
+
+/* number of kernels launched by this handle so far, and layout information
+ * (out[0]=threads per row team U, out[1]=entries per thread U, out[2],out[3] same
+ * for V, out[4]=padded entries U, out[5]=padded entries V, out[6]=nnz local U
+ * side, out[7]=nnz local V side). */
+int64_t bnmtf_nmf_launch_count(bnmtf_nmf_t h);
+int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8);
+/* device-event milliseconds spent in the U sweep / V sweep kernels of the last
+ * bnmtf_nmf_run (sum over iterations), and their launch counts. out[4]. */
+int bnmtf_nmf_sweep_times(bnmtf_nmf_t h, double* out4);
+
+/* ------------------------------------------------------------------------- *
+ * Distributions (code/models/distributions/*.py) on the device; n-element
+ * host arrays in, host arrays out.  Draws use Philox4x32-10 keyed by `seed`.
+ *   bnmtf_tn_draw        TN_vector_draw        truncated_normal_vector.py:37-50
+ *   bnmtf_tn_moments     TN_vector_expectation/variance          :53-73
+ *   bnmtf_gamma_draw     gamma_draw(alpha, beta) (shape, RATE)    gamma.py:11-14
+ *   bnmtf_exp_draw       exponential_draw(lambda) (RATE)          exponential.py:7-9
+ * ------------------------------------------------------------------------- */
+int bnmtf_tn_draw(int device, uint64_t seed, int64_t n, const double* mu, const double* tau, double* out);
+int bnmtf_tn_moments(int device, int64_t n, const double* mu, const double* tau, double* exp_out, double* var_out);
+int bnmtf_gamma_draw(int device, uint64_t seed, int64_t n, const double* alpha, const double* beta, double* out);
+int bnmtf_exp_draw(int device, uint64_t seed, int64_t n, const double* lambda, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNMTF_B200_H */
