@@ -32,8 +32,8 @@ METRIC = "BNMF-ARD Gibbs iters/sec, 20k x 20k K=50"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--I", type=int, default=20000)
     ap.add_argument("--J", type=int, default=20000)
@@ -222,17 +222,18 @@ def main():
     eng.set_scalars(1.0, np.ones(K))
     eng.init_factors(_lib.GIBBS, True, 12345)
 
-    eng.run(_lib.GIBBS, args.warmup, seed=1, traces=False)
-    launches0 = eng.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    eng.run(_lib.GIBBS, args.warmup, seed=1, traces=False)
+    launches0 = eng.launch_count()
     barrier()
+    sampler.rows = []
     t0 = time.perf_counter()
     res = eng.run(_lib.GIBBS, args.steps, seed=2, traces=False)
     barrier()
     wall = time.perf_counter() - t0
-    sampler.stop_flag = True
+    clocks = sampler.summary()
     dev_s = float(res["seconds"][-1])
     t = torch.tensor([dev_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -242,6 +243,34 @@ def main():
     sweeps = eng.sweep_times()
     perf = eng.performances(res["stats"][-1])
     info = eng.layout_info()
+
+    # ---- end to end through the reference-facing call with HOST buffers: the state
+    # (U, V, tau, lambda_k) is uploaded from numpy, run() executes on the device and
+    # every iteration's draws (all_U[it], all_V[it]) and statistics are copied back
+    # to host numpy arrays -- exactly what bnmf_gibbs.run() of this package does.
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 20))
+        U_h = eng.get_factor(_lib.SIDE_U, _lib.F_VALUE)
+        V_h = eng.get_factor(_lib.SIDE_V, _lib.F_VALUE)
+        barrier()
+        t0 = time.perf_counter()
+        eng.set_factor(_lib.SIDE_U, _lib.F_VALUE, U_h)
+        eng.set_factor(_lib.SIDE_V, _lib.F_VALUE, V_h)
+        eng.set_scalars(1.0, np.ones(K))
+        r2 = eng.run(_lib.GIBBS, e2e_steps, seed=3, traces=True)
+        _ = float(r2["all_U"][-1, 0, 0]) + float(r2["stats"][-1, 0])
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        e2e = {"value": e2e_steps / e2e_s, "unit": "iterations/s", "steps": e2e_steps,
+               "h2d_bytes_per_step": int(((I + J) * K * 8 + (K + 1) * 8) / e2e_steps),
+               "d2h_bytes_per_step": int((I + J) * K * 8 + K * 8 + 16 * 8),
+               "note": "engine.run() through the C ABI with host numpy state and host trace buffers (pageable)"}
+    sampler.stop_flag = True
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -253,7 +282,7 @@ def main():
                            "cache": "inputs (R packed: %.2f GB/GPU) exceed the 126 MB L2" % (
                                (info["slots_U"] + info["slots_V"]) * 12 / 1e9),
                            "layout": info, "wall_s": wall, "train_mse_last": perf["MSE"]},
-                "gpu_launches": launches, "clocks": sampler.summary()}
+                "gpu_launches": launches, "clocks": clocks}
         # roofline of the dominant kernel (row sweep): algorithmic DRAM bytes of OUR formulation
         if sweeps["n_U"] > 0:
             ms = (sweeps["ms_U"] + sweeps["ms_V"]) / (sweeps["n_U"] + sweeps["n_V"])
@@ -265,6 +294,7 @@ def main():
                                 "kernel_ms": ms, "kernel_share_of_step": (sweeps["ms_U"] + sweeps["ms_V"]) / (1e3 * dev_s),
                                 "north_star_equiv_gbs": northstar_bytes * value / 1e9,
                                 "north_star_equiv_frac": northstar_bytes * value / 1e9 / peak}
+        line["e2e"] = e2e
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))

@@ -7,18 +7,22 @@ from . import _dist, _lib
 from ._lib import (F_MU, F_TAU, F_VALUE, F_VAR, NSTATS, SIDE_U, SIDE_V, check, dptr, f64)
 
 
+def numpy_copy(v):
+    return np.array(v, dtype=np.float64)
+
+
 class NMFEngine(object):
     """Owns a bnmtf_nmf_t.  R, M are the full I x J matrices (every rank passes the
     same ones, like the reference constructors); this rank packs its row shard for
     the U sweep and its column shard for the V sweep."""
 
-    def __init__(self, R, M, K, device=None):
+    def __init__(self, R, M, K, device=None, distributed=True):
         lib = _lib.require_device()
         self.lib = lib
         self.I, self.J = R.shape
         self.K = int(K)
         self.device = _lib.current_device() if device is None else int(device)
-        self.rank, self.world = _dist.info()
+        self.rank, self.world = _dist.info() if distributed else (0, 1)
         r0, r1, rs = _dist.shard_bounds(self.I, self.rank, self.world)
         c0, c1, cs = _dist.shard_bounds(self.J, self.rank, self.world)
         R = f64(R)
@@ -53,12 +57,13 @@ class NMFEngine(object):
         lib = self.lib
         out = np.zeros(3)
         check(lib.bnmtf_nmf_data_stats(self.h, dptr(out)))
-        tot = _dist.allreduce_sum(out[:2])
+        reduce = _dist.allreduce_sum if self.world > 1 else (lambda v: numpy_copy(v))
+        tot = reduce(out[:2])
         self.size_Omega = float(tot[0])
         self.mean_R = float(tot[1] / tot[0]) if tot[0] > 0 else 0.0
         check(lib.bnmtf_nmf_set_data_stats(self.h, self.size_Omega, self.mean_R))
         check(lib.bnmtf_nmf_data_stats(self.h, dptr(out)))
-        self.ss_total = float(_dist.allreduce_sum(out[2:3])[0])
+        self.ss_total = float(reduce(out[2:3])[0])
         if self.world > 1:
             ident = np.zeros(128, dtype=np.uint8)
             if self.rank == 0:

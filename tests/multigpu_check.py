@@ -1,0 +1,74 @@
+"""Multi-GPU parity check (run under torchrun on N GPUs of one box):
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+         --master-port 29511 tests/multigpu_check.py
+
+Every rank builds the sharded engine; rank 0 also builds a single-GPU engine on
+the same data.  Because the Philox streams are keyed by global row/column
+indices and every reduction runs over the gathered global arrays in a fixed
+order, the sharded chain must be BITWISE identical to the single-GPU chain
+(Gibbs, ICM, VB, NP)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from bnmtf_ard_b200 import _lib
+    from bnmtf_ard_b200._engine import NMFEngine
+    from bnmtf_ard_b200._lib import F_MU, F_TAU, F_VALUE, F_VAR, SIDE_U, SIDE_V
+
+    ok = True
+    for (I, J, K, dens) in [(257, 190, 5, 0.6), (1001, 777, 8, 0.3), (64, 2500, 4, 0.7)]:
+        rng = np.random.default_rng(I + J)
+        R = np.abs(rng.exponential(1, (I, K)) @ rng.exponential(1, (J, K)).T + rng.normal(0, 1, (I, J))) + 0.05
+        M = (rng.random((I, J)) < dens).astype(float)
+        M[np.arange(I), rng.integers(0, J, I)] = 1
+        M[rng.integers(0, I, J), np.arange(J)] = 1
+        U0, V0 = rng.exponential(1, (I, K)), rng.exponential(1, (J, K))
+        engs = [NMFEngine(R, M, K, device=local)]
+        if rank == 0:
+            engs.append(NMFEngine(R, M, K, device=local, distributed=False))
+        for method in (_lib.GIBBS, _lib.ICM, _lib.VB, _lib.NP):
+            outs = []
+            for e in engs:
+                e.set_hyper(True, 1., 1., 1., 1.)
+                e.set_factor(SIDE_U, F_VALUE, U0); e.set_factor(SIDE_V, F_VALUE, V0)
+                if method == _lib.VB:
+                    for s, X in ((SIDE_U, U0), (SIDE_V, V0)):
+                        e.set_factor(s, F_MU, X); e.set_factor(s, F_TAU, np.ones_like(X)); e.set_factor(s, F_VAR, 0.1 * np.ones_like(X))
+                    e.set_vb_scalars(1.2, 0.1, 3., 2.5, np.ones(K), np.ones(K), np.ones(K), np.zeros(K))
+                else:
+                    e.set_scalars(1.2, np.ones(K))
+                res = e.run(method, 4, seed=99, traces=True)
+                outs.append((res, e.get_factor(SIDE_U, F_VALUE), e.get_factor(SIDE_V, F_VALUE)))
+            if rank == 0:
+                a, b = outs
+                same = (np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+                        and np.array_equal(a[0]["stats"], b[0]["stats"], equal_nan=True)
+                        and np.array_equal(a[0]["all_U"], b[0]["all_U"]) and np.array_equal(a[0]["all_lambdak"], b[0]["all_lambdak"]))
+                print("shape %s method %d world %d: %s (max |dU| %.3e)" % ((I, J, K), method, world, "BITWISE EQUAL" if same else "MISMATCH",
+                                                                            np.max(np.abs(a[1] - b[1]))))
+                ok = ok and same
+        for e in engs:
+            e.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTIGPU_CHECK", "PASS" if ok else "FAIL")
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

