@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--density", type=float, default=0.2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=1000, help="side of the CPU-baseline sample block")
+    ap.add_argument("--cpu-sample", type=int, default=2000, help="side of the CPU-baseline sample block")
     return ap.parse_args()
 
 
@@ -128,21 +128,22 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_baseline(args, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    res = cpu_baseline(args, steps=max(1, args.steps), warmup=min(args.warmup, 1), budget_s=90.0)
     line = {"metric": METRIC, "value": res["value"], "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "BNMF Gibbs+ARD %dx%d rho=%.2f K=%d" % (args.I, args.J, args.density, args.K)},
+            "config": {"workload": "BNMF Gibbs+ARD %dx%d rho=%.2f K=%d (BASELINE configs[2])" % (args.I, args.J, args.density, args.K)},
             "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def cpu_baseline(args, steps=1, warmup=0):
+def cpu_baseline(args, steps=1, warmup=0, budget_s=20.0):
+    """Time the reference's CPU implementation on a bounded sample: the s x s block
+    (same synthetic recipe, same K, same density), s chosen from a calibration
+    iteration so that warmup+steps iterations take about `budget_s` seconds."""
     import contextlib
     import io
-    s = min(args.cpu_sample, args.I, args.J)
-    R, M = synth_host(s, s, args.K, args.density)
     try:
         from threadpoolctl import threadpool_info
         threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
@@ -150,31 +151,38 @@ def cpu_baseline(args, steps=1, warmup=0):
         threads = os.cpu_count() or 1
     import refimport
     ref = refimport.load()
-    np.random.seed(0)
-    if ref is not None:
-        kind = "reference"
-        m = ref.bnmf_gibbs(R, M, args.K, True, HYPER)
-        with contextlib.redirect_stdout(io.StringIO()):
-            m.initialise("random")
-            if warmup:
-                m.run(warmup)
-            t0 = time.perf_counter()
-            m.run(steps)
-            dt = time.perf_counter() - t0
-    else:
+    kind = "reference" if ref is not None else "port"
+
+    def time_block(s, n_steps, n_warm):
+        R, M = synth_host(s, s, args.K, args.density)
+        np.random.seed(0)
+        if ref is not None:
+            m = ref.bnmf_gibbs(R, M, args.K, True, HYPER)
+            with contextlib.redirect_stdout(io.StringIO()):
+                m.initialise("random")
+                if n_warm:
+                    m.run(n_warm)
+                t0 = time.perf_counter()
+                m.run(n_steps)
+                return time.perf_counter() - t0
         import nmf_oracle as orc
-        kind = "port"
         rng = np.random.default_rng(0)
         U, V = rng.exponential(1.0, (s, args.K)), rng.exponential(1.0, (s, args.K))
         lam = np.ones(args.K)
         t0 = time.perf_counter()
-        for _ in range(steps):
+        for _ in range(n_steps):
             orc.gibbs_replay_iteration(R, M, U, V, 1.0, lam, lam, np.abs(U), np.abs(V))
-        dt = time.perf_counter() - t0
+        return time.perf_counter() - t0
+
+    s_cal = min(400, args.I, args.J)
+    per_cell = time_block(s_cal, 1, 0) / float(s_cal * s_cal)          # seconds per iteration per matrix cell
+    s = int(min(args.cpu_sample, args.I, args.J, max(200, (budget_s / ((steps + warmup) * per_cell)) ** 0.5)))
+    dt = time_block(s, steps, warmup)
     scale = (s * s) / float(args.I * args.J)
     return {"value": steps / dt * scale, "unit": "iterations/s", "cores": int(threads), "kind": kind,
-            "sample": "top-left %dx%d block of the same synthetic recipe, %d iteration(s) in %.1f s, "
-                      "it/s scaled by (s*s)/(I*J) (reference cost is proportional to I*J)" % (s, s, steps, dt),
+            "sample": "%dx%d block of the same synthetic recipe (rho=%.2f, K=%d), %d timed iteration(s) in %.1f s; "
+                      "it/s scaled by (s*s)/(I*J): the reference's cost per iteration is proportional to I*J "
+                      "(BASELINE.md section 2)" % (s, s, args.density, args.K, steps, dt),
             "sample_it_per_s": steps / dt}
 
 
