@@ -49,6 +49,18 @@ def allreduce_sum(values):
     return t.cpu().numpy()
 
 
+def allreduce_max(values):
+    """Element-wise MAX of a small int64 vector over all ranks."""
+    values = np.asarray(values, dtype=np.int64)
+    td = _pg()
+    if td is None or td.get_world_size() == 1:
+        return values.copy()
+    import torch
+    t = torch.from_numpy(values.copy()).to(_device_for_backend(td))
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return t.cpu().numpy()
+
+
 def broadcast_bytes(payload, src=0):
     """Broadcast a fixed-length bytes object from `src` to every rank."""
     td = _pg()

@@ -55,6 +55,12 @@ class NMFEngine(object):
 
     def _finish_setup(self):
         lib = self.lib
+        # global layout statistics (MAX over ranks) -> sharding-independent packing
+        st = np.zeros(4, dtype=np.int64)
+        check(lib.bnmtf_nmf_layout_stats(self.h, st.ctypes.data_as(C.POINTER(C.c_int64))))
+        if self.world > 1:
+            st = _dist.allreduce_max(st)
+        check(lib.bnmtf_nmf_pack(self.h, st.ctypes.data_as(C.POINTER(C.c_int64))))
         out = np.zeros(3)
         check(lib.bnmtf_nmf_data_stats(self.h, dptr(out)))
         reduce = _dist.allreduce_sum if self.world > 1 else (lambda v: numpy_copy(v))
@@ -154,9 +160,11 @@ class NMFEngine(object):
         return int(self.lib.bnmtf_nmf_launch_count(self.h))
 
     def layout_info(self):
-        out = np.zeros(8, dtype=np.int64)
+        out = np.zeros(16, dtype=np.int64)
         check(self.lib.bnmtf_nmf_layout_info(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
-        return dict(zip(["tpr_U", "npt_U", "tpr_V", "npt_V", "slots_U", "slots_V", "nnz_U", "nnz_V"], out.tolist()))
+        names = ["tpr_U", "npt_U", "tpr_V", "npt_V", "slots_U", "slots_V", "nnz_U", "nnz_V",
+                 "v2_U", "v2_npt_U", "v2_rows_per_set_U", "v2_slots_U", "v2_V", "v2_npt_V", "v2_rows_per_set_V", "v2_slots_V"]
+        return dict(zip(names, out.tolist()))
 
     def sweep_times(self):
         out = np.zeros(4)

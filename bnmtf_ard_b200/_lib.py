@@ -29,6 +29,8 @@ SIGNATURES = {
     "bnmtf_nmf_create_dev": (C.c_int, [C.POINTER(_h), C.c_int, C.c_int64, C.c_int64, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "bnmtf_nmf_layout_stats": (C.c_int, [_h, _i64p]),
+    "bnmtf_nmf_pack": (C.c_int, [_h, _i64p]),
     "bnmtf_nmf_destroy": (C.c_int, [_h]),
     "bnmtf_nmf_data_stats": (C.c_int, [_h, _dp]),
     "bnmtf_nmf_set_data_stats": (C.c_int, [_h, C.c_double, C.c_double]),

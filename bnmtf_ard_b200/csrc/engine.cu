@@ -10,6 +10,7 @@
 
 #include "../../include/bnmtf_b200.h"
 #include "kernels.cuh"
+#include "kernels_v2.cuh"
 
 using namespace bnmtf;
 
@@ -88,7 +89,22 @@ struct Side {
   double* rowstats = nullptr;  // [n_padglob][NRS]
   double* trace[2] = {nullptr, nullptr};
   int occ[4] = {0, 0, 0, 0};  // cached resident blocks/SM of the sweep kernel per method
+  // dense block kept between create() and pack()
+  const double* dR = nullptr;
+  const uint8_t* dM = nullptr;
+  bool own_dense = false;
+  int* rowlen_dev = nullptr;
+  int64_t maxlen_local = 0, maxseg_local = 0;
+  bool packed = false;
+  // v2 (cluster) layout
+  bool v2 = false;
+  int cs = 8, tw = 0, rs = 0, npt2 = 0;
+  int64_t nsets = 0, tslots = 0;
+  double* tvals = nullptr;
+  uint16_t* tcols = nullptr;
+  int nclusters[4] = {0, 0, 0, 0};
 };
+constexpr int V2_CS = 8;
 }  // namespace
 
 struct bnmtf_nmf_s {
@@ -126,40 +142,82 @@ static void choose_team(int64_t maxlen, int* tpr, int* npt) {
   *npt = n;
 }
 
-// pack a dense device block (n x m, row-major, leading dim ld) into padded rows
-static int pack_block(bnmtf_nmf_s* h, Side& sd, const double* R_dev, const uint8_t* M_dev, int64_t n, int64_t m, int64_t ld,
-                      uint32_t padcol) {
-  int* rowlen_dev = nullptr;
-  CK(cudaMalloc(&rowlen_dev, sizeof(int) * std::max<int64_t>(n, 1)));
+static int v2_tile_width(int64_t m) { return (int)roundup((m + V2_CS - 1) / V2_CS, 32); }
+
+// phase 1: observed entries per row and the longest (row, tile) segment of a dense block
+static int count_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld) {
+  CK(cudaMalloc(&sd.rowlen_dev, sizeof(int) * std::max<int64_t>(n + 1, 2)));
+  CK(cudaMemsetAsync(sd.rowlen_dev, 0, sizeof(int) * std::max<int64_t>(n + 1, 2), h->stream));
+  sd.tw = v2_tile_width(m);
   if (n > 0) {
-    count_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, h->stream>>>(M_dev, n, m, ld, rowlen_dev);
+    count_rows_tiles_kernel<<<(unsigned)((n + 7) / 8), 256, 0, h->stream>>>(sd.dM, n, m, ld, sd.tw, sd.rowlen_dev, sd.rowlen_dev + n);
     h->launches++;
   }
-  std::vector<int> rowlen(n);
-  CK(cudaMemcpyAsync(rowlen.data(), rowlen_dev, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<int> rowlen(n + 1);
+  CK(cudaMemcpyAsync(rowlen.data(), sd.rowlen_dev, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   int64_t maxlen = 1, nnz = 0;
   for (int64_t i = 0; i < n; ++i) { maxlen = std::max<int64_t>(maxlen, rowlen[i]); nnz += rowlen[i]; }
+  sd.maxlen_local = maxlen; sd.maxseg_local = std::max(1, rowlen[n]); sd.nnz = nnz;
+  return 0;
+}
+
+// phase 2: pack the dense block (n x m, row-major, leading dim ld) into padded rows (v1
+// layout) and, for long rows, into cluster tiles (v2 layout).  maxlen / maxseg are the
+// GLOBAL maxima over all ranks so that the layout -- and with it every summation
+// order -- does not depend on how the matrix is sharded.
+static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld, uint32_t padcol, int64_t maxlen,
+                      int64_t maxseg) {
   choose_team(maxlen, &sd.tpr, &sd.npt);
   if ((int64_t)sd.tpr * sd.npt < maxlen || sd.tpr > 512)
     FAIL("a row/column of R has %lld observed entries; this build supports at most 16384 per row", (long long)maxlen);
+  std::vector<int> rowlen(n);
+  CK(cudaMemcpyAsync(rowlen.data(), sd.rowlen_dev, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   std::vector<int64_t> rowstart(n + 1);
   rowstart[0] = 0;
   for (int64_t i = 0; i < n; ++i) rowstart[i + 1] = rowstart[i] + roundup(rowlen[i], sd.tpr);
   sd.nslots = rowstart[n];
-  sd.nnz = nnz;
   sd.padcol = padcol;
   CK(cudaMalloc(&sd.rowstart, sizeof(int64_t) * (n + 1)));
   CK(cudaMalloc(&sd.vals, sizeof(double) * std::max<int64_t>(sd.nslots, 1)));
   CK(cudaMalloc(&sd.cols, sizeof(uint32_t) * std::max<int64_t>(sd.nslots, 1)));
   CK(cudaMemcpyAsync(sd.rowstart, rowstart.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, h->stream));
   if (n > 0) {
-    pack_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, h->stream>>>(R_dev, M_dev, n, m, ld, sd.rowstart, padcol, sd.vals, sd.cols);
+    pack_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, h->stream>>>(sd.dR, sd.dM, n, m, ld, sd.rowstart, padcol, sd.vals, sd.cols);
     h->launches++;
   }
+  // v2 eligibility depends on global quantities only
+  const char* mode = getenv("BNMTF_SWEEP");
+  const bool force_v1 = mode && strcmp(mode, "v1") == 0;
+  int npt2 = (int)roundup((maxseg + 31) / 32, 2);
+  if (npt2 < 4) npt2 = 4;
+  if (npt2 > 4 && npt2 < 8) npt2 = 8;
+  if (npt2 > 8 && npt2 < 12) npt2 = 12;
+  if (npt2 > 12 && npt2 < 16) npt2 = 16;
+  const int wpc = npt2 <= 16 ? 32 : (npt2 <= 18 ? 28 : 24);   // Sweep2Cfg<NPT>::WPC
+  const int rs = wpc - 1;                                      // rows per set (warp 0 is the control warp)
+  const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, h->K, V2_CS) * sizeof(double);
+  sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && h->K >= 3 && smem_vb <= 200 * 1024 && sd.tw * 2 < 65535;
+  if (sd.v2 && n > 0) {
+    sd.cs = V2_CS; sd.npt2 = npt2; sd.rs = rs;
+    sd.nsets = (n + rs - 1) / rs;
+    sd.tslots = sd.nsets * V2_CS * (int64_t)npt2 * rs * 32;
+    CK(cudaMalloc(&sd.tvals, sizeof(double) * sd.tslots));
+    CK(cudaMalloc(&sd.tcols, sizeof(uint16_t) * sd.tslots));
+    fill_pads_kernel<<<1024, 256, 0, h->stream>>>(sd.tvals, sd.tcols, sd.tslots, (uint16_t)sd.tw);
+    pack_tiles_kernel<<<(unsigned)((n * V2_CS + 7) / 8), 256, 0, h->stream>>>(sd.dR, sd.dM, n, m, ld, V2_CS, sd.tw, rs, npt2,
+                                                                             sd.tvals, sd.tcols);
+    h->launches += 2;
+  } else {
+    sd.v2 = false;
+  }
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaFree(rowlen_dev));
   CK(cudaGetLastError());
+  CK(cudaFree(sd.rowlen_dev)); sd.rowlen_dev = nullptr;
+  if (sd.own_dense) { cudaFree((void*)sd.dR); cudaFree((void*)sd.dM); }
+  sd.dR = nullptr; sd.dM = nullptr; sd.own_dense = false;
+  sd.packed = true;
   return 0;
 }
 
@@ -168,7 +226,7 @@ static int alloc_side_state(bnmtf_nmf_s* h, Side& sd, int K) {
   CK(cudaMalloc(&sd.val, nb)); CK(cudaMalloc(&sd.var, nb)); CK(cudaMalloc(&sd.mu, nb)); CK(cudaMalloc(&sd.tau, nb));
   CK(cudaMemsetAsync(sd.val, 0, nb, h->stream)); CK(cudaMemsetAsync(sd.var, 0, nb, h->stream));
   CK(cudaMemsetAsync(sd.mu, 0, nb, h->stream)); CK(cudaMemsetAsync(sd.tau, 0, nb, h->stream));
-  sd.ld = roundup(std::max(sd.n_padglob, sd.n_glob + 1), 16);
+  sd.ld = roundup(std::max(sd.n_padglob, sd.n_glob + 1) + V2_CS * 32, 16);  // >= CS * tile width
   CK(cudaMalloc(&sd.km, sizeof(double) * 2 * sd.ld * K));
   CK(cudaMemsetAsync(sd.km, 0, sizeof(double) * 2 * sd.ld * K, h->stream));
   CK(cudaMalloc(&sd.rowstats, sizeof(double) * sd.n_padglob * NRS));
@@ -207,9 +265,10 @@ int bnmtf_nmf_create_dev(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int
   su.n_padglob = std::max(I, ((I + shard_rows - 1) / shard_rows) * shard_rows);
   sv.n_padglob = std::max(J, ((J + shard_cols - 1) / shard_cols) * shard_cols);
 
-  // U side: rows [row0,row1) x J
-  if (pack_block(h, su, Rrow_dev, Mrow_dev, su.n_loc, J, J, (uint32_t)J)) { return 1; }
-  // V side: columns [col0,col1): transpose the I x Jloc block, then pack its rows
+  // U side: rows [row0,row1) x J (the caller's block, read again by bnmtf_nmf_pack)
+  su.dR = Rrow_dev; su.dM = Mrow_dev; su.own_dense = false;
+  if (count_block(h, su, su.n_loc, J, J)) return 1;
+  // V side: columns [col0,col1): transposed copy of the I x Jloc block, owned by the handle
   {
     const int64_t jl = sv.n_loc;
     double* Rt = nullptr; uint8_t* Mt = nullptr;
@@ -221,9 +280,8 @@ int bnmtf_nmf_create_dev(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int
       transpose_kernel<uint8_t><<<grd, blk, 0, h->stream>>>(Mcol_dev, I, jl, jl, Mt, I);
       h->launches += 2;
     }
-    int rc = pack_block(h, sv, Rt, Mt, jl, I, I, (uint32_t)I);
-    cudaFree(Rt); cudaFree(Mt);
-    if (rc) return 1;
+    sv.dR = Rt; sv.dM = Mt; sv.own_dense = true;
+    if (count_block(h, sv, jl, I, I)) return 1;
   }
   if (alloc_side_state(h, su, K) || alloc_side_state(h, sv, K)) return 1;
   CK(cudaMalloc(&h->scal, sizeof(double) * SC_COUNT));
@@ -238,6 +296,25 @@ int bnmtf_nmf_create_dev(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int
   h->hyper.size_Omega = (double)su.nnz;
   CK(cudaStreamSynchronize(h->stream));
   *out = h;
+  return 0;
+}
+
+int bnmtf_nmf_layout_stats(bnmtf_nmf_t h, int64_t* out4) {
+  if (!h || !out4) FAIL("bad argument");
+  out4[0] = h->s[0].maxlen_local; out4[1] = h->s[0].maxseg_local;
+  out4[2] = h->s[1].maxlen_local; out4[3] = h->s[1].maxseg_local;
+  return 0;
+}
+
+int bnmtf_nmf_pack(bnmtf_nmf_t h, const int64_t* global4) {
+  if (!h) FAIL("NULL handle");
+  CK(cudaSetDevice(h->device));
+  Side& su = h->s[0]; Side& sv = h->s[1];
+  if (su.packed) FAIL("already packed");
+  int64_t g[4] = {su.maxlen_local, su.maxseg_local, sv.maxlen_local, sv.maxseg_local};
+  if (global4) for (int q = 0; q < 4; ++q) g[q] = std::max(g[q], global4[q]);
+  if (pack_block(h, su, su.n_loc, h->J, h->J, (uint32_t)h->J, g[0], g[1])) return 1;
+  if (pack_block(h, sv, sv.n_loc, h->I, h->I, (uint32_t)h->I, g[2], g[3])) return 1;
   return 0;
 }
 
@@ -267,9 +344,10 @@ int bnmtf_nmf_create(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, 
     }
   }
   int rc = bnmtf_nmf_create_dev(out, device, I, J, K, Rrow, Mrow, Rcol, Mcol, row0, row1, shard_rows, col0, col1, shard_cols);
-  cudaFree(Rrow); cudaFree(Mrow);
   if (!full) { cudaFree(Rcol); cudaFree(Mcol); }
-  return rc;
+  if (rc) { cudaFree(Rrow); cudaFree(Mrow); return rc; }
+  (*out)->s[0].own_dense = true;   // released by bnmtf_nmf_pack
+  return 0;
 }
 
 static void free_side(Side& sd) {
@@ -277,6 +355,8 @@ static void free_side(Side& sd) {
   cudaFree(sd.val); cudaFree(sd.var); cudaFree(sd.mu); cudaFree(sd.tau);
   cudaFree(sd.km); cudaFree(sd.lam_rm); cudaFree(sd.rowstats);
   cudaFree(sd.trace[0]); cudaFree(sd.trace[1]);
+  cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev);
+  if (sd.own_dense) { cudaFree((void*)sd.dR); cudaFree((void*)sd.dM); }
 }
 
 int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
@@ -294,6 +374,7 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
 
 int bnmtf_nmf_data_stats(bnmtf_nmf_t h, double* out) {
   if (!h || !out) FAIL("NULL argument");
+  if (!h->s[0].packed) FAIL("call bnmtf_nmf_pack first");
   CK(cudaSetDevice(h->device));
   Side& su = h->s[0];
   const int nb = 256;
@@ -463,7 +544,7 @@ static int launch_sweep_t(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int* 
   const size_t smem = sizeof(double) * teams * (4 * (size_t)p.K + 3 * nw + 2);
   auto kern = sweep_kernel<NPT, MODE>;
   if (*occ_cache == 0) {
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
     if (occ < 1) FAIL("sweep kernel does not fit: block %d smem %zu", block, smem);
@@ -489,36 +570,98 @@ static int launch_sweep_m(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int n
   FAIL("unsupported entries-per-thread %d", npt);
 }
 
+template <int NPT, int MODE>
+static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
+  constexpr int NV = (MODE == M_VB) ? 2 : 1;
+  auto kern = sweep2_kernel<NPT, MODE, V2_CS>;
+  const size_t smem = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS) * sizeof(double);
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3((p.rs + 1) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = V2_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (sd.nclusters[method] == 0) {
+    // one fixed opt-in limit per instantiation: both sides (and other handles) share the kernel
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg.gridDim = dim3(V2_CS * 64);
+    int ncl = 0;
+    CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
+    if (ncl < 1) FAIL("cluster sweep kernel does not fit (smem %zu bytes, %d threads)", smem, (p.rs + 1) * 32);
+    sd.nclusters[method] = ncl;
+  }
+  const int ncl = (int)std::min<int64_t>(sd.nclusters[method], p.nsets);
+  if (ncl < 1) return 0;
+  cfg.gridDim = dim3(V2_CS * ncl);
+  CK(cudaLaunchKernelEx(&cfg, kern, p));
+  h->launches++;
+  return 0;
+}
+
+template <int MODE>
+static int launch_sweep2_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
+  switch (sd.npt2) {
+    case 4: return launch_sweep2_t<4, MODE>(h, p, sd, method);
+    case 8: return launch_sweep2_t<8, MODE>(h, p, sd, method);
+    case 12: return launch_sweep2_t<12, MODE>(h, p, sd, method);
+    case 16: return launch_sweep2_t<16, MODE>(h, p, sd, method);
+    case 18: return launch_sweep2_t<18, MODE>(h, p, sd, method);
+    case 20: return launch_sweep2_t<20, MODE>(h, p, sd, method);
+  }
+  FAIL("unsupported v2 entries-per-lane %d", sd.npt2);
+}
+
 // side: which factor is updated.  single_k: see SweepParams.
 static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint64_t seed, uint32_t iteration,
                         double* out_tau, double* out_mu, bool want_mu) {
   Side& sd = h->s[side];
   Side& other = h->s[1 - side];
-  SweepParams p{};
-  p.vals = sd.vals; p.cols = sd.cols; p.rowstart = sd.rowstart;
-  p.n_loc = (int)sd.n_loc; p.row0 = sd.row0; p.K = h->K; p.tpr = sd.tpr; p.padcol = sd.padcol;
-  p.Ykm = other.km; p.ldy = other.ld;
-  p.Xval = sd.val; p.Xvar = sd.var;
+  if (!sd.packed) FAIL("call bnmtf_nmf_pack first");
   const bool mu_out = (method == BNMTF_VB) || want_mu;
-  p.Xmu = mu_out ? sd.mu : nullptr; p.Xtau = mu_out ? sd.tau : nullptr;
-  p.lam_rm = h->hyper.ARD ? nullptr : sd.lam_rm;
-  p.lamk = (h->hyper.ARD && method != BNMTF_NP) ? h->lamk : nullptr;
-  p.scal = h->scal;
-  p.out_tau = out_tau; p.out_mu = out_mu;
-  p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
-  p.rmean = h->rmean;
-  p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
-  p.single_k = single_k;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const bool timed = h->time_sweeps && single_k == -1;
   if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
   int rc;
-  switch (method) {
-    case BNMTF_GIBBS: rc = launch_sweep_m<M_GIBBS>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
-    case BNMTF_ICM: rc = launch_sweep_m<M_ICM>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
-    case BNMTF_VB: rc = launch_sweep_m<M_VB>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
-    case BNMTF_NP: rc = launch_sweep_m<M_NP>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
-    default: FAIL("unknown method %d", method);
+  if (sd.v2 && single_k == -1 && method != BNMTF_NP) {
+    Sweep2Params p{};
+    p.tvals = sd.tvals; p.tcols = sd.tcols; p.nsets = (int)sd.nsets; p.n_loc = (int)sd.n_loc; p.row0 = sd.row0;
+    p.K = h->K; p.tw = sd.tw; p.rs = sd.rs; p.Ykm = other.km; p.ldy = other.ld;
+    p.Xval = sd.val; p.Xvar = sd.var; p.Xmu = mu_out ? sd.mu : nullptr; p.Xtau = mu_out ? sd.tau : nullptr;
+    p.lam_rm = h->hyper.ARD ? nullptr : sd.lam_rm;
+    p.lamk = h->hyper.ARD ? h->lamk : nullptr;
+    p.scal = h->scal;
+    p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
+    p.rmean = h->rmean; p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
+    switch (method) {
+      case BNMTF_GIBBS: rc = launch_sweep2_m<M_GIBBS>(h, p, sd, method); break;
+      case BNMTF_ICM: rc = launch_sweep2_m<M_ICM>(h, p, sd, method); break;
+      case BNMTF_VB: rc = launch_sweep2_m<M_VB>(h, p, sd, method); break;
+      default: FAIL("unknown method %d", method);
+    }
+  } else {
+    SweepParams p{};
+    p.vals = sd.vals; p.cols = sd.cols; p.rowstart = sd.rowstart;
+    p.n_loc = (int)sd.n_loc; p.row0 = sd.row0; p.K = h->K; p.tpr = sd.tpr; p.padcol = sd.padcol;
+    p.Ykm = other.km; p.ldy = other.ld;
+    p.Xval = sd.val; p.Xvar = sd.var;
+    p.Xmu = mu_out ? sd.mu : nullptr; p.Xtau = mu_out ? sd.tau : nullptr;
+    p.lam_rm = h->hyper.ARD ? nullptr : sd.lam_rm;
+    p.lamk = (h->hyper.ARD && method != BNMTF_NP) ? h->lamk : nullptr;
+    p.scal = h->scal;
+    p.out_tau = out_tau; p.out_mu = out_mu;
+    p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
+    p.rmean = h->rmean;
+    p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
+    p.single_k = single_k;
+    switch (method) {
+      case BNMTF_GIBBS: rc = launch_sweep_m<M_GIBBS>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
+      case BNMTF_ICM: rc = launch_sweep_m<M_ICM>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
+      case BNMTF_VB: rc = launch_sweep_m<M_VB>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
+      case BNMTF_NP: rc = launch_sweep_m<M_NP>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
+      default: FAIL("unknown method %d", method);
+    }
   }
   if (timed) {
     cudaEventRecord(e1, h->stream);
@@ -749,10 +892,15 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
 
 int64_t bnmtf_nmf_launch_count(bnmtf_nmf_t h) { return h ? h->launches : 0; }
 
-int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {
+int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {  // out8: 16 values
   if (!h || !out8) FAIL("bad argument");
   out8[0] = h->s[0].tpr; out8[1] = h->s[0].npt; out8[2] = h->s[1].tpr; out8[3] = h->s[1].npt;
   out8[4] = h->s[0].nslots; out8[5] = h->s[1].nslots; out8[6] = h->s[0].nnz; out8[7] = h->s[1].nnz;
+  for (int q = 0; q < 2; ++q) {
+    const Side& sd = h->s[q];
+    out8[8 + 4 * q] = sd.v2 ? 1 : 0; out8[9 + 4 * q] = sd.v2 ? sd.npt2 : 0;
+    out8[10 + 4 * q] = sd.v2 ? sd.rs : 0; out8[11 + 4 * q] = sd.v2 ? sd.tslots : 0;
+  }
   return 0;
 }
 

@@ -87,6 +87,52 @@ __device__ __forceinline__ void team_reduce_to_leader(double (&v)[NR], double* r
   }
 }
 
+// The update of one factor entry from the reduced sums of its row:
+//   s0 = sum y^2 (NP: numerator), s1 = sum (var_y + y^2) (NP: denominator), s2 = sum e*y.
+// Returns the conditional precision / mean actually used (ct, cm), the new value
+// and (VB) the new variance, and accumulates the VB ELBO/ESD row terms.
+//   Gibbs: bnmf_gibbs.py:203-210 + TN_vector_draw     ICM: nmf_icm.py:159-160
+//   VB   : bnmf_vb.py:251-255,275-278                  NP : nmf_np.py:120-122
+struct UpdateCtx {
+  uint64_t seed;
+  uint32_t purpose, iteration;
+  bool dry;
+};
+template <int MODE>
+__device__ __forceinline__ double conditional_update(const double (&s)[3], double x_old, double lam, double tau,
+                                                     const UpdateCtx& u, uint64_t grow, int k, double old_mu,
+                                                     double old_tau, double old_var, double& ct, double& cm,
+                                                     double& v_new, double& acc_esd, double& acc_q, double& acc_prior) {
+  double x_new;
+  v_new = old_var;
+  if (MODE == M_NP) {
+    x_new = x_old * s[0] / s[1];  // nmf_np.py:122
+    ct = s[1]; cm = x_new;
+  } else if (MODE == M_VB) {
+    ct = tau * s[1];                                   // bnmf_vb.py:254
+    cm = (-lam + tau * (s[2] + x_old * s[0])) / ct;    // bnmf_vb.py:255
+    double en, vn;
+    if (u.dry) { cm = old_mu; ct = old_tau; en = x_old; vn = old_var; }
+    else tn_moments(cm, ct, en, vn);
+    x_new = en;
+    v_new = vn;
+    acc_esd += (vn + en * en) * s[1] - (en * en) * s[0];
+    acc_q += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951))
+             + 0.5 * ct * (vn + (en - cm) * (en - cm));
+    acc_prior += lam * en;
+  } else {
+    ct = tau * s[0];                                   // bnmf_gibbs.py:205
+    cm = (-lam + tau * (s[2] + x_old * s[0])) / ct;    // bnmf_gibbs.py:210
+    if (MODE == M_GIBBS) {
+      Rng rng(u.seed, u.purpose, grow, (uint32_t)k, u.iteration);
+      x_new = tn_draw(cm, ct, rng);                    // bnmf_gibbs.py:158
+    } else {
+      x_new = fmax(fmax(0.0, cm), MINIMUM_TN);         // nmf_icm.py:159-160
+    }
+  }
+  return x_new;
+}
+
 // -----------------------------------------------------------------------------
 // Row-fused K-column sweep.  One team of `tpr` threads per row; thread t owns the
 // entries t, t+tpr, ... of the row (coalesced loads), NPT of them at most.
@@ -209,32 +255,11 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
         const double x_old = xs[k];
         const double lam = p.lamk ? p.lamk[k] : (p.lam_rm ? p.lam_rm[grow * K + k] : 0.0);
         const double tau = p.scal[0];
-        double x_new, cm = 0.0, ct = 0.0;
-        if (MODE == M_NP) {
-          x_new = x_old * s[0] / s[1];  // nmf_np.py:122
-          ct = s[1]; cm = x_new;
-        } else if (MODE == M_VB) {
-          ct = tau * s[1];                                   // bnmf_vb.py:254
-          cm = (-lam + tau * (s[2] + x_old * s[0])) / ct;    // bnmf_vb.py:255
-          double en, vn;
-          if (dry) { cm = xmu[k]; ct = xtau[k]; en = x_old; vn = xvar[k]; }
-          else tn_moments(cm, ct, en, vn);
-          x_new = en;
-          xvar[k] = vn;
-          acc_esd += (vn + en * en) * s[1] - (en * en) * s[0];
-          acc_q += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951))
-                   + 0.5 * ct * (vn + (en - cm) * (en - cm));
-          acc_prior += lam * en;
-        } else {
-          ct = tau * s[0];                                   // bnmf_gibbs.py:205
-          cm = (-lam + tau * (s[2] + x_old * s[0])) / ct;    // bnmf_gibbs.py:210
-          if (MODE == M_GIBBS) {
-            Rng rng(p.seed, p.purpose, (uint64_t)grow, (uint32_t)k, p.iteration);
-            x_new = tn_draw(cm, ct, rng);                    // bnmf_gibbs.py:158
-          } else {
-            x_new = fmax(fmax(0.0, cm), MINIMUM_TN);         // nmf_icm.py:159-160
-          }
-        }
+        const UpdateCtx uc{p.seed, p.purpose, p.iteration, dry};
+        double cm, ct, vn;
+        double x_new = conditional_update<MODE>(s, x_old, lam, tau, uc, (uint64_t)grow, k, xmu[k], xtau[k], xvar[k], ct, cm,
+                                                vn, acc_esd, acc_q, acc_prior);
+        if (MODE == M_VB) xvar[k] = vn;
         if (p.single_k >= 0) {
           p.out_tau[grow] = ct;
           p.out_mu[grow] = cm;

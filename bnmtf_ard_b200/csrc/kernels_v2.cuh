@@ -1,0 +1,431 @@
+// Cluster / distributed-shared-memory sweep ("v2") for long rows.
+//
+// The v1 sweep (kernels.cuh) gathers the other factor straight from L2: one 32-byte
+// sector per 8-byte value, 192 GB per sweep at the north-star size.  Here a
+// thread-block cluster of CS CTAs owns a set of RS rows; CTA c owns column tile c
+// (TW columns) of those rows:
+//   * the residual of the RS x TW block (observed entries only) lives in registers,
+//     one warp per row segment;
+//   * column k of the other factor, restricted to the tile, is staged in shared
+//     memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier) through a 3-stage ring
+//     and gathered from there (entries are placed so that a half-warp hits 16
+//     distinct 8-byte banks);
+//   * the per-row partial sums of the CS tiles meet in CTA 0's shared memory through
+//     DSMEM stores; one warp of CTA 0 computes the RS updates of the column in
+//     parallel (lane = row) and pushes the RS deltas back into every CTA's shared
+//     memory; cluster barriers order the two exchanges;
+//   * the rank-1 correction of column k is folded into the accumulation loop of
+//     column k+1 ("lazy"), so nothing but e[] has to stay in registers.
+// L2 -> SM traffic drops from 192 GB to ~10 GB per sweep; the kernel becomes
+// shared-memory-gather bound.
+#pragma once
+#include <cooperative_groups.h>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace bnmtf {
+
+// ---- mbarrier / TMA bulk helpers (PTX) ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// ---- layout statistics: observed entries per row and the longest (row, tile) segment
+__global__ void count_rows_tiles_kernel(const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld, int tw,
+                                        int* __restrict__ rowlen, int* __restrict__ maxseg) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  int total = 0, seg = 0, best = 0;
+  for (int64_t j0 = 0; j0 < m; j0 += 32) {
+    if (j0 % tw == 0) { best = max(best, seg); seg = 0; }
+    const int64_t j = j0 + lane;
+    const bool obs = (j < m) && (M[row * ld + j] != 0);
+    const int c = __popc(__ballot_sync(0xffffffffu, obs));
+    seg += c; total += c;
+  }
+  best = max(best, seg);
+  if (lane == 0) { rowlen[row] = total; atomicMax(maxseg, best); }
+}
+
+__global__ void fill_pads_kernel(double* __restrict__ tvals, uint16_t* __restrict__ tcols, int64_t nslots, uint16_t padcol) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nslots; q += (int64_t)gridDim.x * blockDim.x) {
+    tvals[q] = 0.0;
+    tcols[q] = padcol;
+  }
+}
+
+// Slab layout: slot(set, c, n, r, lane) = ((((set*CS + c)*NPT + n)*RS + r)*32 + lane.
+// One warp packs one (row, tile) segment.  Placement: the t-th observed entry (in
+// column order) of bank class q = col_local % 16 goes to n = t/2, lane = q + 16*(t%2),
+// so each half-warp of a gather instruction reads 16 distinct 8-byte banks; classes
+// with more than 2*NPT entries spill, in canonical order, into the slots that
+// shorter classes leave empty.  The placement depends only on the segment and NPT.
+__global__ void pack_tiles_kernel(const double* __restrict__ R, const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld,
+                                  int cs, int tw, int rs, int npt, double* __restrict__ tvals, uint16_t* __restrict__ tcols) {
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= n * cs) return;
+  const int64_t row = wid / cs;
+  const int c = (int)(wid - row * cs);
+  const int64_t set = row / rs;
+  const int r = (int)(row - set * rs);
+  const int64_t seg_base = ((set * cs + c) * npt) * (int64_t)rs * 32;
+  const int64_t j_begin = (int64_t)c * tw, j_end = min(m, j_begin + tw);
+  const int q = lane & 15;
+  const int cap = 2 * npt;
+  // pass 1: class totals
+  int pc = 0;
+  for (int64_t j0 = j_begin; j0 < j_end; j0 += 32) {
+    const int64_t j = j0 + lane;
+    pc += (j < j_end) && (M[row * ld + j] != 0);
+  }
+  const int cnt = pc + __shfl_xor_sync(0xffffffffu, pc, 16);   // entries of class q in the segment
+  const int over = max(0, cnt - cap), holes = max(0, cap - cnt);
+  // exclusive prefix sums over the 16 classes (both half-warps compute the same)
+  int ovbase = over, holebase = holes;
+  for (int o = 1; o < 16; o <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, ovbase, o, 16), b = __shfl_up_sync(0xffffffffu, holebase, o, 16);
+    if (q >= o) { ovbase += a; holebase += b; }
+  }
+  ovbase -= over; holebase -= holes;
+  // pass 2: placement
+  int seen = 0;  // entries of this lane's column residue (mod 32) seen so far
+  for (int64_t j0 = j_begin; j0 < j_end; j0 += 32) {
+    const int64_t j = j0 + lane;
+    const bool obs = (j < j_end) && (M[row * ld + j] != 0);
+    const unsigned bal = __ballot_sync(0xffffffffu, obs);
+    const int partner_seen = __shfl_xor_sync(0xffffffffu, seen, 16);
+    int t = seen + partner_seen + ((lane >= 16) ? (int)((bal >> (lane - 16)) & 1u) : 0);
+    int qq = q;
+    const bool overflow = obs && (t >= cap);
+    if (__any_sync(0xffffffffu, overflow)) {
+      // canonical overflow index -> the o-th empty slot, in class order
+      const int o = ovbase + (t - cap);
+      int found_q = 0, found_t = 0;
+      for (int z = 0; z < 16; ++z) {
+        const int hb = __shfl_sync(0xffffffffu, holebase, z), hh = __shfl_sync(0xffffffffu, holes, z);
+        const int cz = __shfl_sync(0xffffffffu, cnt, z);
+        if (overflow && o >= hb && o < hb + hh) { found_q = z; found_t = cz + (o - hb); }
+      }
+      if (overflow) { qq = found_q; t = found_t; }
+    }
+    if (obs) {
+      const int nn = t >> 1, ll = qq + 16 * (t & 1);
+      const int64_t slot = seg_base + ((int64_t)nn * rs + r) * 32 + ll;
+      tvals[slot] = R[row * ld + j];
+      tcols[slot] = (uint16_t)(j - j_begin);
+    }
+    seen += obs ? 1 : 0;
+  }
+}
+
+struct Sweep2Params {
+  const double* __restrict__ tvals;
+  const uint16_t* __restrict__ tcols;
+  int nsets;
+  int n_loc;
+  int64_t row0;
+  int K;
+  int tw;                                // tile width in columns (multiple of 32)
+  int rs;                                // rows per set == warps per CTA
+  const double* __restrict__ Ykm;        // other factor, k-major [K][ldy][NV], zero padded to >= CS*tw
+  int64_t ldy;
+  double* Xval;
+  double* Xvar;
+  double* Xmu;
+  double* Xtau;
+  const double* __restrict__ lam_rm;
+  const double* __restrict__ lamk;
+  const double* __restrict__ scal;
+  double* rowstats;                      // [n_loc][NRS]
+  double rmean;
+  uint64_t seed;
+  uint32_t iteration;
+  uint32_t purpose;
+};
+
+// dynamic shared memory of sweep2_kernel, in doubles
+__host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs) {
+  return (size_t)3 * (tw + 2) * nv + 4 /*mbarriers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ + (size_t)cs * rs * 4;
+}
+
+// Warps per CTA that the register budget of NPT entries per lane allows.  Warp 0 of
+// every CTA is the control warp (TMA producer; in CTA 0 also the updater of the RS
+// rows of the set, lane = row); warps 1..WPC-1 each own one row segment, so a set
+// has RS = WPC - 1 rows.  The two roles run separate loop nests with matching barrier
+// sequences, so the compute warps never carry a function call in their loop.
+template <int NPT>
+struct Sweep2Cfg {
+  static constexpr int WPC = NPT <= 16 ? 32 : (NPT <= 18 ? 28 : 24);
+  static constexpr int RS = WPC - 1;
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int NPT, int MODE, int CS>
+__global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC * 32, 1) sweep2_kernel(const Sweep2Params p) {
+  constexpr int NV = (MODE == M_VB) ? 2 : 1;
+  constexpr int RS = Sweep2Cfg<NPT>::RS;
+  static_assert(MODE != M_NP, "the NP updates run on the v1 kernel");
+  cg::cluster_group cluster = cg::this_cluster();
+  const int c = (int)cluster.block_rank();
+  const int cid = blockIdx.x / CS, nclusters = gridDim.x / CS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = p.K, tw = p.tw;
+  const int tile_doubles = (tw + 2) * NV;
+  const uint32_t tile_bytes = (uint32_t)tw * NV * 8u;
+
+  extern __shared__ __align__(128) double smem2[];
+  double* tiles = smem2;                                  // 3 stages
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(tiles + 3 * tile_doubles);
+  double* delta = reinterpret_cast<double*>(mbar + 4);    // [RS]
+  double* xs = delta + RS + 1;                            // [RS][K]
+  double* xvar = xs + (size_t)RS * K;
+  double* xmu = xvar + (size_t)RS * K;
+  double* xtau = xmu + (size_t)RS * K;
+  double* part = xtau + (size_t)RS * K;                   // [CS][RS][4]  (used in CTA 0)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 3; ++s) mbar_init(&mbar[s], 1);
+    fence_mbar_init();
+  }
+  for (int s = threadIdx.x; s < 3; s += blockDim.x) {     // the zero slots read by padded entries
+    for (int z = 0; z < 2 * NV; ++z) tiles[s * tile_doubles + tw * NV + z] = 0.0;
+  }
+  __syncthreads();
+
+  const double* ybase = p.Ykm + (size_t)c * tw * NV;      // this CTA's tile of column 0
+  const size_t ystride = (size_t)p.ldy * NV;
+
+  if (warp == 0) {
+    // =========================== control warp ===========================
+    uint32_t gseq = 0;
+    const UpdateCtx uc{p.seed, p.purpose, p.iteration, false};
+    const double tau = p.scal[0];
+    for (int set = cid; set < p.nsets; set += nclusters) {
+      const int rows_here = min(RS, p.n_loc - set * RS);
+      for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
+        const size_t g = (size_t)(p.row0 + set * RS) * K + q;
+        xs[q] = p.Xval[g];
+      }
+      if (lane == 0) {   // prime the ring: first three tiles of this set's sequence (K init + K sweep)
+        fence_proxy_async();
+        for (int q = 0; q < 3 && q < 2 * K; ++q) {
+          const uint32_t g = gseq + q;
+          mbar_expect_tx(&mbar[g % 3], tile_bytes);
+          tma_load_1d(tiles + (g % 3) * tile_doubles, ybase + (size_t)(q % K) * ystride, tile_bytes, &mbar[g % 3]);
+        }
+      }
+      cluster_sync_all();
+      for (int q = 0; q < K; ++q) {          // residual pass: refill the stage each tile leaves
+        __syncthreads();
+        if (lane == 0 && q + 3 < 2 * K) {
+          const uint32_t g = gseq + q;
+          fence_proxy_async();
+          mbar_expect_tx(&mbar[g % 3], tile_bytes);
+          tma_load_1d(tiles + (g % 3) * tile_doubles, ybase + (size_t)((q + 3) % K) * ystride, tile_bytes, &mbar[g % 3]);
+        }
+      }
+      double acc_esd = 0.0, acc_q = 0.0, acc_prior = 0.0;
+      const int64_t grow = p.row0 + (int64_t)set * RS + lane;
+      const bool sampler = (c == 0 && lane < rows_here);
+      double lam_next = 0.0;
+      if (sampler) lam_next = p.lamk ? p.lamk[0] : (p.lam_rm ? p.lam_rm[grow * K] : 0.0);
+      for (int k = 0; k < K; ++k) {
+        const double lam = lam_next;         // prefetched: no global load on the critical path
+        if (sampler && k + 1 < K) lam_next = p.lamk ? p.lamk[k + 1] : (p.lam_rm ? p.lam_rm[grow * K + k + 1] : 0.0);
+        cluster_sync_all();                  // partial sums of column k are in CTA 0
+        if (lane == 0 && k >= 1 && K + k + 2 < 2 * K) {   // tile of column k-1 is dead cluster-wide
+          const uint32_t gn = gseq + K + k + 2;
+          fence_proxy_async();
+          mbar_expect_tx(&mbar[gn % 3], tile_bytes);
+          tma_load_1d(tiles + (gn % 3) * tile_doubles, ybase + (size_t)((k + 2) % K) * ystride, tile_bytes, &mbar[gn % 3]);
+        }
+        if (sampler) {
+          double t3[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+          for (int cc = 0; cc < CS; ++cc) {
+            const double* src = part + ((size_t)cc * RS + lane) * 4;
+            t3[0] += src[0]; t3[1] += src[1]; t3[2] += src[2];
+          }
+          const double x_old = xs[lane * K + k];
+          double ct, cm, vn;
+          const double x_new = conditional_update<MODE>(t3, x_old, lam, tau, uc, (uint64_t)grow, k, 0.0, 0.0, 0.0, ct,
+                                                        cm, vn, acc_esd, acc_q, acc_prior);
+          xs[lane * K + k] = x_new;
+          xmu[lane * K + k] = cm; xtau[lane * K + k] = ct;
+          if (MODE == M_VB) xvar[lane * K + k] = vn;
+          const double d = x_new - x_old;
+          for (int cc = 0; cc < CS; ++cc) cluster.map_shared_rank(delta, cc)[lane] = d;
+        }
+        cluster_sync_all();                  // deltas of column k are in every CTA
+      }
+      cluster_sync_all();                    // row-statistics partials are in CTA 0
+      if (c == 0) {
+        if (lane < rows_here && p.rowstats != nullptr) {
+          double t3[3] = {0.0, 0.0, 0.0};
+          for (int cc = 0; cc < CS; ++cc) {
+            const double* src = part + ((size_t)cc * RS + lane) * 4;
+            t3[0] += src[0]; t3[1] += src[1]; t3[2] += src[2];
+          }
+          double* rs = p.rowstats + (size_t)(set * RS + lane) * NRS;
+          rs[RS_RSS] = t3[0]; rs[RS_SUM_E] = t3[1]; rs[RS_SUM_RCE] = t3[2];
+          rs[RS_ESDVAR] = acc_esd; rs[RS_ELBOQ] = acc_q; rs[RS_PRIOR] = acc_prior;
+          rs[RS_IDIV] = 0.0; rs[RS_SPARE] = 0.0;
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
+          const size_t g = (size_t)(p.row0 + set * RS) * K + q;
+          p.Xval[g] = xs[q];
+          if (MODE == M_VB) p.Xvar[g] = xvar[q];
+          if (p.Xmu != nullptr) { p.Xmu[g] = xmu[q]; p.Xtau[g] = xtau[q]; }
+        }
+      }
+      gseq += 2 * K;
+      __syncthreads();
+    }
+  } else {
+    // =========================== compute warps ===========================
+    const int r = warp - 1;                                 // row of the set owned by this warp
+    double* part0 = cluster.map_shared_rank(part, 0);       // CTA 0's copy, through DSMEM
+    uint32_t gseq = 0;
+    for (int set = cid; set < p.nsets; set += nclusters) {
+      const int rows_here = min(RS, p.n_loc - set * RS);
+      const int64_t seg = ((int64_t)(set * CS + c) * NPT) * RS * 32 + (int64_t)r * 32 + lane;
+      double e[NPT];
+      uint32_t cp[NPT / 2];
+#pragma unroll
+      for (int n = 0; n < NPT; ++n) e[n] = p.tvals[seg + (int64_t)n * RS * 32];
+#pragma unroll
+      for (int n = 0; n < NPT; n += 2) {
+        const uint32_t a = p.tcols[seg + (int64_t)n * RS * 32], b = p.tcols[seg + (int64_t)(n + 1) * RS * 32];
+        cp[n / 2] = (a * (NV * 8)) | ((b * (NV * 8)) << 16);   // byte offsets inside a tile stage
+      }
+      for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
+        const size_t g = (size_t)(p.row0 + set * RS) * K + q;
+        xs[q] = p.Xval[g];
+      }
+      cluster_sync_all();   // xs visible; CTA 0 has finished with `part` of the previous set
+
+      // ---- residual of the segment: e = r - sum_k x_k y_k   (tile sequence 0 .. K-1)
+      for (int q = 0; q < K; ++q) {
+        const uint32_t g = gseq + q;
+        mbar_wait(&mbar[g % 3], (g / 3) & 1u);
+        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+        const double xk = (r < rows_here) ? xs[r * K + q] : 0.0;
+#pragma unroll
+        for (int n = 0; n < NPT; ++n) {
+          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+          e[n] = fma(-xk, *reinterpret_cast<const double*>(T + off), e[n]);
+        }
+        __syncthreads();
+      }
+
+      // ---- the K column updates   (tile sequence K .. 2K-1)
+      double dprev = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const uint32_t g = gseq + K + k;
+        mbar_wait(&mbar[g % 3], (g / 3) & 1u);
+        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+        const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + ((g + 2) % 3) * tile_doubles);   // tile g-1
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        if (k > 0) {
+#pragma unroll
+          for (int n = 0; n < NPT; ++n) {
+            const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+            e[n] = fma(-dprev, *reinterpret_cast<const double*>(Tp + off), e[n]);
+            double v;
+            if (MODE == M_VB) { const double2 vv = *reinterpret_cast<const double2*>(T + off); v = vv.x; s1 += vv.y; }
+            else v = *reinterpret_cast<const double*>(T + off);
+            s0 = fma(v, v, s0);
+            s2 = fma(e[n], v, s2);
+          }
+        } else {
+#pragma unroll
+          for (int n = 0; n < NPT; ++n) {
+            const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+            double v;
+            if (MODE == M_VB) { const double2 vv = *reinterpret_cast<const double2*>(T + off); v = vv.x; s1 += vv.y; }
+            else v = *reinterpret_cast<const double*>(T + off);
+            s0 = fma(v, v, s0);
+            s2 = fma(e[n], v, s2);
+          }
+        }
+        s0 = warp_sum(s0); s2 = warp_sum(s2);
+        if (MODE == M_VB) s1 = warp_sum(s1);
+        if (lane == 0) {
+          double* dst = part0 + ((size_t)c * RS + r) * 4;
+          dst[0] = s0; dst[1] = s1; dst[2] = s2;
+        }
+        cluster_sync_all();
+        cluster_sync_all();
+        dprev = (r < rows_here) ? delta[r] : 0.0;
+      }
+
+      // ---- last correction, then the row statistics of the final residual
+      {
+        const uint32_t g = gseq + 2 * K - 1;
+        const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+        double st0 = 0.0, st1 = 0.0, st2 = 0.0;
+#pragma unroll
+        for (int n = 0; n < NPT; ++n) {
+          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+          e[n] = fma(-dprev, *reinterpret_cast<const double*>(Tp + off), e[n]);
+          const double rr = p.tvals[seg + (int64_t)n * RS * 32];
+          st0 = fma(e[n], e[n], st0);
+          st1 += e[n];
+          st2 = fma(rr - p.rmean, e[n], st2);   // padded slots hold e == 0
+        }
+        st0 = warp_sum(st0); st1 = warp_sum(st1); st2 = warp_sum(st2);
+        if (lane == 0) {
+          double* dst = part0 + ((size_t)c * RS + r) * 4;
+          dst[0] = st0; dst[1] = st1; dst[2] = st2;
+        }
+      }
+      cluster_sync_all();
+      if (c == 0) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
+          const size_t g = (size_t)(p.row0 + set * RS) * K + q;
+          p.Xval[g] = xs[q];
+          if (MODE == M_VB) p.Xvar[g] = xvar[q];
+          if (p.Xmu != nullptr) { p.Xmu[g] = xmu[q]; p.Xtau[g] = xtau[q]; }
+        }
+      }
+      gseq += 2 * K;
+      __syncthreads();   // xs / tiles are reused by the next set
+    }
+  }
+  cluster_sync_all();    // no CTA may exit while its shared memory can still be written remotely
+}
+
+}  // namespace bnmtf

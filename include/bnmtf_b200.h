@@ -94,6 +94,18 @@ int bnmtf_nmf_create_dev(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int
                          int64_t row0, int64_t row1, int64_t shard_rows,
                          int64_t col0, int64_t col1, int64_t shard_cols);
 
+/* Layout statistics of this rank's shards after create (out4: longest row of the U
+ * shard, longest (row, column-tile) segment of it, and the same two for the V
+ * shard), and the packing step.  The caller reduces the statistics with MAX over
+ * ranks and passes the global values to bnmtf_nmf_pack, so that the packed
+ * layout -- and every summation order -- is independent of the sharding (a
+ * chain is bitwise identical on 1, 2, 4 or 8 GPUs).  global4 may be NULL for a
+ * single rank.  The dense blocks given to bnmtf_nmf_create_dev must stay valid
+ * until bnmtf_nmf_pack returns; every other entry point requires a packed
+ * handle. */
+int bnmtf_nmf_layout_stats(bnmtf_nmf_t h, int64_t* out4);
+int bnmtf_nmf_pack(bnmtf_nmf_t h, const int64_t* global4);
+
 int bnmtf_nmf_destroy(bnmtf_nmf_t h);
 
 /* size_Omega, sum_Omega R, sum_Omega (R-mean)^2 of the LOCAL row shard
@@ -162,12 +174,13 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed,
                   double* all_U, double* all_V, double* all_lambdak,
                   double* iter_stats, double* iter_seconds);
 
-/* number of kernels launched by this handle so far, and layout information
- * (out[0]=threads per row team U, out[1]=entries per thread U, out[2],out[3] same
- * for V, out[4]=padded entries U, out[5]=padded entries V, out[6]=nnz local U
- * side, out[7]=nnz local V side). */
+/* number of kernels launched by this handle so far, and layout information, 16
+ * values: [0]=threads per row team U, [1]=entries per thread U, [2],[3] same for
+ * V, [4],[5]=padded entries U,V (row layout), [6],[7]=observed entries of the
+ * local U,V shards, [8..11]=cluster-tile layout of the U side (in use, entries
+ * per lane, rows per set, padded entries), [12..15] same for the V side. */
 int64_t bnmtf_nmf_launch_count(bnmtf_nmf_t h);
-int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8);
+int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out16);
 /* device-event milliseconds spent in the U sweep / V sweep kernels of the last
  * bnmtf_nmf_run (sum over iterations), and their launch counts. out[4]. */
 int bnmtf_nmf_sweep_times(bnmtf_nmf_t h, double* out4);

@@ -53,9 +53,15 @@ def main():
                 outs.append((res, e.get_factor(SIDE_U, F_VALUE), e.get_factor(SIDE_V, F_VALUE)))
             if rank == 0:
                 a, b = outs
+                # the chain (factors, traces, tau, lambda) must be bitwise identical; the
+                # R-mean-centred metric sums may differ in the last bits because mean_Omega(R)
+                # itself is summed shard by shard
+                st_a, st_b = a[0]["stats"], b[0]["stats"]
                 same = (np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
-                        and np.array_equal(a[0]["stats"], b[0]["stats"], equal_nan=True)
-                        and np.array_equal(a[0]["all_U"], b[0]["all_U"]) and np.array_equal(a[0]["all_lambdak"], b[0]["all_lambdak"]))
+                        and np.array_equal(st_a[:, 3], st_b[:, 3]) and np.array_equal(st_a[:, 0], st_b[:, 0])
+                        and np.allclose(st_a, st_b, rtol=1e-11, atol=1e-9, equal_nan=True)
+                        and np.array_equal(a[0]["all_U"], b[0]["all_U"]) and np.array_equal(a[0]["all_V"], b[0]["all_V"])
+                        and np.array_equal(a[0]["all_lambdak"], b[0]["all_lambdak"]))
                 print("shape %s method %d world %d: %s (max |dU| %.3e)" % ((I, J, K), method, world, "BITWISE EQUAL" if same else "MISMATCH",
                                                                             np.max(np.abs(a[1] - b[1]))))
                 ok = ok and same

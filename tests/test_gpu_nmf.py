@@ -151,8 +151,10 @@ def test_np_golden(golden):
 
 # shapes chosen to exercise every row-team configuration: one warp per row with
 # 2/4/8/16 entries per thread, multi-warp teams (named barriers), and ragged rows
+# The last four also exercise the cluster-tile kernel (>= 2048 columns): tail tiles,
+# tail row sets, both sides tiled, and spill placement of crowded bank classes.
 SHAPES = [(37, 23, 3, 0.8), (120, 150, 5, 0.9), (90, 400, 4, 0.55), (64, 3000, 6, 0.7), (700, 140, 7, 0.8),
-          (33, 9000, 3, 0.9)]
+          (33, 9000, 3, 0.9), (100, 4096, 5, 0.5), (2300, 2500, 4, 0.3), (41, 5000, 3, 0.45), (70, 2049, 8, 0.95)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -190,7 +192,16 @@ def test_gibbs_iteration_vs_oracle(shape, monkeypatch):
     assert (lam > 0).all() and m.all_tau[0] > 0 and m.all_tau[0] != tau0
 
 
-@pytest.mark.parametrize("shape", SHAPES[:4])
+def test_cluster_kernel_is_selected():
+    from bnmtf_ard_b200._engine import NMFEngine
+    R, M, _ = make_problem(3, 100, 4096, 3, 0.5)
+    eng = NMFEngine(R, M, 5)
+    info = eng.layout_info()
+    assert info["v2_U"] == 1 and info["v2_V"] == 0 and info["v2_npt_U"] in (8, 12)
+    eng.close()
+
+
+@pytest.mark.parametrize("shape", SHAPES[:4] + SHAPES[6:8])
 def test_icm_vb_np_iterations_vs_oracle(shape):
     from bnmtf_ard_b200 import bnmf_vb, nmf_icm, nmf_np
     I, J, K, dens = shape
