@@ -49,11 +49,10 @@ def test_tn_moments_golden(golden):
     mu, tau = g["dist_mu"], g["dist_tau"]
     e, v = np.array(TN_vector_expectation(mu, tau)), np.array(TN_vector_variance(mu, tau))
     np.testing.assert_allclose(e, g["dist_tn_exp_vec"], rtol=1e-9, atol=1e-300)
-    # var = sigma^2 (1 - lambda(lambda - x)) cancels for large x: compare on the scale sigma^2
+    # var = sigma^2 (1 - lambda(lambda - x)) cancels for large x (erfc/exp differ from scipy's
+    # by an ulp, amplified by x^2): absolute slack on the scale sigma^2 next to the 1e-9 relative bar
     scale = 1.0 / tau
-    assert np.max(np.abs(v - g["dist_tn_var_vec"]) / np.maximum(np.abs(g["dist_tn_var_vec"]), 1e-9 * scale)) < 1e-6
-    ok = g["dist_tn_var_vec"] > 1e-3 * scale
-    np.testing.assert_allclose(v[ok], g["dist_tn_var_vec"][ok], rtol=1e-9)
+    assert np.all(np.abs(v - g["dist_tn_var_vec"]) <= 1e-9 * np.abs(g["dist_tn_var_vec"]) + 2e-11 * scale)
     # reference literals (test_truncated_normal.py:12-38)
     sigma = 0.5773502691896258
     lam = stats.norm.pdf(-1.0 / sigma) / (1 - stats.norm.cdf(-1.0 / sigma))
