@@ -1,0 +1,46 @@
+"""CPU: pin the NMTF numpy oracle to golden vectors produced by the real reference."""
+import numpy as np
+import pytest
+
+import nmtf_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def gold():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nmtf_golden.npz"))
+
+
+def close(a, b, rtol=1e-10, atol=0.0):
+    np.testing.assert_allclose(np.asarray(a, dtype=float), np.asarray(b, dtype=float), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+@pytest.mark.parametrize("ard", [True, False])
+def test_gibbs_conditionals(gold, name, ard):
+    g, p = gold, "tg_%s_%s_" % (name, "ard" if ard else "noard")
+    R, M, F, S, G, tau = g[p + "R"], g[p + "M"], g[p + "F"], g[p + "S"], g[p + "G"], float(g[p + "tau"])
+    I, J = R.shape
+    K, L = S.shape
+    lamF = np.broadcast_to(g[p + "lamFk"], (I, K)) if ard else g[p + "lamF"]
+    lamG = np.broadcast_to(g[p + "lamGl"], (J, L)) if ard else g[p + "lamG"]
+    tF, mF, tS, mS, tG, mG = orc.params_all(R, M, F, S, G, tau, lamF, g[p + "lamS"], lamG)
+    close(tF, g[p + "tauF"]); close(tS, g[p + "tauS"]); close(tG, g[p + "tauG"])
+    close(mF, g[p + "muF"], 1e-9, 1e-11); close(mS, g[p + "muS"], 1e-9, 1e-11); close(mG, g[p + "muG"], 1e-9, 1e-11)
+    close(orc.beta_s(R, M, F, S, G, g[p + "hyper"][1]), g[p + "beta_s"])
+
+
+@pytest.mark.parametrize("ard", [True, False])
+def test_icm_trajectory(gold, ard):
+    g, p = gold, "ti_%s_" % ("ard" if ard else "noard")
+    R, M = g[p + "R"], g[p + "M"]
+    F, S, G, tau = g[p + "F0"].copy(), g[p + "S0"].copy(), g[p + "G0"].copy(), float(g[p + "tau0"])
+    lF, lG = g[p + "lamFk0"].copy(), g[p + "lamGl0"].copy()
+    h = g[p + "hyper"]
+    hyper = {"alphatau": h[0], "betatau": h[1], "alpha0": h[2], "beta0": h[3]}
+    for it in range(int(g[p + "its"])):
+        tau = orc.icm_iteration(R, M, F, S, G, tau, lF, lG, hyper, ard, g[p + "lamS"], g[p + "lamF"], g[p + "lamG"])
+        close(F, g[p + "all_F"][it], 1e-8); close(S, g[p + "all_S"][it], 1e-8); close(G, g[p + "all_G"][it], 1e-8)
+        close(tau, g[p + "all_tau"][it], 1e-8)
+        if ard:
+            close(lF, g[p + "all_lambdaFk"][it], 1e-8); close(lG, g[p + "all_lambdaGl"][it], 1e-8)
