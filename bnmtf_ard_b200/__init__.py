@@ -8,5 +8,7 @@ from .bnmf_gibbs import bnmf_gibbs  # noqa: F401
 from .bnmf_vb import bnmf_vb  # noqa: F401
 from .nmf_icm import nmf_icm  # noqa: F401
 from .nmf_np import nmf_np  # noqa: F401
+from .bnmtf_gibbs import bnmtf_gibbs  # noqa: F401
+from .nmtf_icm import nmtf_icm  # noqa: F401
 
-__all__ = ["bnmf_gibbs", "bnmf_vb", "nmf_icm", "nmf_np"]
+__all__ = ["bnmf_gibbs", "bnmf_vb", "nmf_icm", "nmf_np", "bnmtf_gibbs", "nmtf_icm"]

@@ -16,11 +16,12 @@ class NMFEngine(object):
     same ones, like the reference constructors); this rank packs its row shard for
     the U sweep and its column shard for the V sweep."""
 
-    def __init__(self, R, M, K, device=None, distributed=True):
+    def __init__(self, R, M, K, device=None, distributed=True, L=None):
         lib = _lib.require_device()
         self.lib = lib
         self.I, self.J = R.shape
         self.K = int(K)
+        self.L = None if L is None else int(L)
         self.device = _lib.current_device() if device is None else int(device)
         self.rank, self.world = _dist.info() if distributed else (0, 1)
         r0, r1, rs = _dist.shard_bounds(self.I, self.rank, self.world)
@@ -28,27 +29,35 @@ class NMFEngine(object):
         R = f64(R)
         M8 = np.ascontiguousarray(np.asarray(M) != 0, dtype=np.uint8)
         h = C.c_void_p()
-        check(lib.bnmtf_nmf_create(C.byref(h), self.device, self.I, self.J, self.K, dptr(R),
-                                   M8.ctypes.data_as(C.POINTER(C.c_uint8)), r0, r1, rs, c0, c1, cs))
+        if self.L is None:
+            check(lib.bnmtf_nmf_create(C.byref(h), self.device, self.I, self.J, self.K, dptr(R),
+                                       M8.ctypes.data_as(C.POINTER(C.c_uint8)), r0, r1, rs, c0, c1, cs))
+        else:
+            check(lib.bnmtf_nmtf_create(C.byref(h), self.device, self.I, self.J, self.K, self.L, dptr(R),
+                                        M8.ctypes.data_as(C.POINTER(C.c_uint8)), r0, r1, rs, c0, c1, cs))
         self.h = h
         self._finish_setup()
 
     @classmethod
-    def from_device_blocks(cls, I, J, K, Rrow_ptr, Mrow_ptr, Rcol_ptr, Mcol_ptr, device=None):
+    def from_device_blocks(cls, I, J, K, Rrow_ptr, Mrow_ptr, Rcol_ptr, Mcol_ptr, device=None, L=None):
         """Build from dense blocks already on the device (raw device addresses): rows
         [r0,r1) x J and I x columns [c0,c1) of this rank's shards (see shard_bounds)."""
         self = cls.__new__(cls)
         lib = _lib.require_device()
         self.lib = lib
         self.I, self.J, self.K = int(I), int(J), int(K)
+        self.L = None if L is None else int(L)
         self.device = _lib.current_device() if device is None else int(device)
         self.rank, self.world = _dist.info()
         r0, r1, rs = _dist.shard_bounds(self.I, self.rank, self.world)
         c0, c1, cs = _dist.shard_bounds(self.J, self.rank, self.world)
         h = C.c_void_p()
-        check(lib.bnmtf_nmf_create_dev(C.byref(h), self.device, self.I, self.J, self.K,
-                                       C.c_void_p(Rrow_ptr), C.c_void_p(Mrow_ptr), C.c_void_p(Rcol_ptr),
-                                       C.c_void_p(Mcol_ptr), r0, r1, rs, c0, c1, cs))
+        ptrs = (C.c_void_p(Rrow_ptr), C.c_void_p(Mrow_ptr), C.c_void_p(Rcol_ptr), C.c_void_p(Mcol_ptr))
+        if self.L is None:
+            check(lib.bnmtf_nmf_create_dev(C.byref(h), self.device, self.I, self.J, self.K, *ptrs, r0, r1, rs, c0, c1, cs))
+        else:
+            check(lib.bnmtf_nmtf_create_dev(C.byref(h), self.device, self.I, self.J, self.K, self.L, *ptrs,
+                                            r0, r1, rs, c0, c1, cs))
         self.h = h
         self._finish_setup()
         return self
@@ -92,6 +101,9 @@ class NMFEngine(object):
     def n_of(self, side):
         return self.I if side == SIDE_U else self.J
 
+    def k_of(self, side):
+        return self.K if (side == SIDE_U or self.L is None) else self.L
+
     def set_hyper(self, ARD, alphatau, betatau, alpha0=1.0, beta0=1.0, lambdaU=None, lambdaV=None):
         lu = None if lambdaU is None else f64(lambdaU, (self.I, self.K))
         lv = None if lambdaV is None else f64(lambdaV, (self.J, self.K))
@@ -99,11 +111,11 @@ class NMFEngine(object):
                                            float(beta0), dptr(lu), dptr(lv)))
 
     def set_factor(self, side, field, arr):
-        a = f64(arr, (self.n_of(side), self.K))
+        a = f64(arr, (self.n_of(side), self.k_of(side)))
         check(self.lib.bnmtf_nmf_set_factor(self.h, side, field, dptr(a)))
 
     def get_factor(self, side, field):
-        out = np.empty((self.n_of(side), self.K))
+        out = np.empty((self.n_of(side), self.k_of(side)))
         check(self.lib.bnmtf_nmf_get_factor(self.h, side, field, dptr(out)))
         return out
 
@@ -184,3 +196,62 @@ class NMFEngine(object):
         with np.errstate(all="ignore"):
             rp = cov / (np.sqrt(sst) * np.sqrt(var_pred))
         return {"MSE": float(mse), "R^2": float(r2), "Rp": float(rp)}
+
+
+class NMTFEngine(NMFEngine):
+    """Handle for the tri-factorisation R ~ F S G^T: side U is F (I x K), side V is G (J x L)."""
+
+    def __init__(self, R, M, K, L, device=None, distributed=True):
+        NMFEngine.__init__(self, R, M, K, device=device, distributed=distributed, L=L)
+
+    def set_hyper(self, ARD, alphatau, betatau, alpha0=1.0, beta0=1.0, lambdaF=None, lambdaG=None, lambdaS=None):
+        lf = None if lambdaF is None else f64(lambdaF, (self.I, self.K))
+        lg = None if lambdaG is None else f64(lambdaG, (self.J, self.L))
+        ls = f64(lambdaS, (self.K, self.L))
+        check(self.lib.bnmtf_nmtf_set_hyper(self.h, int(bool(ARD)), float(alphatau), float(betatau), float(alpha0),
+                                            float(beta0), dptr(lf), dptr(lg), dptr(ls)))
+
+    def set_S(self, field, arr):
+        a = f64(arr, (self.K, self.L))
+        check(self.lib.bnmtf_nmtf_set_S(self.h, field, dptr(a)))
+
+    def get_S(self, field):
+        out = np.empty((self.K, self.L))
+        check(self.lib.bnmtf_nmtf_get_S(self.h, field, dptr(out)))
+        return out
+
+    def set_scalars(self, tau, lambdaFk=None, lambdaGl=None):
+        lf = None if lambdaFk is None else f64(lambdaFk, (self.K,))
+        lg = None if lambdaGl is None else f64(lambdaGl, (self.L,))
+        check(self.lib.bnmtf_nmtf_set_scalars(self.h, float(tau), dptr(lf), dptr(lg)))
+
+    def init(self, method, random_FG, random_S, seed_FG, seed_S):
+        check(self.lib.bnmtf_nmtf_init(self.h, method, int(bool(random_FG)), int(bool(random_S)),
+                                       C.c_uint64(seed_FG), C.c_uint64(seed_S)))
+
+    def column_params(self, method, which, k=0, l=0):
+        n = (self.I, self.J, 1)[which]
+        t, m = np.empty(n), np.empty(n)
+        check(self.lib.bnmtf_nmtf_column_params(self.h, method, which, int(k), int(l), dptr(t), dptr(m)))
+        return t, m
+
+    def stats(self, method):
+        out = np.zeros(NSTATS)
+        check(self.lib.bnmtf_nmtf_stats(self.h, method, dptr(out)))
+        return out
+
+    def run(self, method, iterations, seed=0, traces=True):
+        it = int(iterations)
+        res = {
+            "all_F": np.zeros((it, self.I, self.K)) if traces else None,
+            "all_S": np.zeros((it, self.K, self.L)) if traces else None,
+            "all_G": np.zeros((it, self.J, self.L)) if traces else None,
+            "all_lambdaFk": np.zeros((it, self.K)),
+            "all_lambdaGl": np.zeros((it, self.L)),
+            "stats": np.zeros((it, NSTATS)),
+            "seconds": np.zeros(it),
+        }
+        check(self.lib.bnmtf_nmtf_run(self.h, method, it, C.c_uint64(seed), dptr(res["all_F"]), dptr(res["all_S"]),
+                                      dptr(res["all_G"]), dptr(res["all_lambdaFk"]), dptr(res["all_lambdaGl"]),
+                                      dptr(res["stats"]), dptr(res["seconds"])))
+        return res

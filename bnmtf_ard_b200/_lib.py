@@ -50,6 +50,20 @@ SIGNATURES = {
     "bnmtf_nmf_launch_count": (C.c_int64, [_h]),
     "bnmtf_nmf_layout_info": (C.c_int, [_h, _i64p]),
     "bnmtf_nmf_sweep_times": (C.c_int, [_h, _dp]),
+    "bnmtf_nmtf_create": (C.c_int, [C.POINTER(_h), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, _dp, _u8p,
+                                    C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "bnmtf_nmtf_create_dev": (C.c_int, [C.POINTER(_h), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
+    "bnmtf_nmtf_set_hyper": (C.c_int, [_h, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp]),
+    "bnmtf_nmtf_set_S": (C.c_int, [_h, C.c_int, _dp]),
+    "bnmtf_nmtf_get_S": (C.c_int, [_h, C.c_int, _dp]),
+    "bnmtf_nmtf_set_scalars": (C.c_int, [_h, C.c_double, _dp, _dp]),
+    "bnmtf_nmtf_get_scalars": (C.c_int, [_h, _dp, _dp, _dp]),
+    "bnmtf_nmtf_init": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64]),
+    "bnmtf_nmtf_column_params": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]),
+    "bnmtf_nmtf_stats": (C.c_int, [_h, C.c_int, _dp]),
+    "bnmtf_nmtf_run": (C.c_int, [_h, C.c_int, C.c_int, C.c_uint64, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "bnmtf_tn_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),
     "bnmtf_tn_moments": (C.c_int, [C.c_int, C.c_int64, _dp, _dp, _dp, _dp]),
     "bnmtf_gamma_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),

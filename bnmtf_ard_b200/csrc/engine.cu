@@ -11,6 +11,7 @@
 #include "../../include/bnmtf_b200.h"
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
+#include "kernels_nmtf.cuh"
 
 using namespace bnmtf;
 
@@ -103,6 +104,12 @@ struct Side {
   double* tvals = nullptr;
   uint16_t* tcols = nullptr;
   int nclusters[4] = {0, 0, 0, 0};
+  // factor geometry: kf columns; sweeps on this side gather from ysrc ([kf][ysrc_ld][NV])
+  int kf = 0;
+  const double* ysrc = nullptr;
+  int64_t ysrc_ld = 0;
+  double* ycomb = nullptr;   // NMTF: W = G S^T (F side) / Z = F S (G side), owned
+  double* lamk = nullptr;    // ARD prior of this side's columns (not owned for NMF)
 };
 constexpr int V2_CS = 8;
 }  // namespace
@@ -128,6 +135,15 @@ struct bnmtf_nmf_s {
   double sweep_ms[2] = {0, 0};
   int64_t sweep_n[2] = {0, 0};
   int km_mode = -1;            // NV layout currently held by the km copies
+  // ---- tri-factorisation (R ~ F S G^T): side 0 = F (I x K), side 1 = G (J x L)
+  bool nmtf = false;
+  int L = 0;
+  double *S = nullptr, *Svar = nullptr, *Smu = nullptr, *Stau = nullptr, *lamS = nullptr;   // [K][L]
+  double* lamG = nullptr;      // [L] (lamk holds lambdaFk)
+  double *Prow = nullptr, *Hrow = nullptr;   // [I_pad][L], [I_pad][L(L+1)/2]
+  double *cvec = nullptr, *TT = nullptr;     // [K*L], [K(K+1)/2][L(L+1)/2]
+  double* sumlog_lamS_dev = nullptr;
+  double sumlog_lamS = 0.0;
 };
 
 // ---- packing -------------------------------------------------------------------
@@ -197,8 +213,8 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   if (npt2 > 12 && npt2 < 16) npt2 = 16;
   const int wpc = npt2 <= 16 ? 32 : (npt2 <= 18 ? 28 : 24);   // Sweep2Cfg<NPT>::WPC
   const int rs = wpc - 1;                                      // rows per set (warp 0 is the control warp)
-  const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, h->K, V2_CS) * sizeof(double);
-  sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && h->K >= 3 && smem_vb <= 200 * 1024 && sd.tw * 2 < 65535;
+  const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, V2_CS) * sizeof(double);
+  sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && sd.kf >= 3 && smem_vb <= 200 * 1024 && sd.tw * 2 < 65535;
   if (sd.v2 && n > 0) {
     sd.cs = V2_CS; sd.npt2 = npt2; sd.rs = rs;
     sd.nsets = (n + rs - 1) / rs;
@@ -222,6 +238,7 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
 }
 
 static int alloc_side_state(bnmtf_nmf_s* h, Side& sd, int K) {
+  sd.kf = K;
   const size_t nb = sizeof(double) * sd.n_padglob * K;
   CK(cudaMalloc(&sd.val, nb)); CK(cudaMalloc(&sd.var, nb)); CK(cudaMalloc(&sd.mu, nb)); CK(cudaMalloc(&sd.tau, nb));
   CK(cudaMemsetAsync(sd.val, 0, nb, h->stream)); CK(cudaMemsetAsync(sd.var, 0, nb, h->stream));
@@ -234,18 +251,30 @@ static int alloc_side_state(bnmtf_nmf_s* h, Side& sd, int K) {
   return 0;
 }
 
+static int nmtf_alloc(bnmtf_nmf_s* h);
+static int create_dev_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, int L, bool nmtf, const double* Rrow_dev,
+                           const uint8_t* Mrow_dev, const double* Rcol_dev, const uint8_t* Mcol_dev, int64_t row0,
+                           int64_t row1, int64_t shard_rows, int64_t col0, int64_t col1, int64_t shard_cols);
+
 int bnmtf_nmf_create_dev(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, const double* Rrow_dev,
                          const uint8_t* Mrow_dev, const double* Rcol_dev, const uint8_t* Mcol_dev, int64_t row0,
                          int64_t row1, int64_t shard_rows, int64_t col0, int64_t col1, int64_t shard_cols) {
+  return create_dev_impl(out, device, I, J, K, K, false, Rrow_dev, Mrow_dev, Rcol_dev, Mcol_dev, row0, row1, shard_rows, col0,
+                         col1, shard_cols);
+}
+
+static int create_dev_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, int L, bool nmtf, const double* Rrow_dev,
+                           const uint8_t* Mrow_dev, const double* Rcol_dev, const uint8_t* Mcol_dev, int64_t row0,
+                           int64_t row1, int64_t shard_rows, int64_t col0, int64_t col1, int64_t shard_cols) {
   if (!out) FAIL("out is NULL");
   *out = nullptr;
-  if (I <= 0 || J <= 0 || K <= 0) FAIL("bad shape I=%lld J=%lld K=%d", (long long)I, (long long)J, K);
+  if (I <= 0 || J <= 0 || K <= 0 || L <= 0) FAIL("bad shape I=%lld J=%lld K=%d L=%d", (long long)I, (long long)J, K, L);
   if (I >= (int64_t)0xFFFFFFF0ll || J >= (int64_t)0xFFFFFFF0ll) FAIL("dimension too large for 32-bit column indices");
   if (row0 < 0 || row1 < row0 || row1 > I || col0 < 0 || col1 < col0 || col1 > J) FAIL("bad shard bounds");
   if (shard_rows < row1 - row0 || shard_cols < col1 - col0) FAIL("shard size smaller than the owned range");
   CK(cudaSetDevice(device));
   bnmtf_nmf_s* h = new bnmtf_nmf_s();
-  h->device = device; h->I = I; h->J = J; h->K = K;
+  h->device = device; h->I = I; h->J = J; h->K = K; h->L = L; h->nmtf = nmtf;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) {
@@ -260,6 +289,7 @@ int bnmtf_nmf_create_dev(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int
 
   Side& su = h->s[BNMTF_SIDE_U];
   Side& sv = h->s[BNMTF_SIDE_V];
+  su.kf = K; sv.kf = L;
   su.n_glob = I; su.m_glob = J; su.row0 = row0; su.n_loc = row1 - row0; su.n_shard = shard_rows;
   sv.n_glob = J; sv.m_glob = I; sv.row0 = col0; sv.n_loc = col1 - col0; sv.n_shard = shard_cols;
   su.n_padglob = std::max(I, ((I + shard_rows - 1) / shard_rows) * shard_rows);
@@ -283,7 +313,9 @@ int bnmtf_nmf_create_dev(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int
     sv.dR = Rt; sv.dM = Mt; sv.own_dense = true;
     if (count_block(h, sv, jl, I, I)) return 1;
   }
-  if (alloc_side_state(h, su, K) || alloc_side_state(h, sv, K)) return 1;
+  su.kf = K; sv.kf = L;
+  if (alloc_side_state(h, su, K) || alloc_side_state(h, sv, L)) return 1;
+  su.lamk = nullptr; sv.lamk = nullptr;
   CK(cudaMalloc(&h->scal, sizeof(double) * SC_COUNT));
   CK(cudaMalloc(&h->colsum, sizeof(double) * 2 * K));
   CK(cudaMalloc(&h->lamstate, sizeof(double) * 4 * K));
@@ -292,6 +324,12 @@ int bnmtf_nmf_create_dev(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int
   CK(cudaMemsetAsync(h->colsum, 0, sizeof(double) * 2 * K, h->stream));
   CK(cudaMemsetAsync(h->lamstate, 0, sizeof(double) * 4 * K, h->stream));
   CK(cudaMemsetAsync(h->lamk, 0, sizeof(double) * K, h->stream));
+  if (!nmtf) {
+    su.lamk = h->lamk; sv.lamk = h->lamk;
+    su.ysrc = sv.km; su.ysrc_ld = sv.ld; sv.ysrc = su.km; sv.ysrc_ld = su.ld;
+  } else if (nmtf_alloc(h)) {
+    return 1;
+  }
   h->hyper.ARD = 1; h->hyper.alphatau = h->hyper.betatau = h->hyper.alpha0 = h->hyper.beta0 = 1.0;
   h->hyper.size_Omega = (double)su.nnz;
   CK(cudaStreamSynchronize(h->stream));
@@ -318,8 +356,16 @@ int bnmtf_nmf_pack(bnmtf_nmf_t h, const int64_t* global4) {
   return 0;
 }
 
+static int create_host_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, int L, bool nmtf, const double* R,
+                            const uint8_t* M, int64_t row0, int64_t row1, int64_t shard_rows, int64_t col0, int64_t col1,
+                            int64_t shard_cols);
 int bnmtf_nmf_create(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, const double* R, const uint8_t* M,
                      int64_t row0, int64_t row1, int64_t shard_rows, int64_t col0, int64_t col1, int64_t shard_cols) {
+  return create_host_impl(out, device, I, J, K, K, false, R, M, row0, row1, shard_rows, col0, col1, shard_cols);
+}
+static int create_host_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, int L, bool nmtf, const double* R,
+                            const uint8_t* M, int64_t row0, int64_t row1, int64_t shard_rows, int64_t col0, int64_t col1,
+                            int64_t shard_cols) {
   if (!R || !M) FAIL("R or M is NULL");
   if (I <= 0 || J <= 0) FAIL("bad shape");
   CK(cudaSetDevice(device));
@@ -343,7 +389,7 @@ int bnmtf_nmf_create(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, 
       CK(cudaMemcpy2D(Mcol, nc, M + col0, J, nc, I, cudaMemcpyHostToDevice));
     }
   }
-  int rc = bnmtf_nmf_create_dev(out, device, I, J, K, Rrow, Mrow, Rcol, Mcol, row0, row1, shard_rows, col0, col1, shard_cols);
+  int rc = create_dev_impl(out, device, I, J, K, L, nmtf, Rrow, Mrow, Rcol, Mcol, row0, row1, shard_rows, col0, col1, shard_cols);
   if (!full) { cudaFree(Rcol); cudaFree(Mcol); }
   if (rc) { cudaFree(Rrow); cudaFree(Mrow); return rc; }
   (*out)->s[0].own_dense = true;   // released by bnmtf_nmf_pack
@@ -355,7 +401,7 @@ static void free_side(Side& sd) {
   cudaFree(sd.val); cudaFree(sd.var); cudaFree(sd.mu); cudaFree(sd.tau);
   cudaFree(sd.km); cudaFree(sd.lam_rm); cudaFree(sd.rowstats);
   cudaFree(sd.trace[0]); cudaFree(sd.trace[1]);
-  cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev);
+  cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev); cudaFree(sd.ycomb);
   if (sd.own_dense) { cudaFree((void*)sd.dR); cudaFree((void*)sd.dM); }
 }
 
@@ -366,6 +412,8 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   free_side(h->s[0]); free_side(h->s[1]);
   cudaFree(h->scal); cudaFree(h->colsum); cudaFree(h->lamstate); cudaFree(h->lamk); cudaFree(h->stats_dev);
+  cudaFree(h->S); cudaFree(h->Svar); cudaFree(h->Smu); cudaFree(h->Stau); cudaFree(h->lamS); cudaFree(h->lamG);
+  cudaFree(h->Prow); cudaFree(h->Hrow); cudaFree(h->cvec); cudaFree(h->TT);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -439,10 +487,10 @@ int bnmtf_nmf_set_hyper(bnmtf_nmf_t h, int ARD, double alphatau, double betatau,
     Side& sd = h->s[sidx];
     if (!ARD) {
       if (!src[sidx]) FAIL("lambda%c is required when ARD is off", sidx ? 'V' : 'U');
-      if (!sd.lam_rm) CK(cudaMalloc(&sd.lam_rm, sizeof(double) * sd.n_glob * h->K));
-      CK(cudaMemcpy(sd.lam_rm, src[sidx], sizeof(double) * sd.n_glob * h->K, cudaMemcpyHostToDevice));
+      if (!sd.lam_rm) CK(cudaMalloc(&sd.lam_rm, sizeof(double) * sd.n_glob * sd.kf));
+      CK(cudaMemcpy(sd.lam_rm, src[sidx], sizeof(double) * sd.n_glob * sd.kf, cudaMemcpyHostToDevice));
       double sl = 0.0;
-      for (int64_t q = 0; q < sd.n_glob * h->K; ++q) sl += log(src[sidx][q]);
+      for (int64_t q = 0; q < sd.n_glob * sd.kf; ++q) sl += log(src[sidx][q]);
       (sidx ? h->hyper.sumlog_lamV : h->hyper.sumlog_lamU) = sl;
     }
   }
@@ -464,7 +512,7 @@ int bnmtf_nmf_set_factor(bnmtf_nmf_t h, int side, int field, const double* src) 
   double* p = field_ptr(h->s[side], field);
   if (!p) FAIL("bad field %d", field);
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpy(p, src, sizeof(double) * h->s[side].n_glob * h->K, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p, src, sizeof(double) * h->s[side].n_glob * h->s[side].kf, cudaMemcpyHostToDevice));
   h->km_mode = -1;
   return 0;
 }
@@ -475,7 +523,7 @@ int bnmtf_nmf_get_factor(bnmtf_nmf_t h, int side, int field, double* dst) {
   if (!p) FAIL("bad field %d", field);
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(dst, p, sizeof(double) * h->s[side].n_glob * h->K, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(dst, p, sizeof(double) * h->s[side].n_glob * h->s[side].kf, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -526,11 +574,11 @@ int bnmtf_nmf_get_vb_scalars(bnmtf_nmf_t h, double* scal4, double* lamstate4K) {
 // ---- launches --------------------------------------------------------------------
 static int refresh_km(bnmtf_nmf_s* h, int side, int method) {
   Side& sd = h->s[side];
-  dim3 blk(32, 8), grd((unsigned)((sd.ld + 31) / 32), (unsigned)((h->K + 31) / 32));
+  dim3 blk(32, 8), grd((unsigned)((sd.ld + 31) / 32), (unsigned)((sd.kf + 31) / 32));
   if (method == BNMTF_VB)
-    rm_to_km_kernel<2><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, h->K, sd.ld);
+    rm_to_km_kernel<2><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, sd.kf, sd.ld);
   else
-    rm_to_km_kernel<1><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, h->K, sd.ld);
+    rm_to_km_kernel<1><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, sd.kf, sd.ld);
   h->launches++;
   return 0;
 }
@@ -615,9 +663,9 @@ static int launch_sweep2_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
 
 // side: which factor is updated.  single_k: see SweepParams.
 static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint64_t seed, uint32_t iteration,
-                        double* out_tau, double* out_mu, bool want_mu) {
+                        double* out_tau, double* out_mu, bool want_mu, const double* proj_y2 = nullptr,
+                        int64_t proj_ld2 = 0, int proj_k2 = 0) {
   Side& sd = h->s[side];
-  Side& other = h->s[1 - side];
   if (!sd.packed) FAIL("call bnmtf_nmf_pack first");
   const bool mu_out = (method == BNMTF_VB) || want_mu;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -627,10 +675,10 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
   if (sd.v2 && single_k == -1 && method != BNMTF_NP) {
     Sweep2Params p{};
     p.tvals = sd.tvals; p.tcols = sd.tcols; p.nsets = (int)sd.nsets; p.n_loc = (int)sd.n_loc; p.row0 = sd.row0;
-    p.K = h->K; p.tw = sd.tw; p.rs = sd.rs; p.Ykm = other.km; p.ldy = other.ld;
+    p.K = sd.kf; p.tw = sd.tw; p.rs = sd.rs; p.Ykm = sd.ysrc; p.ldy = sd.ysrc_ld;
     p.Xval = sd.val; p.Xvar = sd.var; p.Xmu = mu_out ? sd.mu : nullptr; p.Xtau = mu_out ? sd.tau : nullptr;
     p.lam_rm = h->hyper.ARD ? nullptr : sd.lam_rm;
-    p.lamk = h->hyper.ARD ? h->lamk : nullptr;
+    p.lamk = h->hyper.ARD ? sd.lamk : nullptr;
     p.scal = h->scal;
     p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
     p.rmean = h->rmean; p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
@@ -643,12 +691,13 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
   } else {
     SweepParams p{};
     p.vals = sd.vals; p.cols = sd.cols; p.rowstart = sd.rowstart;
-    p.n_loc = (int)sd.n_loc; p.row0 = sd.row0; p.K = h->K; p.tpr = sd.tpr; p.padcol = sd.padcol;
-    p.Ykm = other.km; p.ldy = other.ld;
+    p.n_loc = (int)sd.n_loc; p.row0 = sd.row0; p.K = sd.kf; p.tpr = sd.tpr; p.padcol = sd.padcol;
+    p.Ykm = sd.ysrc; p.ldy = sd.ysrc_ld;
+    p.Ykm2 = proj_y2; p.ldy2 = proj_ld2; p.K2 = proj_k2;
     p.Xval = sd.val; p.Xvar = sd.var;
     p.Xmu = mu_out ? sd.mu : nullptr; p.Xtau = mu_out ? sd.tau : nullptr;
     p.lam_rm = h->hyper.ARD ? nullptr : sd.lam_rm;
-    p.lamk = (h->hyper.ARD && method != BNMTF_NP) ? h->lamk : nullptr;
+    p.lamk = (h->hyper.ARD && method != BNMTF_NP) ? sd.lamk : nullptr;
     p.scal = h->scal;
     p.out_tau = out_tau; p.out_mu = out_mu;
     p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
@@ -712,11 +761,11 @@ static int launch_finalize(bnmtf_nmf_s* h, int method, double* stats_out, uint64
 static int allgather_side(bnmtf_nmf_s* h, int method, int side, bool stats) {
   if (h->world <= 1) return 0;
   Side& sd = h->s[side];
-  const size_t cnt = (size_t)sd.n_shard * h->K;
+  const size_t cnt = (size_t)sd.n_shard * sd.kf;
   double* fields[4] = {sd.val, method == BNMTF_VB ? sd.var : nullptr, nullptr, nullptr};
   for (double* f : fields) {
     if (!f) continue;
-    int rc = g_nccl.AllGather(f + (size_t)sd.row0 * h->K, f, cnt, NCCL_FLOAT64, h->comm, h->stream);
+    int rc = g_nccl.AllGather(f + (size_t)sd.row0 * sd.kf, f, cnt, NCCL_FLOAT64, h->comm, h->stream);
     if (rc != 0) FAIL("ncclAllGather: %s", g_nccl.GetErrorString(rc));
   }
   if (stats) {
@@ -732,10 +781,10 @@ int bnmtf_nmf_init_factors(bnmtf_nmf_t h, int method, int random, uint64_t seed)
   CK(cudaSetDevice(h->device));
   for (int sidx = 0; sidx < 2; ++sidx) {
     Side& sd = h->s[sidx];
-    const int64_t n = sd.n_glob * h->K;
+    const int64_t n = sd.n_glob * sd.kf;
     double* dst = method == BNMTF_VB ? sd.mu : sd.val;
     init_factor_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
-        dst, sd.n_glob, h->K, h->hyper.ARD ? nullptr : sd.lam_rm, h->hyper.ARD ? h->lamk : nullptr, random, seed,
+        dst, sd.n_glob, sd.kf, h->hyper.ARD ? nullptr : sd.lam_rm, h->hyper.ARD ? sd.lamk : nullptr, random, seed,
         sidx == 0 ? RNG_INIT_U : RNG_INIT_V);
     h->launches++;
     if (method == BNMTF_VB) {
@@ -751,7 +800,8 @@ int bnmtf_nmf_init_factors(bnmtf_nmf_t h, int method, int random, uint64_t seed)
 
 int bnmtf_nmf_column_params(bnmtf_nmf_t h, int method, int side, int k, double* out_tau, double* out_mu) {
   if (!h || !out_tau || !out_mu || side < 0 || side > 1) FAIL("bad argument");
-  if (k < 0 || k >= h->K) FAIL("k out of range");
+  if (k < 0 || k >= h->s[side].kf) FAIL("k out of range");
+  if (h->nmtf) FAIL("use bnmtf_nmtf_column_params for a tri-factorisation handle");
   if (h->world > 1) FAIL("column_params is single-GPU only");
   CK(cudaSetDevice(h->device));
   Side& sd = h->s[side];
@@ -795,6 +845,7 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   if (!h) FAIL("NULL handle");
   if (iterations < 0) FAIL("negative iteration count");
   if (method < 0 || method > 3) FAIL("unknown method %d", method);
+  if (h->nmtf) FAIL("use bnmtf_nmtf_run for a tri-factorisation handle");
   CK(cudaSetDevice(h->device));
   const int K = h->K;
   Side& su = h->s[0]; Side& sv = h->s[1];
@@ -966,3 +1017,5 @@ int bnmtf_exp_draw(int device, uint64_t seed, int64_t n, const double* lambda, d
   CK(cudaMemcpy(out, o[0].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
   return 0;
 }
+
+#include "engine_nmtf.inc"

@@ -47,7 +47,11 @@ struct SweepParams {
   uint64_t seed;
   uint32_t iteration;
   uint32_t purpose;
-  int single_k;                          // >=0 one column, no state change; -1 sweep; -2 dry (stats only)
+  int single_k;                          // >=0 one column, no state change; -1 sweep; -2 dry (stats only);
+                                         // -3 project: out_mu[row][l] = sum_j e_j Y2[l][j], l < K2 (NMTF S statistics)
+  const double* __restrict__ Ykm2;       // second gather source [K2][ldy2] (project mode)
+  int64_t ldy2;
+  int K2;
 };
 
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
@@ -211,6 +215,21 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
         if (MODE == M_NP) e[n] = fma(xk, __ldg(y + c[n]), e[n]);
         else e[n] = fma(-xk, __ldg(y + c[n]), e[n]);
       }
+    }
+
+    if (p.single_k == -3) {
+      // projections of the residual onto the columns of a second factor (bnmtf_gibbs.py:277-283:
+      // sum_j M_ij E_ij G_jl, the row part of the S_kl numerators)
+      for (int l = 0; l < p.K2; ++l) {
+        const double* __restrict__ y2 = p.Ykm2 + (size_t)l * p.ldy2 * NV;
+        double s[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int n = 0; n < NPT; ++n) s[2] = fma(e[n], __ldg(y2 + c[n]), s[2]);
+        team_reduce_to_leader<3>(s, red, nw, wteam, lane, barA, tpr);
+        if (leader) p.out_mu[grow * p.K2 + l] = s[2];
+        if (nw > 1) bar_sync(barB, tpr);
+      }
+      continue;
     }
 
     double acc_esd = 0.0, acc_q = 0.0, acc_prior = 0.0;  // leader only

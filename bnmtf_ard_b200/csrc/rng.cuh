@@ -33,7 +33,7 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_
 }
 
 // Purposes (stream tags) -- part of the counter so that streams never collide.
-enum : uint32_t { RNG_TN_U = 1, RNG_TN_V = 2, RNG_LAMBDA = 3, RNG_TAU = 4, RNG_INIT_U = 5, RNG_INIT_V = 6, RNG_API = 7 };
+enum : uint32_t { RNG_TN_U = 1, RNG_TN_V = 2, RNG_LAMBDA = 3, RNG_TAU = 4, RNG_INIT_U = 5, RNG_INIT_V = 6, RNG_API = 7, RNG_S = 8, RNG_INIT_S = 9 };
 
 // One stream = (seed, purpose, index, k, iteration); successive calls bump a
 // draw counter.  Results depend only on these identifiers, never on the launch

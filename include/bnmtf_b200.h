@@ -186,6 +186,45 @@ int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out16);
 int bnmtf_nmf_sweep_times(bnmtf_nmf_t h, double* out4);
 
 /* ------------------------------------------------------------------------- *
+ * Tri-factorisation R ~ F S G^T (code/models/bnmtf_gibbs.py, nmtf_icm.py).
+ * The handle type is shared with the NMF family: side BNMTF_SIDE_U is F (I x K),
+ * side BNMTF_SIDE_V is G (J x L); layout_stats / pack / data_stats / set_comm /
+ * set_factor / get_factor / destroy / launch_count / layout_info apply unchanged.
+ * Methods available: BNMTF_GIBBS (bnmtf_gibbs.py) and BNMTF_ICM (nmtf_icm.py).
+ * ------------------------------------------------------------------------- */
+int bnmtf_nmtf_create(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, int L,
+                      const double* R, const uint8_t* M,
+                      int64_t row0, int64_t row1, int64_t shard_rows,
+                      int64_t col0, int64_t col1, int64_t shard_cols);
+int bnmtf_nmtf_create_dev(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, int L,
+                          const double* Rrow_dev, const uint8_t* Mrow_dev,
+                          const double* Rcol_dev, const uint8_t* Mcol_dev,
+                          int64_t row0, int64_t row1, int64_t shard_rows,
+                          int64_t col0, int64_t col1, int64_t shard_cols);
+/* bnmtf_gibbs.py:76-99: lambdaF (I x K) / lambdaG (J x L) when ARD == 0; lambdaS (K x L) always. */
+int bnmtf_nmtf_set_hyper(bnmtf_nmf_t h, int ARD, double alphatau, double betatau, double alpha0, double beta0,
+                         const double* lambdaF, const double* lambdaG, const double* lambdaS);
+/* S (K x L row-major); field as BNMTF_F_*. */
+int bnmtf_nmtf_set_S(bnmtf_nmf_t h, int field, const double* src);
+int bnmtf_nmtf_get_S(bnmtf_nmf_t h, int field, double* dst);
+/* tau, lambdaFk (K), lambdaGl (L); vectors may be NULL. */
+int bnmtf_nmtf_set_scalars(bnmtf_nmf_t h, double tau, const double* lambdaFk, const double* lambdaGl);
+int bnmtf_nmtf_get_scalars(bnmtf_nmf_t h, double* tau, double* lambdaFk, double* lambdaGl);
+/* initialise(init_FG, init_S) draws (bnmtf_gibbs.py:121-164; 'random' -> Exp(rate lambda), 'exp' -> 1/lambda). */
+int bnmtf_nmtf_init(bnmtf_nmf_t h, int method, int random_FG, int random_S, uint64_t seed_FG, uint64_t seed_S);
+/* Single conditionals from the current state, nothing modified (bnmtf_gibbs.py:268-292):
+ *   which 0: tauF(k), muF(.,k) (I values)   which 1: tauG(l), muG(.,l) (J values)
+ *   which 2: tauS(k,l), muS(.,k,l) (one value each).  Single-GPU only. */
+int bnmtf_nmtf_column_params(bnmtf_nmf_t h, int method, int which, int k, int l, double* out_tau, double* out_mu);
+/* beta_s() / predict_while_running() sums of the current state into out[BNMTF_NSTATS]. */
+int bnmtf_nmtf_stats(bnmtf_nmf_t h, int method, double* out);
+/* run(iterations) (bnmtf_gibbs.py:170-229, nmtf_icm.py:172-232).  Traces may be NULL:
+ * all_F [it][I][K], all_S [it][K][L], all_G [it][J][L], all_lambdaFk [it][K], all_lambdaGl [it][L]. */
+int bnmtf_nmtf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed,
+                   double* all_F, double* all_S, double* all_G, double* all_lambdaFk, double* all_lambdaGl,
+                   double* iter_stats, double* iter_seconds);
+
+/* ------------------------------------------------------------------------- *
  * Distributions (code/models/distributions/*.py) on the device; n-element
  * host arrays in, host arrays out.  Draws use Philox4x32-10 keyed by `seed`.
  *   bnmtf_tn_draw        TN_vector_draw        truncated_normal_vector.py:37-50

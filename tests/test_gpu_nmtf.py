@@ -1,0 +1,160 @@
+"""GPU parity tests for the tri-factorisation path (bnmtf_gibbs, nmtf_icm): golden
+vectors from the real reference and the numpy oracle on seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+import nmtf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+RTOL_STEP, RTOL_TRAJ = 1e-9, 1e-6
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nmtf_golden.npz"))
+
+
+def close(a, b, rtol, atol=0.0):
+    np.testing.assert_allclose(np.asarray(a, dtype=float), np.asarray(b, dtype=float), rtol=rtol, atol=atol)
+
+
+def mu_close(mu, mu_ref, tau_ref, rtol=RTOL_STEP):
+    mu, mu_ref = np.asarray(mu, dtype=float), np.asarray(mu_ref, dtype=float)
+    scale = np.maximum(np.abs(mu_ref), 1.0 / np.sqrt(np.asarray(tau_ref, dtype=float)))
+    assert np.max(np.abs(mu - mu_ref) / scale) < rtol
+
+
+def hyper_of(g, p, ard):
+    h = g[p + "hyper"]
+    d = {"alphatau": h[0], "betatau": h[1], "alpha0": h[2], "beta0": h[3], "lambdaS": g[p + "lamS"]}
+    if not ard:
+        d.update(lambdaF=g[p + "lamF"], lambdaG=g[p + "lamG"])
+    return d
+
+
+def make_problem(seed, I, J, K, L, density):
+    rng = np.random.default_rng(seed)
+    R = rng.exponential(1.0, (I, K)) @ rng.exponential(1.0, (K, L)) @ rng.exponential(1.0, (J, L)).T + rng.normal(0, 1, (I, J))
+    M = (rng.random((I, J)) < density).astype(float)
+    M[np.arange(I), rng.integers(0, J, I)] = 1
+    M[rng.integers(0, I, J), np.arange(J)] = 1
+    return R, M, rng
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+@pytest.mark.parametrize("ard", [True, False])
+def test_conditionals_golden(gold, name, ard):
+    from bnmtf_ard_b200 import bnmtf_gibbs, nmtf_icm
+    g, p = gold, "tg_%s_%s_" % (name, "ard" if ard else "noard")
+    K, L = g[p + "S"].shape
+    for cls in (bnmtf_gibbs, nmtf_icm):
+        m = cls(g[p + "R"], g[p + "M"], K, L, ard, hyper_of(g, p, ard))
+        m.F, m.S, m.G, m.tau = g[p + "F"].copy(), g[p + "S"].copy(), g[p + "G"].copy(), float(g[p + "tau"])
+        m.lambdaFk, m.lambdaGl = g[p + "lamFk"].copy(), g[p + "lamGl"].copy()
+        for k in range(K):
+            t = m.tauF(k)
+            close(t, g[p + "tauF"][:, k], RTOL_STEP); mu_close(m.muF(t, k), g[p + "muF"][:, k], g[p + "tauF"][:, k])
+        for l in range(L):
+            t = m.tauG(l)
+            close(t, g[p + "tauG"][:, l], RTOL_STEP); mu_close(m.muG(t, l), g[p + "muG"][:, l], g[p + "tauG"][:, l])
+        for k in range(K):
+            for l in range(L):
+                t = m.tauS(k, l)
+                close(t, g[p + "tauS"][k, l], RTOL_STEP); mu_close(m.muS(t, k, l), g[p + "muS"][k, l], g[p + "tauS"][k, l])
+        close(m.beta_s(), g[p + "beta_s"], RTOL_STEP)
+        assert m.alpha_s() == float(g[p + "alpha_s"])
+        if ard:
+            close([m.betaFk_s(k) for k in range(K)], g[p + "betaFk_s"], 1e-13)
+            close([m.betaGl_s(l) for l in range(L)], g[p + "betaGl_s"], 1e-13)
+
+
+@pytest.mark.parametrize("ard", [True, False])
+def test_icm_trajectory_golden(gold, ard):
+    from bnmtf_ard_b200 import nmtf_icm
+    g, p = gold, "ti_%s_" % ("ard" if ard else "noard")
+    K, L = g[p + "S0"].shape
+    m = nmtf_icm(g[p + "R"], g[p + "M"], K, L, ard, hyper_of(g, p, ard))
+    m.verbose = False
+    m.F, m.S, m.G, m.tau = g[p + "F0"].copy(), g[p + "S0"].copy(), g[p + "G0"].copy(), float(g[p + "tau0"])
+    m.lambdaFk, m.lambdaGl = g[p + "lamFk0"].copy(), g[p + "lamGl0"].copy()
+    its = int(g[p + "its"])
+    m.run(its)
+    close(m.all_F, g[p + "all_F"], RTOL_TRAJ); close(m.all_S, g[p + "all_S"], RTOL_TRAJ); close(m.all_G, g[p + "all_G"], RTOL_TRAJ)
+    close(m.all_tau, g[p + "all_tau"], RTOL_TRAJ)
+    if ard:
+        close(m.all_lambdaFk, g[p + "all_lambdaFk"], RTOL_TRAJ); close(m.all_lambdaGl, g[p + "all_lambdaGl"], RTOL_TRAJ)
+    close(m.all_performances["MSE"], g[p + "MSE"], RTOL_TRAJ)
+    close(m.all_performances["R^2"], g[p + "R2"], RTOL_TRAJ)
+    close(m.all_performances["Rp"], g[p + "Rp"], RTOL_TRAJ)
+
+
+SHAPES = [(40, 30, 3, 4, 0.7), (150, 220, 5, 3, 0.5), (64, 3000, 4, 6, 0.6), (700, 90, 7, 2, 0.8)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gibbs_iteration_vs_oracle(shape, monkeypatch):
+    """One Gibbs iteration on the GPU; the oracle replays the same draws and must
+    reproduce every conditional (tau, mu) of F, S and G that the kernels used."""
+    from bnmtf_ard_b200 import bnmtf_gibbs
+    from bnmtf_ard_b200._lib import F_MU, F_TAU, SIDE_U, SIDE_V
+    monkeypatch.setenv("BNMTF_TRACE_PARAMS", "1")
+    I, J, K, L, dens = shape
+    R, M, rng = make_problem(I * 31 + J, I, J, K, L, dens)
+    hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0, "lambdaS": 0.1}
+    m = bnmtf_gibbs(R, M, K, L, True, hyper)
+    m.verbose = False
+    np.random.seed(4)
+    m.initialise("random", "random")
+    F0, S0, G0, tau0 = m.F.copy(), m.S.copy(), m.G.copy(), m.tau
+    assert (F0 >= 0).all() and (S0 >= 0).all() and (G0 >= 0).all() and tau0 > 0
+    m.run(1)
+    eng = m._engine()
+    lamF, lamG = m.all_lambdaFk[0], m.all_lambdaGl[0]
+    F, S, G = F0.copy(), S0.copy(), G0.copy()
+    tF, mF, tS, mS, tG, mG, rss = orc.gibbs_replay_iteration(R, M, F, S, G, tau0, lamF, m.lambdaS, lamG,
+                                                            m.all_F[0], m.all_S[0], m.all_G[0])
+    close(eng.get_factor(SIDE_U, F_TAU), tF, RTOL_STEP); mu_close(eng.get_factor(SIDE_U, F_MU), mF, tF)
+    close(eng.get_S(F_TAU), tS, RTOL_STEP); mu_close(eng.get_S(F_MU), mS, tS, 1e-8)
+    close(eng.get_factor(SIDE_V, F_TAU), tG, RTOL_STEP); mu_close(eng.get_factor(SIDE_V, F_MU), mG, tG)
+    assert (m.all_F[0] >= 0).all() and (m.all_S[0] >= 0).all() and (m.all_G[0] >= 0).all()
+    close(m.all_performances["MSE"][0], rss / M.sum(), 1e-9)
+    assert (lamF > 0).all() and (lamG > 0).all() and m.all_tau[0] > 0
+
+
+@pytest.mark.parametrize("shape", SHAPES[:3])
+def test_icm_iterations_vs_oracle(shape):
+    from bnmtf_ard_b200 import nmtf_icm
+    I, J, K, L, dens = shape
+    R, M, rng = make_problem(I * 17 + J, I, J, K, L, dens)
+    hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0, "lambdaS": 0.1}
+    F0, S0, G0 = rng.exponential(1.0, (I, K)), rng.exponential(1.0, (K, L)), rng.exponential(1.0, (J, L))
+    m = nmtf_icm(R, M, K, L, True, hyper); m.verbose = False
+    m.F, m.S, m.G, m.tau, m.lambdaFk, m.lambdaGl = F0.copy(), S0.copy(), G0.copy(), 1.1, np.ones(K), np.ones(L)
+    m.run(3)
+    F, S, G, tau, lF, lG = F0.copy(), S0.copy(), G0.copy(), 1.1, np.ones(K), np.ones(L)
+    for _ in range(3):
+        tau = orc.icm_iteration(R, M, F, S, G, tau, lF, lG, hyper, True, 0.1 * np.ones((K, L)))
+    close(m.F, F, RTOL_TRAJ); close(m.S, S, RTOL_TRAJ); close(m.G, G, RTOL_TRAJ); close(m.tau, tau, RTOL_TRAJ)
+    close(m.lambdaFk, lF, RTOL_TRAJ); close(m.lambdaGl, lG, RTOL_TRAJ)
+
+
+def test_gibbs_reproducible_and_converges():
+    from bnmtf_ard_b200 import bnmtf_gibbs
+    I, J, K, L = 100, 80, 4, 3
+    R, M, _ = make_problem(5, I, J, K, L, 0.7)
+    hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0, "lambdaS": 0.1}
+    runs = []
+    for _ in range(2):
+        np.random.seed(0)
+        m = bnmtf_gibbs(R, M, K, L, True, hyper); m.verbose = False
+        m.train("random", "random", 300)
+        runs.append(m)
+    assert np.array_equal(runs[0].all_F, runs[1].all_F) and np.array_equal(runs[0].all_S, runs[1].all_S)
+    mse = runs[0].all_performances["MSE"]
+    assert 0.6 < np.mean(mse[-50:]) < 1.4 and mse[-1] < mse[0]
+    perf = runs[0].predict(M, 150, 2)
+    assert perf["MSE"] < 1.4 and perf["Rp"] > 0.9
+    assert runs[0].all_S.shape == (300, K, L) and runs[0].all_lambdaGl.shape == (300, L)
+    assert runs[0].quality("loglikelihood", 150, 2) < 0
