@@ -87,7 +87,10 @@ def test_icm_trajectory_golden(gold, ard):
         close(m.all_lambdaFk, g[p + "all_lambdaFk"], RTOL_TRAJ); close(m.all_lambdaGl, g[p + "all_lambdaGl"], RTOL_TRAJ)
     close(m.all_performances["MSE"], g[p + "MSE"], RTOL_TRAJ)
     close(m.all_performances["R^2"], g[p + "R2"], RTOL_TRAJ)
-    close(m.all_performances["Rp"], g[p + "Rp"], RTOL_TRAJ)
+    # Rp is 0/0 when the prediction is constant (all factors at the 0.1 floor): the reference
+    # returns rounding noise there (1e-17), so compare only where it is defined
+    ok = np.abs(g[p + "Rp"]) > 1e-9
+    close(np.asarray(m.all_performances["Rp"])[ok], g[p + "Rp"][ok], RTOL_TRAJ)
 
 
 SHAPES = [(40, 30, 3, 4, 0.7), (150, 220, 5, 3, 0.5), (64, 3000, 4, 6, 0.6), (700, 90, 7, 2, 0.8)]
