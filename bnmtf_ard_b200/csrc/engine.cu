@@ -99,7 +99,7 @@ struct Side {
   bool packed = false;
   // v2 (cluster) layout
   bool v2 = false;
-  int cs = 8, tw = 0, rs = 0, npt2 = 0;
+  int cs = 8, tw = 0, rs = 0, npt2 = 0, v2div = 1;
   int64_t nsets = 0, tslots = 0;
   double* tvals = nullptr;
   uint16_t* tcols = nullptr;
@@ -211,8 +211,12 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   if (npt2 > 4 && npt2 < 8) npt2 = 8;
   if (npt2 > 8 && npt2 < 12) npt2 = 12;
   if (npt2 > 12 && npt2 < 16) npt2 = 16;
-  const int wpc = npt2 <= 16 ? 32 : (npt2 <= 18 ? 28 : 24);   // Sweep2Cfg<NPT>::WPC
-  const int rs = wpc - 1;                                      // rows per set (warp 0 is the control warp)
+  const int wpc_full = npt2 <= 16 ? 32 : (npt2 <= 18 ? 28 : 24);   // Sweep2Cfg<NPT>::WPC
+  int div = 2;                                                     // CTAs (of different clusters) per SM
+  if (getenv("BNMTF_V2_DIV")) div = std::max(1, std::min(3, atoi(getenv("BNMTF_V2_DIV"))));
+  if (npt2 == 18 && div == 3) div = 2;                             // 28 warps do not split in three
+  const int rs = wpc_full / div - 1;                               // rows per set (warp 0 is the control warp)
+  sd.v2div = div;
   const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, V2_CS) * sizeof(double);
   sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && sd.kf >= 3 && smem_vb <= 200 * 1024 && sd.tw * 2 < 65535;
   if (sd.v2 && n > 0) {
@@ -618,10 +622,10 @@ static int launch_sweep_m(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int n
   FAIL("unsupported entries-per-thread %d", npt);
 }
 
-template <int NPT, int MODE>
+template <int NPT, int MODE, int DIV>
 static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  auto kern = sweep2_kernel<NPT, MODE, V2_CS>;
+  auto kern = sweep2_kernel<NPT, MODE, V2_CS, DIV>;
   const size_t smem = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS) * sizeof(double);
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3((p.rs + 1) * 32);
@@ -634,7 +638,7 @@ static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
   if (sd.nclusters[method] == 0) {
     // one fixed opt-in limit per instantiation: both sides (and other handles) share the kernel
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    cfg.gridDim = dim3(V2_CS * 64);
+    cfg.gridDim = dim3(V2_CS * 128);
     int ncl = 0;
     CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
     if (ncl < 1) FAIL("cluster sweep kernel does not fit (smem %zu bytes, %d threads)", smem, (p.rs + 1) * 32);
@@ -648,17 +652,27 @@ static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
   return 0;
 }
 
-template <int MODE>
-static int launch_sweep2_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
+template <int MODE, int DIV>
+static int launch_sweep2_d(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
   switch (sd.npt2) {
-    case 4: return launch_sweep2_t<4, MODE>(h, p, sd, method);
-    case 8: return launch_sweep2_t<8, MODE>(h, p, sd, method);
-    case 12: return launch_sweep2_t<12, MODE>(h, p, sd, method);
-    case 16: return launch_sweep2_t<16, MODE>(h, p, sd, method);
-    case 18: return launch_sweep2_t<18, MODE>(h, p, sd, method);
-    case 20: return launch_sweep2_t<20, MODE>(h, p, sd, method);
+    case 4: return launch_sweep2_t<4, MODE, DIV>(h, p, sd, method);
+    case 8: return launch_sweep2_t<8, MODE, DIV>(h, p, sd, method);
+    case 12: return launch_sweep2_t<12, MODE, DIV>(h, p, sd, method);
+    case 16: return launch_sweep2_t<16, MODE, DIV>(h, p, sd, method);
+    case 18: return launch_sweep2_t<18, MODE, (DIV == 3 ? 2 : DIV)>(h, p, sd, method);
+    case 20: return launch_sweep2_t<20, MODE, DIV>(h, p, sd, method);
   }
   FAIL("unsupported v2 entries-per-lane %d", sd.npt2);
+}
+
+template <int MODE>
+static int launch_sweep2_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
+  switch (sd.v2div) {
+    case 1: return launch_sweep2_d<MODE, 1>(h, p, sd, method);
+    case 2: return launch_sweep2_d<MODE, 2>(h, p, sd, method);
+    case 3: return launch_sweep2_d<MODE, 3>(h, p, sd, method);
+  }
+  FAIL("bad v2 block divisor %d", sd.v2div);
 }
 
 // side: which factor is updated.  single_k: see SweepParams.
@@ -682,6 +696,7 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     p.scal = h->scal;
     p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
     p.rmean = h->rmean; p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
+    p.dbg = getenv("BNMTF_V2_DBG") ? atoi(getenv("BNMTF_V2_DBG")) : 0;
     switch (method) {
       case BNMTF_GIBBS: rc = launch_sweep2_m<M_GIBBS>(h, p, sd, method); break;
       case BNMTF_ICM: rc = launch_sweep2_m<M_ICM>(h, p, sd, method); break;

@@ -102,6 +102,15 @@ struct UpdateCtx {
   uint32_t purpose, iteration;
   bool dry;
 };
+
+// Gibbs update with the Philox stream opened (and its first uniform drawn) before the
+// row sums are known; see tn_draw_pre.
+__device__ __forceinline__ double gibbs_update_pre(const double (&s)[3], double x_old, double lam, double tau, Rng& rng,
+                                                   double u1, double& ct, double& cm) {
+  ct = tau * s[0];                                        // bnmtf_gibbs tauU, bnmf_gibbs.py:205
+  const double num = -lam + tau * (s[2] + x_old * s[0]);  // numerator of muU, bnmf_gibbs.py:210
+  return tn_draw_pre(num, ct, u1, rng, cm);
+}
 template <int MODE>
 __device__ __forceinline__ double conditional_update(const double (&s)[3], double x_old, double lam, double tau,
                                                      const UpdateCtx& u, uint64_t grow, int k, double old_mu,
@@ -129,7 +138,8 @@ __device__ __forceinline__ double conditional_update(const double (&s)[3], doubl
     cm = (-lam + tau * (s[2] + x_old * s[0])) / ct;    // bnmf_gibbs.py:210
     if (MODE == M_GIBBS) {
       Rng rng(u.seed, u.purpose, grow, (uint32_t)k, u.iteration);
-      x_new = tn_draw(cm, ct, rng);                    // bnmf_gibbs.py:158
+      const double u1 = rng.u01();
+      x_new = gibbs_update_pre(s, x_old, lam, tau, rng, u1, ct, cm);   // bnmf_gibbs.py:158
     } else {
       x_new = fmax(fmax(0.0, cm), MINIMUM_TN);         // nmf_icm.py:159-160
     }

@@ -169,11 +169,12 @@ struct Sweep2Params {
   uint64_t seed;
   uint32_t iteration;
   uint32_t purpose;
+  int dbg;                               // timing experiments only: 1 = no update math
 };
 
 // dynamic shared memory of sweep2_kernel, in doubles
 __host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs) {
-  return (size_t)3 * (tw + 2) * nv + 4 /*mbarriers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ + (size_t)cs * rs * 4;
+  return (size_t)3 * (tw + 2) * nv + 4 /*mbarriers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ + (size_t)2 * cs * rs * 4 /*part, double buffered*/;
 }
 
 // Warps per CTA that the register budget of NPT entries per lane allows.  Warp 0 of
@@ -181,20 +182,22 @@ __host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, in
 // rows of the set, lane = row); warps 1..WPC-1 each own one row segment, so a set
 // has RS = WPC - 1 rows.  The two roles run separate loop nests with matching barrier
 // sequences, so the compute warps never carry a function call in their loop.
+// WPC is the largest block the register file allows (1 CTA per SM); smaller blocks
+// (WPC/2, WPC/3: 2 or 3 CTAs of different clusters per SM) let one cluster's barrier
+// and update latency overlap with another cluster's gathers.
 template <int NPT>
 struct Sweep2Cfg {
   static constexpr int WPC = NPT <= 16 ? 32 : (NPT <= 18 ? 28 : 24);
-  static constexpr int RS = WPC - 1;
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int NPT, int MODE, int CS>
-__global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC * 32, 1) sweep2_kernel(const Sweep2Params p) {
+template <int NPT, int MODE, int CS, int DIV>
+__global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_kernel(const Sweep2Params p) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  constexpr int RS = Sweep2Cfg<NPT>::RS;
+  constexpr int RS = Sweep2Cfg<NPT>::WPC / DIV - 1;
   static_assert(MODE != M_NP, "the NP updates run on the v1 kernel");
   cg::cluster_group cluster = cg::this_cluster();
   const int c = (int)cluster.block_rank();
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC * 32, 1) sweep2_kernel(con
   double* xvar = xs + (size_t)RS * K;
   double* xmu = xvar + (size_t)RS * K;
   double* xtau = xmu + (size_t)RS * K;
-  double* part = xtau + (size_t)RS * K;                   // [CS][RS][4]  (used in CTA 0)
+  double* part = xtau + (size_t)RS * K;                   // [2][CS][RS][4]: partial sums, double buffered by column parity
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 3; ++s) mbar_init(&mbar[s], 1);
@@ -257,13 +260,17 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC * 32, 1) sweep2_kernel(con
       }
       double acc_esd = 0.0, acc_q = 0.0, acc_prior = 0.0;
       const int64_t grow = p.row0 + (int64_t)set * RS + lane;
-      const bool sampler = (c == 0 && lane < rows_here);
-      double lam_next = 0.0;
-      if (sampler) lam_next = p.lamk ? p.lamk[0] : (p.lam_rm ? p.lam_rm[grow * K] : 0.0);
+      const bool sampler = (lane < rows_here);   // every CTA updates the RS rows redundantly (bitwise identical)
       for (int k = 0; k < K; ++k) {
-        const double lam = lam_next;         // prefetched: no global load on the critical path
-        if (sampler && k + 1 < K) lam_next = p.lamk ? p.lamk[k + 1] : (p.lam_rm ? p.lam_rm[grow * K + k + 1] : 0.0);
-        cluster_sync_all();                  // partial sums of column k are in CTA 0
+        // everything that does not need the row sums happens before they arrive
+        double lam = 0.0, x_old = 0.0, u1 = 0.5;
+        Rng rng(uc.seed, uc.purpose, (uint64_t)grow, (uint32_t)k, uc.iteration);
+        if (sampler) {
+          lam = p.lamk ? p.lamk[k] : (p.lam_rm ? p.lam_rm[grow * K + k] : 0.0);
+          x_old = xs[lane * K + k];
+          if (MODE == M_GIBBS) u1 = rng.u01();
+        }
+        cluster_sync_all();                  // partial sums of column k are in every CTA
         if (lane == 0 && k >= 1 && K + k + 2 < 2 * K) {   // tile of column k-1 is dead cluster-wide
           const uint32_t gn = gseq + K + k + 2;
           fence_proxy_async();
@@ -274,20 +281,20 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC * 32, 1) sweep2_kernel(con
           double t3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
           for (int cc = 0; cc < CS; ++cc) {
-            const double* src = part + ((size_t)cc * RS + lane) * 4;
+            const double* src = part + ((size_t)((k & 1) * CS + cc) * RS + lane) * 4;
             t3[0] += src[0]; t3[1] += src[1]; t3[2] += src[2];
           }
-          const double x_old = xs[lane * K + k];
-          double ct, cm, vn;
-          const double x_new = conditional_update<MODE>(t3, x_old, lam, tau, uc, (uint64_t)grow, k, 0.0, 0.0, 0.0, ct,
-                                                        cm, vn, acc_esd, acc_q, acc_prior);
+          double ct, cm, vn = 0.0, x_new;
+          if (p.dbg & 1) { x_new = x_old + 1e-3 * t3[0]; ct = cm = 0.0; }
+          else if (MODE == M_GIBBS) x_new = gibbs_update_pre(t3, x_old, lam, tau, rng, u1, ct, cm);
+          else x_new = conditional_update<MODE>(t3, x_old, lam, tau, uc, (uint64_t)grow, k, 0.0, 0.0, 0.0, ct, cm, vn, acc_esd,
+                                                acc_q, acc_prior);
           xs[lane * K + k] = x_new;
           xmu[lane * K + k] = cm; xtau[lane * K + k] = ct;
           if (MODE == M_VB) xvar[lane * K + k] = vn;
-          const double d = x_new - x_old;
-          for (int cc = 0; cc < CS; ++cc) cluster.map_shared_rank(delta, cc)[lane] = d;
+          delta[lane] = x_new - x_old;
         }
-        cluster_sync_all();                  // deltas of column k are in every CTA
+        __syncthreads();                     // deltas of column k are in this CTA's shared memory
       }
       cluster_sync_all();                    // row-statistics partials are in CTA 0
       if (c == 0) {
@@ -382,12 +389,12 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC * 32, 1) sweep2_kernel(con
         }
         s0 = warp_sum(s0); s2 = warp_sum(s2);
         if (MODE == M_VB) s1 = warp_sum(s1);
-        if (lane == 0) {
-          double* dst = part0 + ((size_t)c * RS + r) * 4;
+        if (lane < CS) {   // lane cc sends this warp's partial sums to CTA cc (every CTA updates redundantly)
+          double* dst = cluster.map_shared_rank(part, lane) + ((size_t)((k & 1) * CS + c) * RS + r) * 4;
           dst[0] = s0; dst[1] = s1; dst[2] = s2;
         }
-        cluster_sync_all();
-        cluster_sync_all();
+        cluster_sync_all();                  // partial sums of column k are in every CTA
+        __syncthreads();                     // the control warp of this CTA has written the deltas
         dprev = (r < rows_here) ? delta[r] : 0.0;
       }
 

@@ -114,6 +114,35 @@ __device__ __noinline__ double tn_draw(double mu, double tau, Rng& rng) {
   return (d >= 0.0 && isfinite(d)) ? d : 0.0;
 }
 
+// Same draw with the inputs the sweeps have at hand -- num = -lambda + tau*b and
+// prec = tau*s, i.e. mu = num/prec -- and with the first uniform already drawn (the
+// Philox rounds run before the row sums arrive).  No division or square root on the
+// critical path: sigma = rsqrt(prec), a = -mu/sigma = -num*sigma, and the draw is
+// sigma*(z - a), which also never cancels.  mu_out returns num/prec (to 1-2 ulp).
+__device__ __noinline__ double tn_draw_pre(double num, double prec, double u1, Rng& rng, double& mu_out) {
+  if (prec == 0.0) { mu_out = num / prec; return 0.0; }
+  const double sigma = rsqrt(prec);
+  mu_out = num * sigma * sigma;
+  const double a = -num * sigma;
+  double x;   // z - a >= 0
+  if (!(a > 4.0)) {
+    const double q = 0.5 * erfc(a * 0.70710678118654752440);
+    x = -normcdfinv(u1 * q) - a;
+  } else {
+    const double alpha = 0.5 * (a + sqrt(a * a + 4.0));
+    double u = u1;
+    x = 0.0;
+    for (int it = 0; it < 1000; ++it) {
+      x = -log(u) / alpha;
+      const double t = (a + x) - alpha;
+      if (log(rng.u01()) <= -0.5 * t * t) break;
+      u = rng.u01();
+    }
+  }
+  const double d = sigma * x;
+  return (d >= 0.0 && isfinite(d)) ? d : 0.0;
+}
+
 // ---- TN_vector_expectation / TN_vector_variance -----------------------------
 // truncated_normal_vector.py:53-73 (same operation order as the reference so
 // that the results agree to rounding): sigma = 1/sqrt(tau); x = -mu/sigma;
