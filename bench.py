@@ -32,7 +32,7 @@ METRIC = "BNMF-ARD Gibbs iters/sec, 20k x 20k K=50"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--I", type=int, default=20000)
@@ -77,23 +77,48 @@ def synth_host(I, J, K, density, seed=20250):
 
 # --------------------------------------------------------------------------- #
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md), sampled
+    through NVML (falls back to the nvidia-smi command line)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:  # noqa: BLE001
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        return [sm, mx] + ["Active" if r & bit else "Not Active"
+                           for bit in (flags["hw_slowdown"], flags["hw_thermal_slowdown"], flags["sw_thermal_slowdown"],
+                                       flags["sw_power_cap"])]
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                if self.nvml is not None:
+                    self.rows.append([str(x) for x in self._sample_nvml()])
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02 if self.nvml is not None else 0.2)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -107,7 +132,17 @@ class ClockSampler(threading.Thread):
             except Exception:  # noqa: BLE001
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def load_peaks():
@@ -287,18 +322,23 @@ def main():
                 "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "BNMF Gibbs+ARD %dx%d rho=%.2f K=%d (BASELINE configs[2])" % (I, J, args.density, K),
-                           "cache": "inputs (R packed: %.2f GB/GPU) exceed the 126 MB L2" % (
-                               (info["slots_U"] + info["slots_V"]) * 12 / 1e9),
+                           "cache": "inputs (packed R: %.2f GB/GPU read per iteration) exceed the 126 MB L2" % (
+                               ((info["v2_slots_U"] + info["v2_slots_V"]) * 10 if info.get("v2_U") else
+                                (info["slots_U"] + info["slots_V"]) * 12) / 1e9),
                            "layout": info, "wall_s": wall, "train_mse_last": perf["MSE"]},
                 "gpu_launches": launches, "clocks": clocks}
         # roofline of the dominant kernel (row sweep): algorithmic DRAM bytes of OUR formulation
         if sweeps["n_U"] > 0:
             ms = (sweeps["ms_U"] + sweeps["ms_V"]) / (sweeps["n_U"] + sweeps["n_V"])
-            bytes_per_launch = 0.5 * (info["slots_U"] + info["slots_V"]) * 12.0 + (I + J) * K * 8 * 1.5
+            if info.get("v2_U") and info.get("v2_V"):   # cluster-tile layout: f64 value + u16 column per slot, read once
+                bytes_per_launch = 0.5 * (info["v2_slots_U"] + info["v2_slots_V"]) * 10.0 + (I + J) * K * 8 * 1.5
+            else:
+                bytes_per_launch = 0.5 * (info["slots_U"] + info["slots_V"]) * 12.0 + (I + J) * K * 8 * 1.5
             ach = bytes_per_launch / (ms * 1e-3) / 1e9
             northstar_bytes = 2 * K * 16.125 * I * J
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                "traffic": None, "peak_source": peak_src, "kernel": "sweep_kernel",
+                                "traffic": load_traffic(), "peak_source": peak_src,
+                                "kernel": "sweep2_kernel" if info.get("v2_U") else "sweep_kernel",
                                 "kernel_ms": ms, "kernel_share_of_step": (sweeps["ms_U"] + sweeps["ms_V"]) / (1e3 * dev_s),
                                 "north_star_equiv_gbs": northstar_bytes * value / 1e9,
                                 "north_star_equiv_frac": northstar_bytes * value / 1e9 / peak}
