@@ -73,6 +73,50 @@ def gen_icm_run(ref, out):
                     p + "hyper": np.array([hyper[k] for k in ("alphatau", "betatau", "alpha0", "beta0")])})
 
 
+VB_FIELDS = ["mu_F", "tau_F", "exp_F", "var_F", "mu_S", "tau_S", "exp_S", "var_S", "mu_G", "tau_G", "exp_G", "var_G"]
+VB_SCAL = ["exp_tau", "exp_logtau", "alpha_s", "beta_s"]
+VB_ARD = ["alphaFk_s", "betaFk_s", "exp_lambdaFk", "exp_loglambdaFk", "alphaGl_s", "betaGl_s", "exp_lambdaGl", "exp_loglambdaGl"]
+
+
+def gen_vb_run(ref, out):
+    rng = np.random.default_rng(909)
+    hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0}
+    I, J, K, L, its = 24, 19, 4, 3, 8
+    R, M = make_problem(rng, I, J, max(K, L), 0.65)
+    lamS = rng.gamma(2.0, 0.3, (K, L))
+    for ard in (True, False):
+        lamF, lamG = rng.gamma(2.0, 0.5, (I, K)), rng.gamma(2.0, 0.5, (J, L))
+        h = dict(hyper, lambdaS=lamS)
+        if not ard:
+            h.update(lambdaF=lamF, lambdaG=lamG)
+        m = ref.bnmtf_vb(R, M, K, L, ard, h)
+        np.random.seed(13)
+        m.initialise("random", "random")
+        p = "tv_%s_" % ("ard" if ard else "noard")
+        fields = VB_FIELDS + VB_SCAL + (VB_ARD if ard else [])
+        for f in fields:
+            out[p + f + "0"] = np.array(getattr(m, f), dtype=np.float64).copy()
+        out[p + "elbo0"] = m.elbo()
+        out[p + "esd0"] = m.exp_square_diff()
+        # single-step updates from the initial state (what tests/code/test_bnmtf_vb.py pokes)
+        m2 = ref.bnmtf_vb(R, M, K, L, ard, h)
+        for f in fields:
+            v = getattr(m, f)
+            setattr(m2, f, np.array(v, dtype=np.float64).copy() if np.ndim(v) else v)
+        m2.update_F(1); m2.update_exp_F(1); m2.update_S(2, 1); m2.update_exp_S(2, 1); m2.update_G(2); m2.update_exp_G(2)
+        for f in VB_FIELDS:
+            out[p + "step_" + f] = np.array(getattr(m2, f), dtype=np.float64).copy()
+        elbos, taus, mses = [], [], []
+        for _ in range(its):
+            quiet(m.run, 1)
+            elbos.append(m.elbo()); taus.append(m.exp_tau); mses.append(m.all_performances["MSE"][0])
+        for f in fields:
+            out[p + f] = np.array(getattr(m, f), dtype=np.float64).copy()
+        out.update({p + "R": R, p + "M": M, p + "lamF": lamF, p + "lamG": lamG, p + "lamS": lamS, p + "its": its,
+                    p + "elbo": np.array(elbos), p + "all_exp_tau": np.array(taus), p + "MSE": np.array(mses),
+                    p + "hyper": np.array([hyper[k] for k in ("alphatau", "betatau", "alpha0", "beta0")])})
+
+
 def main():
     ref = refimport.load()
     if ref is None:
@@ -80,6 +124,7 @@ def main():
     out = {}
     gen_params(ref, out)
     gen_icm_run(ref, out)
+    gen_vb_run(ref, out)
     path = os.path.join(OUT, "nmtf_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote %s (%d arrays, %.1f KB)" % (path, len(out), os.path.getsize(path) / 1024.0))

@@ -44,3 +44,34 @@ def test_icm_trajectory(gold, ard):
         close(tau, g[p + "all_tau"][it], 1e-8)
         if ard:
             close(lF, g[p + "all_lambdaFk"][it], 1e-8); close(lG, g[p + "all_lambdaGl"][it], 1e-8)
+
+
+@pytest.mark.parametrize("ard", [True, False])
+def test_vb_trajectory_and_steps(gold, ard):
+    g, p = gold, "tv_%s_" % ("ard" if ard else "noard")
+    R, M, lamS = g[p + "R"], g[p + "M"], g[p + "lamS"]
+    h = g[p + "hyper"]
+    hyper = {"alphatau": h[0], "betatau": h[1], "alpha0": h[2], "beta0": h[3]}
+    fields = orc.VB_FIELDS + orc.VB_SCAL + (orc.VB_ARD if ard else [])
+    st = {f: (g[p + f + "0"].copy() if g[p + f + "0"].ndim else float(g[p + f + "0"])) for f in fields}
+    close(orc.vb_exp_square_diff(R, M, st), g[p + "esd0"])
+    close(orc.vb_elbo(R, M, st, hyper, ard, lamS, g[p + "lamF"], g[p + "lamG"]), g[p + "elbo0"], 1e-10)
+    # single-step F(1), S(2,1), G(2) as generated
+    s2 = {f: (np.array(v).copy() if np.ndim(v) else v) for f, v in st.items()}
+    lam = s2["exp_lambdaFk"][1] if ard else g[p + "lamF"][:, 1]
+    s2["tau_F"][:, 1], s2["mu_F"][:, 1] = orc.vb_update_F(R, M, s2, lam, 1)
+    s2["exp_F"][:, 1] = orc.tn_expectation(s2["mu_F"][:, 1], s2["tau_F"][:, 1])
+    s2["var_F"][:, 1] = orc.tn_variance(s2["mu_F"][:, 1], s2["tau_F"][:, 1])
+    s2["tau_S"][2, 1], s2["mu_S"][2, 1] = orc.vb_update_S(R, M, s2, lamS, 2, 1)
+    s2["exp_S"][2, 1] = float(orc.tn_expectation(s2["mu_S"][2, 1], s2["tau_S"][2, 1]))
+    s2["var_S"][2, 1] = float(orc.tn_variance(s2["mu_S"][2, 1], s2["tau_S"][2, 1]))
+    lam = s2["exp_lambdaGl"][2] if ard else g[p + "lamG"][:, 2]
+    s2["tau_G"][:, 2], s2["mu_G"][:, 2] = orc.vb_update_G(R, M, s2, lam, 2)
+    for f in ("tau_F", "mu_F", "exp_F", "tau_S", "mu_S", "exp_S", "tau_G", "mu_G"):
+        close(s2[f], g[p + "step_" + f], 1e-9, 1e-12)
+    for it in range(int(g[p + "its"])):
+        orc.vb_iteration(R, M, st, hyper, ard, lamS, g[p + "lamF"], g[p + "lamG"])
+        close(orc.vb_elbo(R, M, st, hyper, ard, lamS, g[p + "lamF"], g[p + "lamG"]), g[p + "elbo"][it], 1e-8)
+        close(st["exp_tau"], g[p + "all_exp_tau"][it], 1e-8)
+    for f in fields:
+        close(st[f], g[p + f], 1e-7, 1e-12)
