@@ -10,5 +10,6 @@ from .nmf_icm import nmf_icm  # noqa: F401
 from .nmf_np import nmf_np  # noqa: F401
 from .bnmtf_gibbs import bnmtf_gibbs  # noqa: F401
 from .nmtf_icm import nmtf_icm  # noqa: F401
+from .bnmtf_vb import bnmtf_vb  # noqa: F401
 
-__all__ = ["bnmf_gibbs", "bnmf_vb", "nmf_icm", "nmf_np", "bnmtf_gibbs", "nmtf_icm"]
+__all__ = ["bnmf_gibbs", "bnmf_vb", "nmf_icm", "nmf_np", "bnmtf_gibbs", "nmtf_icm", "bnmtf_vb"]

@@ -255,3 +255,32 @@ class NMTFEngine(NMFEngine):
                                       dptr(res["all_G"]), dptr(res["all_lambdaFk"]), dptr(res["all_lambdaGl"]),
                                       dptr(res["stats"]), dptr(res["seconds"])))
         return res
+
+    # -- VB (bnmtf_vb) -------------------------------------------------------------
+    def set_vb_scalars(self, exp_tau, exp_logtau, alpha_s, beta_s, stateF=None, stateG=None):
+        sf = None if stateF is None else f64(stateF, (4, self.K))
+        sg = None if stateG is None else f64(stateG, (4, self.L))
+        check(self.lib.bnmtf_nmtf_set_vb_scalars(self.h, float(exp_tau), float(exp_logtau), float(alpha_s), float(beta_s),
+                                                 dptr(sf), dptr(sg)))
+
+    def get_vb_scalars(self):
+        sc, sf, sg = np.zeros(4), np.zeros((4, self.K)), np.zeros((4, self.L))
+        check(self.lib.bnmtf_nmtf_get_vb_scalars(self.h, dptr(sc), dptr(sf), dptr(sg)))
+        return sc, sf, sg
+
+    def vb_update_params(self, which, k=0, l=0):
+        n = (self.I, self.J, 1)[which]
+        t, m = np.empty(n), np.empty(n)
+        check(self.lib.bnmtf_nmtf_vb_update_params(self.h, which, int(k), int(l), dptr(t), dptr(m)))
+        return t, m
+
+    def vb_stats(self):
+        out = np.zeros(NSTATS)
+        check(self.lib.bnmtf_nmtf_vb_stats(self.h, dptr(out)))
+        return out
+
+    def vb_run(self, iterations):
+        it = int(iterations)
+        res = {"stats": np.zeros((it, NSTATS)), "seconds": np.zeros(it)}
+        check(self.lib.bnmtf_nmtf_vb_run(self.h, it, dptr(res["stats"]), dptr(res["seconds"])))
+        return res

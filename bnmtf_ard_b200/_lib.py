@@ -64,6 +64,11 @@ SIGNATURES = {
     "bnmtf_nmtf_column_params": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "bnmtf_nmtf_stats": (C.c_int, [_h, C.c_int, _dp]),
     "bnmtf_nmtf_run": (C.c_int, [_h, C.c_int, C.c_int, C.c_uint64, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "bnmtf_nmtf_set_vb_scalars": (C.c_int, [_h, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp]),
+    "bnmtf_nmtf_get_vb_scalars": (C.c_int, [_h, _dp, _dp, _dp]),
+    "bnmtf_nmtf_vb_update_params": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, _dp, _dp]),
+    "bnmtf_nmtf_vb_stats": (C.c_int, [_h, _dp]),
+    "bnmtf_nmtf_vb_run": (C.c_int, [_h, C.c_int, _dp, _dp]),
     "bnmtf_tn_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),
     "bnmtf_tn_moments": (C.c_int, [C.c_int, C.c_int64, _dp, _dp, _dp, _dp]),
     "bnmtf_gamma_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),

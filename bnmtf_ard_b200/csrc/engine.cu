@@ -144,6 +144,15 @@ struct bnmtf_nmf_s {
   double *cvec = nullptr, *TT = nullptr;     // [K*L], [K(K+1)/2][L(L+1)/2]
   double* sumlog_lamS_dev = nullptr;
   double sumlog_lamS = 0.0;
+  // BNMTF VB
+  double* proj_out3 = nullptr;           // third output of the project modes (transient)
+  int cov_side = -1;                     // side whose VB sweep carries the covariance term (transient)
+  const double* covA = nullptr; const double* covS = nullptr;
+  int covL = 0, cov_sk = 0, cov_sl = 0;
+  double *Arow = nullptr, *Brow = nullptr, *Crow = nullptr;   // [I_pad][L], [I_pad][L], [J_pad][K]
+  double *BS = nullptr, *PA = nullptr, *QC = nullptr;         // [K*L], [K(K+1)/2][L], [L(L+1)/2][K]
+  double* lamstateG = nullptr;           // [4][L]  (lamstate holds the F block [4][K])
+  double* vbmisc = nullptr;              // [8]: S q-term, sum lambdaS*ES, T3
 };
 
 // ---- packing -------------------------------------------------------------------
@@ -321,11 +330,11 @@ static int create_dev_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, i
   if (alloc_side_state(h, su, K) || alloc_side_state(h, sv, L)) return 1;
   su.lamk = nullptr; sv.lamk = nullptr;
   CK(cudaMalloc(&h->scal, sizeof(double) * SC_COUNT));
-  CK(cudaMalloc(&h->colsum, sizeof(double) * 2 * K));
+  CK(cudaMalloc(&h->colsum, sizeof(double) * 2 * (K + L)));
   CK(cudaMalloc(&h->lamstate, sizeof(double) * 4 * K));
   CK(cudaMalloc(&h->lamk, sizeof(double) * K));
   CK(cudaMemsetAsync(h->scal, 0, sizeof(double) * SC_COUNT, h->stream));
-  CK(cudaMemsetAsync(h->colsum, 0, sizeof(double) * 2 * K, h->stream));
+  CK(cudaMemsetAsync(h->colsum, 0, sizeof(double) * 2 * (K + L), h->stream));
   CK(cudaMemsetAsync(h->lamstate, 0, sizeof(double) * 4 * K, h->stream));
   CK(cudaMemsetAsync(h->lamk, 0, sizeof(double) * K, h->stream));
   if (!nmtf) {
@@ -418,6 +427,8 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   cudaFree(h->scal); cudaFree(h->colsum); cudaFree(h->lamstate); cudaFree(h->lamk); cudaFree(h->stats_dev);
   cudaFree(h->S); cudaFree(h->Svar); cudaFree(h->Smu); cudaFree(h->Stau); cudaFree(h->lamS); cudaFree(h->lamG);
   cudaFree(h->Prow); cudaFree(h->Hrow); cudaFree(h->cvec); cudaFree(h->TT);
+  cudaFree(h->Arow); cudaFree(h->Brow); cudaFree(h->Crow); cudaFree(h->BS); cudaFree(h->PA); cudaFree(h->QC);
+  cudaFree(h->lamstateG); cudaFree(h->vbmisc);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -593,7 +604,7 @@ static int launch_sweep_t(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int* 
   const int teams = tpr >= 128 ? 1 : 128 / tpr;
   const int block = tpr * teams;
   const int nw = tpr / 32;
-  const size_t smem = sizeof(double) * teams * (4 * (size_t)p.K + 3 * nw + 2);
+  const size_t smem = sizeof(double) * teams * (4 * (size_t)p.K + 3 * nw + 2 + 2 * (size_t)p.covL);
   auto kern = sweep_kernel<NPT, MODE>;
   if (*occ_cache == 0) {
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -686,7 +697,7 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
   const bool timed = h->time_sweeps && single_k == -1;
   if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
   int rc;
-  if (sd.v2 && single_k == -1 && method != BNMTF_NP) {
+  if (sd.v2 && single_k == -1 && method != BNMTF_NP && !(h->nmtf && method == BNMTF_VB)) {
     Sweep2Params p{};
     p.tvals = sd.tvals; p.tcols = sd.tcols; p.nsets = (int)sd.nsets; p.n_loc = (int)sd.n_loc; p.row0 = sd.row0;
     p.K = sd.kf; p.tw = sd.tw; p.rs = sd.rs; p.Ykm = sd.ysrc; p.ldy = sd.ysrc_ld;
@@ -708,7 +719,10 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     p.vals = sd.vals; p.cols = sd.cols; p.rowstart = sd.rowstart;
     p.n_loc = (int)sd.n_loc; p.row0 = sd.row0; p.K = sd.kf; p.tpr = sd.tpr; p.padcol = sd.padcol;
     p.Ykm = sd.ysrc; p.ldy = sd.ysrc_ld;
-    p.Ykm2 = proj_y2; p.ldy2 = proj_ld2; p.K2 = proj_k2;
+    p.Ykm2 = proj_y2; p.ldy2 = proj_ld2; p.K2 = proj_k2; p.out3 = h->proj_out3;
+    if (h->cov_side == side && method == BNMTF_VB && single_k >= -2) {
+      p.covA = h->covA; p.covS = h->covS; p.covL = h->covL; p.cov_sk = h->cov_sk; p.cov_sl = h->cov_sl;
+    }
     p.Xval = sd.val; p.Xvar = sd.var;
     p.Xmu = mu_out ? sd.mu : nullptr; p.Xtau = mu_out ? sd.tau : nullptr;
     p.lam_rm = h->hyper.ARD ? nullptr : sd.lam_rm;

@@ -49,9 +49,16 @@ struct SweepParams {
   uint32_t purpose;
   int single_k;                          // >=0 one column, no state change; -1 sweep; -2 dry (stats only);
                                          // -3 project: out_mu[row][l] = sum_j e_j Y2[l][j], l < K2 (NMTF S statistics)
-  const double* __restrict__ Ykm2;       // second gather source [K2][ldy2] (project mode)
+                                         // -4 masked sums only (no residual): out_tau = sum y2, out3 = sum y2 - sum y^2
+  const double* __restrict__ Ykm2;       // second gather source [K2][ldy2][NV] (project modes)
   int64_t ldy2;
   int K2;
+  double* out3;
+  // BNMTF VB covariance term of update_F / update_G (bnmtf_vb.py:343,371):
+  //   cov_i = sum_l S(k,l) A_il ((X S)_il - x_ik S(k,l)),  A = masked sums of the other factor's variance
+  const double* __restrict__ covA;       // [n_glob][covL] or nullptr
+  const double* __restrict__ covS;       // S(k,l) = covS[k*cov_sk + l*cov_sl]
+  int covL, cov_sk, cov_sl;
 };
 
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
@@ -177,13 +184,16 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
   const int wteam = t >> 5;
   const int nw = tpr >> 5;
   const int barA = 1 + 2 * team, barB = 2 + 2 * team;
-  const int team_stride = 4 * K + 3 * nw + 2;
+  const int team_stride = 4 * K + 3 * nw + 2 + 2 * p.covL;
   double* xs = smem + (size_t)team * team_stride;  // [K] current values of the row
   double* xvar = xs + K;                            // [K] VB variance
   double* xmu = xvar + K;                           // [K] conditional mean
   double* xtau = xmu + K;                           // [K] conditional precision
   double* red = xtau + K;                           // [3*nw]
   double* bc = red + 3 * nw;                        // [2]
+  double* fsv = bc + 2;                             // [covL] (X S)_il of the row   (BNMTF VB)
+  double* arow = fsv + p.covL;                      // [covL] A_il of the row
+  const bool has_cov = (MODE == M_VB) && (p.covA != nullptr);
   const bool leader = (t == 0);
   const bool dry = (p.single_k == -2);
 
@@ -215,9 +225,18 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
       }
     }
     if (nw == 1) __syncwarp(); else bar_sync(barB, tpr);
+    if (has_cov) {
+      for (int l = t; l < p.covL; l += tpr) {
+        double a = 0.0;
+        for (int kk = 0; kk < K; ++kk) a = fma(xs[kk], p.covS[kk * p.cov_sk + l * p.cov_sl], a);
+        fsv[l] = a;
+        arow[l] = p.covA[grow * p.covL + l];
+      }
+      if (nw == 1) __syncwarp(); else bar_sync(barB, tpr);
+    }
 
     // ---- residual of the row from the current factors: e = r - sum_k x_k y_k
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K && p.single_k != -4; ++k) {
       const double xk = xs[k];
       const double* __restrict__ y = p.Ykm + (size_t)k * p.ldy * NV;
 #pragma unroll
@@ -227,16 +246,28 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
       }
     }
 
-    if (p.single_k == -3) {
+    if (p.single_k == -3 || p.single_k == -4) {
       // projections of the residual onto the columns of a second factor (bnmtf_gibbs.py:277-283:
-      // sum_j M_ij E_ij G_jl, the row part of the S_kl numerators)
+      // sum_j M_ij E_ij G_jl, the row part of the S_kl numerators) and, in VB mode, the masked
+      // sums of its second moments and variances (bnmtf_vb.py:343,352-357)
       for (int l = 0; l < p.K2; ++l) {
         const double* __restrict__ y2 = p.Ykm2 + (size_t)l * p.ldy2 * NV;
         double s[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-        for (int n = 0; n < NPT; ++n) s[2] = fma(e[n], __ldg(y2 + c[n]), s[2]);
+        for (int n = 0; n < NPT; ++n) {
+          if (MODE == M_VB) {
+            const double2 yy = __ldg(reinterpret_cast<const double2*>(y2 + c[n]));
+            s[0] = fma(yy.x, yy.x, s[0]); s[1] += yy.y; s[2] = fma(e[n], yy.x, s[2]);
+          } else {
+            s[2] = fma(e[n], __ldg(y2 + c[n]), s[2]);
+          }
+        }
         team_reduce_to_leader<3>(s, red, nw, wteam, lane, barA, tpr);
-        if (leader) p.out_mu[grow * p.K2 + l] = s[2];
+        if (leader) {
+          if (p.out_mu) p.out_mu[grow * p.K2 + l] = s[2];
+          if (p.out_tau) p.out_tau[grow * p.K2 + l] = s[1];
+          if (p.out3) p.out3[grow * p.K2 + l] = s[1] - s[0];
+        }
         if (nw > 1) bar_sync(barB, tpr);
       }
       continue;
@@ -286,6 +317,14 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
         const double tau = p.scal[0];
         const UpdateCtx uc{p.seed, p.purpose, p.iteration, dry};
         double cm, ct, vn;
+        if (has_cov) {   // diff_term - cov_term (bnmtf_vb.py:342-348)
+          double cov = 0.0;
+          for (int l = 0; l < p.covL; ++l) {
+            const double skl = p.covS[k * p.cov_sk + l * p.cov_sl];
+            cov = fma(skl * arow[l], fsv[l] - x_old * skl, cov);
+          }
+          s[2] -= cov;
+        }
         double x_new = conditional_update<MODE>(s, x_old, lam, tau, uc, (uint64_t)grow, k, xmu[k], xtau[k], xvar[k], ct, cm,
                                                 vn, acc_esd, acc_q, acc_prior);
         if (MODE == M_VB) xvar[k] = vn;
@@ -297,6 +336,8 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
         xmu[k] = cm; xtau[k] = ct;
         bc[0] = x_new - x_old;
         xs[k] = x_new;
+        if (has_cov && x_new != x_old)
+          for (int l = 0; l < p.covL; ++l) fsv[l] = fma(x_new - x_old, p.covS[k * p.cov_sk + l * p.cov_sl], fsv[l]);
       }
       if (nw == 1) __syncwarp(); else bar_sync(barB, tpr);
       const double delta = bc[0];

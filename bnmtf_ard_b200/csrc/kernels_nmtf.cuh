@@ -187,6 +187,214 @@ __global__ void nmtf_lambda_kernel(const double* __restrict__ F, int64_t I, int 
   }
 }
 
+// ---------------------------------------------------------------------------------
+// BNMTF VB (code/models/bnmtf_vb.py)
+// ---------------------------------------------------------------------------------
+// Pair-layout gather source of update_F / update_G (bnmtf_vb.py:337-339,365-366):
+//   out[c][i] = ( w, var + w^2 ),  w = sum_q EX[i][q] ES(q,c),
+//   var = sum_q (VX+EX^2)[i][q] (VS+ES^2)(q,c) - sum_q EX[i][q]^2 ES(q,c)^2      (var_SkG / var_FSl)
+__global__ void vb_combine_km_kernel(const double* __restrict__ EX, const double* __restrict__ VX, int64_t n, int kq,
+                                     const double* __restrict__ ES, const double* __restrict__ VS, int s_q, int s_c,
+                                     double* __restrict__ out_km, int64_t ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (i >= ld) return;
+  double w = 0.0, a2 = 0.0, b2 = 0.0;
+  if (i < n) {
+    for (int q = 0; q < kq; ++q) {
+      const double ex = EX[i * kq + q], vx = VX[i * kq + q];
+      const double es = ES[q * s_q + c * s_c], vs = VS[q * s_q + c * s_c];
+      w = fma(ex, es, w);
+      a2 = fma(vx + ex * ex, vs + es * es, a2);
+      b2 = fma(ex * ex, es * es, b2);
+    }
+  }
+  reinterpret_cast<double2*>(out_km)[(size_t)c * ld + i] = make_double2(w, (a2 - b2) + w * w);
+}
+
+// out[k][l] = sum_i f(i,k) P[i][l]  with f = F (Fvar == nullptr) or Fvar + F^2
+__global__ void nmtf_reduce_c2_kernel(const double* __restrict__ F, const double* __restrict__ Fvar, const double* __restrict__ P,
+                                      int64_t I, int K, int L, double* __restrict__ out) {
+  __shared__ double sh[32];
+  const int k = blockIdx.x / L, l = blockIdx.x % L;
+  double a = 0.0;
+  for (int64_t i = threadIdx.x; i < I; i += blockDim.x) {
+    const double f = F[i * K + k];
+    a = fma(Fvar ? Fvar[i * K + k] + f * f : f, P[i * L + l], a);
+  }
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = a;
+}
+
+__device__ __forceinline__ double tmat(const double* TT, int k, int l, int k2, int l2, int K, int L, int NPL) {
+  return TT[(size_t)pair_index(min(k, k2), max(k, k2), K) * NPL + pair_index(min(l, l2), max(l, l2), L)];
+}
+
+// The K*L sequential update_S(k,l) + update_exp_S(k,l) (bnmtf_vb.py:220-223,350-362,393-396) on the small tensors:
+//   tau_S = Etau BS[k][l],  diff = c_d + ES_d T[d,d],
+//   covG = sum_{k'!=k} ES(k',l) PA[pair(k,k')][l],  covF = sum_{l'!=l} ES(k,l') QC[pair(l,l')][k]
+// mode: -1 full sweep, -2 dry (ELBO terms of the stored state), d >= 0 report (tau, mu) of entry d.
+// misc[0] = sum_d q-terms of S for the ELBO (bnmtf_vb.py:290-292), misc[1] = sum lambdaS*ES (:268).
+__global__ void nmtf_s_sweep_vb_kernel(const double* __restrict__ c_in, const double* __restrict__ TT, const double* __restrict__ BS,
+                                       const double* __restrict__ PA, const double* __restrict__ QC, int K, int L, double* Sexp,
+                                       double* Svar, double* Smu, double* Stau, const double* __restrict__ lamS,
+                                       const double* __restrict__ scal, int mode, double* out_tau, double* out_mu, double* misc) {
+  extern __shared__ double shs[];
+  const int KL = K * L, NPL = L * (L + 1) / 2;
+  double* c = shs;            // [KL]
+  double* es = c + KL;        // [KL]
+  double* bc = es + KL;       // [1]
+  for (int d = threadIdx.x; d < KL; d += blockDim.x) { c[d] = c_in[d]; es[d] = Sexp[d]; }
+  __syncthreads();
+  const double etau = scal[0];
+  double acc_q = 0.0, acc_prior = 0.0;
+  const int d_begin = mode >= 0 ? mode : 0, d_end = mode >= 0 ? mode + 1 : KL;
+  for (int d = d_begin; d < d_end; ++d) {
+    const int k = d / L, l = d - k * L;
+    if (threadIdx.x == 0) {
+      double ct, cm, en, vn;
+      if (mode == -2) {
+        ct = Stau[d]; cm = Smu[d]; en = es[d]; vn = Svar[d];
+      } else {
+        const double Tdd = tmat(TT, k, l, k, l, K, L, NPL);
+        ct = etau * BS[d];
+        double covG = 0.0, covF = 0.0;
+        for (int k2 = 0; k2 < K; ++k2)
+          if (k2 != k) covG = fma(es[k2 * L + l], PA[(size_t)pair_index(min(k, k2), max(k, k2), K) * L + l], covG);
+        for (int l2 = 0; l2 < L; ++l2)
+          if (l2 != l) covF = fma(es[k * L + l2], QC[(size_t)pair_index(min(l, l2), max(l, l2), L) * K + k], covF);
+        cm = (-lamS[d] + etau * (c[d] + es[d] * Tdd) - etau * covG - etau * covF) / ct;
+        tn_moments(cm, ct, en, vn);
+      }
+      if (mode >= 0) {
+        out_tau[0] = ct; out_mu[0] = cm;
+        bc[0] = 0.0;
+      } else {
+        acc_q += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951)) + 0.5 * ct * (vn + (en - cm) * (en - cm));
+        acc_prior += lamS[d] * en;
+        bc[0] = en - es[d];
+        if (mode == -1) { Smu[d] = cm; Stau[d] = ct; Svar[d] = vn; es[d] = en; }
+      }
+    }
+    __syncthreads();
+    const double delta = bc[0];
+    if (delta != 0.0)
+      for (int d2 = threadIdx.x; d2 < KL; d2 += blockDim.x) {
+        const int k2 = d2 / L, l2 = d2 - k2 * L;
+        c[d2] = fma(-delta, tmat(TT, k, l, k2, l2, K, L, NPL), c[d2]);
+      }
+    __syncthreads();
+  }
+  if (mode == -1)
+    for (int d = threadIdx.x; d < KL; d += blockDim.x) Sexp[d] = es[d];
+  if (threadIdx.x == 0 && mode < 0) { misc[0] = acc_q; misc[1] = acc_prior; }
+}
+
+// third term of exp_square_diff (bnmtf_vb.py:323): sum_Omega VarF ((ES EG^T)^2 - ES^2 EG^2^T)
+//   = sum_j sum_k C_jk ((sum_l ES_kl EG_jl)^2 - sum_l ES_kl^2 EG_jl^2),  C = masked column sums of VarF.  One block.
+__global__ void nmtf_t3_kernel(const double* __restrict__ C, const double* __restrict__ EG, const double* __restrict__ ES, int64_t J,
+                               int K, int L, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double a = 0.0;
+  for (int64_t j = threadIdx.x; j < J; j += blockDim.x) {
+    for (int k = 0; k < K; ++k) {
+      double w = 0.0, w2 = 0.0;
+      for (int l = 0; l < L; ++l) {
+        const double t = ES[k * L + l] * EG[j * L + l];
+        w += t; w2 = fma(t, t, w2);
+      }
+      a = fma(C[j * K + k], w * w - w2, a);
+    }
+  }
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) out[0] = a;
+}
+
+// VB lambda updates of both ARD blocks (bnmtf_vb.py:207-213,326-334,383-391): block per column.
+// state[4][K+L]: alpha*, beta*, E[lambda], E[log lambda] (F columns first, then G columns).
+__global__ void nmtf_lambda_vb_kernel(const double* __restrict__ F, int64_t I, int K, const double* __restrict__ G, int64_t J, int L,
+                                      Hyper h, double* colsum, double* state, double* lamF, double* lamG, int update) {
+  __shared__ double sh[32];
+  const int c = blockIdx.x;
+  const bool isF = c < K;
+  const double* X = isF ? F : G;
+  const int64_t n = isF ? I : J;
+  const int kf = isF ? K : L, col = isF ? c : c - K;
+  double a = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a += X[i * kf + col];
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) {
+    colsum[c] = a;
+    if (h.ARD && update) {
+      const int KL = K + L;
+      const double alpha = h.alpha0 + (double)n, beta = h.beta0 + a;
+      state[0 * KL + c] = alpha; state[1 * KL + c] = beta;
+      state[2 * KL + c] = alpha / beta; state[3 * KL + c] = digamma(alpha) - log(beta);
+      (isF ? lamF : lamG)[col] = alpha / beta;
+    }
+  }
+}
+
+// update_tau / update_exp_tau / elbo of bnmtf_vb (bnmtf_vb.py:225-229,248-324).  Single block.
+// misc: [0] q-terms of S, [1] sum lambdaS*ES, [2] T3.
+__global__ void nmtf_vb_finalize_kernel(const double* __restrict__ rsF, int64_t nF, const double* __restrict__ rsG, int64_t nG, int K,
+                                        int L, Hyper h, double sumlog_lamS, const double* __restrict__ colsum,
+                                        const double* __restrict__ state, const double* __restrict__ misc, double* scal,
+                                        double* stats_out, int update, int64_t I, int64_t J) {
+  __shared__ double sh[32];
+  __shared__ double tot[2 * NRS];
+  for (int sidx = 0; sidx < 2; ++sidx) {
+    const double* rs = sidx == 0 ? rsF : rsG;
+    const int64_t n = sidx == 0 ? nF : nG;
+    for (int f = 0; f < NRS; ++f) {
+      double a = 0.0;
+      for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a += rs[i * NRS + f];
+      a = block_sum(a, sh);
+      if (threadIdx.x == 0) tot[sidx * NRS + f] = a;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double rss = tot[NRS + RS_RSS];
+  for (int i = 0; i < 16; ++i) stats_out[i] = 0.0;
+  stats_out[0] = rss; stats_out[1] = tot[NRS + RS_SUM_E]; stats_out[2] = tot[NRS + RS_SUM_RCE];
+  // exp_square_diff: residual + (second + fourth term, from the G sweep) + third term
+  const double esd = rss + tot[NRS + RS_ESDVAR] + misc[2];
+  const double alpha_s = h.alphatau + h.size_Omega / 2.0, beta_s = h.betatau + 0.5 * esd;
+  double tau = scal[SC_TAU], exp_logtau = scal[SC_LOGTAU], a_s = scal[SC_ALPHA_S], b_s = scal[SC_BETA_S];
+  if (update) {
+    a_s = alpha_s; b_s = beta_s; tau = a_s / b_s; exp_logtau = digamma(a_s) - log(b_s);
+    scal[SC_TAU] = tau; scal[SC_LOGTAU] = exp_logtau; scal[SC_ALPHA_S] = a_s; scal[SC_BETA_S] = b_s;
+  }
+  const double log2pi = 1.8378770664093454836;
+  double elbo = h.size_Omega / 2.0 * (exp_logtau - log2pi) - tau / 2.0 * esd;
+  if (h.ARD) {
+    const int KL = K + L;
+    for (int blk = 0; blk < 2; ++blk) {
+      const int c0 = blk == 0 ? 0 : K, c1 = blk == 0 ? K : K + L;
+      const double n = blk == 0 ? (double)I : (double)J;
+      double s_ll = 0.0, s_l = 0.0, s_logl = 0.0, s_lcol = 0.0, q = 0.0;
+      for (int c = c0; c < c1; ++c) {
+        const double al = state[0 * KL + c], be = state[1 * KL + c], el = state[2 * KL + c], ell = state[3 * KL + c];
+        s_ll += ell; s_l += el; s_logl += log(el); s_lcol += el * colsum[c];
+        q += -al * log(be) + lgamma(al) - (al - 1.0) * ell + be * el;
+      }
+      elbo += h.alpha0 * log(h.beta0) - lgamma(h.alpha0) + (h.alpha0 - 1.0) * s_ll - h.beta0 * s_l;
+      elbo += n * s_logl - s_lcol;
+      elbo += q;
+    }
+  } else {
+    elbo += h.sumlog_lamU - tot[RS_PRIOR] + h.sumlog_lamV - tot[NRS + RS_PRIOR];
+  }
+  elbo += sumlog_lamS - misc[1];
+  elbo += h.alphatau * log(h.betatau) - lgamma(h.alphatau) + (h.alphatau - 1.0) * exp_logtau - h.betatau * tau;
+  elbo += tot[RS_ELBOQ] + (double)I * K / 2.0 * log2pi + tot[NRS + RS_ELBOQ] + (double)J * L / 2.0 * log2pi
+          + misc[0] + (double)K * L / 2.0 * log2pi;
+  elbo += -a_s * log(b_s) + lgamma(a_s) - (a_s - 1.0) * exp_logtau + b_s * tau;
+  stats_out[3] = tau; stats_out[4] = beta_s; stats_out[5] = esd; stats_out[6] = elbo; stats_out[8] = exp_logtau;
+  stats_out[9] = alpha_s;
+}
+
 __global__ void init_vector_kernel(double* __restrict__ X, int64_t n, const double* __restrict__ lam, int random, uint64_t seed,
                                    uint32_t purpose) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

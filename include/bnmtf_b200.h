@@ -224,6 +224,22 @@ int bnmtf_nmtf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed,
                    double* all_F, double* all_S, double* all_G, double* all_lambdaFk, double* all_lambdaGl,
                    double* iter_stats, double* iter_seconds);
 
+/* BNMTF VB (code/models/bnmtf_vb.py).  State: set_factor/get_factor (fields VALUE=exp, VAR,
+ * MU, TAU of F and G), bnmtf_nmtf_set_S/get_S (same fields of S) and the scalars below:
+ * scal4 = {exp_tau, exp_logtau, alpha_s, beta_s}; stateF4K = alphaFk_s, betaFk_s, exp_lambdaFk,
+ * exp_loglambdaFk back to back (4 x K), stateG4L likewise (4 x L); both NULL when not ARD. */
+int bnmtf_nmtf_set_vb_scalars(bnmtf_nmf_t h, double exp_tau, double exp_logtau, double alpha_s, double beta_s,
+                              const double* stateF4K, const double* stateG4L);
+int bnmtf_nmtf_get_vb_scalars(bnmtf_nmf_t h, double* scal4, double* stateF4K, double* stateG4L);
+/* update_F(k) / update_G(l) / update_S(k,l) from the current state, nothing modified
+ * (bnmtf_vb.py:336-375): which 0 -> tau_F[:,k], mu_F[:,k] (I values); 1 -> tau_G[:,l], mu_G[:,l]
+ * (J values); 2 -> tau_S[k,l], mu_S[k,l] (one value each).  Single-GPU only. */
+int bnmtf_nmtf_vb_update_params(bnmtf_nmf_t h, int which, int k, int l, double* out_tau, double* out_mu);
+/* exp_square_diff() (:319-324), elbo() (:248-299) and the training-metric sums of the current state. */
+int bnmtf_nmtf_vb_stats(bnmtf_nmf_t h, double* out);
+/* run(iterations) (bnmtf_vb.py:193-245); read the final state back with the getters. */
+int bnmtf_nmtf_vb_run(bnmtf_nmf_t h, int iterations, double* iter_stats, double* iter_seconds);
+
 /* ------------------------------------------------------------------------- *
  * Distributions (code/models/distributions/*.py) on the device; n-element
  * host arrays in, host arrays out.  Draws use Philox4x32-10 keyed by `seed`.

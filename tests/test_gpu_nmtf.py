@@ -161,3 +161,72 @@ def test_gibbs_reproducible_and_converges():
     assert perf["MSE"] < 1.4 and perf["Rp"] > 0.9
     assert runs[0].all_S.shape == (300, K, L) and runs[0].all_lambdaGl.shape == (300, L)
     assert runs[0].quality("loglikelihood", 150, 2) < 0
+
+
+# ------------------------------------------------------------------ BNMTF VB
+VB_FIELDS = orc.VB_FIELDS
+VB_SCAL = orc.VB_SCAL
+VB_ARD = orc.VB_ARD
+
+
+def load_vb(g, p, ard):
+    from bnmtf_ard_b200 import bnmtf_vb
+    K, L = g[p + "exp_S0"].shape
+    m = bnmtf_vb(g[p + "R"], g[p + "M"], K, L, ard, hyper_of(g, p, ard))
+    m.verbose = False
+    for f in VB_FIELDS + (VB_ARD if ard else []):
+        setattr(m, f, g[p + f + "0"].copy())
+    for f in VB_SCAL:
+        setattr(m, f, float(g[p + f + "0"]))
+    return m
+
+
+@pytest.mark.parametrize("ard", [True, False])
+def test_vb_single_step_golden(gold, ard):
+    g, p = gold, "tv_%s_" % ("ard" if ard else "noard")
+    m = load_vb(g, p, ard)
+    close(m.exp_square_diff(), g[p + "esd0"], RTOL_STEP)
+    close(m.elbo(), g[p + "elbo0"], RTOL_STEP)
+    m.update_F(1); m.update_exp_F(1); m.update_S(2, 1); m.update_exp_S(2, 1); m.update_G(2); m.update_exp_G(2)
+    for X in ("F", "S", "G"):
+        close(getattr(m, "tau_" + X), g[p + "step_tau_" + X], RTOL_STEP)
+        mu_close(getattr(m, "mu_" + X), g[p + "step_mu_" + X], g[p + "step_tau_" + X], 1e-8)
+        close(getattr(m, "exp_" + X), g[p + "step_exp_" + X], 1e-7, 1e-300)
+        close(getattr(m, "var_" + X), g[p + "step_var_" + X], 1e-6, 1e-300)
+
+
+@pytest.mark.parametrize("ard", [True, False])
+def test_vb_trajectory_golden(gold, ard):
+    g, p = gold, "tv_%s_" % ("ard" if ard else "noard")
+    m = load_vb(g, p, ard)
+    its = int(g[p + "its"])
+    m.run(its)
+    ok = np.isfinite(g[p + "elbo"])
+    close(np.asarray(m.all_elbo)[ok], g[p + "elbo"][ok], RTOL_TRAJ)
+    assert np.array_equal(np.isfinite(m.all_elbo), ok)
+    close(m.all_exp_tau, g[p + "all_exp_tau"], RTOL_TRAJ)
+    close(m.all_performances["MSE"], g[p + "MSE"], RTOL_TRAJ)
+    for f in VB_FIELDS + VB_SCAL + (VB_ARD if ard else []):
+        close(getattr(m, f), g[p + f], 1e-5, 1e-9)
+    close(m.quality("ELBO"), g[p + "elbo"][-1], RTOL_TRAJ)
+
+
+@pytest.mark.parametrize("shape", [(150, 220, 5, 3, 0.5), (64, 3000, 4, 6, 0.6)])
+def test_vb_iterations_vs_oracle(shape):
+    from bnmtf_ard_b200 import bnmtf_vb
+    I, J, K, L, dens = shape
+    R, M, rng = make_problem(I * 13 + J, I, J, K, L, dens)
+    hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0, "lambdaS": 0.1}
+    v = bnmtf_vb(R, M, K, L, True, hyper); v.verbose = False
+    np.random.seed(2)
+    v.initialise("random", "random")
+    st = {f: getattr(v, f).copy() for f in VB_FIELDS + VB_ARD}
+    st.update({f: float(getattr(v, f)) for f in VB_SCAL})
+    lamS = 0.1 * np.ones((K, L))
+    close(v.elbo(), orc.vb_elbo(R, M, st, hyper, True, lamS), 1e-8)
+    v.run(3)
+    for _ in range(3):
+        orc.vb_iteration(R, M, st, hyper, True, lamS)
+    close(v.exp_F, st["exp_F"], 1e-6, 1e-10); close(v.exp_S, st["exp_S"], 1e-6, 1e-10); close(v.exp_G, st["exp_G"], 1e-6, 1e-10)
+    close(v.exp_tau, st["exp_tau"], RTOL_TRAJ)
+    close(v.all_elbo[-1], orc.vb_elbo(R, M, st, hyper, True, lamS), RTOL_TRAJ)
