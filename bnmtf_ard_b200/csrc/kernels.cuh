@@ -508,7 +508,7 @@ __global__ void lambda_kernel(const double* __restrict__ Ukm, int64_t ldu, int64
 // stats_out[BNMTF_NSTATS] layout: see include/bnmtf_b200.h.
 // -----------------------------------------------------------------------------
 template <int MODE>
-__global__ void finalize_kernel(const double* __restrict__ rsU, int64_t nU, const double* __restrict__ rsV, int64_t nV,
+__global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ rsU, int64_t nU, const double* __restrict__ rsV, int64_t nV,
                                 int K, Hyper h, const double* __restrict__ colsum, const double* __restrict__ lamstate,
                                 double* scal, double* stats_out, uint64_t seed, uint32_t iteration, int update,
                                 int64_t I, int64_t J) {

@@ -111,7 +111,7 @@ __global__ void nmtf_reduce_T_kernel(const double* __restrict__ F, const double*
 //   Gibbs: S_kl ~ TN(muS, tauS)  bnmtf_gibbs.py:200-203      ICM: max(max(0,mu),0.1)  nmtf_icm.py:203-207
 // single_d >= 0: only report (tau, mu) of entry d from the current state.
 template <int MODE>
-__global__ void nmtf_s_sweep_kernel(const double* __restrict__ c_in, const double* __restrict__ TT, int K, int L, double* S,
+__global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restrict__ c_in, const double* __restrict__ TT, int K, int L, double* S,
                                     const double* __restrict__ lamS, const double* __restrict__ scal, uint64_t seed,
                                     uint32_t iteration, double* mu_out, double* tau_out, int single_d) {
   extern __shared__ double shs[];
@@ -235,7 +235,7 @@ __device__ __forceinline__ double tmat(const double* TT, int k, int l, int k2, i
 //   covG = sum_{k'!=k} ES(k',l) PA[pair(k,k')][l],  covF = sum_{l'!=l} ES(k,l') QC[pair(l,l')][k]
 // mode: -1 full sweep, -2 dry (ELBO terms of the stored state), d >= 0 report (tau, mu) of entry d.
 // misc[0] = sum_d q-terms of S for the ELBO (bnmtf_vb.py:290-292), misc[1] = sum lambdaS*ES (:268).
-__global__ void nmtf_s_sweep_vb_kernel(const double* __restrict__ c_in, const double* __restrict__ TT, const double* __restrict__ BS,
+__global__ void __launch_bounds__(512) nmtf_s_sweep_vb_kernel(const double* __restrict__ c_in, const double* __restrict__ TT, const double* __restrict__ BS,
                                        const double* __restrict__ PA, const double* __restrict__ QC, int K, int L, double* Sexp,
                                        double* Svar, double* Smu, double* Stau, const double* __restrict__ lamS,
                                        const double* __restrict__ scal, int mode, double* out_tau, double* out_mu, double* misc) {
@@ -292,7 +292,7 @@ __global__ void nmtf_s_sweep_vb_kernel(const double* __restrict__ c_in, const do
 
 // third term of exp_square_diff (bnmtf_vb.py:323): sum_Omega VarF ((ES EG^T)^2 - ES^2 EG^2^T)
 //   = sum_j sum_k C_jk ((sum_l ES_kl EG_jl)^2 - sum_l ES_kl^2 EG_jl^2),  C = masked column sums of VarF.  One block.
-__global__ void nmtf_t3_kernel(const double* __restrict__ C, const double* __restrict__ EG, const double* __restrict__ ES, int64_t J,
+__global__ void __launch_bounds__(1024) nmtf_t3_kernel(const double* __restrict__ C, const double* __restrict__ EG, const double* __restrict__ ES, int64_t J,
                                int K, int L, double* __restrict__ out) {
   __shared__ double sh[32];
   double a = 0.0;
@@ -337,7 +337,7 @@ __global__ void nmtf_lambda_vb_kernel(const double* __restrict__ F, int64_t I, i
 
 // update_tau / update_exp_tau / elbo of bnmtf_vb (bnmtf_vb.py:225-229,248-324).  Single block.
 // misc: [0] q-terms of S, [1] sum lambdaS*ES, [2] T3.
-__global__ void nmtf_vb_finalize_kernel(const double* __restrict__ rsF, int64_t nF, const double* __restrict__ rsG, int64_t nG, int K,
+__global__ void __launch_bounds__(1024) nmtf_vb_finalize_kernel(const double* __restrict__ rsF, int64_t nF, const double* __restrict__ rsG, int64_t nG, int K,
                                         int L, Hyper h, double sumlog_lamS, const double* __restrict__ colsum,
                                         const double* __restrict__ state, const double* __restrict__ misc, double* scal,
                                         double* stats_out, int update, int64_t I, int64_t J) {
