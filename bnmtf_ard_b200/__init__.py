@@ -11,5 +11,6 @@ from .nmf_np import nmf_np  # noqa: F401
 from .bnmtf_gibbs import bnmtf_gibbs  # noqa: F401
 from .nmtf_icm import nmtf_icm  # noqa: F401
 from .bnmtf_vb import bnmtf_vb  # noqa: F401
+from .nmtf_np import nmtf_np  # noqa: F401
 
-__all__ = ["bnmf_gibbs", "bnmf_vb", "nmf_icm", "nmf_np", "bnmtf_gibbs", "nmtf_icm", "bnmtf_vb"]
+__all__ = ["bnmf_gibbs", "bnmf_vb", "nmf_icm", "nmf_np", "bnmtf_gibbs", "nmtf_icm", "bnmtf_vb", "nmtf_np"]

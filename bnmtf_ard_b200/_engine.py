@@ -284,3 +284,15 @@ class NMTFEngine(NMFEngine):
         res = {"stats": np.zeros((it, NSTATS)), "seconds": np.zeros(it)}
         check(self.lib.bnmtf_nmtf_vb_run(self.h, it, dptr(res["stats"]), dptr(res["seconds"])))
         return res
+
+    # -- NP (nmtf_np) ----------------------------------------------------------------
+    def np_update(self, which, k=0, l=0):
+        out = np.empty((self.I, self.J, 1)[which])
+        check(self.lib.bnmtf_nmtf_np_update(self.h, which, int(k), int(l), dptr(out)))
+        return out
+
+    def np_run(self, iterations):
+        it = int(iterations)
+        res = {"stats": np.zeros((it, NSTATS)), "seconds": np.zeros(it)}
+        check(self.lib.bnmtf_nmtf_np_run(self.h, it, dptr(res["stats"]), dptr(res["seconds"])))
+        return res

@@ -69,6 +69,8 @@ SIGNATURES = {
     "bnmtf_nmtf_vb_update_params": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "bnmtf_nmtf_vb_stats": (C.c_int, [_h, _dp]),
     "bnmtf_nmtf_vb_run": (C.c_int, [_h, C.c_int, _dp, _dp]),
+    "bnmtf_nmtf_np_update": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, _dp]),
+    "bnmtf_nmtf_np_run": (C.c_int, [_h, C.c_int, _dp, _dp]),
     "bnmtf_tn_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),
     "bnmtf_tn_moments": (C.c_int, [C.c_int, C.c_int64, _dp, _dp, _dp, _dp]),
     "bnmtf_gamma_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),

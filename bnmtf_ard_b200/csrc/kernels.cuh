@@ -258,6 +258,10 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
           if (MODE == M_VB) {
             const double2 yy = __ldg(reinterpret_cast<const double2*>(y2 + c[n]));
             s[0] = fma(yy.x, yy.x, s[0]); s[1] += yy.y; s[2] = fma(e[n], yy.x, s[2]);
+          } else if (MODE == M_NP) {   // numerator / denominator row parts of nmtf_np.update_S (nmtf_np.py:181-188)
+            const double g = __ldg(y2 + c[n]);
+            const double ratio = (c[n] != p.padcol) ? q[n] / e[n] : 0.0;
+            s[2] = fma(ratio, g, s[2]); s[1] += g;
           } else {
             s[2] = fma(e[n], __ldg(y2 + c[n]), s[2]);
           }

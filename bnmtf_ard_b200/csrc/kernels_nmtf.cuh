@@ -395,6 +395,24 @@ __global__ void __launch_bounds__(1024) nmtf_vb_finalize_kernel(const double* __
   stats_out[9] = alpha_s;
 }
 
+// nmtf_np.update_S(k,l) (nmtf_np.py:181-188): S_kl <- S_kl * sum_i F_ik num_i / sum_i F_ik den_i with the row parts
+// num_i = sum_j M_ij R_ij/Rhat_ij G_jl, den_i = sum_j M_ij G_jl.  One block; writes S_kl (and the new value to out).
+__global__ void nmtf_np_s_update_kernel(const double* __restrict__ F, const double* __restrict__ num, const double* __restrict__ den,
+                                        int64_t I, int K, int k, double* S_kl, double* out, int apply) {
+  __shared__ double sh[32];
+  double a = 0.0, b = 0.0;
+  for (int64_t i = threadIdx.x; i < I; i += blockDim.x) {
+    const double f = F[i * K + k];
+    a = fma(f, num[i], a); b = fma(f, den[i], b);
+  }
+  a = block_sum(a, sh); b = block_sum(b, sh);
+  if (threadIdx.x == 0) {
+    const double v = S_kl[0] * a / b;
+    if (out) out[0] = v;
+    if (apply) S_kl[0] = v;
+  }
+}
+
 __global__ void init_vector_kernel(double* __restrict__ X, int64_t n, const double* __restrict__ lam, int random, uint64_t seed,
                                    uint32_t purpose) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

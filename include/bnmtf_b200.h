@@ -190,7 +190,8 @@ int bnmtf_nmf_sweep_times(bnmtf_nmf_t h, double* out4);
  * The handle type is shared with the NMF family: side BNMTF_SIDE_U is F (I x K),
  * side BNMTF_SIDE_V is G (J x L); layout_stats / pack / data_stats / set_comm /
  * set_factor / get_factor / destroy / launch_count / layout_info apply unchanged.
- * Methods available: BNMTF_GIBBS (bnmtf_gibbs.py) and BNMTF_ICM (nmtf_icm.py).
+ * bnmtf_nmtf_run / column_params serve BNMTF_GIBBS (bnmtf_gibbs.py) and BNMTF_ICM (nmtf_icm.py);
+ * the VB and NP variants have their own entry points below.
  * ------------------------------------------------------------------------- */
 int bnmtf_nmtf_create(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, int L,
                       const double* R, const uint8_t* M,
@@ -239,6 +240,13 @@ int bnmtf_nmtf_vb_update_params(bnmtf_nmf_t h, int which, int k, int l, double* 
 int bnmtf_nmtf_vb_stats(bnmtf_nmf_t h, double* out);
 /* run(iterations) (bnmtf_vb.py:193-245); read the final state back with the getters. */
 int bnmtf_nmtf_vb_run(bnmtf_nmf_t h, int iterations, double* iter_stats, double* iter_seconds);
+
+/* NMTF NP (code/models/nmtf_np.py): single multiplicative updates from the current state, nothing
+ * modified (nmtf_np.py:165-188): which 0 -> new F[:,k] (I values), 1 -> new G[:,l] (J values),
+ * 2 -> new S[k,l] (one value); and run(iterations) (:139-160).  bnmtf_nmtf_stats(h, BNMTF_NP, out)
+ * gives compute_I_div() and the metric sums. */
+int bnmtf_nmtf_np_update(bnmtf_nmf_t h, int which, int k, int l, double* out);
+int bnmtf_nmtf_np_run(bnmtf_nmf_t h, int iterations, double* iter_stats, double* iter_seconds);
 
 /* ------------------------------------------------------------------------- *
  * Distributions (code/models/distributions/*.py) on the device; n-element

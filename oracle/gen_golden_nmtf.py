@@ -117,6 +117,24 @@ def gen_vb_run(ref, out):
                     p + "hyper": np.array([hyper[k] for k in ("alphatau", "betatau", "alpha0", "beta0")])})
 
 
+def gen_np_run(ref, out):
+    rng = np.random.default_rng(1010)
+    I, J, K, L, its = 23, 27, 3, 4, 7
+    R, M = make_problem(rng, I, J, max(K, L), 0.6, nonneg=True)
+    m = ref.nmtf_np(R, M, K, L)
+    np.random.seed(5)
+    m.initialise("random", "random")
+    F0, S0, G0 = m.F.copy(), m.S.copy(), m.G.copy()
+    m1 = ref.nmtf_np(R, M, K, L)
+    m1.F, m1.S, m1.G = F0.copy(), S0.copy(), G0.copy()
+    m1.update_F(1); m1.update_S(2, 1); m1.update_G(3)
+    quiet(m.run, its)
+    out.update({"tn_R": R, "tn_M": M, "tn_F0": F0, "tn_S0": S0, "tn_G0": G0, "tn_its": its,
+                "tn_F": m.F, "tn_S": m.S, "tn_G": m.G, "tn_step_F": m1.F, "tn_step_S": m1.S, "tn_step_G": m1.G,
+                "tn_idiv": m.compute_I_div(), "tn_MSE": np.array(m.all_performances["MSE"]),
+                "tn_Rp": np.array(m.all_performances["Rp"])})
+
+
 def main():
     ref = refimport.load()
     if ref is None:
@@ -125,6 +143,7 @@ def main():
     gen_params(ref, out)
     gen_icm_run(ref, out)
     gen_vb_run(ref, out)
+    gen_np_run(ref, out)
     path = os.path.join(OUT, "nmtf_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote %s (%d arrays, %.1f KB)" % (path, len(out), os.path.getsize(path) / 1024.0))

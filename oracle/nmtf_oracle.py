@@ -249,3 +249,34 @@ def vb_elbo(R, M, st, hyper, ARD, lamS, lamF=None, lamG=None):
     total += (-st["alpha_s"] * math.log(st["beta_s"]) + gammaln(st["alpha_s"])
               - (st["alpha_s"] - 1.0) * st["exp_logtau"] + st["beta_s"] * st["exp_tau"])
     return float(total)
+
+
+# --------------------------------------------------------------------------- #
+# NMTF NP (code/models/nmtf_np.py:139-195)                                    #
+# --------------------------------------------------------------------------- #
+def np_iteration(R, M, F, S, G):
+    """One iteration of nmtf_np.run: update_F(k) for all k, update_S(k,l) for all (k,l),
+    update_G(l) for all l, each with R_pred recomputed (nmtf_np.py:148-155,173-195)."""
+    K, L = S.shape
+    with np.errstate(all="ignore"):
+        for k in range(K):
+            P = F @ S @ G.T
+            SG = S[k] @ G.T
+            F[:, k] = F[:, k] * (M * R / P * SG).sum(axis=1) / (M * SG).sum(axis=1)
+        for k in range(K):
+            for l in range(L):
+                P = F @ S @ G.T
+                FG = M * np.outer(F[:, k], G[:, l])
+                S[k, l] = S[k, l] * (R * FG / P).sum() / FG.sum()
+        for l in range(L):
+            P = F @ S @ G.T
+            FS = F @ S[:, l]
+            G[:, l] = G[:, l] * ((M * R / P).T * FS).T.sum(axis=0) / (M.T * FS).T.sum(axis=0)
+
+
+def np_i_div(R, M, F, S, G):
+    """nmtf_np.py:222-225."""
+    Rx = np.where(M != 0, R, 1.0)
+    P = F @ S @ G.T
+    with np.errstate(all="ignore"):
+        return float((M * (Rx * np.log(Rx / P) - Rx + P)).sum())

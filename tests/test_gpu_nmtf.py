@@ -230,3 +230,36 @@ def test_vb_iterations_vs_oracle(shape):
     close(v.exp_F, st["exp_F"], 1e-6, 1e-10); close(v.exp_S, st["exp_S"], 1e-6, 1e-10); close(v.exp_G, st["exp_G"], 1e-6, 1e-10)
     close(v.exp_tau, st["exp_tau"], RTOL_TRAJ)
     close(v.all_elbo[-1], orc.vb_elbo(R, M, st, hyper, True, lamS), RTOL_TRAJ)
+
+
+# ------------------------------------------------------------------ NMTF NP
+def test_np_golden(gold):
+    from bnmtf_ard_b200 import nmtf_np
+    g = gold
+    K, L = g["tn_S0"].shape
+    m = nmtf_np(g["tn_R"], g["tn_M"], K, L)
+    m.verbose = False
+    m.F, m.S, m.G = g["tn_F0"].copy(), g["tn_S0"].copy(), g["tn_G0"].copy()
+    m.update_F(1); m.update_S(2, 1); m.update_G(3)
+    close(m.F, g["tn_step_F"], RTOL_STEP); close(m.S, g["tn_step_S"], RTOL_STEP); close(m.G, g["tn_step_G"], RTOL_STEP)
+    m.F, m.S, m.G = g["tn_F0"].copy(), g["tn_S0"].copy(), g["tn_G0"].copy()
+    m.run(int(g["tn_its"]))
+    close(m.F, g["tn_F"], RTOL_TRAJ); close(m.S, g["tn_S"], RTOL_TRAJ); close(m.G, g["tn_G"], RTOL_TRAJ)
+    close(m.compute_I_div(), g["tn_idiv"], RTOL_TRAJ); close(m.all_i_div[-1], g["tn_idiv"], RTOL_TRAJ)
+    close(m.all_performances["MSE"], g["tn_MSE"], RTOL_TRAJ); close(m.all_performances["Rp"], g["tn_Rp"], RTOL_TRAJ)
+
+
+def test_np_iterations_vs_oracle():
+    from bnmtf_ard_b200 import nmtf_np
+    I, J, K, L = 120, 2600, 3, 4
+    R, M, rng = make_problem(77, I, J, K, L, 0.5)
+    R = np.abs(R) + 0.05
+    F0, S0, G0 = rng.random((I, K)) + 0.1, rng.random((K, L)) + 0.1, rng.random((J, L)) + 0.1
+    m = nmtf_np(R, M, K, L); m.verbose = False
+    m.F, m.S, m.G = F0.copy(), S0.copy(), G0.copy()
+    m.run(2)
+    F, S, G = F0.copy(), S0.copy(), G0.copy()
+    for _ in range(2):
+        orc.np_iteration(R, M, F, S, G)
+    close(m.F, F, RTOL_TRAJ); close(m.S, S, RTOL_TRAJ); close(m.G, G, RTOL_TRAJ)
+    close(m.all_i_div[-1], orc.np_i_div(R, M, F, S, G), RTOL_TRAJ)

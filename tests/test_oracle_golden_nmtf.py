@@ -75,3 +75,13 @@ def test_vb_trajectory_and_steps(gold, ard):
         close(st["exp_tau"], g[p + "all_exp_tau"][it], 1e-8)
     for f in fields:
         close(st[f], g[p + f], 1e-7, 1e-12)
+
+
+def test_np_trajectory(gold):
+    g = gold
+    R, M = g["tn_R"], g["tn_M"]
+    F, S, G = g["tn_F0"].copy(), g["tn_S0"].copy(), g["tn_G0"].copy()
+    for _ in range(int(g["tn_its"])):
+        orc.np_iteration(R, M, F, S, G)
+    close(F, g["tn_F"], 1e-8); close(S, g["tn_S"], 1e-8); close(G, g["tn_G"], 1e-8)
+    close(orc.np_i_div(R, M, F, S, G), g["tn_idiv"], 1e-8)
