@@ -128,3 +128,71 @@ def test_host_metrics_and_predict(golden):
     with pytest.raises(AssertionError) as error:
         m.quality('FAIL', 2, 3)
     assert str(error.value) == "Unrecognised metric for model quality: FAIL."
+
+
+@pytest.mark.parametrize("clsname", ["bnmtf_gibbs", "nmtf_icm", "bnmtf_vb"])
+def test_nmtf_constructor_messages(clsname):
+    """tests/code/test_bnmtf_gibbs.py:14-120 (same blocks in test_nmtf_icm.py / test_bnmtf_vb.py)."""
+    import bnmtf_ard_b200 as pkg
+    cls = getattr(pkg, clsname)
+    M = np.ones((2, 3))
+    I, J, K, L = 5, 3, 1, 2
+    lambdaF, lambdaS, lambdaG = np.ones((I, K)), np.ones((K, L)), np.ones((J, L))
+    hp = {'alphatau': 3, 'betatau': 1, 'alpha0': 6, 'beta0': 2, 'lambdaS': lambdaS}
+    with pytest.raises(AssertionError) as error:
+        cls(np.ones(3), M, K, L, True, hp)
+    assert str(error.value) == "Input matrix R is not a two-dimensional array, but instead 1-dimensional."
+    with pytest.raises(AssertionError) as error:
+        cls(np.ones((3, 2)), M, K, L, True, hp)
+    assert str(error.value) == "Input matrix R is not of the same size as the indicator matrix M: (3, 2) and (2, 3) respectively."
+    R4 = np.ones((2, 3))
+    base = {'alphatau': 3, 'betatau': 1}
+    with pytest.raises(AssertionError) as error:
+        cls(R4, M, K, L, False, dict(base, lambdaF=np.ones((3, 1)), lambdaS=lambdaS, lambdaG=lambdaG))
+    assert str(error.value) == "Prior matrix lambdaF has the wrong shape: (3, 1) instead of (2, 1)."
+    with pytest.raises(AssertionError) as error:
+        cls(R4, M, K, L, False, dict(base, lambdaF=np.ones((2, 1)), lambdaS=np.ones((2, 2)), lambdaG=lambdaG))
+    assert str(error.value) == "Prior matrix lambdaS has the wrong shape: (2, 2) instead of (1, 2)."
+    with pytest.raises(AssertionError) as error:
+        cls(R4, M, K, L, False, dict(base, lambdaF=np.ones((2, 1)), lambdaS=lambdaS, lambdaG=np.ones((4, 2))))
+    assert str(error.value) == "Prior matrix lambdaG has the wrong shape: (4, 2) instead of (3, 2)."
+    with pytest.raises(AssertionError) as error:
+        cls(R4, [[1, 1, 1], [0, 0, 0]], K, L, True, hp)
+    assert str(error.value) == "Fully unobserved row in R, row 1."
+    with pytest.raises(AssertionError) as error:
+        cls(R4, [[1, 1, 0], [1, 0, 0]], K, L, True, hp)
+    assert str(error.value) == "Fully unobserved column in R, column 2."
+    m = cls(np.ones((3, 2)), np.ones((3, 2)), 2, 3, False, dict(base, lambdaF=2., lambdaS=4., lambdaG=3.))
+    assert (m.I, m.J, m.K, m.L, m.size_Omega) == (3, 2, 2, 3, 6)
+    assert np.array_equal(m.lambdaF, 2. * np.ones((3, 2))) and np.array_equal(m.lambdaS, 4. * np.ones((2, 3)))
+    assert np.array_equal(m.lambdaG, 3. * np.ones((2, 3)))
+    with pytest.raises(AssertionError) as error:
+        m.initialise('FAIL', 'exp')
+    assert str(error.value) == "Unknown initialisation option for F and G: FAIL. Should be in ['kmeans', 'random', 'exp']."
+    with pytest.raises(AssertionError) as error:
+        m.initialise('exp', 'FAIL')
+    assert str(error.value) == "Unknown initialisation option for S: FAIL. Should be in ['random', 'exp']."
+    with pytest.raises(NotImplementedError):
+        m.initialise('kmeans', 'exp')
+    assert m.number_parameters() == 3 * 2 + 2 * 3 + 2 * 3 + 1
+
+
+def test_nmtf_np_constructor_and_guards():
+    from bnmtf_ard_b200 import nmtf_np
+    with pytest.raises(AssertionError) as error:
+        nmtf_np(np.ones((2, 3)), [[1, 1, 1], [0, 0, 0]], 1, 2)
+    assert str(error.value) == "Fully unobserved row in R, row 1."
+    m = nmtf_np(np.array([[1., 2.], [3., 4.]]), np.array([[1, 0], [1, 1]]), 2, 1)
+    assert np.array_equal(m.R_excl_unknown, [[1., 1.], [3., 4.]])
+    with pytest.raises(AssertionError) as error:
+        m.initialise('FAIL', 'ones')
+    assert str(error.value) == "Unrecognised init option for F,G: FAIL. Should be one in ['kmeans', 'ones', 'random', 'exponential']."
+    with pytest.raises(AssertionError) as error:
+        m.initialise('ones', 'FAIL')
+    assert str(error.value) == "Unrecognised init option for S: FAIL. Should be one in ['ones', 'random', 'exponential']."
+    with pytest.raises(AssertionError) as error:
+        m.run(1)
+    assert str(error.value) == "F, S and G have not been initialised - please run NMTF.initialise() first."
+    m.initialise('ones', 'ones')
+    assert m.F.shape == (2, 2) and m.S.shape == (2, 1) and m.G.shape == (2, 1)
+    np.testing.assert_array_equal(m.triple_dot(m.F, m.S, m.G.T), 2. * np.ones((2, 2)))
