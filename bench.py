@@ -293,7 +293,7 @@ def main():
     # to host numpy arrays -- exactly what bnmf_gibbs.run() of this package does.
     e2e = None
     if not args.no_e2e:
-        e2e_steps = max(3, min(args.steps, 20))
+        e2e_steps = max(3, min(args.steps, 100))
         U_h = eng.get_factor(_lib.SIDE_U, _lib.F_VALUE)
         V_h = eng.get_factor(_lib.SIDE_V, _lib.F_VALUE)
         barrier()

@@ -43,36 +43,69 @@ __host__ __device__ __forceinline__ int pair_index(int a, int b, int L) {   // a
   return a * L - (a * (a - 1)) / 2 + (b - a);
 }
 
-// H_i[pair(l,l')] = sum_{j in Omega_i} G_jl G_jl'   -- one warp per row of the row layout
-template <int PMAX>
-__global__ void nmtf_gram_kernel(const uint32_t* __restrict__ cols, const int64_t* __restrict__ rowstart, int n_loc, int64_t row0,
-                                 uint32_t padcol, const double* __restrict__ G_rm, int L, double* __restrict__ Hrow, int NP) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+// H_i[pair(l,l')] = sum_{j in Omega_i} G_jl G_jl'   -- one warp per row of the row layout.
+// The G rows of 32 consecutive observed entries are staged in shared memory (one coalesced
+// 8*L-byte load each); lane (bi,bj) accumulates the 4x4 block of H_i from two 32-byte shared
+// loads per entry (16 FMAs per 4 loads).  NB = ceil(L/4) blocks per dimension, NB*NB <= 64.
+template <int NBLK>   // blocks handled per lane: 1 (L <= 20) or 2 (L <= 32)
+__global__ void __launch_bounds__(128) nmtf_gram_kernel(const uint32_t* __restrict__ cols, const int64_t* __restrict__ rowstart,
+                                                         int n_loc, int64_t row0, uint32_t padcol, const double* __restrict__ G_rm,
+                                                         int L, double* __restrict__ Hrow, int NP) {
+  constexpr int LP = 36;                       // padded row length in shared memory (>= 32, breaks bank alignment)
+  __shared__ __align__(32) double tile[4][32][LP];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + w;
   if (row >= n_loc) return;
-  int pa[PMAX], pb[PMAX];
-  double acc[PMAX];
+  const int NB = (L + 3) / 4;
+  int bi[NBLK], bj[NBLK];
+  double acc[NBLK][4][4];
 #pragma unroll
-  for (int t = 0; t < PMAX; ++t) {
-    const int p = lane + 32 * t;
-    pa[t] = 0; pb[t] = 0; acc[t] = 0.0;
-    if (p < NP) pair_decode(p, L, pa[t], pb[t]);
+  for (int b = 0; b < NBLK; ++b) {
+    const int id = lane + 32 * b;
+    bi[b] = id / NB; bj[b] = id - bi[b] * NB;
+    if (bi[b] >= NB || bi[b] > bj[b]) { bi[b] = -1; bj[b] = 0; }   // lower-triangle blocks are not needed
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) acc[b][x][y] = 0.0;
   }
+  // zero the padding columns once (entries beyond L stay 0 so that partial blocks add nothing)
+  for (int r = 0; r < 32; ++r)
+    for (int q = L + lane; q < LP; q += 32) tile[w][r][q] = 0.0;
   const int64_t beg = rowstart[row], end = rowstart[row + 1];
   for (int64_t q0 = beg; q0 < end; q0 += 32) {
     const uint32_t mycol = (q0 + lane < end) ? cols[q0 + lane] : padcol;
-    for (int s = 0; s < 32; ++s) {
-      const uint32_t j = __shfl_sync(0xffffffffu, mycol, s);
-      if (j == padcol) continue;
-      const double* __restrict__ g = G_rm + (size_t)j * L;
+    __syncwarp();
+    for (int r = 0; r < 32; ++r) {
+      const uint32_t j = __shfl_sync(0xffffffffu, mycol, r);
+      if (lane < L) tile[w][r][lane] = (j == padcol) ? 0.0 : __ldg(G_rm + (size_t)j * L + lane);
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
 #pragma unroll
-      for (int t = 0; t < PMAX; ++t) acc[t] = fma(__ldg(g + pa[t]), __ldg(g + pb[t]), acc[t]);
+      for (int b = 0; b < NBLK; ++b) {
+        if (bi[b] < 0) continue;
+        const double4 a = *reinterpret_cast<const double4*>(&tile[w][r][4 * bi[b]]);
+        const double4 c = *reinterpret_cast<const double4*>(&tile[w][r][4 * bj[b]]);
+        const double av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) acc[b][x][y] = fma(av[x], cv[y], acc[b][x][y]);
+      }
     }
   }
 #pragma unroll
-  for (int t = 0; t < PMAX; ++t) {
-    const int p = lane + 32 * t;
-    if (p < NP) Hrow[(size_t)(row0 + row) * NP + p] = acc[t];
+  for (int b = 0; b < NBLK; ++b) {
+    if (bi[b] < 0) continue;
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) {
+        const int a = 4 * bi[b] + x, c = 4 * bj[b] + y;
+        if (a <= c && c < L) Hrow[(size_t)(row0 + row) * NP + pair_index(a, c, L)] = acc[b][x][y];
+      }
   }
 }
 

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Timing of the other BASELINE.json configurations (the bench.py line is configs[2]):
+  C1  BNMF Gibbs+ARD, toy-shaped 100 x 80, K=10, all observed
+  C2  BNMF VB+ARD, GDSC-shaped 707 x 139, 81 % observed, K=20
+  C4  BNMTF Gibbs and VB, 10000 x 8000, 30 % observed, K=L=20
+Synthetic data of each shape; iterations/s from CUDA events inside the engine.
+Usage: python tools/bench_configs.py [--out profiles/rNN_configs.json]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+
+def synth(I, J, K, L, density, device, seed=7):
+    import torch
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    ex = lambda *s: -torch.log(1.0 - torch.rand(*s, generator=g, device=device, dtype=torch.float64))  # noqa: E731
+    if L is None:
+        R = ex(I, K) @ ex(J, K).T
+    else:
+        R = ex(I, K) @ ex(K, L) @ ex(J, L).T
+    R += torch.randn(I, J, generator=g, device=device, dtype=torch.float64)
+    M = (torch.rand(I, J, generator=g, device=device) < density).to(torch.uint8)
+    M[torch.arange(I, device=device), torch.randint(0, J, (I,), generator=g, device=device)] = 1
+    M[torch.randint(0, I, (J,), generator=g, device=device), torch.arange(J, device=device)] = 1
+    return R.contiguous(), M.contiguous()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default="", help="substring filter on the configuration name (C1, C2, C4)")
+    ap.add_argument("--its", type=int, default=0, help="override the iteration counts (profiling)")
+    args = ap.parse_args()
+    import torch
+    from bnmtf_ard_b200 import _lib
+    from bnmtf_ard_b200._engine import NMFEngine, NMTFEngine
+    from bnmtf_ard_b200._lib import F_MU, F_TAU, F_VALUE, F_VAR, SIDE_U, SIDE_V
+    dev = torch.device("cuda", 0)
+    out = {}
+
+    def nmf_engine(I, J, K, dens):
+        R, M = synth(I, J, K, None, dens, dev)
+        e = NMFEngine.from_device_blocks(I, J, K, R.data_ptr(), M.data_ptr(), R.data_ptr(), M.data_ptr(), device=0)
+        e.set_hyper(True, 1., 1., 1., 1.)
+        return e
+
+    def record(name, seconds, its, extra=None):
+        s = float(seconds[-1] - seconds[max(0, len(seconds) - its - 1)]) if len(seconds) > its else float(seconds[-1])
+        d = {"iterations_per_s": its / s, "ms_per_iteration": 1e3 * s / its, "timed_iterations": its}
+        d.update(extra or {})
+        out[name] = d
+        print(name, json.dumps(d))
+
+    want = lambda tag: (not args.only) or (tag in args.only)  # noqa: E731
+    n = lambda default: args.its if args.its > 0 else default  # noqa: E731
+    if want("C1"):   # toy-shaped BNMF Gibbs + ARD
+        e = nmf_engine(100, 80, 10, 1.1)
+        e.set_scalars(1.0, np.ones(10)); e.init_factors(_lib.GIBBS, True, 1)
+        r = e.run(_lib.GIBBS, n(1000) + 100, seed=3, traces=True)
+        record("C1 BNMF Gibbs+ARD 100x80 K=10", r["seconds"], n(1000), {"reference_published_it_per_s": 21.1, "train_mse_last": e.performances(r["stats"][-1])["MSE"]})
+        e.close()
+    if want("C2"):   # GDSC-shaped BNMF VB + ARD
+        I, J, K = 707, 139, 20
+        e = nmf_engine(I, J, K, 0.81)
+        e.set_scalars(0.0, np.ones(K)); e.init_factors(_lib.VB, True, 2)
+        e.set_vb_scalars(1.0, 0.0, 1.0, 1.0, np.ones(K), np.ones(K), np.ones(K), np.zeros(K))
+        r = e.run(_lib.VB, n(200) + 20, seed=0, traces=False)
+        record("C2 BNMF VB+ARD 707x139 K=20", r["seconds"], n(200), {"reference_published_it_per_s": 7.65, "elbo_last": float(r["stats"][-1, _lib.ST_ELBO])})
+        e.close()
+    if want("C4"):   # BNMTF Gibbs and VB
+        I, J, K, L = 10000, 8000, 20, 20
+        R, M = synth(I, J, K, L, 0.3, dev)
+        e = NMTFEngine.from_device_blocks(I, J, K, R.data_ptr(), M.data_ptr(), R.data_ptr(), M.data_ptr(), device=0, L=L)
+        del R, M
+        torch.cuda.empty_cache()
+        lamS = 0.1 * np.ones((K, L))
+        e.set_hyper(True, 1., 1., 1., 1., None, None, lamS)
+        if want("gibbs") or args.only in ("", "C4"):
+            e.set_scalars(1.0, np.ones(K), np.ones(L))
+            e.init(_lib.GIBBS, True, True, 5, 6)
+            r = e.run(_lib.GIBBS, n(10) + 3, seed=4, traces=False)
+            record("C4 BNMTF Gibbs+ARD 10000x8000 K=L=20", r["seconds"], n(10), {"layout": e.layout_info(), "train_mse_last": e.performances(r["stats"][-1])["MSE"]})
+        if want("vb") or args.only in ("", "C4"):
+            e.set_scalars(1.0, np.ones(K), np.ones(L))
+            e.init(_lib.VB, True, True, 7, 8)
+            e.set_vb_scalars(1.0, 0.0, 1.0, 1.0, np.ones((4, K)), np.ones((4, L)))
+            r = e.vb_run(n(10) + 3)
+            record("C4 BNMTF VB+ARD 10000x8000 K=L=20", r["seconds"], n(10), {"elbo_last": float(r["stats"][-1, _lib.ST_ELBO]), "train_mse_last": e.performances(r["stats"][-1])["MSE"]})
+        e.close()
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
