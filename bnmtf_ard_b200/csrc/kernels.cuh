@@ -522,10 +522,14 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
     const double* rs = sidx == 0 ? rsU : rsV;
     const int64_t n = sidx == 0 ? nU : nV;
     for (int f = 0; f < NRS; ++f) {
+      // only VB consumes the U-side statistics and the ELBO/ESD columns
+      const bool needed = (MODE == M_VB) ? (f <= RS_PRIOR)
+                                         : (sidx == 1 && (f <= RS_SUM_RCE || (MODE == M_NP && f == RS_IDIV)));
       double a = 0.0;
-      if (rs != nullptr)
+      if (rs != nullptr && needed) {
         for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a += rs[i * NRS + f];
-      a = block_sum(a, sh);
+        a = block_sum(a, sh);
+      }
       if (threadIdx.x == 0) tot[sidx * NRS + f] = a;
     }
   }
