@@ -67,6 +67,44 @@ def main():
                 ok = ok and same
         for e in engs:
             e.close()
+    # ---- tri-factorisation engines (Gibbs, ICM, VB, NP): F/G sweeps sharded, S statistics gathered
+    from bnmtf_ard_b200._engine import NMTFEngine
+    for (I, J, K, L, dens) in [(301, 223, 4, 3, 0.6), (90, 2600, 3, 5, 0.5)]:
+        rng = np.random.default_rng(I * 7 + J)
+        R = np.abs(rng.exponential(1, (I, K)) @ rng.exponential(1, (K, L)) @ rng.exponential(1, (J, L)).T + rng.normal(0, 1, (I, J))) + 0.05
+        M = (rng.random((I, J)) < dens).astype(float)
+        M[np.arange(I), rng.integers(0, J, I)] = 1
+        M[rng.integers(0, I, J), np.arange(J)] = 1
+        F0, S0, G0 = rng.exponential(1, (I, K)), rng.exponential(1, (K, L)), rng.exponential(1, (J, L))
+        engs = [NMTFEngine(R, M, K, L, device=local)]
+        if rank == 0:
+            engs.append(NMTFEngine(R, M, K, L, device=local, distributed=False))
+        for method in (_lib.GIBBS, _lib.ICM, _lib.VB, _lib.NP):
+            outs = []
+            for e in engs:
+                e.set_hyper(True, 1., 1., 1., 1., None, None, 0.1 * np.ones((K, L)))
+                e.set_factor(SIDE_U, F_VALUE, F0); e.set_factor(SIDE_V, F_VALUE, G0); e.set_S(F_VALUE, S0)
+                if method == _lib.VB:
+                    for s, X in ((SIDE_U, F0), (SIDE_V, G0)):
+                        e.set_factor(s, F_MU, X); e.set_factor(s, F_TAU, np.ones_like(X)); e.set_factor(s, F_VAR, 0.1 * np.ones_like(X))
+                    e.set_S(F_MU, S0); e.set_S(F_TAU, np.ones_like(S0)); e.set_S(F_VAR, 0.1 * np.ones_like(S0))
+                    e.set_vb_scalars(1.2, 0.1, 3., 2.5, np.ones((4, K)), np.ones((4, L)))
+                    res = e.vb_run(3)
+                elif method == _lib.NP:
+                    res = e.np_run(3)
+                else:
+                    e.set_scalars(1.2, np.ones(K), np.ones(L))
+                    res = e.run(method, 3, seed=77, traces=False)
+                outs.append((res["stats"], e.get_factor(SIDE_U, F_VALUE), e.get_S(F_VALUE), e.get_factor(SIDE_V, F_VALUE)))
+            if rank == 0:
+                a, b = outs
+                same = (np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+                        and np.array_equal(a[0][:, 3], b[0][:, 3]) and np.allclose(a[0], b[0], rtol=1e-11, atol=1e-9, equal_nan=True))
+                print("NMTF shape %s method %d world %d: %s (max |dF| %.3e, max |dS| %.3e)" % (
+                    (I, J, K, L), method, world, "BITWISE EQUAL" if same else "MISMATCH", np.max(np.abs(a[1] - b[1])), np.max(np.abs(a[2] - b[2]))))
+                ok = ok and same
+        for e in engs:
+            e.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()
