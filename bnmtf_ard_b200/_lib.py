@@ -71,6 +71,9 @@ SIGNATURES = {
     "bnmtf_nmtf_vb_run": (C.c_int, [_h, C.c_int, _dp, _dp]),
     "bnmtf_nmtf_np_update": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, _dp]),
     "bnmtf_nmtf_np_run": (C.c_int, [_h, C.c_int, _dp, _dp]),
+    "bnmtf_kmeans_assign": (C.c_int, [_h, C.c_int, C.c_int, _dp, _u8p, C.POINTER(C.c_int32), _dp]),
+    "bnmtf_kmeans_update": (C.c_int, [_h, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _dp, _u8p]),
+    "bnmtf_kmeans_minmax": (C.c_int, [_h, C.c_int, _dp, _dp]),
     "bnmtf_tn_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),
     "bnmtf_tn_moments": (C.c_int, [C.c_int, C.c_int64, _dp, _dp, _dp, _dp]),
     "bnmtf_gamma_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),

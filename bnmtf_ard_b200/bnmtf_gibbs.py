@@ -84,10 +84,6 @@ class bnmtf_gibbs(NMFCommon):
         ''' Initialise F, S, G, tau, and lambdaFk, lambdaGl (if ARD).  (bnmtf_gibbs.py:121-167) '''
         assert init_FG in OPTIONS_INIT_FG, "Unknown initialisation option for F and G: %s. Should be in %s." % (init_FG, OPTIONS_INIT_FG)
         assert init_S in OPTIONS_INIT_S, "Unknown initialisation option for S: %s. Should be in %s." % (init_S, OPTIONS_INIT_S)
-        if init_FG == 'kmeans':
-            raise NotImplementedError("init_FG='kmeans' (code/models/kmeans/kmeans.py) is outside the ported hot path "
-                                      "(SURVEY.md 8f rank 4); use 'random' or 'exp'.")
-
         self.lambdaFk = numpy.zeros(self.K)
         self.lambdaGl = numpy.zeros(self.L)
         if self.ARD:
@@ -104,9 +100,29 @@ class bnmtf_gibbs(NMFCommon):
         self.F = eng.get_factor(SIDE_U, F_VALUE)
         self.G = eng.get_factor(SIDE_V, F_VALUE)
         self.S = eng.get_S(F_VALUE)
+        if init_FG == 'kmeans':
+            # bnmtf_gibbs.py:140-151: one-hot cluster indicators + 0.2
+            self.F, self.G = self._kmeans_FG(eng)
+            self.F, self.G = self.F + 0.2, self.G + 0.2
 
         # Initialise tau
         self.tau = self._draw_tau(self.alpha_s(), self.beta_s())
+
+    def _kmeans_FG(self, eng):
+        ''' K-means clustering of the rows (K clusters) and of the columns (L clusters) of R on the device,
+            over the engine's packed entries (code/models/kmeans/kmeans.py). '''
+        from .kmeans.kmeans import KMeans
+        if self.verbose:
+            print("Initialising F using KMeans.")
+        kmeans_F = KMeans(self.R, self.M, self.K, _engine=eng, _side=SIDE_U)
+        kmeans_F.initialise()
+        kmeans_F.cluster()
+        if self.verbose:
+            print("Initialising G using KMeans.")
+        kmeans_G = KMeans(self.R.T, self.M.T, self.L, _engine=eng, _side=SIDE_V)
+        kmeans_G.initialise()
+        kmeans_G.cluster()
+        return kmeans_F.clustering_results, kmeans_G.clustering_results
 
     def run(self, iterations):
         ''' Run the Gibbs sampler.  (bnmtf_gibbs.py:170-229) '''

@@ -32,10 +32,6 @@ class bnmtf_vb(bnmtf_gibbs):
         ''' Initialise F, S, G, tau, and lambdaFk, lambdaGl (if ARD).  (bnmtf_vb.py:117-190) '''
         assert init_FG in OPTIONS_INIT_FG, "Unknown initialisation option for F and G: %s. Should be in %s." % (init_FG, OPTIONS_INIT_FG)
         assert init_S in OPTIONS_INIT_S, "Unknown initialisation option for S: %s. Should be in %s." % (init_S, OPTIONS_INIT_S)
-        if init_FG == 'kmeans':
-            raise NotImplementedError("init_FG='kmeans' (code/models/kmeans/kmeans.py) is outside the ported hot path "
-                                      "(SURVEY.md 8f rank 4); use 'random' or 'exp'.")
-
         # Initialise lambdaFk, lambdaGl, and compute expectations
         if self.ARD:
             self.alphaFk_s, self.betaFk_s = numpy.zeros(self.K), numpy.zeros(self.K)
@@ -58,6 +54,14 @@ class bnmtf_vb(bnmtf_gibbs):
         eng.init(self.METHOD, init_FG == 'random', init_S == 'random',
                  next_seed() if init_FG == 'random' else 0, next_seed() if init_S == 'random' else 0)
         self._download_factors(eng)
+        if init_FG == 'kmeans':
+            # bnmtf_vb.py:142-159: mu = one-hot cluster indicators, tau = 1, then the moments (:178-183)
+            self.mu_F, self.mu_G = self._kmeans_FG(eng)
+            self.tau_F, self.tau_G = numpy.ones((self.I, self.K)), numpy.ones((self.J, self.L))
+            for k in range(self.K):
+                self.update_exp_F(k)
+            for l in range(self.L):
+                self.update_exp_G(l)
 
         # Initialise tau and compute expectation
         self.exp_tau, self.exp_logtau = 0., 0.

@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
 #include "kernels_nmtf.cuh"
+#include "kernels_kmeans.cuh"
 
 using namespace bnmtf;
 

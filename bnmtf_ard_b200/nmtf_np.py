@@ -60,8 +60,17 @@ class nmtf_np(NMFCommon):
             self.F = exp_draws(expo_prior * numpy.ones(self.I * self.K)).reshape(self.I, self.K)
             self.G = exp_draws(expo_prior * numpy.ones(self.J * self.L)).reshape(self.J, self.L)
         elif init_FG == 'kmeans':
-            raise NotImplementedError("init_FG='kmeans' (code/models/kmeans/kmeans.py) is outside the ported hot path "
-                                      "(SURVEY.md 8f rank 4); use 'ones', 'random' or 'exponential'.")
+            # nmtf_np.py:113-123: one-hot cluster indicators + 0.2
+            from .kmeans.kmeans import KMeans
+            eng = self._engine()
+            kmeans_F = KMeans(self.R, self.M, self.K, _engine=eng, _side=SIDE_U)
+            kmeans_F.initialise()
+            kmeans_F.cluster()
+            self.F = kmeans_F.clustering_results + 0.2
+            kmeans_G = KMeans(self.R.T, self.M.T, self.L, _engine=eng, _side=SIDE_V)
+            kmeans_G.initialise()
+            kmeans_G.cluster()
+            self.G = kmeans_G.clustering_results + 0.2
 
     def _upload_state(self):
         eng = self._engine()

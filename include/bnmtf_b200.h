@@ -249,6 +249,20 @@ int bnmtf_nmtf_np_update(bnmtf_nmf_t h, int which, int k, int l, double* out);
 int bnmtf_nmtf_np_run(bnmtf_nmf_t h, int iterations, double* iter_stats, double* iter_seconds);
 
 /* ------------------------------------------------------------------------- *
+ * Masked K-means (code/models/kmeans/kmeans.py) on the packed layouts of a handle, used by
+ * init_FG='kmeans' (bnmtf_gibbs.py:140-151).  side 0 clusters the rows of R (m = J coordinates),
+ * side 1 the columns (KMeans(R.T, M.T, L), m = I).  centroids / mask_centroids are [Kc][m].
+ *   assign : assignment() + closest_cluster()     kmeans.py:88-125  -> cluster index and MSE per point
+ *   update : update_cluster() for every cluster with cluster_flag[c] != 0   kmeans.py:131-170
+ *   minmax : per-coordinate min / max of the observed values               kmeans.py:50-52
+ * Single-GPU only. */
+int bnmtf_kmeans_assign(bnmtf_nmf_t h, int side, int Kc, const double* centroids, const uint8_t* mask_centroids,
+                        int32_t* assign_out, double* dist_out);
+int bnmtf_kmeans_update(bnmtf_nmf_t h, int side, int Kc, const int32_t* assign, const int32_t* cluster_flag,
+                        double* centroids, uint8_t* mask_centroids);
+int bnmtf_kmeans_minmax(bnmtf_nmf_t h, int side, double* mins, double* maxs);
+
+/* ------------------------------------------------------------------------- *
  * Distributions (code/models/distributions/*.py) on the device; n-element
  * host arrays in, host arrays out.  Draws use Philox4x32-10 keyed by `seed`.
  *   bnmtf_tn_draw        TN_vector_draw        truncated_normal_vector.py:37-50

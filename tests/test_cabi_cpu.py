@@ -172,8 +172,6 @@ def test_nmtf_constructor_messages(clsname):
     with pytest.raises(AssertionError) as error:
         m.initialise('exp', 'FAIL')
     assert str(error.value) == "Unknown initialisation option for S: FAIL. Should be in ['random', 'exp']."
-    with pytest.raises(NotImplementedError):
-        m.initialise('kmeans', 'exp')
     assert m.number_parameters() == 3 * 2 + 2 * 3 + 2 * 3 + 1
 
 
