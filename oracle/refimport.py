@@ -70,3 +70,34 @@ def load():
     ns.root = REF_ROOT
     _cached = ns
     return ns
+
+
+def load_cv():
+    """Reference cross-validation modules (mask + the four drivers), or None.  The reference
+    imports `sklearn.cross_validation.StratifiedKFold(labels, n_folds, shuffle)` (removed from
+    sklearn): SURVEY.md 8c item 5 -- alias it onto sklearn.model_selection."""
+    if not available():
+        return None
+    _add_paths()
+    if "sklearn.cross_validation" not in sys.modules:
+        from sklearn.model_selection import StratifiedKFold as _SKF
+        import numpy as _np
+
+        class StratifiedKFold(object):
+            def __init__(self, labels, n_folds, shuffle=False):
+                self._labels, self._n, self._shuffle = list(labels), n_folds, shuffle
+
+            def __iter__(self):
+                skf = _SKF(n_splits=self._n, shuffle=self._shuffle)
+                return iter(skf.split(_np.zeros(len(self._labels)), self._labels))
+
+        mod = types.ModuleType("sklearn.cross_validation")
+        mod.StratifiedKFold = StratifiedKFold
+        sys.modules["sklearn.cross_validation"] = mod
+    ns = types.SimpleNamespace()
+    base = "BNMTF_ARD.code.cross_validation."
+    ns.mask = importlib.import_module(base + "mask")
+    ns.MatrixCrossValidation = importlib.import_module(base + "matrix_cross_validation").MatrixCrossValidation
+    ns.MatrixNestedCrossValidation = importlib.import_module(base + "nested_matrix_cross_validation").MatrixNestedCrossValidation
+    ns.MatrixSingleCrossValidation = importlib.import_module(base + "matrix_single_cross_validation").MatrixSingleCrossValidation
+    return ns

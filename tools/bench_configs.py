@@ -92,6 +92,36 @@ def main():
             r = e.vb_run(n(10) + 3)
             record("C4 BNMTF VB+ARD 10000x8000 K=L=20", r["seconds"], n(10), {"elbo_last": float(r["stats"][-1, _lib.ST_ELBO]), "train_mse_last": e.performances(r["stats"][-1])["MSE"]})
         e.close()
+    if want("C5"):   # nested-CV-shaped workload: 10 folds x K in {1..30} of BNMF VB (200 it) on a CTRP-shaped 887 x 545 matrix
+        import contextlib, io, time
+        from bnmtf_ard_b200 import bnmf_vb
+        from bnmtf_ard_b200.cross_validation.parallel_matrix_cross_validation import ParallelMatrixCrossValidation
+        rng = np.random.default_rng(5)
+        I, J = 887, 545
+        Rh = rng.exponential(1, (I, 10)) @ rng.exponential(1, (J, 10)).T + rng.normal(0, 1, (I, J))
+        Mh = (rng.random((I, J)) < 0.8).astype(float)
+        Mh[np.arange(I), rng.integers(0, J, I)] = 1; Mh[rng.integers(0, I, J), np.arange(J)] = 1
+
+        class Quiet(object):
+            def __new__(cls, R, M, **p):
+                m = bnmf_vb(R, M, **p); m.verbose = False
+                return m
+        hp = {'alphatau': 1., 'betatau': 1., 'alpha0': 1., 'beta0': 1.}
+        Ks = list(range(1, 31)) if args.its <= 0 else list(range(1, 1 + args.its))
+        search = [{'K': k, 'ARD': True, 'hyperparameters': hp} for k in Ks]
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            cv = ParallelMatrixCrossValidation(method=Quiet, R=Rh, M=Mh, K=10, parameter_search=search,
+                                               train_config={'iterations': 200, 'init_UV': 'random'}, predict_config={},
+                                               file_performance="/tmp/cv_c5.txt", P=10)
+            cv.run()
+            best, perf = cv.find_best_parameters('MSE', True)
+        dt = time.perf_counter() - t0
+        fits = 10 * len(Ks)
+        out["C5 10-fold CV, K=1..%d, BNMF VB 200 it, 887x545" % Ks[-1]] = {
+            "seconds": dt, "fits": fits, "fits_per_s": fits / dt, "best_K": best['K'], "best_mse": perf,
+            "reference_estimate_s": "0.16-0.59 s/iteration x 200 it x %d fits (BASELINE.md section 2)" % fits}
+        print("C5", json.dumps(out[list(out)[-1]]))
     if args.out:
         with open(args.out, "w") as f:
             json.dump(out, f, indent=1)
