@@ -168,6 +168,35 @@ class NMFEngine(object):
                                      dptr(res["all_lambdak"]), dptr(res["stats"]), dptr(res["seconds"])))
         return res
 
+    # -- on-device posterior summaries / held-out prediction --------------------
+    def set_summary(self, burn_in, thinning):
+        check(self.lib.bnmtf_nmf_set_summary(self.h, int(burn_in), int(thinning)))
+
+    def summary_count(self):
+        n = C.c_int64(0)
+        check(self.lib.bnmtf_nmf_get_summary(self.h, 0, None, C.byref(n)))
+        return int(n.value)
+
+    def get_summary(self, field):
+        L = self.K if self.L is None else self.L
+        shape = {_lib.SUM_FACTOR_U: (self.I, self.K), _lib.SUM_FACTOR_V: (self.J, L), _lib.SUM_S: (self.K, L),
+                 _lib.SUM_LAMBDA_U: (self.K,), _lib.SUM_LAMBDA_V: (L,), _lib.SUM_TAU: (1,)}[field]
+        out = np.empty(shape)
+        check(self.lib.bnmtf_nmf_get_summary(self.h, int(field), dptr(out), None))
+        return out
+
+    def predict_entries(self, source, rows, cols, vals):
+        """compute_MSE / compute_R2 / compute_Rp (bnmf_gibbs.py:252-270) over the listed entries."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        out = np.zeros(8)
+        i32 = C.POINTER(C.c_int32)
+        check(self.lib.bnmtf_nmf_predict(self.h, int(source), rows.size, rows.ctypes.data_as(i32),
+                                         cols.ctypes.data_as(i32), dptr(vals), dptr(out)))
+        return {"n": out[0], "MSE": float(out[1]), "R^2": float(out[2]), "Rp": float(out[3]), "SS_res": float(out[4]),
+                "SS_total": float(out[5])}
+
     def launch_count(self):
         return int(self.lib.bnmtf_nmf_launch_count(self.h))
 

@@ -20,6 +20,9 @@ _i64p = C.POINTER(C.c_int64)
 _h = C.c_void_p
 
 # name -> (restype, argtypes); mirrors include/bnmtf_b200.h declaration by declaration
+SUM_FACTOR_U, SUM_FACTOR_V, SUM_S, SUM_LAMBDA_U, SUM_LAMBDA_V, SUM_TAU = range(6)
+PRED_CURRENT, PRED_SUMMARY = 0, 1
+
 SIGNATURES = {
     "bnmtf_last_error": (C.c_char_p, []),
     "bnmtf_device_count": (C.c_int, []),
@@ -74,6 +77,9 @@ SIGNATURES = {
     "bnmtf_kmeans_assign": (C.c_int, [_h, C.c_int, C.c_int, _dp, _u8p, C.POINTER(C.c_int32), _dp]),
     "bnmtf_kmeans_update": (C.c_int, [_h, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _dp, _u8p]),
     "bnmtf_kmeans_minmax": (C.c_int, [_h, C.c_int, _dp, _dp]),
+    "bnmtf_nmf_set_summary": (C.c_int, [_h, C.c_int, C.c_int]),
+    "bnmtf_nmf_get_summary": (C.c_int, [_h, C.c_int, _dp, C.POINTER(C.c_int64)]),
+    "bnmtf_nmf_predict": (C.c_int, [_h, C.c_int, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _dp, _dp]),
     "bnmtf_tn_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),
     "bnmtf_tn_moments": (C.c_int, [C.c_int, C.c_int64, _dp, _dp, _dp, _dp]),
     "bnmtf_gamma_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),

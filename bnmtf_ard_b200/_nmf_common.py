@@ -100,6 +100,45 @@ class NMFCommon(object):
         variance_pred = (M * (R_pred - mean_pred)**2).sum()
         return covariance / float(math.sqrt(variance_real) * math.sqrt(variance_pred))
 
+    # -- on-device posterior summaries (opt-in, not in the reference API) ------
+    _summary = None        # (burn_in, thinning) handed to summarise_on_device
+    _keep_traces = True
+    _summary_ready = False
+
+    def summarise_on_device(self, burn_in, thinning, keep_traces=False):
+        ''' Before run(): accumulate the posterior means over range(burn_in, iterations, thinning)
+            on the GPU instead of storing every draw (all_U, all_V / all_F, all_S, all_G become None
+            unless keep_traces).  approx_expectation / predict / quality called with the same
+            (burn_in, thinning) then read the device summary.  Pass thinning=None to switch off. '''
+        if thinning is None:
+            self._summary, self._keep_traces, self._summary_ready = None, True, False
+            return
+        assert burn_in >= 0 and thinning >= 1, "Need burn_in >= 0 and thinning >= 1."
+        self._summary, self._keep_traces, self._summary_ready = (int(burn_in), int(thinning)), bool(keep_traces), False
+
+    def _configure_summary(self, eng):
+        if self._summary is None:
+            eng.set_summary(0, 0)
+            return True
+        eng.set_summary(*self._summary)
+        return self._keep_traces
+
+    def _summary_matches(self, burn_in, thinning):
+        return self._summary_ready and self._summary == (int(burn_in), int(thinning))
+
+    def _need_traces(self, traces):
+        if traces is None:
+            raise ValueError("The draws were not stored (summarise_on_device): only the (burn_in, thinning) = %s "
+                             "summary is available." % (self._summary,))
+
+    def _device_predict(self, M_pred, source, eng=None):
+        ''' MSE, R^2, Rp over the entries of M_pred, evaluated on the GPU from the device factors. '''
+        eng = self._engine() if eng is None else eng
+        rows, cols = numpy.nonzero(numpy.asarray(M_pred))
+        res = eng.predict_entries(source, rows, cols, self.R[rows, cols])
+        self._last_predict = res
+        return {'MSE': res['MSE'], 'R^2': res['R^2'], 'Rp': res['Rp']}
+
     def _predict_from(self, M_pred, X, Y):
         R_pred = numpy.dot(X, Y.T)
         MSE = self.compute_MSE(M_pred, self.R, R_pred)

@@ -82,13 +82,18 @@ class bnmf_gibbs(NMFCommon):
 
         eng = self._upload_state()
         seed = next_seed() if self.METHOD == _lib.GIBBS else 0
-        res = eng.run(self.METHOD, iterations, seed=seed, traces=True, want_lambdak=True)
+        traces = self._configure_summary(eng)
+        res = eng.run(self.METHOD, iterations, seed=seed, traces=traces, want_lambdak=True)
+        self._summary_ready = self._summary is not None and eng.summary_count() > 0
 
         self.all_U, self.all_V = res['all_U'], res['all_V']
         self.all_tau = res['stats'][:, _lib.ST_TAU].copy()
         self.all_lambdak = res['all_lambdak'] if self.ARD else numpy.zeros((iterations, self.K))
         if iterations > 0:
-            self.U, self.V = numpy.copy(self.all_U[-1]), numpy.copy(self.all_V[-1])
+            if traces:
+                self.U, self.V = numpy.copy(self.all_U[-1]), numpy.copy(self.all_V[-1])
+            else:
+                self.U, self.V = eng.get_factor(SIDE_U, F_VALUE), eng.get_factor(SIDE_V, F_VALUE)
             self.tau = float(self.all_tau[-1])
             if self.ARD:
                 self.lambdak = numpy.copy(self.all_lambdak[-1])
@@ -135,6 +140,11 @@ class bnmf_gibbs(NMFCommon):
 
     def approx_expectation(self, burn_in, thinning):
         ''' Return our expectation of U, V, tau, lambdak. '''
+        if self._summary_matches(burn_in, thinning):
+            eng = self._engine()
+            return (eng.get_summary(_lib.SUM_FACTOR_U), eng.get_summary(_lib.SUM_FACTOR_V),
+                    float(eng.get_summary(_lib.SUM_TAU)[0]), eng.get_summary(_lib.SUM_LAMBDA_U) if self.ARD else None)
+        self._need_traces(self.all_U)
         indices = range(burn_in, len(self.all_U), thinning)
         exp_U = numpy.array([self.all_U[i] for i in indices]).sum(axis=0) / float(len(indices))
         exp_V = numpy.array([self.all_V[i] for i in indices]).sum(axis=0) / float(len(indices))
@@ -145,6 +155,8 @@ class bnmf_gibbs(NMFCommon):
 
     def predict(self, M_pred, burn_in, thinning):
         ''' Compute the expectation of U and V, and use it to predict missing values. '''
+        if self._summary_matches(burn_in, thinning):
+            return self._device_predict(M_pred, _lib.PRED_SUMMARY)
         (exp_U, exp_V, _, _) = self.approx_expectation(burn_in, thinning)
         return self._predict_from(M_pred, exp_U, exp_V)
 
@@ -157,8 +169,17 @@ class bnmf_gibbs(NMFCommon):
         ''' Return the model quality, either as log likelihood, BIC, AIC, MSE, or ELBO. '''
         assert metric in ALL_QUALITY, 'Unrecognised metric for model quality: %s.' % metric
 
-        (exp_U, exp_V, exp_tau, _) = self.approx_expectation(burn_in, thinning)
-        log_likelihood = self.log_likelihood(exp_U, exp_V, exp_tau)
+        if self._summary_matches(burn_in, thinning):
+            # residual sum of squares of the summary means on Omega, evaluated on the device
+            train = self._device_predict(self.M, _lib.PRED_SUMMARY)
+            if metric == 'MSE':
+                return train['MSE']
+            exp_tau = float(self._engine().get_summary(_lib.SUM_TAU)[0])
+            log_likelihood = self.size_Omega / 2. * (math.log(exp_tau) - math.log(2 * math.pi)) \
+                - exp_tau / 2. * self._last_predict['SS_res']
+        else:
+            (exp_U, exp_V, exp_tau, _) = self.approx_expectation(burn_in, thinning)
+            log_likelihood = self.log_likelihood(exp_U, exp_V, exp_tau)
 
         if metric == 'loglikelihood':
             return log_likelihood

@@ -157,7 +157,7 @@ class bnmf_vb(NMFCommon):
 
     def predict(self, M_pred):
         ''' Predict missing values in R. '''
-        return self._predict_from(M_pred, self.exp_U, self.exp_V)
+        return self._device_predict(M_pred, _lib.PRED_CURRENT, self._upload_state())
 
     def quality(self, metric):
         ''' Return the model quality, either as log likelihood, BIC, AIC, MSE, or ELBO. '''

@@ -133,14 +133,20 @@ class bnmtf_gibbs(NMFCommon):
 
         eng = self._upload_state()
         seed = next_seed() if self.METHOD == _lib.GIBBS else 0
-        res = eng.run(self.METHOD, iterations, seed=seed, traces=True)
+        traces = self._configure_summary(eng)
+        res = eng.run(self.METHOD, iterations, seed=seed, traces=traces)
+        self._summary_ready = self._summary is not None and eng.summary_count() > 0
 
         self.all_F, self.all_S, self.all_G = res['all_F'], res['all_S'], res['all_G']
         self.all_tau = res['stats'][:, _lib.ST_TAU].copy()
         self.all_lambdaFk = res['all_lambdaFk'] if self.ARD else numpy.zeros((iterations, self.K))
         self.all_lambdaGl = res['all_lambdaGl'] if self.ARD else numpy.zeros((iterations, self.L))
         if iterations > 0:
-            self.F, self.S, self.G = numpy.copy(self.all_F[-1]), numpy.copy(self.all_S[-1]), numpy.copy(self.all_G[-1])
+            if traces:
+                self.F, self.S, self.G = numpy.copy(self.all_F[-1]), numpy.copy(self.all_S[-1]), numpy.copy(self.all_G[-1])
+            else:
+                self.F, self.G = eng.get_factor(0, _lib.F_VALUE), eng.get_factor(1, _lib.F_VALUE)
+                self.S = eng.get_S(_lib.F_VALUE)
             self.tau = float(self.all_tau[-1])
             if self.ARD:
                 self.lambdaFk, self.lambdaGl = numpy.copy(self.all_lambdaFk[-1]), numpy.copy(self.all_lambdaGl[-1])
@@ -211,6 +217,13 @@ class bnmtf_gibbs(NMFCommon):
 
     def approx_expectation(self, burn_in, thinning):
         ''' Return our expectation of F, S, G, tau, lambdaFk, lambdaGl. '''
+        if self._summary_matches(burn_in, thinning):
+            eng = self._engine()
+            return (eng.get_summary(_lib.SUM_FACTOR_U), eng.get_summary(_lib.SUM_S), eng.get_summary(_lib.SUM_FACTOR_V),
+                    float(eng.get_summary(_lib.SUM_TAU)[0]),
+                    eng.get_summary(_lib.SUM_LAMBDA_U) if self.ARD else None,
+                    eng.get_summary(_lib.SUM_LAMBDA_V) if self.ARD else None)
+        self._need_traces(self.all_F)
         indices = range(burn_in, len(self.all_F), thinning)
         exp_F = numpy.array([self.all_F[i] for i in indices]).sum(axis=0) / float(len(indices))
         exp_S = numpy.array([self.all_S[i] for i in indices]).sum(axis=0) / float(len(indices))
@@ -222,6 +235,8 @@ class bnmtf_gibbs(NMFCommon):
 
     def predict(self, M_pred, burn_in, thinning):
         ''' Compute the expectation of F, S, G, and use it to predict missing values. '''
+        if self._summary_matches(burn_in, thinning):
+            return self._device_predict(M_pred, _lib.PRED_SUMMARY)
         (exp_F, exp_S, exp_G, _, _, _) = self.approx_expectation(burn_in, thinning)
         R_pred = self.triple_dot(exp_F, exp_S, exp_G.T)
         MSE = self.compute_MSE(M_pred, self.R, R_pred)
@@ -238,8 +253,17 @@ class bnmtf_gibbs(NMFCommon):
         ''' Return the model quality, either as log likelihood, BIC, AIC, MSE, or ELBO. '''
         assert metric in ALL_QUALITY, 'Unrecognised metric for model quality: %s.' % metric
 
-        (exp_F, exp_S, exp_G, exp_tau, _, _) = self.approx_expectation(burn_in, thinning)
-        log_likelihood = self.log_likelihood(exp_F, exp_S, exp_G, exp_tau)
+        if self._summary_matches(burn_in, thinning):
+            # residual sum of squares of the summary means on Omega, evaluated on the device
+            train = self._device_predict(self.M, _lib.PRED_SUMMARY)
+            if metric == 'MSE':
+                return train['MSE']
+            exp_tau = float(self._engine().get_summary(_lib.SUM_TAU)[0])
+            log_likelihood = self.size_Omega / 2. * (math.log(exp_tau) - math.log(2 * math.pi)) \
+                - exp_tau / 2. * self._last_predict['SS_res']
+        else:
+            (exp_F, exp_S, exp_G, exp_tau, _, _) = self.approx_expectation(burn_in, thinning)
+            log_likelihood = self.log_likelihood(exp_F, exp_S, exp_G, exp_tau)
 
         if metric == 'loglikelihood':
             return log_likelihood

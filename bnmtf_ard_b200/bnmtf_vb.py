@@ -189,11 +189,7 @@ class bnmtf_vb(bnmtf_gibbs):
 
     def predict(self, M_pred):
         ''' Predict missing values in R. '''
-        R_pred = self.triple_dot(self.exp_F, self.exp_S, self.exp_G.T)
-        MSE = self.compute_MSE(M_pred, self.R, R_pred)
-        R2 = self.compute_R2(M_pred, self.R, R_pred)
-        Rp = self.compute_Rp(M_pred, self.R, R_pred)
-        return {'MSE': MSE, 'R^2': R2, 'Rp': Rp}
+        return self._device_predict(M_pred, _lib.PRED_CURRENT, self._upload_state())
 
     def quality(self, metric):
         ''' Return the model quality, either as log likelihood, BIC, AIC, MSE, or ELBO. '''

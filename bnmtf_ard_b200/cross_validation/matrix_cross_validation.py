@@ -12,6 +12,7 @@ import json
 import numpy
 
 from .mask import compute_folds_stratify_columns_attempts, compute_folds_stratify_rows_attempts
+from ._device import prepare_summary
 
 attempts_generate_M = 1000
 
@@ -66,6 +67,7 @@ class MatrixCrossValidation:
     def run_model(self, train, test, parameters):
         ''' Initialises and runs the model, and returns the performance on the test set. '''
         model = self.method(self.R, train, **parameters)
+        prepare_summary(model, self.predict_config)
         model.train(**self.train_config)
         return model.predict(test, **self.predict_config)
 

@@ -6,6 +6,7 @@ performance of every fold and their average are written to file_performance.
 import numpy
 
 from .mask import compute_folds_stratify_columns_attempts, compute_folds_stratify_rows_attempts
+from ._device import prepare_summary
 
 ATTEMPTS_GENERATE_M = 1000
 METRICS = ['MSE', 'R^2', 'Rp']
@@ -50,6 +51,7 @@ class MatrixSingleCrossValidation:
     def run_model(self, train, test, parameters):
         ''' Initialises and runs the model, and returns the performance on the test set. '''
         model = self.method(self.R, train, **parameters)
+        prepare_summary(model, self.predict_config)
         model.train(**self.train_config)
         return model.predict(test, **self.predict_config)
 

@@ -9,6 +9,7 @@ import numpy
 from .mask import compute_folds_stratify_columns_attempts, compute_folds_stratify_rows_attempts
 from .matrix_cross_validation import MatrixCrossValidation
 from .parallel_matrix_cross_validation import ParallelMatrixCrossValidation
+from ._device import prepare_summary
 
 attempts_generate_M = 1000
 
@@ -87,6 +88,7 @@ class MatrixNestedCrossValidation:
     def run_model(self, train, test, parameters):
         ''' Initialises and runs the model, and returns the performance on the test set. '''
         model = self.method(self.R, train, **parameters)
+        prepare_summary(model, self.predict_config)
         model.train(**self.train_config)
         return model.predict(test, **self.predict_config)
 

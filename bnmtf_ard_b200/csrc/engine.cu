@@ -13,6 +13,7 @@
 #include "kernels_v2.cuh"
 #include "kernels_nmtf.cuh"
 #include "kernels_kmeans.cuh"
+#include "kernels_summary.cuh"
 
 using namespace bnmtf;
 
@@ -154,7 +155,16 @@ struct bnmtf_nmf_s {
   double *BS = nullptr, *PA = nullptr, *QC = nullptr;         // [K*L], [K(K+1)/2][L], [L(L+1)/2][K]
   double* lamstateG = nullptr;           // [4][L]  (lamstate holds the F block [4][K])
   double* vbmisc = nullptr;              // [8]: S q-term, sum lambdaS*ES, T3
+  // ---- on-device posterior summaries (engine_summary.inc)
+  int sum_burn = 0, sum_thin = 0;        // thinning <= 0: off
+  int64_t sum_count = 0;
+  double* sum_fac[2] = {nullptr, nullptr};
+  double *sum_S = nullptr, *sum_tau = nullptr;
+  double* sum_lam[2] = {nullptr, nullptr};
 };
+static int summary_reset(bnmtf_nmf_s* h);
+static int summary_accumulate(bnmtf_nmf_s* h, int it, const double* stats_it);
+static void summary_free(bnmtf_nmf_s* h);
 
 // ---- packing -------------------------------------------------------------------
 static void choose_team(int64_t maxlen, int* tpr, int* npt) {
@@ -430,6 +440,7 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   cudaFree(h->Prow); cudaFree(h->Hrow); cudaFree(h->cvec); cudaFree(h->TT);
   cudaFree(h->Arow); cudaFree(h->Brow); cudaFree(h->Crow); cudaFree(h->BS); cudaFree(h->PA); cudaFree(h->QC);
   cudaFree(h->lamstateG); cudaFree(h->vbmisc);
+  summary_free(h);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -908,6 +919,7 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
 
   refresh_km(h, 0, method); refresh_km(h, 1, method);
   h->km_mode = method == BNMTF_VB ? 2 : 1;
+  if (summary_reset(h)) return 1;
   CK(cudaEventRecord(ev[0], h->stream));
 
   auto copy_chunk = [&](int c) -> int {
@@ -941,6 +953,7 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
       // tau, statistics                                   bnmf_gibbs.py:166-167,175
       if (method == BNMTF_VB && launch_lambda(h, method, seed, (uint32_t)it, 0)) return 1;
       if (launch_finalize(h, method, h->stats_dev + (size_t)it * BNMTF_NSTATS, seed, (uint32_t)it, 1)) return 1;
+      if (summary_accumulate(h, it, h->stats_dev + (size_t)it * BNMTF_NSTATS)) return 1;
       if (tr) {
         const int slot = it - it0;
         CK(cudaMemcpyAsync(su.trace[b] + (size_t)slot * su.n_glob * K, su.val, sizeof(double) * su.n_glob * K, cudaMemcpyDeviceToDevice, h->stream));
@@ -1049,3 +1062,4 @@ int bnmtf_exp_draw(int device, uint64_t seed, int64_t n, const double* lambda, d
 }
 
 #include "engine_nmtf.inc"
+#include "engine_summary.inc"

@@ -83,7 +83,7 @@ class nmf_np(NMFCommon):
 
     def predict(self, M_pred):
         ''' Predict missing values in R. '''
-        return self._predict_from(M_pred, self.U, self.V)
+        return self._device_predict(M_pred, _lib.PRED_CURRENT, self._upload_state())
 
     def compute_I_div(self):
         ''' Return the I-divergence.  (nmf_np.py:160-163) '''

@@ -124,11 +124,7 @@ class nmtf_np(NMFCommon):
 
     def predict(self, M_pred):
         ''' Predict missing values in R. '''
-        R_pred = self.triple_dot(self.F, self.S, self.G.T)
-        MSE = self.compute_MSE(M_pred, self.R, R_pred)
-        R2 = self.compute_R2(M_pred, self.R, R_pred)
-        Rp = self.compute_Rp(M_pred, self.R, R_pred)
-        return {'MSE': MSE, 'R^2': R2, 'Rp': Rp}
+        return self._device_predict(M_pred, _lib.PRED_CURRENT, self._upload_state())
 
     def compute_I_div(self):
         ''' Return the I-divergence.  (nmtf_np.py:222-225) '''

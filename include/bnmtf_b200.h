@@ -263,6 +263,34 @@ int bnmtf_kmeans_update(bnmtf_nmf_t h, int side, int Kc, const int32_t* assign, 
 int bnmtf_kmeans_minmax(bnmtf_nmf_t h, int side, double* mins, double* maxs);
 
 /* ------------------------------------------------------------------------- *
+ * On-device posterior summaries and held-out prediction (both handle kinds).
+ *
+ * bnmtf_nmf_set_summary: from the next bnmtf_nmf_run / bnmtf_nmtf_run on, add the draws of the
+ *   iterations range(burn_in, iterations, thinning) into running sums on the device -- the
+ *   quantities approx_expectation averages from all_U / all_V / all_tau / all_lambdak
+ *   (bnmf_gibbs.py:222-230; F, S, G, lambdaFk, lambdaGl for bnmtf_gibbs.py:302-315), in the same
+ *   summation order.  The run may then be called with NULL trace pointers.  thinning <= 0 turns
+ *   the summary off and frees it.  Every run restarts the sums.
+ * bnmtf_nmf_get_summary: mean (sum / count) of one field into a host array; `count` (optional)
+ *   receives the number of accumulated draws.  dst may be NULL to query the count only.
+ * bnmtf_nmf_predict: predict(M_pred, ...) (bnmf_gibbs.py:233-240, bnmf_vb.py:265-271,
+ *   bnmtf_gibbs.py:318-326) on n test entries given as (row, column, value): R_pred from the
+ *   current factors (BNMTF_PRED_CURRENT: U V^T, or F S G^T) or from the summary means
+ *   (BNMTF_PRED_SUMMARY), then compute_MSE / compute_R2 / compute_Rp (bnmf_gibbs.py:252-270)
+ *   with the two-pass (centred) sums of the reference.
+ *   out8 = {n, MSE, R^2, Rp, SS_res, SS_total, mean_real, mean_pred}.
+ * ------------------------------------------------------------------------- */
+enum {
+  BNMTF_SUM_FACTOR_U = 0, BNMTF_SUM_FACTOR_V = 1, BNMTF_SUM_S = 2,
+  BNMTF_SUM_LAMBDA_U = 3, BNMTF_SUM_LAMBDA_V = 4, BNMTF_SUM_TAU = 5
+};
+enum { BNMTF_PRED_CURRENT = 0, BNMTF_PRED_SUMMARY = 1 };
+int bnmtf_nmf_set_summary(bnmtf_nmf_t h, int burn_in, int thinning);
+int bnmtf_nmf_get_summary(bnmtf_nmf_t h, int field, double* dst, int64_t* count);
+int bnmtf_nmf_predict(bnmtf_nmf_t h, int source, int64_t n, const int32_t* rows, const int32_t* cols,
+                      const double* vals, double* out8);
+
+/* ------------------------------------------------------------------------- *
  * Distributions (code/models/distributions/*.py) on the device; n-element
  * host arrays in, host arrays out.  Draws use Philox4x32-10 keyed by `seed`.
  *   bnmtf_tn_draw        TN_vector_draw        truncated_normal_vector.py:37-50
