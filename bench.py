@@ -313,6 +313,26 @@ def main():
                "h2d_bytes_per_step": int(((I + J) * K * 8 + (K + 1) * 8) / e2e_steps),
                "d2h_bytes_per_step": int((I + J) * K * 8 + K * 8 + 16 * 8),
                "note": "engine.run() through the C ABI with host numpy state and host trace buffers (pageable)"}
+        # same call with the posterior means accumulated on the device (summarise_on_device):
+        # no all_U / all_V; the means of the second half of the chain are read back at the end
+        eng.set_summary(e2e_steps // 2, 1)
+        barrier()
+        t0 = time.perf_counter()
+        eng.set_factor(_lib.SIDE_U, _lib.F_VALUE, U_h)
+        eng.set_factor(_lib.SIDE_V, _lib.F_VALUE, V_h)
+        eng.set_scalars(1.0, np.ones(K))
+        r3 = eng.run(_lib.GIBBS, e2e_steps, seed=3, traces=False)
+        mU, mV = eng.get_summary(_lib.SUM_FACTOR_U), eng.get_summary(_lib.SUM_FACTOR_V)
+        _ = float(mU[0, 0]) + float(mV[0, 0]) + float(r3["stats"][-1, 0])
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        eng.set_summary(0, 0)
+        e2e["device_summary"] = {"value": e2e_steps / float(t.item()), "unit": "iterations/s",
+                                 "d2h_bytes_per_step": int(((I + J) * K * 8) / e2e_steps + K * 8 + 16 * 8),
+                                 "note": "same call, draws averaged on the device instead of copied out"}
+        del mU, mV, r3
     sampler.stop_flag = True
 
     if rank == 0:
