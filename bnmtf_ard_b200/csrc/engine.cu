@@ -276,6 +276,48 @@ static int alloc_side_state(bnmtf_nmf_s* h, Side& sd, int K) {
 }
 
 static int nmtf_alloc(bnmtf_nmf_s* h);
+// ---- stream-ordered memory and copies ----------------------------------------------
+// Every allocation comes from the device's stream-ordered pool (cudaMallocAsync) and every
+// "synchronous" copy runs on the calling handle's stream followed by a stream synchronise:
+// no call in this library synchronises the whole device, so handles driven from different
+// host threads (the cross-validation folds) overlap on the GPU.
+static thread_local cudaStream_t g_stream = cudaStreamPerThread;
+
+template <class T>
+static cudaError_t pool_malloc(T** p, size_t bytes) { return cudaMallocAsync((void**)p, bytes, g_stream); }
+static cudaError_t pool_free(void* p) { return p ? cudaFreeAsync(p, g_stream) : cudaSuccess; }
+static cudaError_t copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, g_stream);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(g_stream);
+}
+static cudaError_t copy2d_sync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                               cudaMemcpyKind kind) {
+  cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, g_stream);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(g_stream);
+}
+// keep up to 8 GB of freed blocks cached in the pool (default: released at every synchronise)
+static cudaError_t pool_setup(int device) {
+  static bool done[64] = {false};
+  if (device < 0 || device >= 64 || done[device]) return cudaSuccess;
+  cudaMemPool_t pool;
+  cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+  if (e != cudaSuccess) return e;
+  uint64_t keep = (uint64_t)8 << 30;
+  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  done[device] = true;
+  return e;
+}
+#define cudaMalloc pool_malloc
+#define cudaFree pool_free
+#define cudaMemcpy copy_sync
+#define cudaMemcpy2D copy2d_sync
+// entry of every call on a handle: its device and its stream become current for this thread
+#define ENTER(h)                          \
+  do {                                    \
+    CK(cudaSetDevice((h)->device));       \
+    g_stream = (h)->stream;               \
+  } while (0)
+
 static int create_dev_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, int L, bool nmtf, const double* Rrow_dev,
                            const uint8_t* Mrow_dev, const double* Rcol_dev, const uint8_t* Mcol_dev, int64_t row0,
                            int64_t row1, int64_t shard_rows, int64_t col0, int64_t col1, int64_t shard_cols);
@@ -297,17 +339,18 @@ static int create_dev_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, i
   if (row0 < 0 || row1 < row0 || row1 > I || col0 < 0 || col1 < col0 || col1 > J) FAIL("bad shard bounds");
   if (shard_rows < row1 - row0 || shard_cols < col1 - col0) FAIL("shard size smaller than the owned range");
   CK(cudaSetDevice(device));
+  CK(pool_setup(device));
+  int cc_major = 0, cc_minor = 0, sms = 0;
+  CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  CK(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (cc_major < 10) FAIL("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, cc_major, cc_minor);
   bnmtf_nmf_s* h = new bnmtf_nmf_s();
   h->device = device; h->I = I; h->J = J; h->K = K; h->L = L; h->nmtf = nmtf;
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) {
-    delete h;
-    FAIL("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
-  }
-  h->num_sms = prop.multiProcessorCount;
+  h->num_sms = sms;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  g_stream = h->stream;
   const char* ts = getenv("BNMTF_TIME_SWEEPS");
   h->time_sweeps = ts && atoi(ts) != 0;
 
@@ -370,7 +413,7 @@ int bnmtf_nmf_layout_stats(bnmtf_nmf_t h, int64_t* out4) {
 
 int bnmtf_nmf_pack(bnmtf_nmf_t h, const int64_t* global4) {
   if (!h) FAIL("NULL handle");
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   Side& su = h->s[0]; Side& sv = h->s[1];
   if (su.packed) FAIL("already packed");
   int64_t g[4] = {su.maxlen_local, su.maxseg_local, sv.maxlen_local, sv.maxseg_local};
@@ -393,6 +436,8 @@ static int create_host_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, 
   if (!R || !M) FAIL("R or M is NULL");
   if (I <= 0 || J <= 0) FAIL("bad shape");
   CK(cudaSetDevice(device));
+  CK(pool_setup(device));
+  g_stream = cudaStreamPerThread;
   const int64_t nr = row1 - row0, nc = col1 - col0;
   const bool full = (nr == I && nc == J);
   double *Rrow = nullptr, *Rcol = nullptr;
@@ -432,7 +477,9 @@ static void free_side(Side& sd) {
 int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaDeviceSynchronize();
+  g_stream = h->stream;
+  cudaStreamSynchronize(h->copy_stream);
+  cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   free_side(h->s[0]); free_side(h->s[1]);
   cudaFree(h->scal); cudaFree(h->colsum); cudaFree(h->lamstate); cudaFree(h->lamk); cudaFree(h->stats_dev);
@@ -441,6 +488,8 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   cudaFree(h->Arow); cudaFree(h->Brow); cudaFree(h->Crow); cudaFree(h->BS); cudaFree(h->PA); cudaFree(h->QC);
   cudaFree(h->lamstateG); cudaFree(h->vbmisc);
   summary_free(h);
+  cudaStreamSynchronize(h->stream);
+  g_stream = cudaStreamPerThread;
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -450,7 +499,7 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
 int bnmtf_nmf_data_stats(bnmtf_nmf_t h, double* out) {
   if (!h || !out) FAIL("NULL argument");
   if (!h->s[0].packed) FAIL("call bnmtf_nmf_pack first");
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   Side& su = h->s[0];
   const int nb = 256;
   double* part = nullptr;
@@ -488,7 +537,7 @@ int bnmtf_nmf_set_comm(bnmtf_nmf_t h, int rank, int world, const uint8_t* nccl_i
   if (world <= 1) { h->rank = 0; h->world = 1; return 0; }
   if (!nccl_id128) FAIL("NULL nccl id");
   if (!g_nccl.load()) FAIL("cannot load libnccl.so.2: %s", dlerror());
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   for (int sidx = 0; sidx < 2; ++sidx) {
     const Side& sd = h->s[sidx];
     if (sd.n_shard * world != sd.n_padglob) FAIL("shard size %lld x world %d != padded extent %lld", (long long)sd.n_shard, world, (long long)sd.n_padglob);
@@ -505,7 +554,7 @@ int bnmtf_nmf_set_comm(bnmtf_nmf_t h, int rank, int world, const uint8_t* nccl_i
 int bnmtf_nmf_set_hyper(bnmtf_nmf_t h, int ARD, double alphatau, double betatau, double alpha0, double beta0,
                         const double* lambdaU, const double* lambdaV) {
   if (!h) FAIL("NULL handle");
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   h->hyper.ARD = ARD; h->hyper.alphatau = alphatau; h->hyper.betatau = betatau;
   h->hyper.alpha0 = alpha0; h->hyper.beta0 = beta0;
   h->hyper.sumlog_lamU = h->hyper.sumlog_lamV = 0.0;
@@ -538,7 +587,7 @@ int bnmtf_nmf_set_factor(bnmtf_nmf_t h, int side, int field, const double* src) 
   if (!h || !src || side < 0 || side > 1) FAIL("bad argument");
   double* p = field_ptr(h->s[side], field);
   if (!p) FAIL("bad field %d", field);
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaMemcpy(p, src, sizeof(double) * h->s[side].n_glob * h->s[side].kf, cudaMemcpyHostToDevice));
   h->km_mode = -1;
   return 0;
@@ -548,7 +597,7 @@ int bnmtf_nmf_get_factor(bnmtf_nmf_t h, int side, int field, double* dst) {
   if (!h || !dst || side < 0 || side > 1) FAIL("bad argument");
   double* p = field_ptr(h->s[side], field);
   if (!p) FAIL("bad field %d", field);
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaMemcpy(dst, p, sizeof(double) * h->s[side].n_glob * h->s[side].kf, cudaMemcpyDeviceToHost));
   return 0;
@@ -556,7 +605,7 @@ int bnmtf_nmf_get_factor(bnmtf_nmf_t h, int side, int field, double* dst) {
 
 int bnmtf_nmf_set_scalars(bnmtf_nmf_t h, double tau, const double* lambdak) {
   if (!h) FAIL("NULL handle");
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaMemcpy(h->scal + SC_TAU, &tau, sizeof(double), cudaMemcpyHostToDevice));
   if (lambdak) {
     CK(cudaMemcpy(h->lamk, lambdak, sizeof(double) * h->K, cudaMemcpyHostToDevice));
@@ -567,7 +616,7 @@ int bnmtf_nmf_set_scalars(bnmtf_nmf_t h, double tau, const double* lambdak) {
 
 int bnmtf_nmf_get_scalars(bnmtf_nmf_t h, double* tau, double* lambdak) {
   if (!h) FAIL("NULL handle");
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   if (tau) CK(cudaMemcpy(tau, h->scal + SC_TAU, sizeof(double), cudaMemcpyDeviceToHost));
   if (lambdak) CK(cudaMemcpy(lambdak, h->lamk, sizeof(double) * h->K, cudaMemcpyDeviceToHost));
@@ -578,7 +627,7 @@ int bnmtf_nmf_set_vb_scalars(bnmtf_nmf_t h, double exp_tau, double exp_logtau, d
                              const double* alphak_s, const double* betak_s, const double* exp_lambdak,
                              const double* exp_loglambdak) {
   if (!h) FAIL("NULL handle");
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   double sc[SC_COUNT] = {0};
   sc[SC_TAU] = exp_tau; sc[SC_LOGTAU] = exp_logtau; sc[SC_ALPHA_S] = alpha_s; sc[SC_BETA_S] = beta_s;
   CK(cudaMemcpy(h->scal, sc, sizeof(sc), cudaMemcpyHostToDevice));
@@ -591,7 +640,7 @@ int bnmtf_nmf_set_vb_scalars(bnmtf_nmf_t h, double exp_tau, double exp_logtau, d
 
 int bnmtf_nmf_get_vb_scalars(bnmtf_nmf_t h, double* scal4, double* lamstate4K) {
   if (!h) FAIL("NULL handle");
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   CK(cudaStreamSynchronize(h->stream));
   if (scal4) CK(cudaMemcpy(scal4, h->scal, sizeof(double) * 4, cudaMemcpyDeviceToHost));
   if (lamstate4K) CK(cudaMemcpy(lamstate4K, h->lamstate, sizeof(double) * 4 * h->K, cudaMemcpyDeviceToHost));
@@ -819,7 +868,7 @@ static int allgather_side(bnmtf_nmf_s* h, int method, int side, bool stats) {
 
 int bnmtf_nmf_init_factors(bnmtf_nmf_t h, int method, int random, uint64_t seed) {
   if (!h) FAIL("NULL handle");
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   for (int sidx = 0; sidx < 2; ++sidx) {
     Side& sd = h->s[sidx];
     const int64_t n = sd.n_glob * sd.kf;
@@ -844,7 +893,7 @@ int bnmtf_nmf_column_params(bnmtf_nmf_t h, int method, int side, int k, double* 
   if (k < 0 || k >= h->s[side].kf) FAIL("k out of range");
   if (h->nmtf) FAIL("use bnmtf_nmtf_column_params for a tri-factorisation handle");
   if (h->world > 1) FAIL("column_params is single-GPU only");
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   Side& sd = h->s[side];
   double *dt = nullptr, *dm = nullptr;
   CK(cudaMalloc(&dt, sizeof(double) * sd.n_glob));
@@ -862,7 +911,7 @@ int bnmtf_nmf_column_params(bnmtf_nmf_t h, int method, int side, int k, double* 
 
 int bnmtf_nmf_stats(bnmtf_nmf_t h, int method, double* out) {
   if (!h || !out) FAIL("bad argument");
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   refresh_km(h, 0, method); refresh_km(h, 1, method);
   h->km_mode = method == BNMTF_VB ? 2 : 1;
   if (method == BNMTF_VB && launch_sweep(h, method, 0, -2, 0, 0, nullptr, nullptr, false)) return 1;
@@ -887,7 +936,7 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   if (iterations < 0) FAIL("negative iteration count");
   if (method < 0 || method > 3) FAIL("unknown method %d", method);
   if (h->nmtf) FAIL("use bnmtf_nmtf_run for a tri-factorisation handle");
-  CK(cudaSetDevice(h->device));
+  ENTER(h);
   const int K = h->K;
   Side& su = h->s[0]; Side& sv = h->s[1];
   const int want_mu = getenv("BNMTF_TRACE_PARAMS") && atoi(getenv("BNMTF_TRACE_PARAMS")) != 0;
@@ -1016,6 +1065,8 @@ struct DevBuf {
   if (n < 0) FAIL("negative n");                                                                    \
   if (n == 0) return 0;                                                                             \
   CK(cudaSetDevice(device));                                                                        \
+  CK(pool_setup(device));                                                                           \
+  g_stream = cudaStreamPerThread;                                                                   \
   DevBuf in[2], o[2];                                                                               \
   for (int q = 0; q < NIN; ++q) CK(cudaMalloc(&in[q].p, sizeof(double) * n));                       \
   for (int q = 0; q < 2; ++q) CK(cudaMalloc(&o[q].p, sizeof(double) * n));                          \
@@ -1025,8 +1076,8 @@ int bnmtf_tn_draw(int device, uint64_t seed, int64_t n, const double* mu, const 
   DIST_PROLOGUE(2);
   CK(cudaMemcpy(in[0].p, mu, sizeof(double) * n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(in[1].p, tau, sizeof(double) * n, cudaMemcpyHostToDevice));
-  api_tn_draw_kernel<<<grid, 256>>>(in[0].p, in[1].p, o[0].p, n, seed);
-  CK(cudaDeviceSynchronize()); CK(cudaGetLastError());
+  api_tn_draw_kernel<<<grid, 256, 0, g_stream>>>(in[0].p, in[1].p, o[0].p, n, seed);
+  CK(cudaStreamSynchronize(g_stream)); CK(cudaGetLastError());
   CK(cudaMemcpy(out, o[0].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -1035,8 +1086,8 @@ int bnmtf_tn_moments(int device, int64_t n, const double* mu, const double* tau,
   DIST_PROLOGUE(2);
   CK(cudaMemcpy(in[0].p, mu, sizeof(double) * n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(in[1].p, tau, sizeof(double) * n, cudaMemcpyHostToDevice));
-  api_tn_moments_kernel<<<grid, 256>>>(in[0].p, in[1].p, o[0].p, o[1].p, n);
-  CK(cudaDeviceSynchronize()); CK(cudaGetLastError());
+  api_tn_moments_kernel<<<grid, 256, 0, g_stream>>>(in[0].p, in[1].p, o[0].p, o[1].p, n);
+  CK(cudaStreamSynchronize(g_stream)); CK(cudaGetLastError());
   if (exp_out) CK(cudaMemcpy(exp_out, o[0].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
   if (var_out) CK(cudaMemcpy(var_out, o[1].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
   return 0;
@@ -1046,8 +1097,8 @@ int bnmtf_gamma_draw(int device, uint64_t seed, int64_t n, const double* alpha, 
   DIST_PROLOGUE(2);
   CK(cudaMemcpy(in[0].p, alpha, sizeof(double) * n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(in[1].p, beta, sizeof(double) * n, cudaMemcpyHostToDevice));
-  api_gamma_draw_kernel<<<grid, 256>>>(in[0].p, in[1].p, o[0].p, n, seed);
-  CK(cudaDeviceSynchronize()); CK(cudaGetLastError());
+  api_gamma_draw_kernel<<<grid, 256, 0, g_stream>>>(in[0].p, in[1].p, o[0].p, n, seed);
+  CK(cudaStreamSynchronize(g_stream)); CK(cudaGetLastError());
   CK(cudaMemcpy(out, o[0].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -1055,8 +1106,8 @@ int bnmtf_gamma_draw(int device, uint64_t seed, int64_t n, const double* alpha, 
 int bnmtf_exp_draw(int device, uint64_t seed, int64_t n, const double* lambda, double* out) {
   DIST_PROLOGUE(1);
   CK(cudaMemcpy(in[0].p, lambda, sizeof(double) * n, cudaMemcpyHostToDevice));
-  api_exp_draw_kernel<<<grid, 256>>>(in[0].p, o[0].p, n, seed);
-  CK(cudaDeviceSynchronize()); CK(cudaGetLastError());
+  api_exp_draw_kernel<<<grid, 256, 0, g_stream>>>(in[0].p, o[0].p, n, seed);
+  CK(cudaStreamSynchronize(g_stream)); CK(cudaGetLastError());
   CK(cudaMemcpy(out, o[0].p, sizeof(double) * n, cudaMemcpyDeviceToHost));
   return 0;
 }
