@@ -11,6 +11,7 @@
 #include "../../include/bnmtf_b200.h"
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
+#include "kernels_v3.cuh"
 #include "kernels_nmtf.cuh"
 #include "kernels_kmeans.cuh"
 #include "kernels_summary.cuh"
@@ -87,6 +88,7 @@ struct Side {
   int64_t* rowstart = nullptr;
   double *val = nullptr, *var = nullptr, *mu = nullptr, *tau = nullptr;  // [n_padglob][K]
   double* km = nullptr;  // [K][ld][2]
+  double* km3 = nullptr; // [ceil(K/B)][ld][B*NV]: block-major copy read by the blocked cluster sweep of the other side
   int64_t ld = 0;
   double* lam_rm = nullptr;
   double* rowstats = nullptr;  // [n_padglob][NRS]
@@ -106,6 +108,9 @@ struct Side {
   double* tvals = nullptr;
   uint16_t* tcols = nullptr;
   int nclusters[4] = {0, 0, 0, 0};
+  int v3B = 0;                 // columns per cluster exchange of the blocked sweep (0: v2 kernel)
+  int nclusters3[4] = {0, 0, 0, 0};
+  bool v3fit[4] = {false, false, false, false};
   // factor geometry: kf columns; sweeps on this side gather from ysrc ([kf][ysrc_ld][NV])
   int kf = 0;
   const double* ysrc = nullptr;
@@ -237,6 +242,8 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   if (npt2 == 18 && div == 3) div = 2;                             // 28 warps do not split in three
   const int rs = wpc_full / div - 1;                               // rows per set (warp 0 is the control warp)
   sd.v2div = div;
+  sd.v3B = getenv("BNMTF_V3_B") ? atoi(getenv("BNMTF_V3_B")) : 2;
+  if (sd.v3B != 2) sd.v3B = 0;
   const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, V2_CS) * sizeof(double);
   sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && sd.kf >= 3 && smem_vb <= 200 * 1024 && sd.tw * 2 < 65535;
   if (sd.v2 && n > 0) {
@@ -270,6 +277,8 @@ static int alloc_side_state(bnmtf_nmf_s* h, Side& sd, int K) {
   sd.ld = roundup(std::max(sd.n_padglob, sd.n_glob + 1) + V2_CS * 32, 16);  // >= CS * tile width
   CK(cudaMalloc(&sd.km, sizeof(double) * 2 * sd.ld * K));
   CK(cudaMemsetAsync(sd.km, 0, sizeof(double) * 2 * sd.ld * K, h->stream));
+  CK(cudaMalloc(&sd.km3, sizeof(double) * 2 * sd.ld * (K + 3)));
+  CK(cudaMemsetAsync(sd.km3, 0, sizeof(double) * 2 * sd.ld * (K + 3), h->stream));
   CK(cudaMalloc(&sd.rowstats, sizeof(double) * sd.n_padglob * NRS));
   CK(cudaMemsetAsync(sd.rowstats, 0, sizeof(double) * sd.n_padglob * NRS, h->stream));
   return 0;
@@ -317,6 +326,8 @@ static cudaError_t pool_setup(int device) {
     CK(cudaSetDevice((h)->device));       \
     g_stream = (h)->stream;               \
   } while (0)
+
+unsigned long long* bnmtf_prof_last = nullptr;   // timing experiments only (BNMTF_V2_DBG & 2)
 
 static int create_dev_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, int L, bool nmtf, const double* Rrow_dev,
                            const uint8_t* Mrow_dev, const double* Rcol_dev, const uint8_t* Mcol_dev, int64_t row0,
@@ -468,7 +479,7 @@ static int create_host_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, 
 static void free_side(Side& sd) {
   cudaFree(sd.vals); cudaFree(sd.cols); cudaFree(sd.rowstart);
   cudaFree(sd.val); cudaFree(sd.var); cudaFree(sd.mu); cudaFree(sd.tau);
-  cudaFree(sd.km); cudaFree(sd.lam_rm); cudaFree(sd.rowstats);
+  cudaFree(sd.km); cudaFree(sd.km3); cudaFree(sd.lam_rm); cudaFree(sd.rowstats);
   cudaFree(sd.trace[0]); cudaFree(sd.trace[1]);
   cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev); cudaFree(sd.ycomb);
   if (sd.own_dense) { cudaFree((void*)sd.dR); cudaFree((void*)sd.dM); }
@@ -656,6 +667,15 @@ static int refresh_km(bnmtf_nmf_s* h, int side, int method) {
   else
     rm_to_km_kernel<1><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, sd.kf, sd.ld);
   h->launches++;
+  // the blocked cluster sweep of the other side reads the block-major copy
+  const Side& consumer = h->s[1 - side];
+  if (consumer.v2 && consumer.v3B > 0 && !h->nmtf && method != BNMTF_NP) {
+    const int B = consumer.v3B;
+    dim3 g3((unsigned)((sd.ld + 255) / 256), (unsigned)((sd.kf + B - 1) / B));
+    if (method == BNMTF_VB && B == 2) rm_to_kmB_kernel<2, 2><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.km3, sd.n_glob, sd.kf, sd.ld);
+    else if (B == 2) rm_to_kmB_kernel<1, 2><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.km3, sd.n_glob, sd.kf, sd.ld);
+    h->launches++;
+  }
   return 0;
 }
 
@@ -747,6 +767,61 @@ static int launch_sweep2_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
   FAIL("bad v2 block divisor %d", sd.v2div);
 }
 
+template <int NPT, int MODE, int DIV, int B>
+static int launch_sweep3_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method, bool* fits) {
+  constexpr int NV = (MODE == M_VB) ? 2 : 1;
+  auto kern = sweep3_kernel<NPT, MODE, V2_CS, DIV, B>;
+  const size_t smem = sweep3_layout(p.tw, NV, p.rs, p.K, V2_CS, B, Sweep3Rec<B, MODE>::NVAL, MODE == M_VB, p.Xmu != nullptr, MODE == M_GIBBS).total *
+                      sizeof(double);
+  *fits = smem <= (size_t)(227 * 1024) / DIV - 1024;
+  if (!*fits) return 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3((p.rs + 1) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = V2_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (sd.nclusters3[method] == 0) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg.gridDim = dim3(V2_CS * 128);
+    int ncl = 0;
+    CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
+    if (ncl < 1) { *fits = false; return 0; }
+    sd.nclusters3[method] = ncl;
+  }
+  const int ncl = (int)std::min<int64_t>(sd.nclusters3[method], p.nsets);
+  if (ncl < 1) return 0;
+  cfg.gridDim = dim3(V2_CS * ncl);
+  CK(cudaLaunchKernelEx(&cfg, kern, p));
+  h->launches++;
+  return 0;
+}
+
+template <int MODE, int DIV, int B>
+static int launch_sweep3_d(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method, bool* fits) {
+  switch (sd.npt2) {
+    case 4: return launch_sweep3_t<4, MODE, DIV, B>(h, p, sd, method, fits);
+    case 8: return launch_sweep3_t<8, MODE, DIV, B>(h, p, sd, method, fits);
+    case 12: return launch_sweep3_t<12, MODE, DIV, B>(h, p, sd, method, fits);
+    case 16: return launch_sweep3_t<16, MODE, DIV, B>(h, p, sd, method, fits);
+    case 18: return launch_sweep3_t<18, MODE, DIV, B>(h, p, sd, method, fits);
+    case 20: return launch_sweep3_t<20, MODE, DIV, B>(h, p, sd, method, fits);
+  }
+  *fits = false;
+  return 0;
+}
+
+// blocked cluster sweep; *fits = false (and nothing launched) when the configuration does not fit
+template <int MODE>
+static int launch_sweep3_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method, bool* fits) {
+  *fits = false;
+  if (sd.v3B == 2 && sd.v2div == 2) return launch_sweep3_d<MODE, 2, 2>(h, p, sd, method, fits);
+  if (sd.v3B == 2 && sd.v2div == 1) return launch_sweep3_d<MODE, 1, 2>(h, p, sd, method, fits);
+  return 0;
+}
+
 // side: which factor is updated.  single_k: see SweepParams.
 static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint64_t seed, uint32_t iteration,
                         double* out_tau, double* out_mu, bool want_mu, const double* proj_y2 = nullptr,
@@ -769,11 +844,33 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
     p.rmean = h->rmean; p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
     p.dbg = getenv("BNMTF_V2_DBG") ? atoi(getenv("BNMTF_V2_DBG")) : 0;
-    switch (method) {
-      case BNMTF_GIBBS: rc = launch_sweep2_m<M_GIBBS>(h, p, sd, method); break;
-      case BNMTF_ICM: rc = launch_sweep2_m<M_ICM>(h, p, sd, method); break;
-      case BNMTF_VB: rc = launch_sweep2_m<M_VB>(h, p, sd, method); break;
-      default: FAIL("unknown method %d", method);
+    static unsigned long long* prof_buf = nullptr;   // timing experiments only
+    if (p.dbg & 2) {
+      if (!prof_buf) CK(cudaMallocManaged(&prof_buf, sizeof(unsigned long long) * 32));
+      CK(cudaStreamSynchronize(h->stream));
+      memset(prof_buf, 0, sizeof(unsigned long long) * 32);
+      p.prof = prof_buf;
+      bnmtf_prof_last = prof_buf;
+    }
+    bool done3 = false;
+    rc = 0;
+    if (sd.v3B > 0 && !h->nmtf) {
+      p.Ykm = h->s[1 - side].km3;
+      switch (method) {
+        case BNMTF_GIBBS: rc = launch_sweep3_m<M_GIBBS>(h, p, sd, method, &done3); break;
+        case BNMTF_ICM: rc = launch_sweep3_m<M_ICM>(h, p, sd, method, &done3); break;
+        case BNMTF_VB: rc = launch_sweep3_m<M_VB>(h, p, sd, method, &done3); break;
+        default: FAIL("unknown method %d", method);
+      }
+    }
+    if (!done3 && rc == 0) {
+      p.Ykm = sd.ysrc;
+      switch (method) {
+        case BNMTF_GIBBS: rc = launch_sweep2_m<M_GIBBS>(h, p, sd, method); break;
+        case BNMTF_ICM: rc = launch_sweep2_m<M_ICM>(h, p, sd, method); break;
+        case BNMTF_VB: rc = launch_sweep2_m<M_VB>(h, p, sd, method); break;
+        default: FAIL("unknown method %d", method);
+      }
     }
   } else {
     SweepParams p{};
@@ -800,6 +897,16 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
       case BNMTF_VB: rc = launch_sweep_m<M_VB>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
       case BNMTF_NP: rc = launch_sweep_m<M_NP>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
       default: FAIL("unknown method %d", method);
+    }
+  }
+  if (getenv("BNMTF_V2_DBG") && (atoi(getenv("BNMTF_V2_DBG")) & 2) && sd.v2 && single_k == -1 && method != BNMTF_NP) {
+    // phase clocks of cluster 0 / CTA 0 (control warp: slots 0-4, first compute warp: 8-15), in cycles per set
+    cudaStreamSynchronize(h->stream);
+    unsigned long long* pb = bnmtf_prof_last;
+    if (pb && pb[16] > 0) {
+      fprintf(stderr, "[v3 prof side %d] sets %llu | ctrl: pre %llu wait_pass %llu cbar %llu update %llu sync %llu | comp: start %llu resid %llu tilewait %llu pass %llu reduce %llu cbar %llu deltawait %llu tail %llu (cycles/set) | fallback lanes %llu, columns with a fallback %llu of %llu\n",
+              side, pb[16], pb[0] / pb[16], pb[1] / pb[16], pb[2] / pb[16], pb[3] / pb[16], pb[4] / pb[16], pb[8] / pb[16],
+              pb[9] / pb[16], pb[10] / pb[16], pb[11] / pb[16], pb[12] / pb[16], pb[13] / pb[16], pb[14] / pb[16], pb[15] / pb[16], pb[20], pb[21], pb[22]);
     }
   }
   if (timed) {

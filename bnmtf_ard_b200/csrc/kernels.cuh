@@ -405,6 +405,29 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
 // Row-major factor [n_pad][K]  ->  k-major gather layout [K][ld][NV], zero padded
 // for i >= n.  NV == 2 (VB): (exp, var + exp^2) pairs (bnmf_vb.py:254).
 // -----------------------------------------------------------------------------
+// Block-major copy for the blocked cluster sweep (kernels_v3.cuh): the B columns of a block are
+// interleaved per row, Y[(kb * ld + i) * B * NV + j * NV + v] for column kb * B + j; zero for
+// columns >= K and rows >= n.
+template <int NV, int B>
+__global__ void rm_to_kmB_kernel(const double* __restrict__ Xval, const double* __restrict__ Xvar, double* __restrict__ Y,
+                                 int64_t n, int K, int64_t ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int kb = blockIdx.y;
+  if (i >= ld) return;
+  double* dst = Y + ((size_t)kb * ld + i) * (B * NV);
+#pragma unroll
+  for (int j = 0; j < B; ++j) {
+    const int k = kb * B + j;
+    double a = 0.0, b = 0.0;
+    if (i < n && k < K) {
+      a = Xval[i * K + k];
+      if (NV == 2) { const double vv = Xvar[i * K + k]; b = vv + a * a; }
+    }
+    dst[j * NV] = a;
+    if (NV == 2) dst[j * NV + 1] = b;
+  }
+}
+
 template <int NV>
 __global__ void rm_to_km_kernel(const double* __restrict__ Xval, const double* __restrict__ Xvar, double* __restrict__ Ykm,
                                 int64_t n, int K, int64_t ld) {

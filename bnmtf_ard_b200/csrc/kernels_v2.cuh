@@ -169,7 +169,8 @@ struct Sweep2Params {
   uint64_t seed;
   uint32_t iteration;
   uint32_t purpose;
-  int dbg;                               // timing experiments only: 1 = no update math
+  int dbg;                               // timing experiments only: 1 = no update math, 2 = phase clocks into prof
+  unsigned long long* prof;              // [32] clock64 sums of cluster 0 / CTA 0 (dbg & 2)
 };
 
 // dynamic shared memory of sweep2_kernel, in doubles

@@ -143,6 +143,51 @@ __device__ __noinline__ double tn_draw_pre(double num, double prec, double u1, R
   return (d >= 0.0 && isfinite(d)) ? d : 0.0;
 }
 
+// ---- truncated-normal draw with the random material prepared ahead ------------
+// The conditional (num, prec) of a Gibbs update arrives at the end of a latency chain; the
+// inverse-CDF draw above then costs erfc + normcdfinv on that chain.  Everything random can be
+// prepared before the conditional is known: a standard normal z, an Exp(1) variate e, a
+// chi-square-like l = -2 log u and a spare uniform.  With a = -mu/sigma the standardised bound:
+//   a <= 0 : accept z if z >= a                    (plain rejection, acceptance Phi(-a) >= 1/2)
+//   a >  0 : Robert (1995): x = e/alpha, alpha = (a + sqrt(a^2+4))/2, accept if l >= (a+x-alpha)^2
+// and only a rejected proposal falls back to the inverse-CDF draw with the spare uniform.  Each
+// branch returns an exact TN(mu, 1/prec) variate, so the mixture is exact as well.
+struct TnPre { double z, e, l, ufb; };
+
+__device__ __forceinline__ TnPre tn_pre_material(Rng& rng) {
+  TnPre m;
+  const double u1 = rng.u01(), u2 = rng.u01(), u3 = rng.u01();
+  m.ufb = rng.u01();
+  m.z = normcdfinv(u1);
+  m.e = -log(u2);
+  m.l = -2.0 * log(u3);
+  return m;
+}
+
+// rng_fb: the same stream as the material, positioned after it (draw = 2)
+__device__ __forceinline__ double tn_draw_fast(double num, double prec, const TnPre& m, Rng& rng_fb, double& mu_out,
+                                               bool* fell_back = nullptr) {
+  if (prec == 0.0) { mu_out = num / prec; return 0.0; }
+  const double sigma = rsqrt(prec);
+  mu_out = num * sigma * sigma;
+  const double a = -num * sigma;
+  double x;
+  bool ok;
+  if (!(a > 0.0)) {
+    x = m.z - a;
+    ok = (m.z >= a);
+  } else {
+    const double alpha = 0.5 * (a + sqrt(a * a + 4.0));
+    x = m.e / alpha;
+    const double t = (a + x) - alpha;
+    ok = (m.l >= t * t);
+  }
+  if (fell_back) *fell_back = !ok;
+  if (!ok) return tn_draw_pre(num, prec, m.ufb, rng_fb, mu_out);
+  const double d = sigma * x;
+  return (d >= 0.0 && isfinite(d)) ? d : 0.0;
+}
+
 // ---- TN_vector_expectation / TN_vector_variance -----------------------------
 // truncated_normal_vector.py:53-73 (same operation order as the reference so
 // that the results agree to rounding): sigma = 1/sqrt(tau); x = -mu/sigma;

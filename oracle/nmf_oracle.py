@@ -89,6 +89,16 @@ def tn_cdf(x, mu, tau):
     return np.where(x < 0, 0.0, num / den)
 
 
+def tn_cdf_vec(x, mu, tau):
+    """tn_cdf for arrays of (x, mu, tau): 1 - P(Z >= z) / P(Z >= a) through log_ndtr, stable in
+    both tails."""
+    from scipy.special import log_ndtr
+    x, mu, tau = (np.asarray(v, dtype=np.float64) for v in (x, mu, tau))
+    s = np.sqrt(tau)
+    lr = log_ndtr(-(x - mu) * s) - log_ndtr(mu * s)
+    return np.where(x < 0, 0.0, -np.expm1(lr))
+
+
 def gamma_expectation(alpha, beta):
     """code/models/distributions/gamma.py:17-19."""
     return float(alpha) / float(beta)

@@ -290,3 +290,37 @@ def test_reference_literal_cases():
     m2.initialise('exp')
     assert all(m2.lambdak == 3.) and all(m2.alphak_s(k) == 6 + I + J for k in range(K))
     close([m2.betak_s(k) for k in range(K)], [2 + I / 3. + J / 3.] * K, 1e-14)
+
+
+@pytest.mark.parametrize("shape", [(2300, 2500, 6, 0.3), (150, 120, 6, 0.8)])
+def test_gibbs_kernel_draws_follow_their_conditionals(shape, monkeypatch):
+    """The draws made inside the sweep kernels (cluster kernel for the first shape, row-team
+    kernel for the second) are TN(mu, tau) variates of the conditionals the kernel reports:
+    F(draw; mu, tau) must be uniform (KS), on a problem whose surplus components are shrunk
+    (mu < 0: exponential-proposal branch) as well as on active ones (mu > 0)."""
+    from scipy import stats
+    from bnmtf_ard_b200 import bnmf_gibbs
+    from bnmtf_ard_b200._lib import F_MU, F_TAU, SIDE_U, SIDE_V
+    monkeypatch.setenv("BNMTF_TRACE_PARAMS", "1")
+    I, J, K, dens = shape
+    R, M, rng = make_problem(I + J, I, J, 2, dens)          # rank-2 data, K = 6 model
+    hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0}
+    m = bnmf_gibbs(R, M, K, True, hyper)
+    m.verbose = False
+    np.random.seed(17)
+    m.initialise("random")
+    m.run(6)
+    eng = m._engine()
+    for side, X in ((SIDE_U, m.all_U[-1]), (SIDE_V, m.all_V[-1])):
+        mu, tau = eng.get_factor(side, F_MU).ravel(), eng.get_factor(side, F_TAU).ravel()
+        x = X.ravel()
+        assert (x >= 0).all() and np.isfinite(x).all()
+        a = -mu * np.sqrt(tau)
+        for sel, min_frac in ((a <= 0, 0.05), (a > 0, 0.05), ((a > -1) & (a < 1), 0.0)):
+            if x.size >= 5000:
+                assert sel.mean() >= min_frac, "branch not exercised: %.3f" % sel.mean()
+            if sel.sum() < 150:
+                continue
+            u = orc.tn_cdf_vec(x[sel], mu[sel], tau[sel])
+            d, p = stats.kstest(u, "uniform")
+            assert p > 1e-4, (side, sel.mean(), d, p)
