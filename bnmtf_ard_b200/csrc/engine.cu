@@ -685,7 +685,7 @@ static int launch_sweep_t(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int* 
   const int teams = tpr >= 128 ? 1 : 128 / tpr;
   const int block = tpr * teams;
   const int nw = tpr / 32;
-  const size_t smem = sizeof(double) * teams * (4 * (size_t)p.K + 3 * nw + 2 + 2 * (size_t)p.covL);
+  const size_t smem = sizeof(double) * teams * (4 * (size_t)p.K + 3 * nw + 2 + 2 * (size_t)p.covL + (MODE == M_GIBBS ? 4 * (size_t)p.K : 0));
   auto kern = sweep_kernel<NPT, MODE>;
   if (*occ_cache == 0) {
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1148,7 +1148,8 @@ int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {  // out8: 16 values
   out8[4] = h->s[0].nslots; out8[5] = h->s[1].nslots; out8[6] = h->s[0].nnz; out8[7] = h->s[1].nnz;
   for (int q = 0; q < 2; ++q) {
     const Side& sd = h->s[q];
-    out8[8 + 4 * q] = sd.v2 ? 1 : 0; out8[9 + 4 * q] = sd.v2 ? sd.npt2 : 0;
+    out8[8 + 4 * q] = sd.v2 ? ((sd.v3B > 0 && !h->nmtf) ? 3 : 1) : 0;   // 1: cluster sweep, 3: blocked cluster sweep
+    out8[9 + 4 * q] = sd.v2 ? sd.npt2 : 0;
     out8[10 + 4 * q] = sd.v2 ? sd.rs : 0; out8[11 + 4 * q] = sd.v2 ? sd.tslots : 0;
   }
   return 0;

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
   const int wteam = t >> 5;
   const int nw = tpr >> 5;
   const int barA = 1 + 2 * team, barB = 2 + 2 * team;
-  const int team_stride = 4 * K + 3 * nw + 2 + 2 * p.covL;
+  const int team_stride = 4 * K + 3 * nw + 2 + 2 * p.covL + (MODE == M_GIBBS ? 4 * K : 0);
   double* xs = smem + (size_t)team * team_stride;  // [K] current values of the row
   double* xvar = xs + K;                            // [K] VB variance
   double* xmu = xvar + K;                           // [K] conditional mean
@@ -193,6 +193,8 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
   double* bc = red + 3 * nw;                        // [2]
   double* fsv = bc + 2;                             // [covL] (X S)_il of the row   (BNMTF VB)
   double* arow = fsv + p.covL;                      // [covL] A_il of the row
+  double* mat = arow + p.covL;                      // [K][4] Gibbs: random material prepared per column (tn_pre_material)
+  const bool fast_draw = (MODE == M_GIBBS) && p.single_k == -1;
   const bool has_cov = (MODE == M_VB) && (p.covA != nullptr);
   const bool leader = (t == 0);
   const bool dry = (p.single_k == -2);
@@ -215,6 +217,10 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
         c[n] = p.padcol * NV;
       }
       if (MODE == M_NP) { q[n] = e[n]; e[n] = 0.0; }
+    }
+    if (fast_draw) {   // every thread of the team prepares the draw material of some columns, once per row
+      for (int kk = t; kk < K; kk += tpr)
+        tn_pre_material_store(p.seed, p.purpose, (uint64_t)grow, (uint32_t)kk, p.iteration, mat + 4 * kk);
     }
     for (int kk = t; kk < K; kk += tpr) {
       xs[kk] = p.Xval[grow * K + kk];
@@ -329,8 +335,18 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
           }
           s[2] -= cov;
         }
-        double x_new = conditional_update<MODE>(s, x_old, lam, tau, uc, (uint64_t)grow, k, xmu[k], xtau[k], xvar[k], ct, cm,
-                                                vn, acc_esd, acc_q, acc_prior);
+        double x_new;
+        if (fast_draw) {
+          Rng rng(uc.seed, uc.purpose, (uint64_t)grow, (uint32_t)k, uc.iteration);
+          rng.draw = 2;                                         // Philox blocks 0 and 1 made the material
+          const TnPre m{mat[4 * k], mat[4 * k + 1], mat[4 * k + 2], mat[4 * k + 3]};
+          ct = tau * s[0];                                      // tauU, bnmf_gibbs.py:205
+          const double num = -lam + tau * (s[2] + x_old * s[0]);   // numerator of muU, bnmf_gibbs.py:210
+          x_new = tn_draw_fast(num, ct, m, rng, cm);
+        } else {
+          x_new = conditional_update<MODE>(s, x_old, lam, tau, uc, (uint64_t)grow, k, xmu[k], xtau[k], xvar[k], ct, cm, vn,
+                                           acc_esd, acc_q, acc_prior);
+        }
         if (MODE == M_VB) xvar[k] = vn;
         if (p.single_k >= 0) {
           p.out_tau[grow] = ct;

@@ -164,6 +164,14 @@ __device__ __forceinline__ TnPre tn_pre_material(Rng& rng) {
   return m;
 }
 
+// out-of-line version for kernels whose registers are busy when the material is prepared
+__device__ __noinline__ void tn_pre_material_store(uint64_t seed, uint32_t purpose, uint64_t index, uint32_t k, uint32_t iteration,
+                                                   double* dst4) {
+  Rng rng(seed, purpose, index, k, iteration);
+  const TnPre m = tn_pre_material(rng);
+  dst4[0] = m.z; dst4[1] = m.e; dst4[2] = m.l; dst4[3] = m.ufb;
+}
+
 // rng_fb: the same stream as the material, positioned after it (draw = 2)
 __device__ __forceinline__ double tn_draw_fast(double num, double prec, const TnPre& m, Rng& rng_fb, double& mu_out,
                                                bool* fell_back = nullptr) {
