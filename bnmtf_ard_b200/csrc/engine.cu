@@ -142,6 +142,8 @@ struct bnmtf_nmf_s {
   double sweep_ms[2] = {0, 0};
   int64_t sweep_n[2] = {0, 0};
   int km_mode = -1;            // NV layout currently held by the km copies
+  uint32_t* iter_dev = nullptr;        // device-side iteration index (graph replays of the run loop)
+  const uint32_t* iter_ptr = nullptr;  // == iter_dev while a graph-mode run is in progress
   // ---- tri-factorisation (R ~ F S G^T): side 0 = F (I x K), side 1 = G (J x L)
   bool nmtf = false;
   int L = 0;
@@ -497,7 +499,7 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   cudaFree(h->S); cudaFree(h->Svar); cudaFree(h->Smu); cudaFree(h->Stau); cudaFree(h->lamS); cudaFree(h->lamG);
   cudaFree(h->Prow); cudaFree(h->Hrow); cudaFree(h->cvec); cudaFree(h->TT);
   cudaFree(h->Arow); cudaFree(h->Brow); cudaFree(h->Crow); cudaFree(h->BS); cudaFree(h->PA); cudaFree(h->QC);
-  cudaFree(h->lamstateG); cudaFree(h->vbmisc);
+  cudaFree(h->lamstateG); cudaFree(h->vbmisc); cudaFree(h->iter_dev);
   summary_free(h);
   cudaStreamSynchronize(h->stream);
   g_stream = cudaStreamPerThread;
@@ -843,6 +845,7 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     p.scal = h->scal;
     p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
     p.rmean = h->rmean; p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
+    p.iter_ptr = h->iter_ptr;
     p.dbg = getenv("BNMTF_V2_DBG") ? atoi(getenv("BNMTF_V2_DBG")) : 0;
     static unsigned long long* prof_buf = nullptr;   // timing experiments only
     if (p.dbg & 2) {
@@ -890,6 +893,7 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
     p.rmean = h->rmean;
     p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
+    p.iter_ptr = h->iter_ptr;
     p.single_k = single_k;
     switch (method) {
       case BNMTF_GIBBS: rc = launch_sweep_m<M_GIBBS>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
@@ -924,7 +928,7 @@ static int launch_lambda(bnmtf_nmf_s* h, int method, uint64_t seed, uint32_t ite
   const int K = h->K;
 #define LK(MODE)                                                                                                      \
   lambda_kernel<MODE><<<K, 256, 0, h->stream>>>(su.km, su.ld, h->I, sv.km, sv.ld, h->J, K, h->hyper, h->colsum,       \
-                                                h->lamstate, h->lamk, seed, iteration, update)
+                                                h->lamstate, h->lamk, seed, iteration, update, h->iter_ptr)
   switch (method) {
     case BNMTF_GIBBS: LK(M_GIBBS); break;
     case BNMTF_ICM: LK(M_ICM); break;
@@ -941,7 +945,7 @@ static int launch_finalize(bnmtf_nmf_s* h, int method, double* stats_out, uint64
 #define FK(MODE)                                                                                                    \
   finalize_kernel<MODE><<<1, 1024, 0, h->stream>>>(su.rowstats, su.n_glob, sv.rowstats, sv.n_glob, h->K, h->hyper,   \
                                                    h->colsum, h->lamstate, h->scal, stats_out, seed, iteration,     \
-                                                   update, h->I, h->J)
+                                                   update, h->I, h->J, h->iter_ptr ? h->iter_dev : nullptr)
   switch (method) {
     case BNMTF_GIBBS: FK(M_GIBBS); break;
     case BNMTF_ICM: FK(M_ICM); break;
@@ -1089,7 +1093,62 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   };
 
   const int nchunks = (iterations + chunk - 1) / chunk;
-  for (int c = 0; c < nchunks; ++c) {
+  // Small problems are launch-bound (~9 kernels of a few microseconds per iteration): run iteration 0 eagerly, capture
+  // iteration 1 into a CUDA graph and replay it.  The iteration index (Philox counters, trace and statistics slots)
+  // then lives on the device: finalize_kernel advances it.
+  const char* vdbg = getenv("BNMTF_V2_DBG");
+  const bool use_graph = h->world <= 1 && iterations >= 8 && nchunks == 1 && h->sum_thin <= 0 && !h->time_sweeps &&
+                         !getenv("BNMTF_NO_GRAPH") && !(vdbg && (atoi(vdbg) & 2));
+  if (use_graph) {
+    if (!h->iter_dev) CK(cudaMalloc(&h->iter_dev, sizeof(uint32_t)));
+    CK(cudaMemsetAsync(h->iter_dev, 0, sizeof(uint32_t), h->stream));
+    h->iter_ptr = h->iter_dev;
+    const bool lam_tr = h->hyper.ARD && method != BNMTF_NP;
+    auto one_iteration = [&]() -> int {
+      if (launch_lambda(h, method, seed, 0, 1)) return 1;                                  // bnmf_gibbs.py:149-152
+      if (launch_sweep(h, method, 0, -1, seed, 0, nullptr, nullptr, want_mu)) return 1;    // :154-158
+      refresh_km(h, 0, method);
+      if (launch_sweep(h, method, 1, -1, seed, 0, nullptr, nullptr, want_mu)) return 1;    // :160-164
+      refresh_km(h, 1, method);
+      if (method == BNMTF_VB && launch_lambda(h, method, seed, 0, 0)) return 1;
+      if (tr || lam_tr) {
+        const int64_t nU = su.n_glob * K, nV = sv.n_glob * K;
+        const unsigned grid = (unsigned)std::min<int64_t>((std::max(nU, nV) + 255) / 256, (int64_t)h->num_sms * 4);
+        trace_copy_kernel<<<std::max(grid, 1u), 256, 0, h->stream>>>(tr ? su.trace[0] : nullptr, su.val, nU, tr ? sv.trace[0] : nullptr,
+                                                                    sv.val, nV, lam_tr ? lam_trace : nullptr, h->lamk, K, h->iter_dev);
+        h->launches++;
+      }
+      return launch_finalize(h, method, h->stats_dev, seed, 0, 1);                         // :166-167,175
+    };
+    int rc = one_iteration();
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    if (!rc) {
+      cudaError_t ce = cudaEventRecord(ev[1], h->stream);
+      const int64_t l0 = h->launches;
+      if (ce == cudaSuccess) ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+      if (ce == cudaSuccess) {
+        rc = one_iteration();
+        ce = cudaStreamEndCapture(h->stream, &graph);
+      }
+      const int64_t per_it = h->launches - l0;
+      if (!rc && ce == cudaSuccess) ce = cudaGraphInstantiate(&gexec, graph, 0);
+      if (!rc && ce == cudaSuccess) {
+        for (int it = 1; it < iterations && ce == cudaSuccess; ++it) {
+          ce = cudaGraphLaunch(gexec, h->stream);
+          if (ce == cudaSuccess) ce = cudaEventRecord(ev[it + 1], h->stream);
+        }
+        h->launches += per_it * (int64_t)(iterations - 2);
+      }
+      if (gexec) cudaGraphExecDestroy(gexec);
+      if (graph) cudaGraphDestroy(graph);
+      if (!rc && ce != cudaSuccess) { h->iter_ptr = nullptr; FAIL("graph replay of the iteration failed: %s", cudaGetErrorString(ce)); }
+    }
+    h->iter_ptr = nullptr;
+    if (rc) return 1;
+    if (tr) CK(cudaEventRecord(chunk_done[0], h->stream));
+  }
+  for (int c = 0; c < nchunks && !use_graph; ++c) {
     const int b = c & 1;
     if (tr && c >= 2) CK(cudaStreamWaitEvent(h->stream, chunk_copied[b], 0));
     const int it0 = c * chunk, it1 = std::min(iterations, it0 + chunk);

@@ -46,6 +46,7 @@ struct SweepParams {
   double rmean;
   uint64_t seed;
   uint32_t iteration;
+  const uint32_t* iter_ptr;              // when set (graph replays) the iteration index is read from the device
   uint32_t purpose;
   int single_k;                          // >=0 one column, no state change; -1 sweep; -2 dry (stats only);
                                          // -3 project: out_mu[row][l] = sum_j e_j Y2[l][j], l < K2 (NMTF S statistics)
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
   const bool fast_draw = (MODE == M_GIBBS) && p.single_k == -1;
   const bool has_cov = (MODE == M_VB) && (p.covA != nullptr);
   const bool leader = (t == 0);
+  const uint32_t iteration = p.iter_ptr ? *p.iter_ptr : p.iteration;
   const bool dry = (p.single_k == -2);
 
   for (int row = blockIdx.x * teams + team; row < p.n_loc; row += gridDim.x * teams) {
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
     }
     if (fast_draw) {   // every thread of the team prepares the draw material of some columns, once per row
       for (int kk = t; kk < K; kk += tpr)
-        tn_pre_material_store(p.seed, p.purpose, (uint64_t)grow, (uint32_t)kk, p.iteration, mat + 4 * kk);
+        tn_pre_material_store(p.seed, p.purpose, (uint64_t)grow, (uint32_t)kk, iteration, mat + 4 * kk);
     }
     for (int kk = t; kk < K; kk += tpr) {
       xs[kk] = p.Xval[grow * K + kk];
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
         const double x_old = xs[k];
         const double lam = p.lamk ? p.lamk[k] : (p.lam_rm ? p.lam_rm[grow * K + k] : 0.0);
         const double tau = p.scal[0];
-        const UpdateCtx uc{p.seed, p.purpose, p.iteration, dry};
+        const UpdateCtx uc{p.seed, p.purpose, iteration, dry};
         double cm, ct, vn;
         if (has_cov) {   // diff_term - cov_term (bnmtf_vb.py:342-348)
           double cov = 0.0;
@@ -509,10 +511,11 @@ enum { SC_TAU = 0, SC_LOGTAU = 1, SC_ALPHA_S = 2, SC_BETA_S = 3, SC_COUNT = 8 };
 template <int MODE>
 __global__ void lambda_kernel(const double* __restrict__ Ukm, int64_t ldu, int64_t I, const double* __restrict__ Vkm,
                               int64_t ldv, int64_t J, int K, Hyper h, double* colsum, double* lamstate, double* lamk,
-                              uint64_t seed, uint32_t iteration, int update) {
+                              uint64_t seed, uint32_t iteration, int update, const uint32_t* iter_ptr) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
   __shared__ double sh[32];
   const int k = blockIdx.x;
+  if (iter_ptr) iteration = *iter_ptr;
   double a = 0.0, b = 0.0;
   for (int64_t i = threadIdx.x; i < I; i += blockDim.x) a += Ukm[((size_t)k * ldu + i) * NV];
   for (int64_t j = threadIdx.x; j < J; j += blockDim.x) b += Vkm[((size_t)k * ldv + j) * NV];
@@ -554,9 +557,11 @@ template <int MODE>
 __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ rsU, int64_t nU, const double* __restrict__ rsV, int64_t nV,
                                 int K, Hyper h, const double* __restrict__ colsum, const double* __restrict__ lamstate,
                                 double* scal, double* stats_out, uint64_t seed, uint32_t iteration, int update,
-                                int64_t I, int64_t J) {
+                                int64_t I, int64_t J, uint32_t* iter_ctr) {
   __shared__ double sh[32];
   __shared__ double tot[2 * NRS];
+  // graph replays: the iteration index lives on the device; this kernel ends the iteration and advances it
+  if (iter_ctr) { iteration = *iter_ctr; stats_out += (size_t)iteration * 16; }
   for (int sidx = 0; sidx < 2; ++sidx) {
     const double* rs = sidx == 0 ? rsU : rsV;
     const int64_t n = sidx == 0 ? nU : nV;
@@ -621,6 +626,19 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
   }
   if (update) scal[SC_TAU] = tau;
   stats_out[3] = tau; stats_out[4] = beta_s; stats_out[9] = alpha_s;
+  if (iter_ctr && update) *iter_ctr = iteration + 1;
+}
+
+// Graph replays: copy the draws of the iteration *iter_ptr into the trace staging buffers
+// (all_U[it], all_V[it], all_lambdak[it]); runs before finalize_kernel advances the index.
+__global__ void trace_copy_kernel(double* __restrict__ dstU, const double* __restrict__ srcU, int64_t nU, double* __restrict__ dstV,
+                                  const double* __restrict__ srcV, int64_t nV, double* __restrict__ dstL,
+                                  const double* __restrict__ srcL, int64_t nL, const uint32_t* __restrict__ iter_ptr) {
+  const size_t it = *iter_ptr;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (dstU) for (int64_t i = t0; i < nU; i += stride) dstU[it * nU + i] = srcU[i];
+  if (dstV) for (int64_t i = t0; i < nV; i += stride) dstV[it * nV + i] = srcV[i];
+  if (dstL) for (int64_t i = t0; i < nL; i += stride) dstL[it * nL + i] = srcL[i];
 }
 
 // ---- packing -----------------------------------------------------------------

@@ -168,6 +168,7 @@ struct Sweep2Params {
   double rmean;
   uint64_t seed;
   uint32_t iteration;
+  const uint32_t* iter_ptr;              // when set (graph replays) the iteration index is read from the device
   uint32_t purpose;
   int dbg;                               // timing experiments only: 1 = no update math, 2 = phase clocks into prof
   unsigned long long* prof;              // [32] clock64 sums of cluster 0 / CTA 0 (dbg & 2)
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
   if (warp == 0) {
     // =========================== control warp ===========================
     uint32_t gseq = 0;
-    const UpdateCtx uc{p.seed, p.purpose, p.iteration, false};
+    const UpdateCtx uc{p.seed, p.purpose, p.iter_ptr ? *p.iter_ptr : p.iteration, false};
     const double tau = p.scal[0];
     for (int set = cid; set < p.nsets; set += nclusters) {
       const int rows_here = min(RS, p.n_loc - set * RS);

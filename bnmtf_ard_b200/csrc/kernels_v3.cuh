@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep3_ke
   if (warp == 0) {
     // =========================== control warp ===========================
     uint32_t gblk = 0;
-    const UpdateCtx uc{p.seed, p.purpose, p.iteration, false};
+    const UpdateCtx uc{p.seed, p.purpose, p.iter_ptr ? *p.iter_ptr : p.iteration, false};
     const double tau = p.scal[0];
     // Gibbs: the random material of CPR columns x RS rows is produced per round, lane = (column, row)
     constexpr int CPR = (32 / RS) < 1 ? 1 : (32 / RS);
