@@ -103,3 +103,23 @@ def test_driver_logs_match_reference(gold, tmp_path):
         assert open(f).read() == open(f2).read()
         with pytest.raises(Exception):
             p.run_model(None, None, None)
+
+
+def test_stratified_folds_equal_sklearn():
+    """The vectorised stratified assignment reproduces scikit-learn's StratifiedKFold(shuffle=True)
+    draw for draw (same numpy global state in, same folds out)."""
+    from sklearn.model_selection import StratifiedKFold
+    from bnmtf_ard_b200.cross_validation import mask
+    rng = np.random.default_rng(8)
+    for n_classes, n_splits in ((17, 5), (60, 10), (5, 3)):
+        sizes = rng.integers(n_splits, 40, n_classes)
+        labels = np.repeat(np.arange(n_classes) * 3 + 1, sizes)
+        np.random.seed(123)
+        ref = np.empty(labels.size, dtype=int)
+        for f, (_, test) in enumerate(StratifiedKFold(n_splits=n_splits, shuffle=True).split(np.zeros(labels.size), labels)):
+            ref[test] = f
+        state_ref = np.random.get_state()[1].copy()
+        np.random.seed(123)
+        got = mask._stratified_test_folds(labels, n_splits)
+        assert np.array_equal(got, ref)
+        assert np.array_equal(np.random.get_state()[1], state_ref)      # same consumption of the global stream
