@@ -146,13 +146,18 @@ __global__ void nmtf_reduce_T_kernel(const double* __restrict__ F, const double*
 template <int MODE>
 __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restrict__ c_in, const double* __restrict__ TT, int K, int L, double* S,
                                     const double* __restrict__ lamS, const double* __restrict__ scal, uint64_t seed,
-                                    uint32_t iteration, double* mu_out, double* tau_out, int single_d) {
+                                    uint32_t iteration, double* mu_out, double* tau_out, int single_d, const uint32_t* iter_ptr) {
   extern __shared__ double shs[];
   const int KL = K * L, NPL = L * (L + 1) / 2;
   double* c = shs;            // [KL]
   double* sv = c + KL;        // [KL]
-  double* bc = sv + KL;       // [1]
-  for (int d = threadIdx.x; d < KL; d += blockDim.x) { c[d] = c_in[d]; sv[d] = S[d]; }
+  double* bc = sv + KL;       // [2]
+  double* mat = bc + 2;       // [KL][4] Gibbs: random material of every entry, prepared by all threads up front
+  if (iter_ptr) iteration = *iter_ptr;
+  for (int d = threadIdx.x; d < KL; d += blockDim.x) {
+    c[d] = c_in[d]; sv[d] = S[d];
+    if (MODE == M_GIBBS && single_d < 0) tn_pre_material_store(seed, RNG_S, (uint64_t)d, 0u, iteration, mat + 4 * d);
+  }
   __syncthreads();
   const double tau = scal[0];
   const int d_begin = single_d >= 0 ? single_d : 0, d_end = single_d >= 0 ? single_d + 1 : KL;
@@ -163,9 +168,14 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restr
       const double ct = tau * Tdd;                                        // bnmtf_gibbs.py:279
       const double cm = (-lamS[d] + tau * (c[d] + sv[d] * Tdd)) / ct;     // bnmtf_gibbs.py:283
       double x_new;
-      if (MODE == M_GIBBS) {
+      if (MODE == M_GIBBS && single_d < 0) {
         Rng rng(seed, RNG_S, (uint64_t)d, 0u, iteration);
-        x_new = tn_draw(cm, ct, rng);
+        rng.draw = 2;                                   // Philox blocks 0 and 1 made the material
+        const TnPre m{mat[4 * d], mat[4 * d + 1], mat[4 * d + 2], mat[4 * d + 3]};
+        double cm2;
+        x_new = tn_draw_fast(-lamS[d] + tau * (c[d] + sv[d] * Tdd), ct, m, rng, cm2);
+      } else if (MODE == M_GIBBS) {
+        x_new = sv[d];
       } else {
         x_new = fmax(fmax(0.0, cm), MINIMUM_TN);
       }
@@ -194,8 +204,9 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restr
 template <int MODE>
 __global__ void nmtf_lambda_kernel(const double* __restrict__ F, int64_t I, int K, const double* __restrict__ G, int64_t J, int L,
                                    Hyper h, double* colsum, double* lamF, double* lamG, uint64_t seed, uint32_t iteration,
-                                   int update) {
+                                   int update, const uint32_t* iter_ptr) {
   __shared__ double sh[32];
+  if (iter_ptr) iteration = *iter_ptr;
   const int c = blockIdx.x;
   const bool isF = c < K;
   const double* X = isF ? F : G;
