@@ -1040,6 +1040,50 @@ int bnmtf_nmf_stats(bnmtf_nmf_t h, int method, double* out) {
   return 0;
 }
 
+// Launch-bound run loops: iteration 0 eagerly (first-use attribute / occupancy calls happen here), iteration 1 captured
+// into a CUDA graph, the graph replayed for the rest.  While this runs h->iter_ptr is set: kernels read the iteration
+// index (Philox counters, trace and statistics slots) from the device and the finalize kernel advances it.
+static bool graph_mode_allowed(const bnmtf_nmf_s* h, int iterations) {
+  const char* vdbg = getenv("BNMTF_V2_DBG");
+  return h->world <= 1 && iterations >= 8 && h->sum_thin <= 0 && !h->time_sweeps && !getenv("BNMTF_NO_GRAPH") &&
+         !(vdbg && (atoi(vdbg) & 2));
+}
+
+template <class F>
+static int run_graph_replays(bnmtf_nmf_s* h, int iterations, std::vector<cudaEvent_t>& ev, F&& one_iteration) {
+  if (!h->iter_dev) CK(cudaMalloc(&h->iter_dev, sizeof(uint32_t)));
+  CK(cudaMemsetAsync(h->iter_dev, 0, sizeof(uint32_t), h->stream));
+  h->iter_ptr = h->iter_dev;
+  int rc = one_iteration();
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  cudaError_t ce = cudaSuccess;
+  if (!rc) {
+    ce = cudaEventRecord(ev[1], h->stream);
+    const int64_t l0 = h->launches;
+    if (ce == cudaSuccess) ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    if (ce == cudaSuccess) {
+      rc = one_iteration();
+      ce = cudaStreamEndCapture(h->stream, &graph);
+    }
+    const int64_t per_it = h->launches - l0;
+    if (!rc && ce == cudaSuccess) ce = cudaGraphInstantiate(&gexec, graph, 0);
+    if (!rc && ce == cudaSuccess) {
+      for (int it = 1; it < iterations && ce == cudaSuccess; ++it) {
+        ce = cudaGraphLaunch(gexec, h->stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ev[it + 1], h->stream);
+      }
+      h->launches += per_it * (int64_t)(iterations - 2);
+    }
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+  h->iter_ptr = nullptr;
+  if (rc) return 1;
+  if (ce != cudaSuccess) FAIL("graph replay of the iteration failed: %s", cudaGetErrorString(ce));
+  return 0;
+}
+
 // run(iterations): see include/bnmtf_b200.h
 int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, double* all_U, double* all_V,
                   double* all_lambdak, double* iter_stats, double* iter_seconds) {
@@ -1093,16 +1137,9 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   };
 
   const int nchunks = (iterations + chunk - 1) / chunk;
-  // Small problems are launch-bound (~9 kernels of a few microseconds per iteration): run iteration 0 eagerly, capture
-  // iteration 1 into a CUDA graph and replay it.  The iteration index (Philox counters, trace and statistics slots)
-  // then lives on the device: finalize_kernel advances it.
-  const char* vdbg = getenv("BNMTF_V2_DBG");
-  const bool use_graph = h->world <= 1 && iterations >= 8 && nchunks == 1 && h->sum_thin <= 0 && !h->time_sweeps &&
-                         !getenv("BNMTF_NO_GRAPH") && !(vdbg && (atoi(vdbg) & 2));
+  // Small problems are launch-bound (~9 kernels of a few microseconds per iteration): replay the iteration as a graph
+  const bool use_graph = graph_mode_allowed(h, iterations) && nchunks == 1;
   if (use_graph) {
-    if (!h->iter_dev) CK(cudaMalloc(&h->iter_dev, sizeof(uint32_t)));
-    CK(cudaMemsetAsync(h->iter_dev, 0, sizeof(uint32_t), h->stream));
-    h->iter_ptr = h->iter_dev;
     const bool lam_tr = h->hyper.ARD && method != BNMTF_NP;
     auto one_iteration = [&]() -> int {
       if (launch_lambda(h, method, seed, 0, 1)) return 1;                                  // bnmf_gibbs.py:149-152
@@ -1120,32 +1157,7 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
       }
       return launch_finalize(h, method, h->stats_dev, seed, 0, 1);                         // :166-167,175
     };
-    int rc = one_iteration();
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t gexec = nullptr;
-    if (!rc) {
-      cudaError_t ce = cudaEventRecord(ev[1], h->stream);
-      const int64_t l0 = h->launches;
-      if (ce == cudaSuccess) ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
-      if (ce == cudaSuccess) {
-        rc = one_iteration();
-        ce = cudaStreamEndCapture(h->stream, &graph);
-      }
-      const int64_t per_it = h->launches - l0;
-      if (!rc && ce == cudaSuccess) ce = cudaGraphInstantiate(&gexec, graph, 0);
-      if (!rc && ce == cudaSuccess) {
-        for (int it = 1; it < iterations && ce == cudaSuccess; ++it) {
-          ce = cudaGraphLaunch(gexec, h->stream);
-          if (ce == cudaSuccess) ce = cudaEventRecord(ev[it + 1], h->stream);
-        }
-        h->launches += per_it * (int64_t)(iterations - 2);
-      }
-      if (gexec) cudaGraphExecDestroy(gexec);
-      if (graph) cudaGraphDestroy(graph);
-      if (!rc && ce != cudaSuccess) { h->iter_ptr = nullptr; FAIL("graph replay of the iteration failed: %s", cudaGetErrorString(ce)); }
-    }
-    h->iter_ptr = nullptr;
-    if (rc) return 1;
+    if (run_graph_replays(h, iterations, ev, one_iteration)) return 1;
     if (tr) CK(cudaEventRecord(chunk_done[0], h->stream));
   }
   for (int c = 0; c < nchunks && !use_graph; ++c) {

@@ -384,9 +384,11 @@ __global__ void nmtf_lambda_vb_kernel(const double* __restrict__ F, int64_t I, i
 __global__ void __launch_bounds__(1024) nmtf_vb_finalize_kernel(const double* __restrict__ rsF, int64_t nF, const double* __restrict__ rsG, int64_t nG, int K,
                                         int L, Hyper h, double sumlog_lamS, const double* __restrict__ colsum,
                                         const double* __restrict__ state, const double* __restrict__ misc, double* scal,
-                                        double* stats_out, int update, int64_t I, int64_t J) {
+                                        double* stats_out, int update, int64_t I, int64_t J, uint32_t* iter_ctr) {
   __shared__ double sh[32];
   __shared__ double tot[2 * NRS];
+  uint32_t iteration = 0;
+  if (iter_ctr) { iteration = *iter_ctr; stats_out += (size_t)iteration * 16; }   // graph replays: see finalize_kernel
   for (int sidx = 0; sidx < 2; ++sidx) {
     const double* rs = sidx == 0 ? rsF : rsG;
     const int64_t n = sidx == 0 ? nF : nG;
@@ -437,6 +439,7 @@ __global__ void __launch_bounds__(1024) nmtf_vb_finalize_kernel(const double* __
   elbo += -a_s * log(b_s) + lgamma(a_s) - (a_s - 1.0) * exp_logtau + b_s * tau;
   stats_out[3] = tau; stats_out[4] = beta_s; stats_out[5] = esd; stats_out[6] = elbo; stats_out[8] = exp_logtau;
   stats_out[9] = alpha_s;
+  if (iter_ctr && update) *iter_ctr = iteration + 1;
 }
 
 // nmtf_np.update_S(k,l) (nmtf_np.py:181-188): S_kl <- S_kl * sum_i F_ik num_i / sum_i F_ik den_i with the row parts
