@@ -151,6 +151,7 @@ struct bnmtf_nmf_s {
   double* lamG = nullptr;      // [L] (lamk holds lambdaFk)
   double *Prow = nullptr, *Hrow = nullptr;   // [I_pad][L], [I_pad][L(L+1)/2]
   double *cvec = nullptr, *TT = nullptr;     // [K*L], [K(K+1)/2][L(L+1)/2]
+  double* Tpart = nullptr;                   // [RT_RC][max tensor]: partial tiles of nmtf_reduce_T
   double* sumlog_lamS_dev = nullptr;
   double sumlog_lamS = 0.0;
   // BNMTF VB
@@ -497,7 +498,7 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   free_side(h->s[0]); free_side(h->s[1]);
   cudaFree(h->scal); cudaFree(h->colsum); cudaFree(h->lamstate); cudaFree(h->lamk); cudaFree(h->stats_dev);
   cudaFree(h->S); cudaFree(h->Svar); cudaFree(h->Smu); cudaFree(h->Stau); cudaFree(h->lamS); cudaFree(h->lamG);
-  cudaFree(h->Prow); cudaFree(h->Hrow); cudaFree(h->cvec); cudaFree(h->TT);
+  cudaFree(h->Prow); cudaFree(h->Hrow); cudaFree(h->cvec); cudaFree(h->TT); cudaFree(h->Tpart);
   cudaFree(h->Arow); cudaFree(h->Brow); cudaFree(h->Crow); cudaFree(h->BS); cudaFree(h->PA); cudaFree(h->QC);
   cudaFree(h->lamstateG); cudaFree(h->vbmisc); cudaFree(h->iter_dev);
   summary_free(h);

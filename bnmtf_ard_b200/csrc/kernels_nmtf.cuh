@@ -44,57 +44,83 @@ __host__ __device__ __forceinline__ int pair_index(int a, int b, int L) {   // a
 }
 
 // H_i[pair(l,l')] = sum_{j in Omega_i} G_jl G_jl'   -- one warp per row of the row layout.
-// The G rows of 32 consecutive observed entries are staged in shared memory (one coalesced
-// 8*L-byte load each); lane (bi,bj) accumulates the 4x4 block of H_i from two 32-byte shared
-// loads per entry (16 FMAs per 4 loads).  NB = ceil(L/4) blocks per dimension, NB*NB <= 64.
-template <int NBLK>   // blocks handled per lane: 1 (L <= 20) or 2 (L <= 32)
-__global__ void __launch_bounds__(128) nmtf_gram_kernel(const uint32_t* __restrict__ cols, const int64_t* __restrict__ rowstart,
-                                                         int n_loc, int64_t row0, uint32_t padcol, const double* __restrict__ G_rm,
-                                                         int L, double* __restrict__ Hrow, int NP) {
-  constexpr int LP = 36;                       // padded row length in shared memory (>= 32, breaks bank alignment)
-  __shared__ __align__(32) double tile[4][32][LP];
+// The G rows of 32 consecutive observed entries are staged in shared memory with cp.async (16-byte
+// pieces, double buffered: the copies of the next 32 entries fly while the current ones are used).
+// Lane b owns a 4 x 2 block of H_i (rows 4*bi.., columns 2*bj..) of the upper triangle: one 32-byte
+// and one 16-byte shared load and 8 FMAs per entry; L <= 20 needs 30 blocks (NBLK = 1), L <= 28 two
+// per lane, L <= 32 three.
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NBLK, int LP, int WARPS, bool EVEN>   // LP: row length in shared memory (multiple of 4, >= L)
+__global__ void __launch_bounds__(WARPS * 32) nmtf_gram_kernel(const uint32_t* __restrict__ cols, const int64_t* __restrict__ rowstart,
+                                                                int n_loc, int64_t row0, uint32_t padcol, const double* __restrict__ G_rm,
+                                                                int L, double* __restrict__ Hrow, int NP) {
+  __shared__ __align__(32) double tile[WARPS][2][32][LP];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 4 + w;
+  const int row = blockIdx.x * WARPS + w;
   if (row >= n_loc) return;
-  const int NB = (L + 3) / 4;
+  const int NBA = (L + 3) / 4, NBC = (L + 1) / 2;
   int bi[NBLK], bj[NBLK];
-  double acc[NBLK][4][4];
+  double acc[NBLK][4][2];
 #pragma unroll
   for (int b = 0; b < NBLK; ++b) {
-    const int id = lane + 32 * b;
-    bi[b] = id / NB; bj[b] = id - bi[b] * NB;
-    if (bi[b] >= NB || bi[b] > bj[b]) { bi[b] = -1; bj[b] = 0; }   // lower-triangle blocks are not needed
+    // enumerate the needed blocks (bj >= 2 bi) row by row: block id -> (bi, bj)
+    int id = lane + 32 * b, a = 0;
+    while (a < NBA && id >= NBC - 2 * a) { id -= NBC - 2 * a; ++a; }
+    bi[b] = a < NBA ? a : -1;
+    bj[b] = a < NBA ? 2 * a + id : 0;
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-      for (int y = 0; y < 4; ++y) acc[b][x][y] = 0.0;
+    for (int x = 0; x < 4; ++x) { acc[b][x][0] = 0.0; acc[b][x][1] = 0.0; }
   }
-  // zero the padding columns once (entries beyond L stay 0 so that partial blocks add nothing)
-  for (int r = 0; r < 32; ++r)
-    for (int q = L + lane; q < LP; q += 32) tile[w][r][q] = 0.0;
+  // columns L..LP-1 of both buffers stay zero, so partial blocks add nothing
+  for (int q = lane; q < 2 * 32 * LP; q += 32) (&tile[w][0][0][0])[q] = 0.0;
+  __syncwarp();
   const int64_t beg = rowstart[row], end = rowstart[row + 1];
-  for (int64_t q0 = beg; q0 < end; q0 += 32) {
+  constexpr int PD = EVEN ? 2 : 1;             // doubles per copied piece (16-byte pieces need an even L)
+  const int pieces = L / PD;
+  auto stage = [&](int64_t q0, int buf) {
     const uint32_t mycol = (q0 + lane < end) ? cols[q0 + lane] : padcol;
-    __syncwarp();
-    for (int r = 0; r < 32; ++r) {
+    const int total = 32 * pieces;
+    for (int idx0 = 0; idx0 < total; idx0 += 32) {
+      const int idx = idx0 + lane;
+      const int r = min(idx, total - 1) / pieces, pc = min(idx, total - 1) - r * pieces;
       const uint32_t j = __shfl_sync(0xffffffffu, mycol, r);
-      if (lane < L) tile[w][r][lane] = (j == padcol) ? 0.0 : __ldg(G_rm + (size_t)j * L + lane);
+      if (idx < total) {
+        double* dst = &tile[w][buf][r][PD * pc];
+        if (j == padcol) { dst[0] = 0.0; if (EVEN) dst[1] = 0.0; }
+        else if (EVEN) cp_async_16(dst, G_rm + (size_t)j * L + PD * pc);
+        else cp_async_8(dst, G_rm + (size_t)j * L + pc);
+      }
     }
+    cp_async_commit();
+  };
+  if (beg < end) stage(beg, 0);
+  int buf = 0;
+  for (int64_t q0 = beg; q0 < end; q0 += 32, buf ^= 1) {
+    if (q0 + 32 < end) { stage(q0 + 32, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncwarp();
 #pragma unroll 4
     for (int r = 0; r < 32; ++r) {
 #pragma unroll
       for (int b = 0; b < NBLK; ++b) {
         if (bi[b] < 0) continue;
-        const double4 a = *reinterpret_cast<const double4*>(&tile[w][r][4 * bi[b]]);
-        const double4 c = *reinterpret_cast<const double4*>(&tile[w][r][4 * bj[b]]);
-        const double av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-          for (int y = 0; y < 4; ++y) acc[b][x][y] = fma(av[x], cv[y], acc[b][x][y]);
+        const double4 a = *reinterpret_cast<const double4*>(&tile[w][buf][r][4 * bi[b]]);
+        const double2 c = *reinterpret_cast<const double2*>(&tile[w][buf][r][2 * bj[b]]);
+        acc[b][0][0] = fma(a.x, c.x, acc[b][0][0]); acc[b][0][1] = fma(a.x, c.y, acc[b][0][1]);
+        acc[b][1][0] = fma(a.y, c.x, acc[b][1][0]); acc[b][1][1] = fma(a.y, c.y, acc[b][1][1]);
+        acc[b][2][0] = fma(a.z, c.x, acc[b][2][0]); acc[b][2][1] = fma(a.z, c.y, acc[b][2][1]);
+        acc[b][3][0] = fma(a.w, c.x, acc[b][3][0]); acc[b][3][1] = fma(a.w, c.y, acc[b][3][1]);
       }
     }
+    __syncwarp();
   }
 #pragma unroll
   for (int b = 0; b < NBLK; ++b) {
@@ -102,8 +128,8 @@ __global__ void __launch_bounds__(128) nmtf_gram_kernel(const uint32_t* __restri
 #pragma unroll
     for (int x = 0; x < 4; ++x)
 #pragma unroll
-      for (int y = 0; y < 4; ++y) {
-        const int a = 4 * bi[b] + x, c = 4 * bj[b] + y;
+      for (int y = 0; y < 2; ++y) {
+        const int a = 4 * bi[b] + x, c = 2 * bj[b] + y;
         if (a <= c && c < L) Hrow[(size_t)(row0 + row) * NP + pair_index(a, c, L)] = acc[b][x][y];
       }
   }
@@ -120,24 +146,68 @@ __global__ void nmtf_reduce_c_kernel(const double* __restrict__ F, const double*
   if (threadIdx.x == 0) c[blockIdx.x] = a;
 }
 
-// TT[pk][pl] = sum_i F[i][ka] F[i][kb] H[i][pl]; block = 32 (pl) x 8 (row slices), fixed order
-__global__ void nmtf_reduce_T_kernel(const double* __restrict__ F, const double* __restrict__ H, int64_t I, int K, int NPK, int NPL,
-                                     double* __restrict__ TT) {
-  __shared__ double sh[8][33];
-  const int pk = blockIdx.y;
+// TT[pk][pl] = sum_i F[i][ka] F[i][kb] H[i][pl]   (pk = pair (ka <= kb) of K, pl = column of H, W columns).
+// Stage 1: block (32 pl) x (8 row slices) accumulates a tile of RT_PKT pairs x 32 columns over one of RT_RC row
+// chunks: H is read once per (pair tile, row) instead of once per pair, the F products of the chunk are staged in
+// shared memory.  Stage 2 folds the RT_RC partial tiles in a fixed order.
+constexpr int RT_PKT = 14;   // pairs per block
+constexpr int RT_RC = 32;    // row chunks
+constexpr int RT_ROWS = 64;  // rows of F products staged at a time
+__global__ void __launch_bounds__(256) nmtf_reduce_T_kernel(const double* __restrict__ F, const double* __restrict__ H, int64_t I, int K,
+                                                            int NPK, int W, double* __restrict__ part) {
+  __shared__ double ff[RT_ROWS][RT_PKT];
+  __shared__ double red[8][RT_PKT][33];
+  __shared__ int kab[RT_PKT][2];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
   const int pl = blockIdx.x * 32 + threadIdx.x;
-  int ka, kb;
-  pair_decode(pk, K, ka, kb);
-  double a = 0.0;
-  if (pl < NPL)
-    for (int64_t i = threadIdx.y; i < I; i += 8) a = fma(F[i * K + ka] * F[i * K + kb], H[i * NPL + pl], a);
-  sh[threadIdx.y][threadIdx.x] = a;
-  __syncthreads();
-  if (threadIdx.y == 0 && pl < NPL) {
-    double t = 0.0;
-    for (int z = 0; z < 8; ++z) t += sh[z][threadIdx.x];
-    TT[(size_t)pk * NPL + pl] = t;
+  const int pk0 = blockIdx.y * RT_PKT;
+  const int rc = blockIdx.z;
+  const int64_t chunk = (I + RT_RC - 1) / RT_RC;
+  const int64_t i_begin = rc * chunk, i_end = min(I, i_begin + chunk);
+  if (tid < RT_PKT) {
+    int ka = 0, kb = 0;
+    if (pk0 + tid < NPK) pair_decode(pk0 + tid, K, ka, kb);
+    kab[tid][0] = ka; kab[tid][1] = kb;
   }
+  double acc[RT_PKT];
+#pragma unroll
+  for (int p = 0; p < RT_PKT; ++p) acc[p] = 0.0;
+  for (int64_t i0 = i_begin; i0 < i_end; i0 += RT_ROWS) {
+    __syncthreads();
+    for (int q = tid; q < RT_ROWS * RT_PKT; q += 256) {
+      const int r = q / RT_PKT, p = q - r * RT_PKT;
+      const int64_t i = i0 + r;
+      ff[r][p] = (i < i_end && pk0 + p < NPK) ? F[i * K + kab[p][0]] * F[i * K + kab[p][1]] : 0.0;
+    }
+    __syncthreads();
+    if (pl < W) {
+      for (int r = threadIdx.y; r < RT_ROWS; r += 8) {
+        const int64_t i = i0 + r;
+        if (i >= i_end) break;
+        const double hv = H[i * W + pl];
+#pragma unroll
+        for (int p = 0; p < RT_PKT; ++p) acc[p] = fma(ff[r][p], hv, acc[p]);
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < RT_PKT; ++p) red[threadIdx.y][p][threadIdx.x] = acc[p];
+  __syncthreads();
+  if (pl < W) {
+    for (int p = threadIdx.y; p < RT_PKT; p += 8) {
+      if (pk0 + p >= NPK) continue;
+      double t = 0.0;
+      for (int z = 0; z < 8; ++z) t += red[z][p][threadIdx.x];
+      part[((size_t)rc * NPK + pk0 + p) * W + pl] = t;
+    }
+  }
+}
+__global__ void nmtf_reduce_T_fold_kernel(const double* __restrict__ part, int64_t n, double* __restrict__ TT) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  double t = 0.0;
+  for (int rc = 0; rc < RT_RC; ++rc) t += part[(size_t)rc * n + q];
+  TT[q] = t;
 }
 
 // The K*L sequential S updates on the small tensors (single CTA).
