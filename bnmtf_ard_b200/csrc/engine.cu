@@ -156,6 +156,7 @@ struct bnmtf_nmf_s {
   double sumlog_lamS = 0.0;
   // BNMTF VB
   double* proj_out3 = nullptr;           // third output of the project modes (transient)
+  bool fuse_proj = false;                // the next cluster F sweep also projects its final residual onto G (P_il, transient)
   int cov_side = -1;                     // side whose VB sweep carries the covariance term (transient)
   const double* covA = nullptr; const double* covS = nullptr;
   int covL = 0, cov_sk = 0, cov_sl = 0;
@@ -721,7 +722,7 @@ template <int NPT, int MODE, int DIV>
 static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
   auto kern = sweep2_kernel<NPT, MODE, V2_CS, DIV>;
-  const size_t smem = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS) * sizeof(double);
+  const size_t smem = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS, p.K2) * sizeof(double);
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3((p.rs + 1) * 32);
   cfg.dynamicSmemBytes = smem;
@@ -847,6 +848,9 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
     p.rmean = h->rmean; p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
     p.iter_ptr = h->iter_ptr;
+    if (h->fuse_proj && side == 0 && h->nmtf) {   // NMTF: P_il = sum_j e_ij G_jl from the residual the F sweep ends with
+      p.Ykm2 = h->s[1].km; p.ldy2 = h->s[1].ld; p.K2 = h->L; p.proj_out = h->Prow;
+    }
     p.dbg = getenv("BNMTF_V2_DBG") ? atoi(getenv("BNMTF_V2_DBG")) : 0;
     static unsigned long long* prof_buf = nullptr;   // timing experiments only
     if (p.dbg & 2) {

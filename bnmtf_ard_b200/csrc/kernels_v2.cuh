@@ -170,13 +170,20 @@ struct Sweep2Params {
   uint32_t iteration;
   const uint32_t* iter_ptr;              // when set (graph replays) the iteration index is read from the device
   uint32_t purpose;
+  // optional epilogue (NMTF F sweep): project the final residual onto the K2 columns of a second k-major factor,
+  // proj_out[global row][l] = sum_j e_j Y2[l][j]   (the row part of the S_kl numerators, bnmtf_gibbs.py:277-283)
+  const double* __restrict__ Ykm2;
+  int64_t ldy2;
+  int K2;
+  double* proj_out;
   int dbg;                               // timing experiments only: 1 = no update math, 2 = phase clocks into prof
   unsigned long long* prof;              // [32] clock64 sums of cluster 0 / CTA 0 (dbg & 2)
 };
 
 // dynamic shared memory of sweep2_kernel, in doubles
-__host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs) {
-  return (size_t)3 * (tw + 2) * nv + 4 /*mbarriers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ + (size_t)2 * cs * rs * 4 /*part, double buffered*/;
+__host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs, int K2 = 0) {
+  return (size_t)3 * (tw + 2) * nv + 4 /*mbarriers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ +
+         (size_t)2 * cs * rs * 4 /*part, double buffered*/ + (size_t)cs * rs * K2 /*projection partials*/;
 }
 
 // Warps per CTA that the register budget of NPT entries per lane allows.  Warp 0 of
@@ -218,6 +225,9 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
   double* xmu = xvar + (size_t)RS * K;
   double* xtau = xmu + (size_t)RS * K;
   double* part = xtau + (size_t)RS * K;                   // [2][CS][RS][4]: partial sums, double buffered by column parity
+  double* proj = part + (size_t)2 * CS * RS * 4;          // [CS][RS][K2]: projection partials (meet in CTA 0)
+  const int K2 = p.K2;
+  const int total = 2 * K + K2;                           // tiles per set: residual pass, update pass, projection epilogue
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 3; ++s) mbar_init(&mbar[s], 1);
@@ -230,6 +240,11 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
 
   const double* ybase = p.Ykm + (size_t)c * tw * NV;      // this CTA's tile of column 0
   const size_t ystride = (size_t)p.ldy * NV;
+  const double* ybase2 = K2 > 0 ? p.Ykm2 + (size_t)c * tw * NV : nullptr;
+  const size_t ystride2 = (size_t)p.ldy2 * NV;
+  auto tile_src = [&](int t) -> const double* {           // source of tile t of a set's sequence
+    return t < 2 * K ? ybase + (size_t)(t % K) * ystride : ybase2 + (size_t)(t - 2 * K) * ystride2;
+  };
 
   if (warp == 0) {
     // =========================== control warp ===========================
@@ -244,20 +259,20 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
       }
       if (lane == 0) {   // prime the ring: first three tiles of this set's sequence (K init + K sweep)
         fence_proxy_async();
-        for (int q = 0; q < 3 && q < 2 * K; ++q) {
+        for (int q = 0; q < 3 && q < total; ++q) {
           const uint32_t g = gseq + q;
           mbar_expect_tx(&mbar[g % 3], tile_bytes);
-          tma_load_1d(tiles + (g % 3) * tile_doubles, ybase + (size_t)(q % K) * ystride, tile_bytes, &mbar[g % 3]);
+          tma_load_1d(tiles + (g % 3) * tile_doubles, tile_src(q), tile_bytes, &mbar[g % 3]);
         }
       }
       cluster_sync_all();
       for (int q = 0; q < K; ++q) {          // residual pass: refill the stage each tile leaves
         __syncthreads();
-        if (lane == 0 && q + 3 < 2 * K) {
+        if (lane == 0 && q + 3 < total) {
           const uint32_t g = gseq + q;
           fence_proxy_async();
           mbar_expect_tx(&mbar[g % 3], tile_bytes);
-          tma_load_1d(tiles + (g % 3) * tile_doubles, ybase + (size_t)((q + 3) % K) * ystride, tile_bytes, &mbar[g % 3]);
+          tma_load_1d(tiles + (g % 3) * tile_doubles, tile_src(q + 3), tile_bytes, &mbar[g % 3]);
         }
       }
       double acc_esd = 0.0, acc_q = 0.0, acc_prior = 0.0;
@@ -273,11 +288,11 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
           if (MODE == M_GIBBS) u1 = rng.u01();
         }
         cluster_sync_all();                  // partial sums of column k are in every CTA
-        if (lane == 0 && k >= 1 && K + k + 2 < 2 * K) {   // tile of column k-1 is dead cluster-wide
+        if (lane == 0 && k >= 1 && K + k + 2 < total) {   // tile of column k-1 is dead cluster-wide
           const uint32_t gn = gseq + K + k + 2;
           fence_proxy_async();
           mbar_expect_tx(&mbar[gn % 3], tile_bytes);
-          tma_load_1d(tiles + (gn % 3) * tile_doubles, ybase + (size_t)((k + 2) % K) * ystride, tile_bytes, &mbar[gn % 3]);
+          tma_load_1d(tiles + (gn % 3) * tile_doubles, tile_src(K + k + 2), tile_bytes, &mbar[gn % 3]);
         }
         if (sampler) {
           double t3[3] = {0.0, 0.0, 0.0};
@@ -298,7 +313,25 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
         }
         __syncthreads();                     // deltas of column k are in this CTA's shared memory
       }
-      cluster_sync_all();                    // row-statistics partials are in CTA 0
+      if (K2 > 0) {                          // projection epilogue: keep the ring fed (tiles 2K .. 2K+K2-1)
+        __syncthreads();                     // every warp has applied the last correction: the stage of tile 2K-1 is free
+        if (lane == 0 && 2 * K + 2 < total && K >= 2) {
+          const uint32_t gn = gseq + 2 * K + 2;
+          fence_proxy_async();
+          mbar_expect_tx(&mbar[gn % 3], tile_bytes);
+          tma_load_1d(tiles + (gn % 3) * tile_doubles, tile_src(2 * K + 2), tile_bytes, &mbar[gn % 3]);
+        }
+        for (int q = 0; q < K2; ++q) {
+          __syncthreads();
+          if (lane == 0 && 2 * K + q + 3 < total) {
+            const uint32_t gn = gseq + 2 * K + q + 3;
+            fence_proxy_async();
+            mbar_expect_tx(&mbar[gn % 3], tile_bytes);
+            tma_load_1d(tiles + (gn % 3) * tile_doubles, tile_src(2 * K + q + 3), tile_bytes, &mbar[gn % 3]);
+          }
+        }
+      }
+      cluster_sync_all();                    // row-statistics (and projection) partials are in CTA 0
       if (c == 0) {
         if (lane < rows_here && p.rowstats != nullptr) {
           double t3[3] = {0.0, 0.0, 0.0};
@@ -318,8 +351,14 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
           if (MODE == M_VB) p.Xvar[g] = xvar[q];
           if (p.Xmu != nullptr) { p.Xmu[g] = xmu[q]; p.Xtau[g] = xtau[q]; }
         }
+        for (int q = threadIdx.x; q < rows_here * K2; q += blockDim.x) {   // fixed-order sum of the CS projection partials
+          const int rr = q / K2, l = q - rr * K2;
+          double t = 0.0;
+          for (int cc = 0; cc < CS; ++cc) t += proj[((size_t)cc * RS + rr) * K2 + l];
+          p.proj_out[(size_t)(p.row0 + set * RS + rr) * K2 + l] = t;
+        }
       }
-      gseq += 2 * K;
+      gseq += total;
       __syncthreads();
     }
   } else {
@@ -420,6 +459,25 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
           dst[0] = st0; dst[1] = st1; dst[2] = st2;
         }
       }
+      if (K2 > 0) {
+        // ---- projection epilogue: sum_j e_j Y2[l][j] over this segment, partials to CTA 0   (tiles 2K .. 2K+K2-1)
+        double* proj0 = cluster.map_shared_rank(proj, 0);
+        __syncthreads();
+        for (int q = 0; q < K2; ++q) {
+          const uint32_t g = gseq + 2 * K + q;
+          mbar_wait(&mbar[g % 3], (g / 3) & 1u);
+          const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+          double s = 0.0;
+#pragma unroll
+          for (int n = 0; n < NPT; ++n) {
+            const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+            s = fma(e[n], *reinterpret_cast<const double*>(T + off), s);
+          }
+          s = warp_sum(s);
+          if (lane == 0) proj0[((size_t)c * RS + r) * K2 + q] = s;
+          __syncthreads();
+        }
+      }
       cluster_sync_all();
       if (c == 0) {
         __syncthreads();
@@ -429,8 +487,14 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
           if (MODE == M_VB) p.Xvar[g] = xvar[q];
           if (p.Xmu != nullptr) { p.Xmu[g] = xmu[q]; p.Xtau[g] = xtau[q]; }
         }
+        for (int q = threadIdx.x; q < rows_here * K2; q += blockDim.x) {   // fixed-order sum of the CS projection partials
+          const int rr = q / K2, l = q - rr * K2;
+          double t = 0.0;
+          for (int cc = 0; cc < CS; ++cc) t += proj[((size_t)cc * RS + rr) * K2 + l];
+          p.proj_out[(size_t)(p.row0 + set * RS + rr) * K2 + l] = t;
+        }
       }
-      gseq += 2 * K;
+      gseq += total;
       __syncthreads();   // xs / tiles are reused by the next set
     }
   }
