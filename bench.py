@@ -165,7 +165,7 @@ def run_reference(args):
         return
     res = cpu_baseline(args, steps=max(1, args.steps), warmup=min(args.warmup, 1), budget_s=90.0)
     line = {"metric": METRIC, "value": res["value"], "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": "BNMF Gibbs+ARD %dx%d rho=%.2f K=%d (BASELINE configs[2])" % (args.I, args.J, args.density, args.K)},
             "cpu_baseline": res,
