@@ -183,7 +183,8 @@ struct Sweep2Params {
 // dynamic shared memory of sweep2_kernel, in doubles
 __host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs, int K2 = 0) {
   return (size_t)3 * (tw + 2) * nv + 4 /*mbarriers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ +
-         (size_t)2 * cs * rs * 4 /*part, double buffered*/ + (size_t)cs * rs * K2 /*projection partials*/;
+         (size_t)2 * cs * rs * 4 /*part, double buffered*/ + (size_t)cs * rs * K2 /*projection partials*/ +
+         (size_t)cs * rs * 4 /*row-statistics partials*/;
 }
 
 // Warps per CTA that the register budget of NPT entries per lane allows.  Warp 0 of
@@ -227,6 +228,8 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
   double* part = xtau + (size_t)RS * K;                   // [2][CS][RS][4]: partial sums, double buffered by column parity
   double* proj = part + (size_t)2 * CS * RS * 4;          // [CS][RS][K2]: projection partials (meet in CTA 0)
   const int K2 = p.K2;
+  double* statp = proj + (size_t)CS * RS * K2;            // [CS][RS][4]: row-statistics partials (own region: the last
+                                                          // column's records in `part` may still be read when they arrive)
   const int total = 2 * K + K2;                           // tiles per set: residual pass, update pass, projection epilogue
 
   if (threadIdx.x == 0) {
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
         if (lane < rows_here && p.rowstats != nullptr) {
           double t3[3] = {0.0, 0.0, 0.0};
           for (int cc = 0; cc < CS; ++cc) {
-            const double* src = part + ((size_t)cc * RS + lane) * 4;
+            const double* src = statp + ((size_t)cc * RS + lane) * 4;
             t3[0] += src[0]; t3[1] += src[1]; t3[2] += src[2];
           }
           double* rs = p.rowstats + (size_t)(set * RS + lane) * NRS;
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
   } else {
     // =========================== compute warps ===========================
     const int r = warp - 1;                                 // row of the set owned by this warp
-    double* part0 = cluster.map_shared_rank(part, 0);       // CTA 0's copy, through DSMEM
+    double* stat0 = cluster.map_shared_rank(statp, 0);      // CTA 0's copy, through DSMEM
     uint32_t gseq = 0;
     for (int set = cid; set < p.nsets; set += nclusters) {
       const int rows_here = min(RS, p.n_loc - set * RS);
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
         }
         st0 = warp_sum(st0); st1 = warp_sum(st1); st2 = warp_sum(st2);
         if (lane == 0) {
-          double* dst = part0 + ((size_t)c * RS + r) * 4;
+          double* dst = stat0 + ((size_t)c * RS + r) * 4;
           dst[0] = st0; dst[1] = st1; dst[2] = st2;
         }
       }

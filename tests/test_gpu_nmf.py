@@ -324,3 +324,32 @@ def test_gibbs_kernel_draws_follow_their_conditionals(shape, monkeypatch):
             u = orc.tn_cdf_vec(x[sel], mu[sel], tau[sel])
             d, p = stats.kstest(u, "uniform")
             assert p > 1e-4, (side, sel.mean(), d, p)
+
+
+@pytest.mark.parametrize("cls_name,shape", [("bnmf_gibbs", (120, 90, 4)), ("bnmf_vb", (120, 90, 4)), ("nmf_np", (60, 50, 3)),
+                                            ("bnmf_gibbs", (64, 2300, 5))])
+def test_graph_replay_equals_eager_loop(cls_name, shape, monkeypatch):
+    """Runs of >= 8 iterations replay the iteration as a CUDA graph with the iteration index on the
+    device; BNMTF_NO_GRAPH=1 forces the eager loop.  Same seed => bitwise the same chain and traces."""
+    import bnmtf_ard_b200 as pkg
+    I, J, K = shape
+    R, M, _ = make_problem(I + 7 * J, I, J, K, 0.7, nonneg=True)
+    hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0}
+    out = []
+    for no_graph in ("0", "1"):
+        if no_graph == "1":
+            monkeypatch.setenv("BNMTF_NO_GRAPH", "1")
+        np.random.seed(4)
+        cls = getattr(pkg, cls_name)
+        m = cls(R, M, K) if cls_name == "nmf_np" else cls(R, M, K, True, hyper)
+        m.verbose = False
+        m.initialise("random")
+        m.run(25)
+        if cls_name == "bnmf_gibbs":
+            out.append((m.all_U.copy(), m.all_V.copy(), m.all_tau.copy(), m.all_lambdak.copy(), np.array(m.all_performances["MSE"])))
+        elif cls_name == "bnmf_vb":
+            out.append((m.exp_U.copy(), m.exp_V.copy(), np.array(m.all_elbo), np.array(m.all_exp_tau), np.array(m.all_performances["MSE"])))
+        else:
+            out.append((m.U.copy(), m.V.copy(), np.array(m.all_i_div), np.array(m.all_performances["MSE"])))
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)

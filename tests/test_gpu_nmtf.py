@@ -263,3 +263,33 @@ def test_np_iterations_vs_oracle():
         orc.np_iteration(R, M, F, S, G)
     close(m.F, F, RTOL_TRAJ); close(m.S, S, RTOL_TRAJ); close(m.G, G, RTOL_TRAJ)
     close(m.all_i_div[-1], orc.np_i_div(R, M, F, S, G), RTOL_TRAJ)
+
+
+@pytest.mark.parametrize("cls_name", ["bnmtf_gibbs", "nmtf_icm", "bnmtf_vb", "nmtf_np"])
+def test_graph_replay_equals_eager_loop(cls_name, monkeypatch):
+    """Graph replays of the tri-factorisation run loops give bitwise the chain of the eager loop."""
+    import bnmtf_ard_b200 as pkg
+    rng = np.random.default_rng(12)
+    I, J, K, L = 70, 2100, 3, 4        # the F side runs the cluster sweep (with the projection epilogue)
+    R = np.abs(rng.exponential(1, (I, K)) @ rng.exponential(1, (K, L)) @ rng.exponential(1, (J, L)).T + rng.normal(0, 1, (I, J))) + 0.05
+    M = (rng.random((I, J)) < 0.6).astype(float)
+    M[:, 0] = 1; M[0, :] = 1
+    hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0, "lambdaS": np.ones((K, L))}
+    out = []
+    for no_graph in ("0", "1"):
+        if no_graph == "1":
+            monkeypatch.setenv("BNMTF_NO_GRAPH", "1")
+        np.random.seed(9)
+        cls = getattr(pkg, cls_name)
+        m = cls(R, M, K, L) if cls_name == "nmtf_np" else cls(R, M, K, L, True, hyper)
+        m.verbose = False
+        m.initialise("random", "random")
+        m.run(12)
+        if cls_name in ("bnmtf_gibbs", "nmtf_icm"):
+            out.append((m.all_F.copy(), m.all_S.copy(), m.all_G.copy(), m.all_tau.copy(), m.all_lambdaFk.copy(), m.all_lambdaGl.copy()))
+        elif cls_name == "bnmtf_vb":
+            out.append((m.exp_F.copy(), m.exp_S.copy(), m.exp_G.copy(), np.array(m.all_performances["MSE"])))
+        else:
+            out.append((m.F.copy(), m.S.copy(), m.G.copy(), np.array(m.all_performances["MSE"])))
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
