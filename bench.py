@@ -226,6 +226,9 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # NCCL prints its version banner on stdout at VERSION level; stdout carries the one JSON line only
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
 
     import torch
     import torch.distributed as dist
