@@ -44,7 +44,7 @@ __host__ __device__ inline Sweep3Layout sweep3_layout(int tw, int nv, int rs, in
   Sweep3Layout L;
   size_t o = 0;
   L.tiles = o; o += (size_t)2 * (tw + 1) * B * nv;   // 2 slots x (tw + 1 zero entry) x B*NV interleaved doubles
-  L.mbar = o; o += 2;
+  L.mbar = o; o += 4;   // 2 tile mbarriers + 2 record mbarriers
   L.delta = o; o += (size_t)B * rs + (((size_t)B * rs) & 1);
   L.xs = o; o += (size_t)rs * K;
   L.xvar = o; o += vb ? (size_t)rs * K : 0;
@@ -86,6 +86,19 @@ __device__ __forceinline__ void warp_sum_scatter(double (&v)[NVAL], int lane) {
 // shared-memory loads by 32-bit shared address (no generic-address arithmetic in the hot loop)
 __device__ __forceinline__ void lds_f64x2(uint32_t addr, double& a, double& b) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+
+// Remote (DSMEM) store that signals the destination CTA's mbarrier when it lands: the receiver waits on its own
+// mbarrier for the expected byte count -- no cluster barrier, no cluster/GPU-scope fence on either side.
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+               "l"(__double_as_longlong(v)), "r"(remote_mbar)
+               : "memory");
 }
 
 template <int EW>
@@ -149,6 +162,8 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep3_ke
   if (threadIdx.x == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
+    mbar_init(&mbar[2], 1);              // records of even blocks
+    mbar_init(&mbar[3], 1);              // records of odd blocks
     fence_mbar_init();
   }
   // stages start as zeros: tail blocks leave stages unloaded, padded entries read the two
@@ -171,6 +186,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep3_ke
   if (warp == 0) {
     // =========================== control warp ===========================
     uint32_t gblk = 0;
+    uint32_t rec_phase[2] = {0u, 0u};
     const UpdateCtx uc{p.seed, p.purpose, p.iter_ptr ? *p.iter_ptr : p.iteration, false};
     const double tau = p.scal[0];
     // Gibbs: the random material of CPR columns x RS rows is produced per round, lane = (column, row)
@@ -235,8 +251,11 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep3_ke
         named_sync(1, NTHREADS);             // the compute warps of this CTA have finished their pass of block n
         PROF_ADD(1);                         // waiting for the local pass
         if (lane == 0 && n >= 1 && n + 1 < NBK) issue_block(gblk + NBK + n + 1, NBK + n + 1);   // slot of block n-1 is dead
-        cluster_sync_all();                  // the records of block n are in every CTA
-        PROF_ADD(2);                         // cluster barrier
+        // the records of block n: CS x RS warps each send NVAL doubles; their st.async complete this CTA's mbarrier
+        if (lane == 0) mbar_expect_tx(&mbar[2 + (n & 1)], (uint32_t)(CS * RS * NVAL * 8));
+        mbar_wait(&mbar[2 + (n & 1)], rec_phase[n & 1] & 1u);
+        rec_phase[n & 1]++;
+        PROF_ADD(2);                         // waiting for the records
         if (sampler) {
           double rec[NVAL];
           const double* src = part + (size_t)(n & 1) * CS * NVAL * RS + lane;
@@ -314,6 +333,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep3_ke
     const int r = warp - 1;                                 // row of the set owned by this warp
     const uint32_t tiles_u32 = smem_u32(tiles);
     const uint32_t slot_bytes = (uint32_t)slot_doubles * 8u;
+    const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[2]);
     uint32_t gblk = 0;
     // after the scatter reduction lane `lane` holds value index vq and sends it to CTAs t, t+SPAN, ...
     constexpr int GROUP = 32 / NVAL;                        // lanes holding the same value
@@ -407,12 +427,12 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep3_ke
         {
           // value vq goes to every CTA: the GROUP lanes that hold it share the CS destinations
           const size_t rec = ((size_t)(n & 1) * CS * NVAL + (size_t)c * NVAL + vq) * RS + r;
+          const uint32_t dst_local = part_u32 + (uint32_t)rec * 8u, bar_local = rbar_u32 + (uint32_t)(n & 1) * 8u;
 #pragma unroll
-          for (int cc = vt; cc < CS; cc += GROUP) cluster.map_shared_rank(part, cc)[rec] = v[0];
+          for (int cc = vt; cc < CS; cc += GROUP) st_async_f64(map_to_cta(dst_local, cc), v[0], map_to_cta(bar_local, cc));
         }
         PROF_ADD(12);                        // reduction + DSMEM stores
-        cluster_sync_all();                  // the records of block n are in every CTA
-        PROF_ADD(13);                        // cluster barrier
+        PROF_ADD(13);
         __syncthreads();                     // the control warp of this CTA has written the deltas
         PROF_ADD(14);                        // waiting for the deltas
 #pragma unroll
