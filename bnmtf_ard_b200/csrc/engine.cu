@@ -689,7 +689,7 @@ static int launch_sweep_t(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int* 
   const int teams = tpr >= 128 ? 1 : 128 / tpr;
   const int block = tpr * teams;
   const int nw = tpr / 32;
-  const size_t smem = sizeof(double) * teams * (4 * (size_t)p.K + 3 * nw + 2 + 2 * (size_t)p.covL + (MODE == M_GIBBS ? 4 * (size_t)p.K : 0));
+  const size_t smem = sizeof(double) * teams * (4 * (size_t)p.K + 3 * nw + 2 + 2 * (size_t)p.covL + (MODE == M_GIBBS ? TN_PRE_DOUBLES * (size_t)p.K : 0));
   auto kern = sweep_kernel<NPT, MODE>;
   if (*occ_cache == 0) {
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

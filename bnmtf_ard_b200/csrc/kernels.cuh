@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
   const int wteam = t >> 5;
   const int nw = tpr >> 5;
   const int barA = 1 + 2 * team, barB = 2 + 2 * team;
-  const int team_stride = 4 * K + 3 * nw + 2 + 2 * p.covL + (MODE == M_GIBBS ? 4 * K : 0);
+  const int team_stride = 4 * K + 3 * nw + 2 + 2 * p.covL + (MODE == M_GIBBS ? TN_PRE_DOUBLES * K : 0);
   double* xs = smem + (size_t)team * team_stride;  // [K] current values of the row
   double* xvar = xs + K;                            // [K] VB variance
   double* xmu = xvar + K;                           // [K] conditional mean
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
   double* bc = red + 3 * nw;                        // [2]
   double* fsv = bc + 2;                             // [covL] (X S)_il of the row   (BNMTF VB)
   double* arow = fsv + p.covL;                      // [covL] A_il of the row
-  double* mat = arow + p.covL;                      // [K][4] Gibbs: random material prepared per column (tn_pre_material)
+  double* mat = arow + p.covL;                      // [K][6] Gibbs: random material prepared per column (tn_pre_material)
   const bool fast_draw = (MODE == M_GIBBS) && p.single_k == -1;
   const bool has_cov = (MODE == M_VB) && (p.covA != nullptr);
   const bool leader = (t == 0);
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
     }
     if (fast_draw) {   // every thread of the team prepares the draw material of some columns, once per row
       for (int kk = t; kk < K; kk += tpr)
-        tn_pre_material_store(p.seed, p.purpose, (uint64_t)grow, (uint32_t)kk, iteration, mat + 4 * kk);
+        tn_pre_material_store(p.seed, p.purpose, (uint64_t)grow, (uint32_t)kk, iteration, mat + TN_PRE_DOUBLES * kk);
     }
     for (int kk = t; kk < K; kk += tpr) {
       xs[kk] = p.Xval[grow * K + kk];
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
         if (fast_draw) {
           Rng rng(uc.seed, uc.purpose, (uint64_t)grow, (uint32_t)k, uc.iteration);
           rng.draw = 2;                                         // Philox blocks 0 and 1 made the material
-          const TnPre m{mat[4 * k], mat[4 * k + 1], mat[4 * k + 2], mat[4 * k + 3]};
+          const TnPre m = tn_pre_load(mat + TN_PRE_DOUBLES * k);
           ct = tau * s[0];                                      // tauU, bnmf_gibbs.py:205
           const double num = -lam + tau * (s[2] + x_old * s[0]);   // numerator of muU, bnmf_gibbs.py:210
           x_new = tn_draw_fast(num, ct, m, rng, cm);

@@ -222,11 +222,11 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restr
   double* c = shs;            // [KL]
   double* sv = c + KL;        // [KL]
   double* bc = sv + KL;       // [2]
-  double* mat = bc + 2;       // [KL][4] Gibbs: random material of every entry, prepared by all threads up front
+  double* mat = bc + 2;       // [KL][6] Gibbs: random material of every entry, prepared by all threads up front
   if (iter_ptr) iteration = *iter_ptr;
   for (int d = threadIdx.x; d < KL; d += blockDim.x) {
     c[d] = c_in[d]; sv[d] = S[d];
-    if (MODE == M_GIBBS && single_d < 0) tn_pre_material_store(seed, RNG_S, (uint64_t)d, 0u, iteration, mat + 4 * d);
+    if (MODE == M_GIBBS && single_d < 0) tn_pre_material_store(seed, RNG_S, (uint64_t)d, 0u, iteration, mat + TN_PRE_DOUBLES * d);
   }
   __syncthreads();
   const double tau = scal[0];
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restr
       if (MODE == M_GIBBS && single_d < 0) {
         Rng rng(seed, RNG_S, (uint64_t)d, 0u, iteration);
         rng.draw = 2;                                   // Philox blocks 0 and 1 made the material
-        const TnPre m{mat[4 * d], mat[4 * d + 1], mat[4 * d + 2], mat[4 * d + 3]};
+        const TnPre m = tn_pre_load(mat + TN_PRE_DOUBLES * d);
         double cm2;
         x_new = tn_draw_fast(-lamS[d] + tau * (c[d] + sv[d] * Tdd), ct, m, rng, cm2);
       } else if (MODE == M_GIBBS) {

@@ -52,7 +52,7 @@ __host__ __device__ inline Sweep3Layout sweep3_layout(int tw, int nv, int rs, in
   L.xtau = o; o += want_mu ? (size_t)rs * K : 0;
   L.part = o; o += (size_t)2 * cs * nval * rs;       // [2][CS][NVAL][RS]
   L.stat = o; o += (size_t)cs * 3 * rs;              // [CS][3][RS]
-  L.rnd = o; o += gibbs ? (size_t)SWEEP3_RNDW * rs * 4 : 0;   // [W][RS][4]: prepared random material
+  L.rnd = o; o += gibbs ? (size_t)SWEEP3_RNDW * rs * TN_PRE_DOUBLES : 0;   // [W][RS][6]: prepared random material
   L.total = o;
   return L;
 }
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep3_ke
   double* xtau = smem3 + L.xtau;
   double* part = smem3 + L.part;                          // [2][CS][NVAL][RS]
   double* stat = smem3 + L.stat;                          // [CS][3][RS]
-  double* rnd = smem3 + L.rnd;                            // [W][RS][4]
+  double* rnd = smem3 + L.rnd;                            // [W][RS][6]
 
   if (threadIdx.x == 0) {
     mbar_init(&mbar[0], 1);
@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep3_ke
       if (cj < CPR && k < K && rr < rows_here) {
         Rng rng(uc.seed, uc.purpose, (uint64_t)(row_base + rr), (uint32_t)k, uc.iteration);
         const TnPre m = tn_pre_material(rng);
-        double* dst = rnd + ((size_t)(k % SWEEP3_RNDW) * RS + rr) * 4;
-        dst[0] = m.z; dst[1] = m.e; dst[2] = m.l; dst[3] = m.ufb;
+        double* dst = rnd + ((size_t)(k % SWEEP3_RNDW) * RS + rr) * TN_PRE_DOUBLES;
+        dst[0] = m.z1; dst[1] = m.z2; dst[2] = m.e1; dst[3] = m.l1; dst[4] = m.e2; dst[5] = m.l2;
       }
       gen += CPR;
       __syncwarp();
@@ -232,14 +232,13 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep3_ke
 #pragma unroll
         for (int j = 0; j < B; ++j) {
           lam[j] = 0.0; x_old[j] = 0.0;
-          mat[j].z = 0.0; mat[j].e = 1.0; mat[j].l = 1.0; mat[j].ufb = 0.5;
+          mat[j].z1 = 0.0; mat[j].z2 = 0.0; mat[j].e1 = 1.0; mat[j].l1 = 1.0; mat[j].e2 = 1.0; mat[j].l2 = 1.0;
           if (sampler && j < nb) {
             const int k = k0 + j;
             lam[j] = p.lamk ? p.lamk[k] : (p.lam_rm ? p.lam_rm[grow * K + k] : 0.0);
             x_old[j] = xs[lane * K + k];
             if (MODE == M_GIBBS) {
-              const double* src = rnd + ((size_t)(k % SWEEP3_RNDW) * RS + lane) * 4;
-              mat[j].z = src[0]; mat[j].e = src[1]; mat[j].l = src[2]; mat[j].ufb = src[3];
+              mat[j] = tn_pre_load(rnd + ((size_t)(k % SWEEP3_RNDW) * RS + lane) * TN_PRE_DOUBLES);
             }
           }
         }

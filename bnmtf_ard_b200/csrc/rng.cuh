@@ -146,30 +146,42 @@ __device__ __noinline__ double tn_draw_pre(double num, double prec, double u1, R
 // ---- truncated-normal draw with the random material prepared ahead ------------
 // The conditional (num, prec) of a Gibbs update arrives at the end of a latency chain; the
 // inverse-CDF draw above then costs erfc + normcdfinv on that chain.  Everything random can be
-// prepared before the conditional is known: a standard normal z, an Exp(1) variate e, a
-// chi-square-like l = -2 log u and a spare uniform.  With a = -mu/sigma the standardised bound:
-//   a <= 0 : accept z if z >= a                    (plain rejection, acceptance Phi(-a) >= 1/2)
-//   a >  0 : Robert (1995): x = e/alpha, alpha = (a + sqrt(a^2+4))/2, accept if l >= (a+x-alpha)^2
-// and only a rejected proposal falls back to the inverse-CDF draw with the spare uniform.  Each
-// branch returns an exact TN(mu, 1/prec) variate, so the mixture is exact as well.
-struct TnPre { double z, e, l, ufb; };
+// prepared before the conditional is known: two standard normals (Box-Muller), two Exp(1)
+// variates e and two l = -2 log u.  With a = -mu/sigma the standardised bound:
+//   a <= A0 : plain rejection, accept z if z >= a            (acceptance Phi(-a) >= 0.67)
+//   a >  A0 : Robert (1995): x = e/alpha, alpha = (a + sqrt(a^2+4))/2, accept if l >= (a+x-alpha)^2
+//             (valid for any a; acceptance >= 0.67 beyond A0 = -0.45, -> 1 for large a)
+// two proposals each; only when both are rejected (<= 11 %, typically ~0.1 %) the draw falls back to the
+// inverse CDF with a fresh uniform.  Every branch returns an exact TN(mu, 1/prec) variate and
+// the branch taken depends on a only, so the mixture is exact as well.
+constexpr int TN_PRE_DOUBLES = 6;
+constexpr double TN_FAST_A0 = -0.45;
+struct TnPre { double z1, z2, e1, l1, e2, l2; };
 
 __device__ __forceinline__ TnPre tn_pre_material(Rng& rng) {
   TnPre m;
-  const double u1 = rng.u01(), u2 = rng.u01(), u3 = rng.u01();
-  m.ufb = rng.u01();
-  m.z = normcdfinv(u1);
-  m.e = -log(u2);
-  m.l = -2.0 * log(u3);
+  const double u1 = rng.u01(), u2 = rng.u01(), u3 = rng.u01(), u4 = rng.u01();
+  const double g1 = -log(u1), g2 = -log(u2), g3 = -log(u3), g4 = -log(u4);
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  const double r = sqrt(2.0 * g1);
+  m.z1 = r * cs; m.z2 = r * sn;       // Box-Muller: independent standard normals (used when a <= A0)
+  m.e1 = g1; m.l1 = 2.0 * g2;         // Exp(1) and -2 log u pairs (used when a > A0)
+  m.e2 = g3; m.l2 = 2.0 * g4;
   return m;
 }
 
 // out-of-line version for kernels whose registers are busy when the material is prepared
 __device__ __noinline__ void tn_pre_material_store(uint64_t seed, uint32_t purpose, uint64_t index, uint32_t k, uint32_t iteration,
-                                                   double* dst4) {
+                                                   double* dst) {
   Rng rng(seed, purpose, index, k, iteration);
   const TnPre m = tn_pre_material(rng);
-  dst4[0] = m.z; dst4[1] = m.e; dst4[2] = m.l; dst4[3] = m.ufb;
+  dst[0] = m.z1; dst[1] = m.z2; dst[2] = m.e1; dst[3] = m.l1; dst[4] = m.e2; dst[5] = m.l2;
+}
+__device__ __forceinline__ TnPre tn_pre_load(const double* src) {
+  TnPre m;
+  m.z1 = src[0]; m.z2 = src[1]; m.e1 = src[2]; m.l1 = src[3]; m.e2 = src[4]; m.l2 = src[5];
+  return m;
 }
 
 // rng_fb: the same stream as the material, positioned after it (draw = 2)
@@ -179,19 +191,22 @@ __device__ __forceinline__ double tn_draw_fast(double num, double prec, const Tn
   const double sigma = rsqrt(prec);
   mu_out = num * sigma * sigma;
   const double a = -num * sigma;
-  double x;
+  double x;      // z - a >= 0
   bool ok;
-  if (!(a > 0.0)) {
-    x = m.z - a;
-    ok = (m.z >= a);
+  if (!(a > TN_FAST_A0)) {
+    ok = (m.z1 >= a);
+    x = m.z1 - a;
+    if (!ok) { ok = (m.z2 >= a); x = m.z2 - a; }
   } else {
     const double alpha = 0.5 * (a + sqrt(a * a + 4.0));
-    x = m.e / alpha;
-    const double t = (a + x) - alpha;
-    ok = (m.l >= t * t);
+    const double ia = 1.0 / alpha, am = a - alpha;
+    x = m.e1 * ia;
+    double t = am + x;
+    ok = (m.l1 >= t * t);
+    if (!ok) { x = m.e2 * ia; t = am + x; ok = (m.l2 >= t * t); }
   }
   if (fell_back) *fell_back = !ok;
-  if (!ok) return tn_draw_pre(num, prec, m.ufb, rng_fb, mu_out);
+  if (!ok) return tn_draw_pre(num, prec, rng_fb.u01(), rng_fb, mu_out);
   const double d = sigma * x;
   return (d >= 0.0 && isfinite(d)) ? d : 0.0;
 }
