@@ -255,16 +255,29 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep3_ke
         mbar_wait(&mbar[2 + (n & 1)], rec_phase[n & 1] & 1u);
         rec_phase[n & 1]++;
         PROF_ADD(2);                         // waiting for the records
-        if (sampler) {
-          double rec[NVAL];
-          const double* src = part + (size_t)(n & 1) * CS * NVAL * RS + lane;
+        // sum the CS records of every row in a fixed order; with RS <= 16 two lanes share a row (lane and lane + 16
+        // take four CTAs each), halving the loads on this warp's critical path
+        constexpr int RAW = Sweep3Rec<B, MODE>::RAW;
+        constexpr bool SPLIT = (RS <= 16);
+        double rec[RAW];
 #pragma unroll
-          for (int q = 0; q < NVAL; ++q) rec[q] = 0.0;
+        for (int q = 0; q < RAW; ++q) rec[q] = 0.0;
+        {
+          const int rl = SPLIT ? (lane & 15) : lane, cc0 = SPLIT ? (lane >> 4) * (CS / 2) : 0;
+          if (rl < rows_here) {
+            const double* src = part + (size_t)(n & 1) * CS * NVAL * RS + rl;
 #pragma unroll
-          for (int cc = 0; cc < CS; ++cc) {
+            for (int cq = 0; cq < (SPLIT ? CS / 2 : CS); ++cq) {
 #pragma unroll
-            for (int q = 0; q < Sweep3Rec<B, MODE>::RAW; ++q) rec[q] += src[(size_t)(cc * NVAL + q) * RS];
+              for (int q = 0; q < RAW; ++q) rec[q] += src[(size_t)((cc0 + cq) * NVAL + q) * RS];
+            }
           }
+          if (SPLIT) {
+#pragma unroll
+            for (int q = 0; q < RAW; ++q) rec[q] += __shfl_down_sync(0xffffffffu, rec[q], 16);
+          }
+        }
+        if (sampler) {
           double d[B];
 #pragma unroll
           for (int j = 0; j < B; ++j) {
