@@ -182,7 +182,7 @@ struct Sweep2Params {
 
 // dynamic shared memory of sweep2_kernel, in doubles
 __host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs, int K2 = 0) {
-  return (size_t)3 * (tw + 2) * nv + 4 /*mbarriers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ +
+  return (size_t)3 * (tw + 2) * nv + 6 /*mbarriers: 3 tile stages, 2 record buffers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ +
          (size_t)2 * cs * rs * 4 /*part, double buffered*/ + (size_t)cs * rs * K2 /*projection partials*/ +
          (size_t)cs * rs * 4 /*row-statistics partials*/;
 }
@@ -199,6 +199,26 @@ template <int NPT>
 struct Sweep2Cfg {
   static constexpr int WPC = NPT <= 16 ? 32 : (NPT <= 18 ? 28 : 24);
 };
+
+// Remote (DSMEM) store that signals the destination CTA's mbarrier when it lands: the receiver waits on its own
+// mbarrier for the expected byte count -- no cluster barrier, no cluster/GPU-scope fence on either side.
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+               "l"(__double_as_longlong(v)), "r"(remote_mbar)
+               : "memory");
+}
+
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -220,7 +240,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
   extern __shared__ __align__(128) double smem2[];
   double* tiles = smem2;                                  // 3 stages
   uint64_t* mbar = reinterpret_cast<uint64_t*>(tiles + 3 * tile_doubles);
-  double* delta = reinterpret_cast<double*>(mbar + 4);    // [RS]
+  double* delta = reinterpret_cast<double*>(mbar + 6);    // [RS]
   double* xs = delta + RS + 1;                            // [RS][K]
   double* xvar = xs + (size_t)RS * K;
   double* xmu = xvar + (size_t)RS * K;
@@ -233,7 +253,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
   const int total = 2 * K + K2;                           // tiles per set: residual pass, update pass, projection epilogue
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 3; ++s) mbar_init(&mbar[s], 1);
+    for (int s = 0; s < 5; ++s) mbar_init(&mbar[s], 1);   // 0-2: tile stages, 3-4: records of even / odd columns
     fence_mbar_init();
   }
   for (int s = threadIdx.x; s < 3; s += blockDim.x) {     // the zero slots read by padded entries
@@ -252,6 +272,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
   if (warp == 0) {
     // =========================== control warp ===========================
     uint32_t gseq = 0;
+    uint32_t rec_phase[2] = {0u, 0u};
     const UpdateCtx uc{p.seed, p.purpose, p.iter_ptr ? *p.iter_ptr : p.iteration, false};
     const double tau = p.scal[0];
     for (int set = cid; set < p.nsets; set += nclusters) {
@@ -290,13 +311,17 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
           x_old = xs[lane * K + k];
           if (MODE == M_GIBBS) u1 = rng.u01();
         }
-        cluster_sync_all();                  // partial sums of column k are in every CTA
-        if (lane == 0 && k >= 1 && K + k + 2 < total) {   // tile of column k-1 is dead cluster-wide
+        named_sync(1, (RS + 1) * 32);        // the compute warps of this CTA have finished their pass of column k
+        if (lane == 0 && k >= 1 && K + k + 2 < total) {   // tile of column k-1 is dead
           const uint32_t gn = gseq + K + k + 2;
           fence_proxy_async();
           mbar_expect_tx(&mbar[gn % 3], tile_bytes);
           tma_load_1d(tiles + (gn % 3) * tile_doubles, tile_src(K + k + 2), tile_bytes, &mbar[gn % 3]);
         }
+        // the partial sums of column k: CS x RS warps each send 3 doubles by st.async; they complete this CTA's mbarrier
+        if (lane == 0) mbar_expect_tx(&mbar[3 + (k & 1)], (uint32_t)(CS * RS * 3 * 8));
+        mbar_wait(&mbar[3 + (k & 1)], rec_phase[k & 1] & 1u);
+        rec_phase[k & 1]++;
         if (sampler) {
           double t3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -368,6 +393,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
     // =========================== compute warps ===========================
     const int r = warp - 1;                                 // row of the set owned by this warp
     double* stat0 = cluster.map_shared_rank(statp, 0);      // CTA 0's copy, through DSMEM
+    const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[3]);
     uint32_t gseq = 0;
     for (int set = cid; set < p.nsets; set += nclusters) {
       const int rows_here = min(RS, p.n_loc - set * RS);
@@ -431,13 +457,14 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
             s2 = fma(e[n], v, s2);
           }
         }
+        named_arrive(1, (RS + 1) * 32);      // this warp no longer reads the tile of column k-1
         s0 = warp_sum(s0); s2 = warp_sum(s2);
         if (MODE == M_VB) s1 = warp_sum(s1);
         if (lane < CS) {   // lane cc sends this warp's partial sums to CTA cc (every CTA updates redundantly)
-          double* dst = cluster.map_shared_rank(part, lane) + ((size_t)((k & 1) * CS + c) * RS + r) * 4;
-          dst[0] = s0; dst[1] = s1; dst[2] = s2;
+          const uint32_t dst = map_to_cta(part_u32 + (uint32_t)(((k & 1) * CS + c) * RS + r) * 32u, lane);
+          const uint32_t bar = map_to_cta(rbar_u32 + (uint32_t)(k & 1) * 8u, lane);
+          st_async_f64(dst, s0, bar); st_async_f64(dst + 8, s1, bar); st_async_f64(dst + 16, s2, bar);
         }
-        cluster_sync_all();                  // partial sums of column k are in every CTA
         __syncthreads();                     // the control warp of this CTA has written the deltas
         dprev = (r < rows_here) ? delta[r] : 0.0;
       }

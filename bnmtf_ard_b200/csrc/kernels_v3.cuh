@@ -88,31 +88,11 @@ __device__ __forceinline__ void lds_f64x2(uint32_t addr, double& a, double& b) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
 
-// Remote (DSMEM) store that signals the destination CTA's mbarrier when it lands: the receiver waits on its own
-// mbarrier for the expected byte count -- no cluster barrier, no cluster/GPU-scope fence on either side.
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
-  return r;
-}
-__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_mbar) {
-  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
-               "l"(__double_as_longlong(v)), "r"(remote_mbar)
-               : "memory");
-}
-
 template <int EW>
 __device__ __forceinline__ void load_entry(uint32_t addr, double (&y)[EW]) {
   static_assert(EW % 2 == 0, "entries are loaded as 16-byte pairs");
 #pragma unroll
   for (int q = 0; q < EW; q += 2) lds_f64x2(addr + q * 8, y[q], y[q + 1]);
-}
-
-__device__ __forceinline__ void named_arrive(int id, int nthreads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void named_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 #define PROF_T0() long long t_prof = prof_on ? clock64() : 0
