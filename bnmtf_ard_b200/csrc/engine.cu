@@ -722,7 +722,7 @@ template <int NPT, int MODE, int DIV>
 static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
   auto kern = sweep2_kernel<NPT, MODE, V2_CS, DIV>;
-  const size_t smem = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS, p.K2) * sizeof(double);
+  const size_t smem = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS, p.K2, MODE == M_GIBBS) * sizeof(double);
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3((p.rs + 1) * 32);
   cfg.dynamicSmemBytes = smem;

@@ -181,10 +181,12 @@ struct Sweep2Params {
 };
 
 // dynamic shared memory of sweep2_kernel, in doubles
-__host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs, int K2 = 0) {
+// columns of prepared random material kept in shared memory (Gibbs): one round of 32/rs columns ahead of the updates
+__host__ __device__ constexpr int sweep2_rnd_window(int rs) { return (1 + 2 * ((32 / rs) < 1 ? 1 : (32 / rs))) <= 8 ? 8 : 16; }
+__host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs, int K2 = 0, bool gibbs = false) {
   return (size_t)3 * (tw + 2) * nv + 6 /*mbarriers: 3 tile stages, 2 record buffers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ +
          (size_t)2 * cs * rs * 4 /*part, double buffered*/ + (size_t)cs * rs * K2 /*projection partials*/ +
-         (size_t)cs * rs * 4 /*row-statistics partials*/;
+         (size_t)cs * rs * 4 /*row-statistics partials*/ + (gibbs ? (size_t)sweep2_rnd_window(rs) * rs * 6 : 0) /*random material*/;
 }
 
 // Warps per CTA that the register budget of NPT entries per lane allows.  Warp 0 of
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
   double* part = xtau + (size_t)RS * K;                   // [2][CS][RS][4]: partial sums, double buffered by column parity
   double* proj = part + (size_t)2 * CS * RS * 4;          // [CS][RS][K2]: projection partials (meet in CTA 0)
   const int K2 = p.K2;
+  double* rnd = proj + (size_t)CS * RS * K2 + (size_t)CS * RS * 4;   // [RW][RS][6]: prepared random material (Gibbs)
   double* statp = proj + (size_t)CS * RS * K2;            // [CS][RS][4]: row-statistics partials (own region: the last
                                                           // column's records in `part` may still be read when they arrive)
   const int total = 2 * K + K2;                           // tiles per set: residual pass, update pass, projection epilogue
@@ -275,11 +278,30 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
     uint32_t rec_phase[2] = {0u, 0u};
     const UpdateCtx uc{p.seed, p.purpose, p.iter_ptr ? *p.iter_ptr : p.iteration, false};
     const double tau = p.scal[0];
+    // Gibbs: the random material of upcoming columns is prepared lane-parallel (lane = (column, row)) while the
+    // compute warps run their pass; the conditional itself then costs an rsqrt and a compare (tn_draw_fast)
+    constexpr int RW = sweep2_rnd_window(RS);
+    constexpr int CPR = (32 / RS) < 1 ? 1 : (32 / RS);
+    static_assert(1 + 2 * CPR <= RW || MODE != M_GIBBS, "random-material window too small");
+    int gen = 0;
+    auto gen_round = [&](int rows_here, int64_t row_base) {
+      const int cj = lane / RS, rr = lane - cj * RS;
+      const int k = gen + cj;
+      if (cj < CPR && k < K && rr < rows_here)
+        tn_pre_material_store(uc.seed, uc.purpose, (uint64_t)(row_base + rr), (uint32_t)k, uc.iteration,
+                              rnd + ((size_t)(k % RW) * RS + rr) * TN_PRE_DOUBLES);
+      gen += CPR;
+      __syncwarp();
+    };
     for (int set = cid; set < p.nsets; set += nclusters) {
       const int rows_here = min(RS, p.n_loc - set * RS);
       for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
         const size_t g = (size_t)(p.row0 + set * RS) * K + q;
         xs[q] = p.Xval[g];
+      }
+      if (MODE == M_GIBBS) {
+        gen = 0;
+        while (gen < min(K, 1 + CPR)) gen_round(rows_here, p.row0 + (int64_t)set * RS);
       }
       if (lane == 0) {   // prime the ring: first three tiles of this set's sequence (K init + K sweep)
         fence_proxy_async();
@@ -304,12 +326,17 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
       const bool sampler = (lane < rows_here);   // every CTA updates the RS rows redundantly (bitwise identical)
       for (int k = 0; k < K; ++k) {
         // everything that does not need the row sums happens before they arrive
-        double lam = 0.0, x_old = 0.0, u1 = 0.5;
-        Rng rng(uc.seed, uc.purpose, (uint64_t)grow, (uint32_t)k, uc.iteration);
+        double lam = 0.0, x_old = 0.0;
+        TnPre mat;
+        mat.z1 = mat.z2 = 0.0; mat.e1 = mat.l1 = mat.e2 = mat.l2 = 1.0;
         if (sampler) {
           lam = p.lamk ? p.lamk[k] : (p.lam_rm ? p.lam_rm[grow * K + k] : 0.0);
           x_old = xs[lane * K + k];
-          if (MODE == M_GIBBS) u1 = rng.u01();
+          if (MODE == M_GIBBS) mat = tn_pre_load(rnd + ((size_t)(k % RW) * RS + lane) * TN_PRE_DOUBLES);
+        }
+        if (MODE == M_GIBBS) {               // stay one round ahead of the updates
+          __syncwarp();
+          while (gen < min(K, k + 1 + CPR)) gen_round(rows_here, p.row0 + (int64_t)set * RS);
         }
         named_sync(1, (RS + 1) * 32);        // the compute warps of this CTA have finished their pass of column k
         if (lane == 0 && k >= 1 && K + k + 2 < total) {   // tile of column k-1 is dead
@@ -331,7 +358,13 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
           }
           double ct, cm, vn = 0.0, x_new;
           if (p.dbg & 1) { x_new = x_old + 1e-3 * t3[0]; ct = cm = 0.0; }
-          else if (MODE == M_GIBBS) x_new = gibbs_update_pre(t3, x_old, lam, tau, rng, u1, ct, cm);
+          else if (MODE == M_GIBBS) {
+            Rng rng(uc.seed, uc.purpose, (uint64_t)grow, (uint32_t)k, uc.iteration);
+            rng.draw = 2;                    // Philox blocks 0 and 1 of this stream made the material
+            ct = tau * t3[0];                                            // tauU, bnmf_gibbs.py:205
+            const double num = -lam + tau * (t3[2] + x_old * t3[0]);     // numerator of muU, bnmf_gibbs.py:210
+            x_new = tn_draw_fast(num, ct, mat, rng, cm);
+          }
           else x_new = conditional_update<MODE>(t3, x_old, lam, tau, uc, (uint64_t)grow, k, 0.0, 0.0, 0.0, ct, cm, vn, acc_esd,
                                                 acc_q, acc_prior);
           xs[lane * K + k] = x_new;
