@@ -246,7 +246,7 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   if (npt2 == 18 && div == 3) div = 2;                             // 28 warps do not split in three
   const int rs = wpc_full / div - 1;                               // rows per set (warp 0 is the control warp)
   sd.v2div = div;
-  sd.v3B = getenv("BNMTF_V3_B") ? atoi(getenv("BNMTF_V3_B")) : 2;
+  sd.v3B = getenv("BNMTF_V3_B") ? atoi(getenv("BNMTF_V3_B")) : 0;   // blocked variant (kernels_v3.cuh): opt-in, the B = 1 sweep is faster since both use st.async exchanges
   if (sd.v3B != 2) sd.v3B = 0;
   const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, V2_CS) * sizeof(double);
   sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && sd.kf >= 3 && smem_vb <= 200 * 1024 && sd.tw * 2 < 65535;
