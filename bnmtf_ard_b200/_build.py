@@ -6,8 +6,8 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SRC = os.path.join(PKG, "csrc", "engine.cu")
-DEPS = [SRC] + [os.path.join(PKG, "csrc", f) for f in ("kernels.cuh", "kernels_v2.cuh", "kernels_v3.cuh", "kernels_nmtf.cuh", "kernels_kmeans.cuh", "kernels_summary.cuh", "rng.cuh",
-                                                        "engine_nmtf.inc", "engine_summary.inc")] + [os.path.join(ROOT, "include", "bnmtf_b200.h")]
+DEPS = [SRC] + [os.path.join(PKG, "csrc", f) for f in ("kernels.cuh", "kernels_v2.cuh", "kernels_v3.cuh", "kernels_nmtf.cuh", "kernels_kmeans.cuh", "kernels_summary.cuh", "kernels_batch.cuh", "rng.cuh",
+                                                        "engine_nmtf.inc", "engine_summary.inc", "engine_batch.inc")] + [os.path.join(ROOT, "include", "bnmtf_b200.h")]
 LIB = os.path.join(PKG, "libbnmtf_b200.so")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

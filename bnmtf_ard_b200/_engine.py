@@ -16,9 +16,10 @@ class NMFEngine(object):
     same ones, like the reference constructors); this rank packs its row shard for
     the U sweep and its column shard for the V sweep."""
 
-    def __init__(self, R, M, K, device=None, distributed=True, L=None):
+    def __init__(self, R, M, K, device=None, distributed=True, L=None, layout_floor=None):
         lib = _lib.require_device()
         self.lib = lib
+        self.layout_floor = layout_floor
         self.I, self.J = R.shape
         self.K = int(K)
         self.L = None if L is None else int(L)
@@ -45,6 +46,7 @@ class NMFEngine(object):
         self = cls.__new__(cls)
         lib = _lib.require_device()
         self.lib = lib
+        self.layout_floor = None
         self.I, self.J, self.K = int(I), int(J), int(K)
         self.L = None if L is None else int(L)
         self.device = _lib.current_device() if device is None else int(device)
@@ -69,6 +71,8 @@ class NMFEngine(object):
         check(lib.bnmtf_nmf_layout_stats(self.h, st.ctypes.data_as(C.POINTER(C.c_int64))))
         if self.world > 1:
             st = _dist.allreduce_max(st)
+        if self.layout_floor is not None:   # models of one batch share one row-team layout (bnmtf_batch_run)
+            st = np.maximum(st, np.asarray(self.layout_floor, dtype=np.int64))
         check(lib.bnmtf_nmf_pack(self.h, st.ctypes.data_as(C.POINTER(C.c_int64))))
         out = np.zeros(3)
         check(lib.bnmtf_nmf_data_stats(self.h, dptr(out)))

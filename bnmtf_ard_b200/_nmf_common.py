@@ -60,11 +60,26 @@ class NMFCommon(object):
         assert empty_columns.size == 0, "Fully unobserved column in R, column %s." % (empty_columns[0] if empty_columns.size else -1)
 
     # -- engine ----------------------------------------------------------------
+    _layout_floor = None    # batched runs: lower bounds of the packing maxima, so that all models share one layout
+    _defer_run = False      # batched runs: run() uploads the state and stops; _batch.run_deferred() finishes it
+    _deferred = None
+
     def _engine(self):
         ''' The device handle, created on first use (packs R, M on the GPU). '''
         if self._eng is None:
-            self._eng = NMFEngine(self.R, self.M, self.K)
+            self._eng = NMFEngine(self.R, self.M, self.K, layout_floor=self._layout_floor)
         return self._eng
+
+    def run(self, iterations):
+        ''' run(iterations) of the reference classes: upload the host state, iterate on the device,
+            download.  The three steps are separate so that many small models can share the device
+            loop (bnmtf_ard_b200._batch). '''
+        eng, seed, traces = self._run_begin(iterations)
+        if self._defer_run:
+            self._deferred = (int(iterations), eng, seed, traces)
+            return
+        res = eng.run(self.METHOD, iterations, seed=seed, traces=traces, want_lambdak=self._WANT_LAMBDAK)
+        self._run_end(iterations, eng, res)
 
     def _upload_hyper(self, eng):
         if getattr(self, 'ARD', True):

@@ -73,8 +73,10 @@ class bnmf_gibbs(NMFCommon):
         eng.set_scalars(self.tau if hasattr(self, 'tau') else 0., self.lambdak if self.ARD else None)
         return eng
 
-    def run(self, iterations):
-        ''' Run the Gibbs sampler.  (bnmf_gibbs.py:135-183) '''
+    _WANT_LAMBDAK = True
+
+    def _run_begin(self, iterations):
+        ''' Run the Gibbs sampler (bnmf_gibbs.py:135-183): reset the traces, upload the state. '''
         self.all_times = []  # to plot performance against time
         self.all_performances = {}  # for plotting convergence of metrics
         for metric in ALL_METRICS:
@@ -83,12 +85,18 @@ class bnmf_gibbs(NMFCommon):
         eng = self._upload_state()
         seed = next_seed() if self.METHOD == _lib.GIBBS else 0
         traces = self._configure_summary(eng)
-        res = eng.run(self.METHOD, iterations, seed=seed, traces=traces, want_lambdak=True)
+        return eng, seed, traces
+
+    def _run_end(self, iterations, eng, res):
+        traces = res['all_U'] is not None
         self._summary_ready = self._summary is not None and eng.summary_count() > 0
 
         self.all_U, self.all_V = res['all_U'], res['all_V']
         self.all_tau = res['stats'][:, _lib.ST_TAU].copy()
-        self.all_lambdak = res['all_lambdak'] if self.ARD else numpy.zeros((iterations, self.K))
+        if res['all_lambdak'] is None:      # batched run: the lambdak draws are not traced
+            self.all_lambdak = None
+        else:
+            self.all_lambdak = res['all_lambdak'] if self.ARD else numpy.zeros((iterations, self.K))
         if iterations > 0:
             if traces:
                 self.U, self.V = numpy.copy(self.all_U[-1]), numpy.copy(self.all_V[-1])
@@ -96,7 +104,7 @@ class bnmf_gibbs(NMFCommon):
                 self.U, self.V = eng.get_factor(SIDE_U, F_VALUE), eng.get_factor(SIDE_V, F_VALUE)
             self.tau = float(self.all_tau[-1])
             if self.ARD:
-                self.lambdak = numpy.copy(self.all_lambdak[-1])
+                self.lambdak = numpy.copy(self.all_lambdak[-1]) if self.all_lambdak is not None else eng.get_scalars()[1]
         self._fill_performances(eng, res['stats'])
         self.all_times = list(res['seconds'])
         if self.verbose:

@@ -80,16 +80,18 @@ class bnmf_vb(NMFCommon):
             eng.set_vb_scalars(self.exp_tau, self.exp_logtau, self.alpha_s, self.beta_s)
         return eng
 
-    def run(self, iterations):
-        ''' Run the VB updates.  (bnmf_vb.py:145-188) '''
+    _WANT_LAMBDAK = False
+
+    def _run_begin(self, iterations):
+        ''' Run the VB updates (bnmf_vb.py:145-188): reset the traces, upload the state. '''
         self.all_exp_tau = []  # to check for convergence
         self.all_times = []  # to plot performance against time
         self.all_performances = {}  # for plotting convergence of metrics
         for metric in ALL_METRICS:
             self.all_performances[metric] = []
+        return self._upload_state(), 0, False
 
-        eng = self._upload_state()
-        res = eng.run(self.METHOD, iterations, seed=0, traces=False, want_lambdak=False)
+    def _run_end(self, iterations, eng, res):
         self._download_factors(eng)
         sc, ls = eng.get_vb_scalars()
         if iterations > 0:

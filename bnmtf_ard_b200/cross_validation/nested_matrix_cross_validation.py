@@ -9,6 +9,7 @@ import numpy
 from .mask import compute_folds_stratify_columns_attempts, compute_folds_stratify_rows_attempts
 from .matrix_cross_validation import MatrixCrossValidation
 from .parallel_matrix_cross_validation import ParallelMatrixCrossValidation
+from .batched_matrix_cross_validation import BatchedMatrixCrossValidation
 from ._device import prepare_summary
 
 attempts_generate_M = 1000
@@ -44,8 +45,17 @@ class MatrixNestedCrossValidation:
             if self.verbose:
                 print("Fold %s of nested cross-validation." % (i + 1))
 
-            # Run the cross-validation
-            crossval = ParallelMatrixCrossValidation(
+            # Run the cross-validation (parallel='batched': all inner fits of the fold share one device loop)
+            crossval = BatchedMatrixCrossValidation(
+                method=self.method,
+                R=self.R,
+                M=train,
+                K=self.K,
+                parameter_search=self.parameter_search,
+                train_config=self.train_config,
+                predict_config=self.predict_config,
+                file_performance=self.files_nested_performances[i],
+            ) if parallel == 'batched' else ParallelMatrixCrossValidation(
                 method=self.method,
                 R=self.R,
                 M=train,

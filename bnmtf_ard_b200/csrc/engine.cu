@@ -15,6 +15,7 @@
 #include "kernels_nmtf.cuh"
 #include "kernels_kmeans.cuh"
 #include "kernels_summary.cuh"
+#include "kernels_batch.cuh"
 
 using namespace bnmtf;
 
@@ -826,6 +827,32 @@ static int launch_sweep3_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
   return 0;
 }
 
+// argument block of the row-team sweep (v1 layout) on `side`
+static void fill_sweep_params(bnmtf_nmf_s* h, int method, int side, int single_k, uint64_t seed, uint32_t iteration,
+                              double* out_tau, double* out_mu, bool want_mu, const double* proj_y2, int64_t proj_ld2,
+                              int proj_k2, SweepParams& p) {
+  Side& sd = h->s[side];
+  const bool mu_out = (method == BNMTF_VB) || want_mu;
+  p.vals = sd.vals; p.cols = sd.cols; p.rowstart = sd.rowstart;
+  p.n_loc = (int)sd.n_loc; p.row0 = sd.row0; p.K = sd.kf; p.tpr = sd.tpr; p.padcol = sd.padcol;
+  p.Ykm = sd.ysrc; p.ldy = sd.ysrc_ld;
+  p.Ykm2 = proj_y2; p.ldy2 = proj_ld2; p.K2 = proj_k2; p.out3 = h->proj_out3;
+  if (h->cov_side == side && method == BNMTF_VB && single_k >= -2) {
+    p.covA = h->covA; p.covS = h->covS; p.covL = h->covL; p.cov_sk = h->cov_sk; p.cov_sl = h->cov_sl;
+  }
+  p.Xval = sd.val; p.Xvar = sd.var;
+  p.Xmu = mu_out ? sd.mu : nullptr; p.Xtau = mu_out ? sd.tau : nullptr;
+  p.lam_rm = h->hyper.ARD ? nullptr : sd.lam_rm;
+  p.lamk = (h->hyper.ARD && method != BNMTF_NP) ? sd.lamk : nullptr;
+  p.scal = h->scal;
+  p.out_tau = out_tau; p.out_mu = out_mu;
+  p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
+  p.rmean = h->rmean;
+  p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
+  p.iter_ptr = h->iter_ptr;
+  p.single_k = single_k;
+}
+
 // side: which factor is updated.  single_k: see SweepParams.
 static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint64_t seed, uint32_t iteration,
                         double* out_tau, double* out_mu, bool want_mu, const double* proj_y2 = nullptr,
@@ -882,24 +909,7 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     }
   } else {
     SweepParams p{};
-    p.vals = sd.vals; p.cols = sd.cols; p.rowstart = sd.rowstart;
-    p.n_loc = (int)sd.n_loc; p.row0 = sd.row0; p.K = sd.kf; p.tpr = sd.tpr; p.padcol = sd.padcol;
-    p.Ykm = sd.ysrc; p.ldy = sd.ysrc_ld;
-    p.Ykm2 = proj_y2; p.ldy2 = proj_ld2; p.K2 = proj_k2; p.out3 = h->proj_out3;
-    if (h->cov_side == side && method == BNMTF_VB && single_k >= -2) {
-      p.covA = h->covA; p.covS = h->covS; p.covL = h->covL; p.cov_sk = h->cov_sk; p.cov_sl = h->cov_sl;
-    }
-    p.Xval = sd.val; p.Xvar = sd.var;
-    p.Xmu = mu_out ? sd.mu : nullptr; p.Xtau = mu_out ? sd.tau : nullptr;
-    p.lam_rm = h->hyper.ARD ? nullptr : sd.lam_rm;
-    p.lamk = (h->hyper.ARD && method != BNMTF_NP) ? sd.lamk : nullptr;
-    p.scal = h->scal;
-    p.out_tau = out_tau; p.out_mu = out_mu;
-    p.rowstats = sd.rowstats + (size_t)sd.row0 * NRS;
-    p.rmean = h->rmean;
-    p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
-    p.iter_ptr = h->iter_ptr;
-    p.single_k = single_k;
+    fill_sweep_params(h, method, side, single_k, seed, iteration, out_tau, out_mu, want_mu, proj_y2, proj_ld2, proj_k2, p);
     switch (method) {
       case BNMTF_GIBBS: rc = launch_sweep_m<M_GIBBS>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
       case BNMTF_ICM: rc = launch_sweep_m<M_ICM>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
@@ -1298,3 +1308,4 @@ int bnmtf_exp_draw(int device, uint64_t seed, int64_t n, const double* lambda, d
 
 #include "engine_nmtf.inc"
 #include "engine_summary.inc"
+#include "engine_batch.inc"

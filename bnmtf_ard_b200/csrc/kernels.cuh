@@ -172,8 +172,11 @@ struct SweepCfg {
   static constexpr bool HOLDV = NPT <= 16;
 };
 
+// bid / nblk: index of this thread block among the nblk blocks that share the rows of p
+// (blockIdx.x / gridDim.x for a single model; the batched launch of kernels_batch.cuh maps
+// blockIdx.y to the model).
 template <int NPT, int MODE>
-__global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepParams p) {
+__device__ __forceinline__ void sweep_body(const SweepParams& p, const int bid, const int nblk) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
   constexpr bool HOLDV = SweepCfg<NPT>::HOLDV;
   extern __shared__ double smem[];
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
   const uint32_t iteration = p.iter_ptr ? *p.iter_ptr : p.iteration;
   const bool dry = (p.single_k == -2);
 
-  for (int row = blockIdx.x * teams + team; row < p.n_loc; row += gridDim.x * teams) {
+  for (int row = bid * teams + team; row < p.n_loc; row += nblk * teams) {
     const int64_t grow = p.row0 + row;
     const int64_t base = p.rowstart[row];
     const int npt = (int)((p.rowstart[row + 1] - base) / tpr);
@@ -419,6 +422,11 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepP
   }
 }
 
+template <int NPT, int MODE>
+__global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepParams p) {
+  sweep_body<NPT, MODE>(p, (int)blockIdx.x, (int)gridDim.x);
+}
+
 // -----------------------------------------------------------------------------
 // Row-major factor [n_pad][K]  ->  k-major gather layout [K][ld][NV], zero padded
 // for i >= n.  NV == 2 (VB): (exp, var + exp^2) pairs (bnmf_vb.py:254).
@@ -447,12 +455,12 @@ __global__ void rm_to_kmB_kernel(const double* __restrict__ Xval, const double* 
 }
 
 template <int NV>
-__global__ void rm_to_km_kernel(const double* __restrict__ Xval, const double* __restrict__ Xvar, double* __restrict__ Ykm,
-                                int64_t n, int K, int64_t ld) {
+__device__ __forceinline__ void rm_to_km_body(const double* __restrict__ Xval, const double* __restrict__ Xvar,
+                                              double* __restrict__ Ykm, int64_t n, int K, int64_t ld, int bx, int by) {
   __shared__ double tile[32][33];
   __shared__ double tile2[(NV == 2) ? 32 : 1][33];
-  const int64_t i0 = (int64_t)blockIdx.x * 32;
-  const int k0 = blockIdx.y * 32;
+  const int64_t i0 = (int64_t)bx * 32;
+  const int k0 = by * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int64_t i = i0 + r;
     const int k = k0 + threadIdx.x;
@@ -477,6 +485,12 @@ __global__ void rm_to_km_kernel(const double* __restrict__ Xval, const double* _
       }
     }
   }
+}
+
+template <int NV>
+__global__ void rm_to_km_kernel(const double* __restrict__ Xval, const double* __restrict__ Xvar, double* __restrict__ Ykm,
+                                int64_t n, int K, int64_t ld) {
+  rm_to_km_body<NV>(Xval, Xvar, Ykm, n, K, ld, (int)blockIdx.x, (int)blockIdx.y);
 }
 
 // deterministic block sum (fixed tree), blockDim.x <= 1024, result on all threads
@@ -509,12 +523,12 @@ enum { SC_TAU = 0, SC_LOGTAU = 1, SC_ALPHA_S = 2, SC_BETA_S = 3, SC_COUNT = 8 };
 // One block per k.  colsum[2][K]; lamstate[4][K] = alphak_s, betak_s, exp_lambdak(lambdak), exp_loglambdak.
 // -----------------------------------------------------------------------------
 template <int MODE>
-__global__ void lambda_kernel(const double* __restrict__ Ukm, int64_t ldu, int64_t I, const double* __restrict__ Vkm,
-                              int64_t ldv, int64_t J, int K, Hyper h, double* colsum, double* lamstate, double* lamk,
-                              uint64_t seed, uint32_t iteration, int update, const uint32_t* iter_ptr) {
+__device__ __forceinline__ void lambda_body(const double* __restrict__ Ukm, int64_t ldu, int64_t I,
+                                            const double* __restrict__ Vkm, int64_t ldv, int64_t J, int K, const Hyper& h,
+                                            double* colsum, double* lamstate, double* lamk, uint64_t seed,
+                                            uint32_t iteration, int update, const uint32_t* iter_ptr, const int k) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
   __shared__ double sh[32];
-  const int k = blockIdx.x;
   if (iter_ptr) iteration = *iter_ptr;
   double a = 0.0, b = 0.0;
   for (int64_t i = threadIdx.x; i < I; i += blockDim.x) a += Ukm[((size_t)k * ldu + i) * NV];
@@ -545,6 +559,13 @@ __global__ void lambda_kernel(const double* __restrict__ Ukm, int64_t ldu, int64
   }
 }
 
+template <int MODE>
+__global__ void lambda_kernel(const double* __restrict__ Ukm, int64_t ldu, int64_t I, const double* __restrict__ Vkm,
+                              int64_t ldv, int64_t J, int K, Hyper h, double* colsum, double* lamstate, double* lamk,
+                              uint64_t seed, uint32_t iteration, int update, const uint32_t* iter_ptr) {
+  lambda_body<MODE>(Ukm, ldu, I, Vkm, ldv, J, K, h, colsum, lamstate, lamk, seed, iteration, update, iter_ptr, (int)blockIdx.x);
+}
+
 // -----------------------------------------------------------------------------
 // End of an iteration: deterministic reduction of the per-row statistics, the
 // tau update and (VB) the ELBO.  Single block.
@@ -554,10 +575,11 @@ __global__ void lambda_kernel(const double* __restrict__ Ukm, int64_t ldu, int64
 // stats_out[BNMTF_NSTATS] layout: see include/bnmtf_b200.h.
 // -----------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ rsU, int64_t nU, const double* __restrict__ rsV, int64_t nV,
-                                int K, Hyper h, const double* __restrict__ colsum, const double* __restrict__ lamstate,
-                                double* scal, double* stats_out, uint64_t seed, uint32_t iteration, int update,
-                                int64_t I, int64_t J, uint32_t* iter_ctr) {
+__device__ __forceinline__ void finalize_body(const double* __restrict__ rsU, int64_t nU, const double* __restrict__ rsV,
+                                              int64_t nV, int K, const Hyper& h, const double* __restrict__ colsum,
+                                              const double* __restrict__ lamstate, double* scal, double* stats_out,
+                                              uint64_t seed, uint32_t iteration, int update, int64_t I, int64_t J,
+                                              uint32_t* iter_ctr) {
   __shared__ double sh[32];
   __shared__ double tot[2 * NRS];
   // graph replays: the iteration index lives on the device; this kernel ends the iteration and advances it
@@ -627,6 +649,14 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
   if (update) scal[SC_TAU] = tau;
   stats_out[3] = tau; stats_out[4] = beta_s; stats_out[9] = alpha_s;
   if (iter_ctr && update) *iter_ctr = iteration + 1;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ rsU, int64_t nU, const double* __restrict__ rsV, int64_t nV,
+                                int K, Hyper h, const double* __restrict__ colsum, const double* __restrict__ lamstate,
+                                double* scal, double* stats_out, uint64_t seed, uint32_t iteration, int update,
+                                int64_t I, int64_t J, uint32_t* iter_ctr) {
+  finalize_body<MODE>(rsU, nU, rsV, nV, K, h, colsum, lamstate, scal, stats_out, seed, iteration, update, I, J, iter_ctr);
 }
 
 // Graph replays: copy the draws of the iteration *iter_ptr into the trace staging buffers

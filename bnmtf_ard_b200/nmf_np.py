@@ -51,17 +51,19 @@ class nmf_np(NMFCommon):
         eng.set_factor(SIDE_V, F_VALUE, self.V)
         return eng
 
-    def run(self, iterations):
-        ''' Run the algorithm.  (nmf_np.py:97-117) '''
+    _WANT_LAMBDAK = False
+
+    def _run_begin(self, iterations):
+        ''' Run the algorithm (nmf_np.py:97-117): reset the traces, upload the state. '''
         assert hasattr(self, 'U') and hasattr(self, 'V'), "U and V have not been initialised - please run NMF.initialise() first."
 
         self.all_times = []  # to plot performance against time
         self.all_performances = {}  # for plotting convergence of metrics
         for metric in ALL_METRICS:
             self.all_performances[metric] = []
+        return self._upload_state(), 0, False
 
-        eng = self._upload_state()
-        res = eng.run(self.METHOD, iterations, seed=0, traces=False, want_lambdak=False)
+    def _run_end(self, iterations, eng, res):
         self.U, self.V = eng.get_factor(SIDE_U, F_VALUE), eng.get_factor(SIDE_V, F_VALUE)
         self._fill_performances(eng, res['stats'])
         self.all_times = list(res['seconds'])

@@ -291,6 +291,28 @@ int bnmtf_nmf_predict(bnmtf_nmf_t h, int source, int64_t n, const int32_t* rows,
                       const double* vals, double* out8);
 
 /* ------------------------------------------------------------------------- *
+ * Batched run of many small NMF models: the fits of a cross-validation sweep, one per (fold,
+ * parameter set), which the reference runs one after the other or in a multiprocessing.Pool
+ * (code/cross_validation/matrix_cross_validation.py:83-101, parallel_matrix_cross_validation.py:53-66,
+ * nested_matrix_cross_validation.py:47-80).
+ *
+ * handles[0..n): NMF handles (bnmtf_nmf_create) on ONE device, single-GPU, each with its hyper-
+ *   parameters and state set exactly as before bnmtf_nmf_run, and all packed with the same global
+ *   maxima (bnmtf_nmf_layout_stats of every model -> element-wise MAX -> bnmtf_nmf_pack) so that they
+ *   share one row-team layout.  The models may differ in K, in their masks and in their shapes.
+ * One launch of each update kernel (lambda_k, U sweep, V sweep, tau / ELBO) serves the whole batch and
+ *   the iteration is replayed as one CUDA graph; model m follows bit for bit the chain
+ *   bnmtf_nmf_run(handles[m], method, iterations, seeds[m], ...) gives it.
+ * seeds[n] (Gibbs; may be NULL otherwise); iter_stats[m] -> [iterations][BNMTF_NSTATS] of model m (entries
+ *   or the array may be NULL); iter_seconds[iterations]: cumulative device seconds of the batch.
+ * Draw traces (all_U, all_V) are not produced: Gibbs / ICM models that need posterior means configure
+ *   bnmtf_nmf_set_summary first.  Read the final states back with the per-handle getters.
+ * launches (optional): kernels launched by this call.
+ * ------------------------------------------------------------------------- */
+int bnmtf_batch_run(int n, const bnmtf_nmf_t* handles, int method, int iterations, const uint64_t* seeds,
+                    double* const* iter_stats, double* iter_seconds, int64_t* launches);
+
+/* ------------------------------------------------------------------------- *
  * Distributions (code/models/distributions/*.py) on the device; n-element
  * host arrays in, host arrays out.  Draws use Philox4x32-10 keyed by `seed`.
  *   bnmtf_tn_draw        TN_vector_draw        truncated_normal_vector.py:37-50

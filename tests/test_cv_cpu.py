@@ -103,6 +103,13 @@ def test_driver_logs_match_reference(gold, tmp_path):
         assert open(f).read() == open(f2).read()
         with pytest.raises(Exception):
             p.run_model(None, None, None)
+        # the batched driver with a model that cannot defer its run: fitted in place, the reference's log
+        from bnmtf_ard_b200.cross_validation.batched_matrix_cross_validation import BatchedMatrixCrossValidation
+        np.random.seed(1)
+        f = str(tmp_path / "bt.txt")
+        c = BatchedMatrixCrossValidation(StandIn, R, M, 3, search, {'iterations': 5}, {'burn_in': 1, 'thinning': 2}, f)
+        c.run(); best = c.find_best_parameters('MSE', True); c.fout.close()
+        assert open(f).read() == logs["matrix"] and json.dumps([best[0], best[1]]) == logs["matrix_best"]
 
 
 def test_stratified_folds_equal_sklearn():

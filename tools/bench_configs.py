@@ -122,6 +122,36 @@ def main():
             "seconds": dt, "fits": fits, "fits_per_s": fits / dt, "best_K": best['K'], "best_mse": perf,
             "reference_estimate_s": "0.16-0.59 s/iteration x 200 it x %d fits (BASELINE.md section 2)" % fits}
         print("C5", json.dumps(out[list(out)[-1]]))
+        # the same sweep with all fits in one batch (one launch per update for the 300 models)
+        from bnmtf_ard_b200.cross_validation.batched_matrix_cross_validation import BatchedMatrixCrossValidation
+        for method_name in (["vb", "icm", "np"] if args.its <= 0 else ["vb"]):
+            import bnmtf_ard_b200 as pkg
+            cls0 = {"vb": pkg.bnmf_vb, "icm": pkg.nmf_icm, "np": pkg.nmf_np}[method_name]
+
+            class QuietB(object):
+                def __new__(cls, R, M, **p):
+                    m = cls0(R, M, **p); m.verbose = False
+                    return m
+            if method_name == "np":
+                srch = [{'K': k} for k in Ks]; Rb = np.abs(Rh); pc = {}
+                tc = {'iterations': 200, 'init_UV': 'random'}
+            elif method_name == "icm":
+                srch = search; Rb = Rh; pc = {'burn_in': 180, 'thinning': 2}
+                tc = {'iterations': 200, 'init_UV': 'random'}
+            else:
+                srch = search; Rb = Rh; pc = {}
+                tc = {'iterations': 200, 'init_UV': 'random'}
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                cvb = BatchedMatrixCrossValidation(method=QuietB, R=Rb, M=Mh, K=10, parameter_search=srch, train_config=tc,
+                                                   predict_config=pc, file_performance="/tmp/cv_c5b.txt")
+                cvb.run()
+                bestb, perfb = cvb.find_best_parameters('MSE', True)
+            dtb = time.perf_counter() - t0
+            key = "C5 batched 10-fold CV, K=1..%d, %s 200 it, 887x545" % (Ks[-1], cls0.__name__)
+            out[key] = {"seconds": dtb, "fits": fits, "fits_per_s": fits / dtb, "best_K": bestb['K'], "best_mse": perfb,
+                        "phases_s": cvb.timing, "launches": cvb.launches}
+            print("C5b", json.dumps(out[key]))
     if args.out:
         with open(args.out, "w") as f:
             json.dump(out, f, indent=1)
