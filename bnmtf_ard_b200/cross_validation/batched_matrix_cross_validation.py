@@ -14,6 +14,7 @@ serves the whole batch (bnmtf_batch_run), replayed as one CUDA graph.
 Models that are not classes of this package (no deferred run) are simply fitted in place.
 """
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 from .. import _batch
 from ._device import prepare_summary
@@ -22,9 +23,10 @@ from .matrix_cross_validation import MatrixCrossValidation
 
 class BatchedMatrixCrossValidation(MatrixCrossValidation):
     def __init__(self, method, R, M, K, parameter_search, train_config, predict_config, file_performance,
-                 batch_models=1024):
+                 batch_models=1024, workers=8):
         MatrixCrossValidation.__init__(self, method, R, M, K, parameter_search, train_config, predict_config, file_performance)
         self.batch_models = int(batch_models)   # at most this many fits share a batch (device memory: ~24 B per observed entry and fit)
+        self.workers = max(1, int(workers))     # host threads that pack the models' data and evaluate their predictions
         self.launches = 0
         self.timing = {'setup_s': 0., 'device_loop_s': 0., 'predict_s': 0.}   # wall clock per phase
 
@@ -40,10 +42,17 @@ class BatchedMatrixCrossValidation(MatrixCrossValidation):
             try:
                 folds_training, folds_test = self._folds()
                 entries = []
-                for i, (train, test) in enumerate(zip(folds_training, folds_test)):
+                models = [self.method(self.R, train, **parameters) for train in folds_training]
+                batchable = [m for m in models if _batch.supports_batching(m)]
+                for m in batchable:
+                    m._layout_floor = floor
+                # device handles (upload and packing of R, M) are independent of the random streams: build them concurrently
+                if len(batchable) > 1 and self.workers > 1:
+                    list(self._pool().map(lambda m: m._engine(), batchable))
+                # initialise() and the seed of run() consume numpy's global stream: serial, in the order of the serial driver
+                for i, (model, test) in enumerate(zip(models, folds_test)):
                     if self.verbose:
                         print("Fold %s (parameters: %s)." % (i + 1, parameters))
-                    model = self.method(self.R, train, **parameters)
                     prepare_summary(model, self.predict_config)
                     if _batch.supports_batching(model):
                         with _batch.deferred(model, floor):
@@ -61,6 +70,16 @@ class BatchedMatrixCrossValidation(MatrixCrossValidation):
                 self._flush(pending)
                 pending, n_models = [], 0
         self._flush(pending)
+        if self._executor is not None:
+            self._executor.shutdown()
+            self._executor = None
+
+    _executor = None
+
+    def _pool(self):
+        if self._executor is None:
+            self._executor = ThreadPoolExecutor(max_workers=self.workers)
+        return self._executor
 
     def _flush(self, pending):
         ''' Run the deferred device loops of the pending fits together, then predict and log
@@ -75,6 +94,19 @@ class BatchedMatrixCrossValidation(MatrixCrossValidation):
                 failure = e
         t1 = time.perf_counter()
         self.timing['device_loop_s'] += t1 - t0
+        # held-out predictions: independent per model, evaluated on the device from `workers` host threads
+        jobs = [(model, test) for (_, entries) in pending if not isinstance(entries, Exception)
+                for (model, test, _) in entries if model is not None] if failure is None else []
+
+        def predict(job):
+            try:
+                return job[0].predict(job[1], **self.predict_config)
+            except Exception as e:      # reported with the parameter set it belongs to
+                return e
+        predicted = {}
+        if jobs:
+            results = list(self._pool().map(predict, jobs)) if self.workers > 1 else [predict(j) for j in jobs]
+            predicted = {id(job[0]): res for job, res in zip(jobs, results)}
         for parameters, entries in pending:
             try:
                 if isinstance(entries, Exception):
@@ -84,7 +116,9 @@ class BatchedMatrixCrossValidation(MatrixCrossValidation):
                 self.all_performances[self.JSON(parameters)] = {}
                 for (model, test, performance_dict) in entries:
                     if model is not None:
-                        performance_dict = model.predict(test, **self.predict_config)
+                        performance_dict = predicted[id(model)]
+                        if isinstance(performance_dict, Exception):
+                            raise performance_dict
                     self.store_performances(performance_dict, parameters)
                 self.log(parameters)
             except Exception as e:

@@ -1,6 +1,9 @@
 // Host side of the engine: model handle, packing of R/M, the iteration loop and
 // the C ABI declared in include/bnmtf_b200.h.  No torch types anywhere.
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -165,6 +168,9 @@ struct bnmtf_nmf_s {
   double *BS = nullptr, *PA = nullptr, *QC = nullptr;         // [K*L], [K(K+1)/2][L], [L(L+1)/2][K]
   double* lamstateG = nullptr;           // [4][L]  (lamstate holds the F block [4][K])
   double* vbmisc = nullptr;              // [8]: S q-term, sum lambdaS*ES, T3
+  // ---- pinned host staging of the draw traces (TraceDrain), kept between runs
+  char* pin[2] = {nullptr, nullptr};
+  size_t pin_bytes = 0;
   // ---- on-device posterior summaries (engine_summary.inc)
   int sum_burn = 0, sum_thin = 0;        // thinning <= 0: off
   int64_t sum_count = 0;
@@ -504,6 +510,7 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   cudaFree(h->Arow); cudaFree(h->Brow); cudaFree(h->Crow); cudaFree(h->BS); cudaFree(h->PA); cudaFree(h->QC);
   cudaFree(h->lamstateG); cudaFree(h->vbmisc); cudaFree(h->iter_dev);
   summary_free(h);
+  for (int b = 0; b < 2; ++b) if (h->pin[b]) cudaFreeHost(h->pin[b]);
   cudaStreamSynchronize(h->stream);
   g_stream = cudaStreamPerThread;
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1055,6 +1062,140 @@ int bnmtf_nmf_stats(bnmtf_nmf_t h, int method, double* out) {
   return 0;
 }
 
+// ---- draw traces to caller memory -------------------------------------------------------
+// all_U / all_V of a long run are gigabytes of pageable (usually never touched) caller memory.  A device-to-
+// host copy straight into it is staged by the driver and blocks the calling thread, which then cannot keep
+// the GPU fed, and the first touch of every page is paid inside that copy.  Instead each chunk of iterations
+// goes device -> pinned slot (asynchronous, PCIe speed) on the copy stream, and a host worker thread moves
+// it from the pinned slot into the caller's arrays while the GPU runs the next chunks.  Two pinned slots,
+// kept with the handle between runs.
+namespace {
+class TraceDrain {
+ public:
+  struct Part { const void* dev; char* host; size_t bytes; };
+  bool active = false;
+
+  int start(bnmtf_nmf_s* h, int nchunks, size_t slot_bytes) {
+    h_ = h;
+    if (h->pin_bytes < slot_bytes) {
+      for (int b = 0; b < 2; ++b) { if (h->pin[b]) cudaFreeHost(h->pin[b]); h->pin[b] = nullptr; }
+      h->pin_bytes = 0;
+      for (int b = 0; b < 2; ++b) CK(cudaHostAlloc((void**)&h->pin[b], slot_bytes, cudaHostAllocDefault));
+      h->pin_bytes = slot_bytes;
+    }
+    ready_.resize(nchunks, nullptr);
+    for (auto& e : ready_) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    jobs_.assign(nchunks, Job{});
+    submitted_ = 0; done_ = 0; stop_ = false; active = true;
+    worker_ = std::thread([this] { this->loop(); });
+    return 0;
+  }
+
+  // chunk c (in order): its parts are complete on the device once `dev_ready` has fired.  Returns after the
+  // copies into pinned slot c & 1 are enqueued on the copy stream; `reusable` is recorded behind them.
+  int submit(int c, cudaEvent_t dev_ready, const Part* parts, int nparts, cudaEvent_t reusable) {
+    {  // the slot is free once the worker has moved chunk c - 2 out of it
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return done_ >= c - 1; });
+    }
+    cudaStream_t cs = h_->copy_stream;
+    CK(cudaStreamWaitEvent(cs, dev_ready, 0));
+    Job j{};
+    char* slot = h_->pin[c & 1];
+    size_t off = 0;
+    for (int q = 0; q < nparts && q < 3; ++q) {
+      if (off + parts[q].bytes > h_->pin_bytes) FAIL("trace chunk larger than its pinned slot");
+      CK(cudaMemcpyAsync(slot + off, parts[q].dev, parts[q].bytes, cudaMemcpyDeviceToHost, cs));
+      j.src[q] = slot + off; j.dst[q] = parts[q].host; j.bytes[q] = parts[q].bytes;
+      off += parts[q].bytes;
+    }
+    j.n = std::min(nparts, 3);
+    CK(cudaEventRecord(ready_[c], cs));
+    CK(cudaEventRecord(reusable, cs));
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      jobs_[c] = j;
+      submitted_ = c + 1;
+    }
+    cv_.notify_all();
+    return 0;
+  }
+
+  // all submitted chunks are in the caller's arrays when this returns
+  int finish() {
+    if (!active) return 0;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    if (worker_.joinable()) worker_.join();
+    for (auto& e : ready_) if (e) cudaEventDestroy(e);
+    ready_.clear();
+    active = false;
+    if (failed_) FAIL("copying the draw traces to host memory failed: %s", cudaGetErrorString(err_));
+    return 0;
+  }
+
+  ~TraceDrain() { finish(); }
+
+ private:
+  struct Job { const char* src[3]; char* dst[3]; size_t bytes[3]; int n; };
+  // the destination pages are usually untouched: four threads take the page faults side by side
+  static void spread_memcpy(char* dst, const char* src, size_t bytes) {
+    constexpr int NT = 4;
+    if (bytes < ((size_t)8 << 20)) { memcpy(dst, src, bytes); return; }
+    const size_t piece = (bytes / NT + 4095) & ~(size_t)4095;
+    std::thread th[NT - 1];
+    for (int q = 1; q < NT; ++q) {
+      const size_t a = std::min(bytes, piece * q), b = std::min(bytes, piece * (q + 1));
+      th[q - 1] = std::thread([=] { if (b > a) memcpy(dst + a, src + a, b - a); });
+    }
+    memcpy(dst, src, std::min(bytes, piece));
+    for (auto& t : th) t.join();
+  }
+  void loop() {
+    cudaSetDevice(h_->device);
+    for (int i = 0;; ++i) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return submitted_ > i || stop_; });
+        if (submitted_ <= i) return;
+        j = jobs_[i];
+      }
+      cudaError_t e = cudaEventSynchronize(ready_[i]);
+      if (e != cudaSuccess) { failed_ = true; err_ = e; }
+      else for (int q = 0; q < j.n; ++q) spread_memcpy(j.dst[q], j.src[q], j.bytes[q]);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        done_ = i + 1;
+      }
+      cv_.notify_all();
+    }
+  }
+  bnmtf_nmf_s* h_ = nullptr;
+  std::vector<cudaEvent_t> ready_;
+  std::vector<Job> jobs_;
+  std::thread worker_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  int submitted_ = 0, done_ = 0;
+  bool stop_ = false, failed_ = false;
+  cudaError_t err_ = cudaSuccess;
+};
+
+// iterations per device-side trace chunk: everything at once while it fits 256 MB (the run loop can then be
+// replayed as a graph), else 64 MB chunks so that the last chunk's way to the caller's arrays is short
+int trace_chunk_iterations(int iterations, size_t per_it) {
+  per_it = std::max<size_t>(per_it, 1);
+  size_t whole = (size_t)256 << 20, piece = (size_t)64 << 20;
+  if (const char* e = getenv("BNMTF_TRACE_CHUNK_BYTES")) whole = piece = (size_t)std::max(1ll, atoll(e));   // tests: chunked traces of small models
+  if ((size_t)iterations * per_it <= whole) return iterations;
+  return (int)std::max<size_t>(1, std::min<size_t>((size_t)iterations, piece / per_it));
+}
+}  // namespace
+
 // Launch-bound run loops: iteration 0 eagerly (first-use attribute / occupancy calls happen here), iteration 1 captured
 // into a CUDA graph, the graph replayed for the rest.  While this runs h->iter_ptr is set: kernels read the iteration
 // index (Philox counters, trace and statistics slots) from the device and the finalize kernel advances it.
@@ -1117,7 +1258,7 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   const size_t per_it = sizeof(double) * ((size_t)su.n_glob + sv.n_glob) * K;
   const bool tr = (all_U != nullptr) || (all_V != nullptr);
   int chunk = iterations;
-  if (tr) chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)iterations, ((size_t)256 << 20) / std::max<size_t>(per_it, 1)));
+  if (tr) chunk = trace_chunk_iterations(iterations, per_it);
   if (tr) {
     for (int b = 0; b < 2; ++b) {
       cudaFree(su.trace[b]); cudaFree(sv.trace[b]); su.trace[b] = sv.trace[b] = nullptr;
@@ -1125,6 +1266,7 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
       CK(cudaMalloc(&sv.trace[b], sizeof(double) * sv.n_glob * K * chunk));
     }
   }
+  TraceDrain drain;   // joins its worker on every way out of this function
   cudaFree(h->stats_dev); h->stats_dev = nullptr;
   double* lam_trace = nullptr;
   CK(cudaMalloc(&h->stats_dev, sizeof(double) * BNMTF_NSTATS * iterations));
@@ -1141,17 +1283,26 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   if (summary_reset(h)) return 1;
   CK(cudaEventRecord(ev[0], h->stream));
 
+  const int nchunks = (iterations + chunk - 1) / chunk;
+  if (tr && nchunks > 1 && !getenv("BNMTF_NO_PINNED_TRACES") && drain.start(h, nchunks, per_it * (size_t)chunk)) return 1;
   auto copy_chunk = [&](int c) -> int {
     const int b = c & 1;
     const int it0 = c * chunk, n_it = std::min(chunk, iterations - it0);
+    const size_t bU = sizeof(double) * su.n_glob * K * n_it, bV = sizeof(double) * sv.n_glob * K * n_it;
+    if (drain.active) {
+      TraceDrain::Part parts[2];
+      int np = 0;
+      if (all_U) parts[np++] = {su.trace[b], (char*)(all_U + (size_t)it0 * su.n_glob * K), bU};
+      if (all_V) parts[np++] = {sv.trace[b], (char*)(all_V + (size_t)it0 * sv.n_glob * K), bV};
+      return drain.submit(c, chunk_done[b], parts, np, chunk_copied[b]);
+    }
     CK(cudaStreamWaitEvent(h->copy_stream, chunk_done[b], 0));
-    if (all_U) CK(cudaMemcpyAsync(all_U + (size_t)it0 * su.n_glob * K, su.trace[b], sizeof(double) * su.n_glob * K * n_it, cudaMemcpyDeviceToHost, h->copy_stream));
-    if (all_V) CK(cudaMemcpyAsync(all_V + (size_t)it0 * sv.n_glob * K, sv.trace[b], sizeof(double) * sv.n_glob * K * n_it, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (all_U) CK(cudaMemcpyAsync(all_U + (size_t)it0 * su.n_glob * K, su.trace[b], bU, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (all_V) CK(cudaMemcpyAsync(all_V + (size_t)it0 * sv.n_glob * K, sv.trace[b], bV, cudaMemcpyDeviceToHost, h->copy_stream));
     CK(cudaEventRecord(chunk_copied[b], h->copy_stream));
     return 0;
   };
 
-  const int nchunks = (iterations + chunk - 1) / chunk;
   // Small problems are launch-bound (~9 kernels of a few microseconds per iteration): replay the iteration as a graph
   const bool use_graph = graph_mode_allowed(h, iterations) && nchunks == 1;
   if (use_graph) {
@@ -1213,6 +1364,7 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   CK(cudaStreamSynchronize(h->copy_stream));
   CK(cudaGetLastError());
   if (iter_stats) CK(cudaMemcpy(iter_stats, h->stats_dev, sizeof(double) * BNMTF_NSTATS * iterations, cudaMemcpyDeviceToHost));
+  if (drain.finish()) return 1;
   if (all_lambdak) CK(cudaMemcpy(all_lambdak, lam_trace, sizeof(double) * K * iterations, cudaMemcpyDeviceToHost));
   if (iter_seconds) {
     for (int it = 0; it < iterations; ++it) {

@@ -119,7 +119,8 @@ __device__ __forceinline__ double gibbs_update_pre(const double (&s)[3], double 
   const double num = -lam + tau * (s[2] + x_old * s[0]);  // numerator of muU, bnmf_gibbs.py:210
   return tn_draw_pre(num, ct, u1, rng, cm);
 }
-template <int MODE>
+// WITH_Q = false: the caller evaluates the q(U) terms of the ELBO itself (vb_row_q)
+template <int MODE, bool WITH_Q = true>
 __device__ __forceinline__ double conditional_update(const double (&s)[3], double x_old, double lam, double tau,
                                                      const UpdateCtx& u, uint64_t grow, int k, double old_mu,
                                                      double old_tau, double old_var, double& ct, double& cm,
@@ -138,8 +139,9 @@ __device__ __forceinline__ double conditional_update(const double (&s)[3], doubl
     x_new = en;
     v_new = vn;
     acc_esd += (vn + en * en) * s[1] - (en * en) * s[0];
-    acc_q += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951))
-             + 0.5 * ct * (vn + (en - cm) * (en - cm));
+    if (WITH_Q)
+      acc_q += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951))
+               + 0.5 * ct * (vn + (en - cm) * (en - cm));
     acc_prior += lam * en;
   } else {
     ct = tau * s[0];                                   // bnmf_gibbs.py:205
@@ -153,6 +155,20 @@ __device__ __forceinline__ double conditional_update(const double (&s)[3], doubl
     }
   }
   return x_new;
+}
+
+// q(U_i) part of the ELBO for one row (bnmf_vb.py:219-229): sum_k -0.5 log tau_ik + log(0.5 erfc(-mu_ik sqrt(tau_ik)/sqrt2))
+// + 0.5 tau_ik (var_ik + (exp_ik - mu_ik)^2).  Each column is updated once per sweep, so the final parameters of
+// the row are the ones every update ended with; one lane per column keeps the two logarithms and the erfc off the
+// leader's serial path.  Called by the leader warp of the team; fixed summation order.
+__device__ __forceinline__ double vb_row_q(const double* xs, const double* xvar, const double* xmu, const double* xtau,
+                                           int K, int lane) {
+  double qq = 0.0;
+  for (int kk = lane; kk < K; kk += 32) {
+    const double ct = xtau[kk], cm = xmu[kk], en = xs[kk], vn = xvar[kk];
+    qq += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951)) + 0.5 * ct * (vn + (en - cm) * (en - cm));
+  }
+  return warp_sum(qq);
 }
 
 // -----------------------------------------------------------------------------
@@ -349,8 +365,9 @@ __device__ __forceinline__ void sweep_body(const SweepParams& p, const int bid, 
           const double num = -lam + tau * (s[2] + x_old * s[0]);   // numerator of muU, bnmf_gibbs.py:210
           x_new = tn_draw_fast(num, ct, m, rng, cm);
         } else {
-          x_new = conditional_update<MODE>(s, x_old, lam, tau, uc, (uint64_t)grow, k, xmu[k], xtau[k], xvar[k], ct, cm, vn,
-                                           acc_esd, acc_q, acc_prior);
+          // the q(U) terms of the ELBO are evaluated lane-parallel after the column loop (vb_row_q)
+          x_new = conditional_update<MODE, false>(s, x_old, lam, tau, uc, (uint64_t)grow, k, xmu[k], xtau[k], xvar[k], ct, cm,
+                                                  vn, acc_esd, acc_q, acc_prior);
         }
         if (MODE == M_VB) xvar[k] = vn;
         if (p.single_k >= 0) {
@@ -375,6 +392,8 @@ __device__ __forceinline__ void sweep_body(const SweepParams& p, const int bid, 
         }
       }
     }
+
+    if (MODE == M_VB && wteam == 0 && p.rowstats != nullptr && p.single_k < 0) acc_q = vb_row_q(xs, xvar, xmu, xtau, K, lane);
 
     // ---- per-row statistics from the final residual
     if (p.rowstats != nullptr && p.single_k < 0) {
