@@ -28,6 +28,16 @@ def layout_floor(masks):
     return np.array([rows, 1, cols, 1], dtype=np.int64)
 
 
+def reserve_device_memory(n_models, I, J, n_observed, workers=1):
+    ''' Grow the device memory pool once for n_models handles of an I x J matrix with n_observed entries:
+        packed rows and columns (12 B per slot and side, padded) plus the dense blocks that `workers`
+        concurrent constructors hold while packing. '''
+    lib = _lib.require_device()
+    per_model = 2 * 16 * int(n_observed) + 64 * (int(I) + int(J)) * 40
+    transient = int(workers) * 20 * int(I) * int(J)
+    check(lib.bnmtf_pool_reserve(_lib.current_device(), int(n_models) * per_model + transient))
+
+
 @contextlib.contextmanager
 def deferred(model, floor=None):
     ''' Inside this block model.run(iterations) -- also when called through train() -- uploads the
@@ -45,6 +55,9 @@ def supports_batching(model):
     return hasattr(model, '_run_begin') and hasattr(model, '_defer_run') and hasattr(model, 'METHOD')
 
 
+last_device_seconds = []     # CUDA-event seconds of each bnmtf_batch_run of the last run_deferred call
+
+
 def run_deferred(models):
     ''' Run the device loops of all models whose run() was deferred.  Models are grouped by
         (method, iterations); every group is one bnmtf_batch_run.  Returns the number of kernel
@@ -60,6 +73,7 @@ def run_deferred(models):
         groups.setdefault((m.METHOD, iterations), []).append(m)
     lib = _lib.require_device()
     total = 0
+    del last_device_seconds[:]
     for (method, iterations), ms in groups.items():
         n = len(ms)
         handles = (C.c_void_p * n)(*[m._deferred[1].h for m in ms])
@@ -71,6 +85,7 @@ def run_deferred(models):
         check(lib.bnmtf_batch_run(n, handles, int(method), int(iterations), seeds, stat_ptrs, dptr(seconds),
                                   C.byref(launches)))
         total += int(launches.value)
+        last_device_seconds.append(float(seconds[-1]) if iterations > 0 else 0.)
         for m, st in zip(ms, stats):
             _, eng, _, _ = m._deferred
             m._deferred = None

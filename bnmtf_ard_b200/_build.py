@@ -6,7 +6,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SRC = os.path.join(PKG, "csrc", "engine.cu")
-DEPS = [SRC] + [os.path.join(PKG, "csrc", f) for f in ("kernels.cuh", "kernels_v2.cuh", "kernels_v3.cuh", "kernels_nmtf.cuh", "kernels_kmeans.cuh", "kernels_summary.cuh", "kernels_batch.cuh", "rng.cuh",
+DEPS = [SRC] + [os.path.join(PKG, "csrc", f) for f in ("kernels.cuh", "kernels_v2.cuh", "kernels_v3.cuh", "kernels_nmtf.cuh", "kernels_kmeans.cuh", "kernels_summary.cuh", "kernels_batch.cuh", "kernels_long.cuh", "rng.cuh",
                                                         "engine_nmtf.inc", "engine_summary.inc", "engine_batch.inc")] + [os.path.join(ROOT, "include", "bnmtf_b200.h")]
 LIB = os.path.join(PKG, "libbnmtf_b200.so")
 

@@ -82,6 +82,7 @@ SIGNATURES = {
     "bnmtf_nmf_predict": (C.c_int, [_h, C.c_int, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _dp, _dp]),
     "bnmtf_batch_run": (C.c_int, [C.c_int, C.POINTER(_h), C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(_dp), _dp,
                                   C.POINTER(C.c_int64)]),
+    "bnmtf_pool_reserve": (C.c_int, [C.c_int, C.c_int64]),
     "bnmtf_tn_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),
     "bnmtf_tn_moments": (C.c_int, [C.c_int, C.c_int64, _dp, _dp, _dp, _dp]),
     "bnmtf_gamma_draw": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, _dp, _dp, _dp]),

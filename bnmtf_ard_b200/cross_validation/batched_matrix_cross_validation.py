@@ -13,6 +13,7 @@ serves the whole batch (bnmtf_batch_run), replayed as one CUDA graph.
 
 Models that are not classes of this package (no deferred run) are simply fitted in place.
 """
+import threading
 import time
 from concurrent.futures import ThreadPoolExecutor
 
@@ -23,11 +24,12 @@ from .matrix_cross_validation import MatrixCrossValidation
 
 class BatchedMatrixCrossValidation(MatrixCrossValidation):
     def __init__(self, method, R, M, K, parameter_search, train_config, predict_config, file_performance,
-                 batch_models=1024, workers=8):
+                 batch_models=128, workers=8):
         MatrixCrossValidation.__init__(self, method, R, M, K, parameter_search, train_config, predict_config, file_performance)
-        self.batch_models = int(batch_models)   # at most this many fits share a batch (device memory: ~24 B per observed entry and fit)
+        self.batch_models = int(batch_models)   # a batch is run once it holds this many fits; while its device loop runs, the next batch is set up
         self.workers = max(1, int(workers))     # host threads that pack the models' data and evaluate their predictions
         self.launches = 0
+        self.device_seconds = 0.     # CUDA-event time of the batched device loops
         self.timing = {'setup_s': 0., 'device_loop_s': 0., 'predict_s': 0.}   # wall clock per phase
 
     def run(self):
@@ -35,6 +37,12 @@ class BatchedMatrixCrossValidation(MatrixCrossValidation):
         pending = []     # (parameters, [(model or None, test, performance or None)] or exception)
         n_models = 0
         floor = _batch.layout_floor([self.M])   # the training masks are subsets of M
+        self._flusher = None
+        try:   # one growth step of the device memory pool for the handles of two batches in flight
+            n_fits = min(2 * self.batch_models + self.K, len(self.parameter_search) * self.K)
+            _batch.reserve_device_memory(n_fits, self.I, self.J, int((self.M != 0).sum()), self.workers)
+        except Exception:
+            pass    # no device: the models raise their own error
         for parameters in self.parameter_search:
             t0 = time.perf_counter()
             if self.verbose:
@@ -42,13 +50,15 @@ class BatchedMatrixCrossValidation(MatrixCrossValidation):
             try:
                 folds_training, folds_test = self._folds()
                 entries = []
-                models = [self.method(self.R, train, **parameters) for train in folds_training]
-                batchable = [m for m in models if _batch.supports_batching(m)]
-                for m in batchable:
-                    m._layout_floor = floor
-                # device handles (upload and packing of R, M) are independent of the random streams: build them concurrently
-                if len(batchable) > 1 and self.workers > 1:
-                    list(self._pool().map(lambda m: m._engine(), batchable))
+                # constructors (copies and checks of R, M) and device handles (upload and packing) do not touch the
+                # random streams: build them concurrently
+                def build(train):
+                    m = self.method(self.R, train, **parameters)
+                    if _batch.supports_batching(m):
+                        m._layout_floor = floor
+                        m._engine()
+                    return m
+                models = list(self._pool().map(build, folds_training)) if self.workers > 1 else [build(t) for t in folds_training]
                 # initialise() and the seed of run() consume numpy's global stream: serial, in the order of the serial driver
                 for i, (model, test) in enumerate(zip(models, folds_test)):
                     if self.verbose:
@@ -67,14 +77,30 @@ class BatchedMatrixCrossValidation(MatrixCrossValidation):
                 pending.append((parameters, e))
             self.timing['setup_s'] += time.perf_counter() - t0
             if n_models >= self.batch_models:
-                self._flush(pending)
+                self._submit(pending)
                 pending, n_models = [], 0
-        self._flush(pending)
+        self._submit(pending)
+        self._join()
         if self._executor is not None:
             self._executor.shutdown()
             self._executor = None
 
     _executor = None
+    _flusher = None
+
+    def _submit(self, pending):
+        ''' Run a batch in the background (its device loop, downloads, predictions and log lines) while the
+            caller sets up the next one.  One batch in flight: the log keeps the order of the parameter sets. '''
+        self._join()
+        if not pending:
+            return
+        self._flusher = threading.Thread(target=self._flush, args=(pending,))
+        self._flusher.start()
+
+    def _join(self):
+        if self._flusher is not None:
+            self._flusher.join()
+            self._flusher = None
 
     def _pool(self):
         if self._executor is None:
@@ -90,6 +116,7 @@ class BatchedMatrixCrossValidation(MatrixCrossValidation):
         if models:
             try:
                 self.launches += _batch.run_deferred(models)
+                self.device_seconds += sum(_batch.last_device_seconds)
             except Exception as e:
                 failure = e
         t1 = time.perf_counter()

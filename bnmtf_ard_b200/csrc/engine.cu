@@ -19,6 +19,7 @@
 #include "kernels_kmeans.cuh"
 #include "kernels_summary.cuh"
 #include "kernels_batch.cuh"
+#include "kernels_long.cuh"
 
 using namespace bnmtf;
 
@@ -112,6 +113,9 @@ struct Side {
   double* tvals = nullptr;
   uint16_t* tcols = nullptr;
   int nclusters[4] = {0, 0, 0, 0};
+  bool long_rows = false;      // rows beyond the register-resident configurations: residual in global scratch (kernels_long.cuh)
+  double* escr = nullptr;      // [nslots]
+  int occ_long[4] = {0, 0, 0, 0};
   int v3B = 0;                 // columns per cluster exchange of the blocked sweep (0: v2 kernel)
   int nclusters3[4] = {0, 0, 0, 0};
   bool v3fit[4] = {false, false, false, false};
@@ -221,8 +225,10 @@ static int count_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t l
 static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld, uint32_t padcol, int64_t maxlen,
                       int64_t maxseg) {
   choose_team(maxlen, &sd.tpr, &sd.npt);
-  if ((int64_t)sd.tpr * sd.npt < maxlen || sd.tpr > 512)
-    FAIL("a row/column of R has %lld observed entries; this build supports at most 16384 per row", (long long)maxlen);
+  if ((int64_t)sd.tpr * sd.npt < maxlen || sd.tpr > 512) {   // longer than 32 x 512 entries: streamed rows
+    if (h->nmtf) FAIL("a row/column of R has %lld observed entries; the tri-factorisation models support at most 16384 per row", (long long)maxlen);
+    sd.long_rows = true; sd.tpr = LONG_T; sd.npt = 0;
+  }
   std::vector<int> rowlen(n);
   CK(cudaMemcpyAsync(rowlen.data(), sd.rowlen_dev, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -234,6 +240,7 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   CK(cudaMalloc(&sd.rowstart, sizeof(int64_t) * (n + 1)));
   CK(cudaMalloc(&sd.vals, sizeof(double) * std::max<int64_t>(sd.nslots, 1)));
   CK(cudaMalloc(&sd.cols, sizeof(uint32_t) * std::max<int64_t>(sd.nslots, 1)));
+  if (sd.long_rows) CK(cudaMalloc(&sd.escr, sizeof(double) * std::max<int64_t>(sd.nslots, 1)));
   CK(cudaMemcpyAsync(sd.rowstart, rowstart.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, h->stream));
   if (n > 0) {
     pack_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, h->stream>>>(sd.dR, sd.dM, n, m, ld, sd.rowstart, padcol, sd.vals, sd.cols);
@@ -327,6 +334,27 @@ static cudaError_t pool_setup(int device) {
   done[device] = true;
   return e;
 }
+// Grow the device's stream-ordered pool to `bytes` in one step: many small first-time allocations (the
+// handles of a batch of models) otherwise grow it a few megabytes at a time, a driver call each.
+int bnmtf_pool_reserve(int device, int64_t bytes) {
+  if (bytes <= 0) return 0;
+  CK(cudaSetDevice(device));
+  CK(pool_setup(device));
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t reserved = 0;
+  CK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
+  uint64_t used = 0;
+  CK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
+  const uint64_t idle = reserved > used ? reserved - used : 0;
+  if (idle >= (uint64_t)bytes) return 0;
+  void* p = nullptr;
+  if (cudaMallocAsync(&p, (size_t)bytes - idle, cudaStreamPerThread) != cudaSuccess) { cudaGetLastError(); return 0; }   // best effort
+  cudaFreeAsync(p, cudaStreamPerThread);
+  CK(cudaStreamSynchronize(cudaStreamPerThread));
+  return 0;
+}
+
 #define cudaMalloc pool_malloc
 #define cudaFree pool_free
 #define cudaMemcpy copy_sync
@@ -492,7 +520,7 @@ static void free_side(Side& sd) {
   cudaFree(sd.val); cudaFree(sd.var); cudaFree(sd.mu); cudaFree(sd.tau);
   cudaFree(sd.km); cudaFree(sd.km3); cudaFree(sd.lam_rm); cudaFree(sd.rowstats);
   cudaFree(sd.trace[0]); cudaFree(sd.trace[1]);
-  cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev); cudaFree(sd.ycomb);
+  cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev); cudaFree(sd.ycomb); cudaFree(sd.escr);
   if (sd.own_dense) { cudaFree((void*)sd.dR); cudaFree((void*)sd.dM); }
 }
 
@@ -860,6 +888,34 @@ static void fill_sweep_params(bnmtf_nmf_s* h, int method, int side, int single_k
   p.single_k = single_k;
 }
 
+// streamed rows (kernels_long.cuh): one CTA per row
+static int launch_sweep_long(bnmtf_nmf_s* h, int method, const SweepParams& p, Side& sd) {
+  const size_t smem = sizeof(double) * (4 * (size_t)p.K + 3 * (LONG_T / 32) + 2 + (method == BNMTF_GIBBS ? TN_PRE_DOUBLES * (size_t)p.K : 0));
+  if (smem > 200 * 1024) FAIL("too many factors (%d) for the streamed row sweep", p.K);
+#define LONGK(MODE)                                                                                              \
+  do {                                                                                                           \
+    auto kern = sweep_long_kernel<MODE>;                                                                         \
+    if (sd.occ_long[method] == 0) {                                                                              \
+      if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      int occ = 0;                                                                                               \
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LONG_T, smem));                               \
+      if (occ < 1) FAIL("streamed row sweep does not fit (smem %zu)", smem);                                     \
+      sd.occ_long[method] = occ;                                                                                 \
+    }                                                                                                            \
+    const int grid = (int)std::min<int64_t>(p.n_loc, (int64_t)sd.occ_long[method] * h->num_sms);                 \
+    if (grid >= 1) { kern<<<grid, LONG_T, smem, h->stream>>>(p, sd.escr); h->launches++; }                       \
+  } while (0)
+  switch (method) {
+    case BNMTF_GIBBS: LONGK(M_GIBBS); break;
+    case BNMTF_ICM: LONGK(M_ICM); break;
+    case BNMTF_VB: LONGK(M_VB); break;
+    case BNMTF_NP: LONGK(M_NP); break;
+    default: FAIL("unknown method %d", method);
+  }
+#undef LONGK
+  return 0;
+}
+
 // side: which factor is updated.  single_k: see SweepParams.
 static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint64_t seed, uint32_t iteration,
                         double* out_tau, double* out_mu, bool want_mu, const double* proj_y2 = nullptr,
@@ -917,6 +973,11 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
   } else {
     SweepParams p{};
     fill_sweep_params(h, method, side, single_k, seed, iteration, out_tau, out_mu, want_mu, proj_y2, proj_ld2, proj_k2, p);
+    if (sd.long_rows) {
+      if (h->nmtf || single_k < -2 || p.covA)
+        FAIL("a row/column of R has more than 16384 observed entries: the tri-factorisation models do not serve such rows");
+      rc = launch_sweep_long(h, method, p, sd);
+    } else
     switch (method) {
       case BNMTF_GIBBS: rc = launch_sweep_m<M_GIBBS>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;
       case BNMTF_ICM: rc = launch_sweep_m<M_ICM>(h, p, p.n_loc, sd.npt, &sd.occ[method]); break;

@@ -442,7 +442,7 @@ __device__ __forceinline__ void sweep_body(const SweepParams& p, const int bid, 
 }
 
 template <int NPT, int MODE>
-__global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_kernel(const SweepParams p) {
+__global__ void __launch_bounds__(SweepCfg<NPT>::MAXT, 1) sweep_kernel(const SweepParams p) {
   sweep_body<NPT, MODE>(p, (int)blockIdx.x, (int)gridDim.x);
 }
 

@@ -59,9 +59,10 @@ __device__ __forceinline__ void load_args(T& dst, const T* __restrict__ src) {
   __syncthreads();
 }
 
-// grid (max blocks per model, models); blocks beyond a model's share leave at once
+// grid (max blocks per model, models); blocks beyond a model's share leave at once.
+// (min blocks = 1: without it ptxas settles on 64 registers for some instantiations and spills the row.)
 template <int NPT, int MODE>
-__global__ void __launch_bounds__(SweepCfg<NPT>::MAXT) sweep_batch_kernel(const SweepParams* __restrict__ pp) {
+__global__ void __launch_bounds__(SweepCfg<NPT>::MAXT, 1) sweep_batch_kernel(const SweepParams* __restrict__ pp) {
   __shared__ SweepParams sp;
   const SweepParams* g = pp + blockIdx.y;
   const int teams = blockDim.x / g->tpr;

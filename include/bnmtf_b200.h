@@ -311,6 +311,10 @@ int bnmtf_nmf_predict(bnmtf_nmf_t h, int source, int64_t n, const int32_t* rows,
  * ------------------------------------------------------------------------- */
 int bnmtf_batch_run(int n, const bnmtf_nmf_t* handles, int method, int iterations, const uint64_t* seeds,
                     double* const* iter_stats, double* iter_seconds, int64_t* launches);
+/* Optional, before creating the handles of a large batch: grow the device's stream-ordered memory pool (which
+ * every allocation of this library comes from) to `bytes` of idle memory in one step instead of a few
+ * megabytes per first-time allocation.  Best effort: returns 0 also when the device cannot spare that much. */
+int bnmtf_pool_reserve(int device, int64_t bytes);
 
 /* ------------------------------------------------------------------------- *
  * Distributions (code/models/distributions/*.py) on the device; n-element

@@ -154,7 +154,8 @@ def test_np_golden(golden):
 # The last four also exercise the cluster-tile kernel (>= 2048 columns): tail tiles,
 # tail row sets, both sides tiled, and spill placement of crowded bank classes.
 SHAPES = [(37, 23, 3, 0.8), (120, 150, 5, 0.9), (90, 400, 4, 0.55), (64, 3000, 6, 0.7), (700, 140, 7, 0.8),
-          (33, 9000, 3, 0.9), (100, 4096, 5, 0.5), (2300, 2500, 4, 0.3), (41, 5000, 3, 0.45), (70, 2049, 8, 0.95)]
+          (33, 9000, 3, 0.9), (100, 4096, 5, 0.5), (2300, 2500, 4, 0.3), (41, 5000, 3, 0.45), (70, 2049, 8, 0.95),
+          (9, 17500, 3, 0.97)]     # the last one: rows of ~17000 observed entries, streamed from global memory (kernels_long.cuh)
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -201,7 +202,32 @@ def test_cluster_kernel_is_selected():
     eng.close()
 
 
-@pytest.mark.parametrize("shape", SHAPES[:4] + SHAPES[6:8])
+def test_streamed_rows_are_selected_and_column_params_match():
+    """Rows beyond 16384 observed entries: the row sweep streams the residual from global memory; the single-column
+    conditionals (tauU / muU of the class API) go through the same kernel and must match the oracle."""
+    from bnmtf_ard_b200 import bnmf_gibbs, bnmtf_gibbs
+    from bnmtf_ard_b200._engine import NMFEngine
+    I, J, K, dens = SHAPES[10]
+    R, M, rng = make_problem(11, I, J, K, dens)
+    eng = NMFEngine(R, M, K)
+    info = eng.layout_info()
+    assert info["tpr_U"] == 512 and info["npt_U"] == 0 and info["v2_U"] == 0 and info["npt_V"] > 0
+    eng.close()
+    hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0}
+    m = bnmf_gibbs(R, M, K, True, hyper); m.verbose = False
+    m.U, m.V, m.tau, m.lambdak = rng.exponential(1.0, (I, K)), rng.exponential(1.0, (J, K)), 0.7, np.array([0.5, 1.0, 2.0])
+    E = orc.residual(R, M, m.U, m.V)
+    for k in range(K):
+        t_ref, mu_ref = orc.col_params(E, M, m.U, m.V, m.tau, m.lambdak[k], k)
+        t = m.tauU(k)
+        close(t, t_ref, RTOL_STEP); mu_close(m.muU(t, k), mu_ref, t_ref)
+    close(m.beta_s(), orc.beta_s(R, M, m.U, m.V, 1.0), RTOL_STEP)
+    with pytest.raises(RuntimeError, match="tri-factorisation models support at most 16384"):
+        t3 = bnmtf_gibbs(R, M, 2, 2, True, dict(hyper, lambdaS=0.1)); t3.verbose = False
+        t3.initialise('random', 'random')
+
+
+@pytest.mark.parametrize("shape", SHAPES[:4] + SHAPES[6:8] + SHAPES[10:])
 def test_icm_vb_np_iterations_vs_oracle(shape):
     from bnmtf_ard_b200 import bnmf_vb, nmf_icm, nmf_np
     I, J, K, dens = shape

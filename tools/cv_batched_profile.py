@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--kmax", type=int, default=30)
     ap.add_argument("--method", default="vb")
     ap.add_argument("--top", type=int, default=45)
+    ap.add_argument("--workers", type=int, default=8)
+    ap.add_argument("--noprofile", action="store_true")
     args = ap.parse_args()
     import bnmtf_ard_b200 as pkg
     from bnmtf_ard_b200.cross_validation.batched_matrix_cross_validation import BatchedMatrixCrossValidation
@@ -40,12 +42,19 @@ def main():
         with contextlib.redirect_stdout(io.StringIO()):
             cv = BatchedMatrixCrossValidation(method=Quiet, R=R, M=M, K=10, parameter_search=box['search'],
                                               train_config={'iterations': 200, 'init_UV': 'random'}, predict_config=pc,
-                                              file_performance="/tmp/cv_prof.txt")
+                                              file_performance="/tmp/cv_prof.txt", workers=args.workers)
             cv.run()
         return cv
     box = {'search': search[:2]}
     go()                      # warm-up: context, module load, pool growth
     box['search'] = search
+    if args.noprofile:
+        import time
+        for rep in range(2):
+            t0 = time.perf_counter()
+            cv = go()
+            print("workers", args.workers, "total_s", time.perf_counter() - t0, "phases", cv.timing, "device_s", cv.device_seconds)
+        return
     pr = cProfile.Profile()
     pr.enable()
     cv = go()
