@@ -398,8 +398,13 @@ static int create_dev_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, i
   bnmtf_nmf_s* h = new bnmtf_nmf_s();
   h->device = device; h->I = I; h->J = J; h->K = K; h->L = L; h->nmtf = nmtf;
   h->num_sms = sms;
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  {  // handle streams run at the highest priority; bnmtf_batch_run drives its long launches at the lowest, so the
+     // short kernels of a model being set up are never queued behind a batch that occupies the GPU
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, greatest));
+    CK(cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, greatest));
+  }
   g_stream = h->stream;
   const char* ts = getenv("BNMTF_TIME_SWEEPS");
   h->time_sweeps = ts && atoi(ts) != 0;
