@@ -1143,16 +1143,11 @@ class TraceDrain {
 
   int start(bnmtf_nmf_s* h, int nchunks, size_t slot_bytes) {
     h_ = h;
-    if (h->pin_bytes < slot_bytes) {
-      for (int b = 0; b < 2; ++b) { if (h->pin[b]) cudaFreeHost(h->pin[b]); h->pin[b] = nullptr; }
-      h->pin_bytes = 0;
-      for (int b = 0; b < 2; ++b) CK(cudaHostAlloc((void**)&h->pin[b], slot_bytes, cudaHostAllocDefault));
-      h->pin_bytes = slot_bytes;
-    }
+    slot_bytes_ = slot_bytes;   // the worker allocates the pinned slots (tens of milliseconds) while the caller enqueues the first chunk
     ready_.resize(nchunks, nullptr);
     for (auto& e : ready_) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     jobs_.assign(nchunks, Job{});
-    submitted_ = 0; done_ = 0; stop_ = false; active = true;
+    submitted_ = 0; done_ = 0; stop_ = false; slots_ready_ = false; active = true;
     worker_ = std::thread([this] { this->loop(); });
     return 0;
   }
@@ -1160,10 +1155,11 @@ class TraceDrain {
   // chunk c (in order): its parts are complete on the device once `dev_ready` has fired.  Returns after the
   // copies into pinned slot c & 1 are enqueued on the copy stream; `reusable` is recorded behind them.
   int submit(int c, cudaEvent_t dev_ready, const Part* parts, int nparts, cudaEvent_t reusable) {
-    {  // the slot is free once the worker has moved chunk c - 2 out of it
+    {  // the slot exists, and is free once the worker has moved chunk c - 2 out of it
       std::unique_lock<std::mutex> lk(mu_);
-      cv_.wait(lk, [&] { return done_ >= c - 1; });
+      cv_.wait(lk, [&] { return slots_ready_ && done_ >= c - 1; });
     }
+    if (failed_) FAIL("pinned host memory for the draw traces: %s", cudaGetErrorString(err_));
     cudaStream_t cs = h_->copy_stream;
     CK(cudaStreamWaitEvent(cs, dev_ready, 0));
     Job j{};
@@ -1222,6 +1218,18 @@ class TraceDrain {
   }
   void loop() {
     cudaSetDevice(h_->device);
+    if (h_->pin_bytes < slot_bytes_) {
+      for (int b = 0; b < 2; ++b) { if (h_->pin[b]) cudaFreeHost(h_->pin[b]); h_->pin[b] = nullptr; }
+      h_->pin_bytes = 0;
+      cudaError_t e = cudaSuccess;
+      for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaHostAlloc((void**)&h_->pin[b], slot_bytes_, cudaHostAllocDefault);
+      if (e == cudaSuccess) h_->pin_bytes = slot_bytes_; else { failed_ = true; err_ = e; }
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      slots_ready_ = true;
+    }
+    cv_.notify_all();
     for (int i = 0;; ++i) {
       Job j;
       {
@@ -1247,15 +1255,18 @@ class TraceDrain {
   std::mutex mu_;
   std::condition_variable cv_;
   int submitted_ = 0, done_ = 0;
+  size_t slot_bytes_ = 0;
+  bool slots_ready_ = false;
   bool stop_ = false, failed_ = false;
   cudaError_t err_ = cudaSuccess;
 };
 
 // iterations per device-side trace chunk: everything at once while it fits 256 MB (the run loop can then be
-// replayed as a graph), else 64 MB chunks so that the last chunk's way to the caller's arrays is short
+// replayed as a graph), else 16 MB chunks (at least one iteration) so that the last chunk's way to the caller's
+// arrays is short
 int trace_chunk_iterations(int iterations, size_t per_it) {
   per_it = std::max<size_t>(per_it, 1);
-  size_t whole = (size_t)256 << 20, piece = (size_t)64 << 20;
+  size_t whole = (size_t)256 << 20, piece = (size_t)16 << 20;
   if (const char* e = getenv("BNMTF_TRACE_CHUNK_BYTES")) whole = piece = (size_t)std::max(1ll, atoll(e));   // tests: chunked traces of small models
   if ((size_t)iterations * per_it <= whole) return iterations;
   return (int)std::max<size_t>(1, std::min<size_t>((size_t)iterations, piece / per_it));
