@@ -395,6 +395,21 @@ __device__ __forceinline__ void sweep_body(const SweepParams& p, const int bid, 
 
     if (MODE == M_VB && wteam == 0 && p.rowstats != nullptr && p.single_k < 0) acc_q = vb_row_q(xs, xvar, xmu, xtau, K, lane);
 
+    // ---- optional epilogue of a sweep: projections of the residual the row ends with onto the columns of a second
+    // factor, out_mu[row][l] = sum_j e_j Y2[l][j] (BNMTF VB: P_il for the S statistics, bnmtf_vb.py:352-357 -- the
+    // residual after update_F is the one update_S starts from, so no separate residual pass is needed)
+    if (p.single_k == -1 && p.Ykm2 != nullptr && MODE != M_NP) {
+      for (int l = 0; l < p.K2; ++l) {
+        const double* __restrict__ y2 = p.Ykm2 + (size_t)l * p.ldy2 * NV;
+        double s1[1] = {0.0};
+#pragma unroll
+        for (int n = 0; n < NPT; ++n) s1[0] = fma(e[n], __ldg(y2 + c[n]), s1[0]);
+        team_reduce_to_leader<1>(s1, red, nw, wteam, lane, barA, tpr);
+        if (leader) p.out_mu[grow * p.K2 + l] = s1[0];
+        if (nw > 1) bar_sync(barB, tpr);
+      }
+    }
+
     // ---- per-row statistics from the final residual
     if (p.rowstats != nullptr && p.single_k < 0) {
       double st[3] = {0.0, 0.0, 0.0};

@@ -404,13 +404,123 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_vb_kernel(const double* __re
   if (threadIdx.x == 0 && mode < 0) { misc[0] = acc_q; misc[1] = acc_prior; }
 }
 
+// The same sweep with everything that is not the conditional itself taken off thread 0's serial path (used while
+// K*L <= 2 * blockDim.x and the arrays fit 48 KB of shared memory; nmtf_s_sweep_vb_kernel is the general form):
+//   * covG_d and covF_d are linear in ES: computed once for every entry in parallel, then maintained like c -- the
+//     update of entry (k,l) by delta adds delta PA[pair(k2,k)][l] to covG of the entries (k2,l) and delta
+//     QC[pair(l2,l)][k] to covF of the entries (k,l2);
+//   * the row of T, PA and QC values an entry needs for the update of step d are loaded before thread 0 starts the
+//     conditional of step d, so their L2 latency is hidden behind it;
+//   * T_dd, BS, lambdaS sit in shared memory; the q(S) terms of the ELBO (two logarithms and an erfc per entry,
+//     bnmtf_vb.py:290-292) and sum lambdaS ES are evaluated by all threads after the sweep (fixed-order block sum).
+// Entry reports (mode >= 0) see exactly the from-scratch sums of the general kernel.
+__global__ void __launch_bounds__(512) nmtf_s_sweep_vb_fast_kernel(const double* __restrict__ c_in, const double* __restrict__ TT,
+                                       const double* __restrict__ BS, const double* __restrict__ PA, const double* __restrict__ QC,
+                                       int K, int L, double* Sexp, double* Svar, double* Smu, double* Stau,
+                                       const double* __restrict__ lamS, const double* __restrict__ scal, int mode, double* out_tau,
+                                       double* out_mu, double* misc) {
+  extern __shared__ double shs[];
+  __shared__ double red[32];
+  const int KL = K * L, NPL = L * (L + 1) / 2;
+  double* c = shs;            // [KL] running c_d
+  double* es = c + KL;        // [KL]
+  double* cg = es + KL;       // [KL] running covG_d
+  double* cf = cg + KL;       // [KL] running covF_d
+  double* tdd = cf + KL;      // [KL]
+  double* bs = tdd + KL;      // [KL]
+  double* lam = bs + KL;      // [KL]
+  double* bc = lam + KL;      // [1]
+  constexpr int ME = 2;       // entries per thread
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int d = tid; d < KL; d += nt) {
+    const int k = d / L, l = d - k * L;
+    c[d] = c_in[d]; es[d] = Sexp[d]; tdd[d] = tmat(TT, k, l, k, l, K, L, NPL); bs[d] = BS[d]; lam[d] = lamS[d];
+  }
+  __syncthreads();
+  const double etau = scal[0];
+  if (mode != -2) {
+    for (int d = tid; d < KL; d += nt) {
+      const int k = d / L, l = d - k * L;
+      double covG = 0.0, covF = 0.0;
+      for (int k2 = 0; k2 < K; ++k2)
+        if (k2 != k) covG = fma(es[k2 * L + l], PA[(size_t)pair_index(min(k, k2), max(k, k2), K) * L + l], covG);
+      for (int l2 = 0; l2 < L; ++l2)
+        if (l2 != l) covF = fma(es[k * L + l2], QC[(size_t)pair_index(min(l, l2), max(l, l2), L) * K + k], covF);
+      cg[d] = covG; cf[d] = covF;
+    }
+    __syncthreads();
+    const int d_begin = mode >= 0 ? mode : 0, d_end = mode >= 0 ? mode + 1 : KL;
+    for (int d = d_begin; d < d_end; ++d) {
+      const int k = d / L, l = d - k * L;
+      // what this thread's entries need from global memory for the update of step d
+      double tv[ME], pv[ME];
+#pragma unroll
+      for (int q = 0; q < ME; ++q) {
+        const int d2 = tid + q * nt;
+        tv[q] = 0.0; pv[q] = 0.0;
+        if (d2 < KL && mode < 0) {
+          const int k2 = d2 / L, l2 = d2 - k2 * L;
+          tv[q] = tmat(TT, k, l, k2, l2, K, L, NPL);
+          if (l2 == l && k2 != k) pv[q] = PA[(size_t)pair_index(min(k, k2), max(k, k2), K) * L + l];
+          else if (k2 == k && l2 != l) pv[q] = QC[(size_t)pair_index(min(l, l2), max(l, l2), L) * K + k];
+        }
+      }
+      if (tid == 0) {
+        const double ct = etau * bs[d];
+        const double cm = (-lam[d] + etau * (c[d] + es[d] * tdd[d]) - etau * cg[d] - etau * cf[d]) / ct;
+        double en, vn;
+        tn_moments(cm, ct, en, vn);
+        if (mode >= 0) {
+          out_tau[0] = ct; out_mu[0] = cm;
+          bc[0] = 0.0;
+        } else {
+          bc[0] = en - es[d];
+          Smu[d] = cm; Stau[d] = ct; Svar[d] = vn; es[d] = en;
+        }
+      }
+      __syncthreads();
+      const double delta = bc[0];
+      if (delta != 0.0) {
+#pragma unroll
+        for (int q = 0; q < ME; ++q) {
+          const int d2 = tid + q * nt;
+          if (d2 < KL) {
+            const int k2 = d2 / L, l2 = d2 - k2 * L;
+            c[d2] = fma(-delta, tv[q], c[d2]);
+            if (l2 == l && k2 != k) cg[d2] = fma(delta, pv[q], cg[d2]);
+            else if (k2 == k && l2 != l) cf[d2] = fma(delta, pv[q], cf[d2]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (mode == -1)
+      for (int d = tid; d < KL; d += nt) Sexp[d] = es[d];
+  }
+  if (mode < 0) {   // ELBO terms from the (new or stored) parameters of every entry
+    double aq = 0.0, ap = 0.0;
+    for (int d = tid; d < KL; d += nt) {
+      const double ct = Stau[d], cm = Smu[d], en = es[d], vn = Svar[d];
+      aq += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951)) + 0.5 * ct * (vn + (en - cm) * (en - cm));
+      ap += lam[d] * en;
+    }
+    aq = block_sum(aq, red);
+    ap = block_sum(ap, red);
+    if (tid == 0) { misc[0] = aq; misc[1] = ap; }
+  }
+}
+
 // third term of exp_square_diff (bnmtf_vb.py:323): sum_Omega VarF ((ES EG^T)^2 - ES^2 EG^2^T)
-//   = sum_j sum_k C_jk ((sum_l ES_kl EG_jl)^2 - sum_l ES_kl^2 EG_jl^2),  C = masked column sums of VarF.  One block.
-__global__ void __launch_bounds__(1024) nmtf_t3_kernel(const double* __restrict__ C, const double* __restrict__ EG, const double* __restrict__ ES, int64_t J,
-                               int K, int L, double* __restrict__ out) {
+//   = sum_j sum_k C_jk ((sum_l ES_kl EG_jl)^2 - sum_l ES_kl^2 EG_jl^2),  C = masked column sums of VarF.
+// T3_BLOCKS blocks over contiguous ranges of j, then a fixed-order fold of their partial sums (nmtf_t3_fold_kernel).
+constexpr int T3_BLOCKS = 128;
+__global__ void __launch_bounds__(256) nmtf_t3_kernel(const double* __restrict__ C, const double* __restrict__ EG, const double* __restrict__ ES, int64_t J,
+                               int K, int L, double* __restrict__ part) {
   __shared__ double sh[32];
   double a = 0.0;
-  for (int64_t j = threadIdx.x; j < J; j += blockDim.x) {
+  const int64_t chunk = (J + gridDim.x - 1) / gridDim.x;
+  const int64_t j_end = min(J, (int64_t)(blockIdx.x + 1) * chunk);
+  for (int64_t j = (int64_t)blockIdx.x * chunk + threadIdx.x; j < j_end; j += blockDim.x) {
     for (int k = 0; k < K; ++k) {
       double w = 0.0, w2 = 0.0;
       for (int l = 0; l < L; ++l) {
@@ -421,7 +531,13 @@ __global__ void __launch_bounds__(1024) nmtf_t3_kernel(const double* __restrict_
     }
   }
   a = block_sum(a, sh);
-  if (threadIdx.x == 0) out[0] = a;
+  if (threadIdx.x == 0) part[blockIdx.x] = a;
+}
+__global__ void nmtf_t3_fold_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double a = 0.0;
+  for (int q = 0; q < n; ++q) a += part[q];
+  out[0] = a;
 }
 
 // VB lambda updates of both ARD blocks (bnmtf_vb.py:207-213,326-334,383-391): block per column.
