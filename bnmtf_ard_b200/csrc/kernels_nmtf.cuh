@@ -135,6 +135,80 @@ __global__ void __launch_bounds__(WARPS * 32) nmtf_gram_kernel(const uint32_t* _
   }
 }
 
+// L <= 20: the two half-warps of the row's warp take alternate entries; lane h of a half-warp owns a 4 x 4 block
+// (bi <= bj) of the 5 x 5 block grid of H_i's upper triangle (15 blocks): two 32-byte shared loads and 16 FMAs per
+// entry and lane, i.e. half the shared-memory traffic per FMA of the 4 x 2 mapping above (which was bound by it).
+// The halves are added at the end (even entries + odd entries: a fixed order).
+template <int WARPS, bool EVEN>
+__global__ void __launch_bounds__(WARPS * 32) nmtf_gram44_kernel(const uint32_t* __restrict__ cols, const int64_t* __restrict__ rowstart,
+                                                                  int n_loc, int64_t row0, uint32_t padcol, const double* __restrict__ G_rm,
+                                                                  int L, double* __restrict__ Hrow, int NP) {
+  constexpr int LP = 20;
+  __shared__ __align__(32) double tile[WARPS][2][32][LP];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * WARPS + w;
+  if (row >= n_loc) return;
+  const int half = lane >> 4, hl = lane & 15;
+  int bi = -1, bj = 0;
+  {
+    int id = hl, a = 0;
+    while (a < 5 && id >= 5 - a) { id -= 5 - a; ++a; }
+    if (a < 5) { bi = a; bj = a + id; }
+  }
+  double acc[4][4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+  for (int q = lane; q < 2 * 32 * LP; q += 32) (&tile[w][0][0][0])[q] = 0.0;   // columns L..LP-1 stay zero
+  __syncwarp();
+  const int64_t beg = rowstart[row], end = rowstart[row + 1];
+  constexpr int PD = EVEN ? 2 : 1;
+  const int pieces = L / PD;
+  auto stage = [&](int64_t q0, int buf) {
+    const uint32_t mycol = (q0 + lane < end) ? cols[q0 + lane] : padcol;
+    const int total = 32 * pieces;
+    for (int idx0 = 0; idx0 < total; idx0 += 32) {
+      const int idx = idx0 + lane;
+      const int r = min(idx, total - 1) / pieces, pc = min(idx, total - 1) - r * pieces;
+      const uint32_t j = __shfl_sync(0xffffffffu, mycol, r);
+      if (idx < total) {
+        double* dst = &tile[w][buf][r][PD * pc];
+        if (j == padcol) { dst[0] = 0.0; if (EVEN) dst[1] = 0.0; }
+        else if (EVEN) cp_async_16(dst, G_rm + (size_t)j * L + PD * pc);
+        else cp_async_8(dst, G_rm + (size_t)j * L + pc);
+      }
+    }
+    cp_async_commit();
+  };
+  if (beg < end) stage(beg, 0);
+  int buf = 0;
+  for (int64_t q0 = beg; q0 < end; q0 += 32, buf ^= 1) {
+    if (q0 + 32 < end) { stage(q0 + 32, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncwarp();
+    if (bi >= 0) {
+#pragma unroll 4
+      for (int r = 0; r < 32; r += 2) {
+        const double4 a = *reinterpret_cast<const double4*>(&tile[w][buf][r + half][4 * bi]);
+        const double4 c = *reinterpret_cast<const double4*>(&tile[w][buf][r + half][4 * bj]);
+        acc[0][0] = fma(a.x, c.x, acc[0][0]); acc[0][1] = fma(a.x, c.y, acc[0][1]); acc[0][2] = fma(a.x, c.z, acc[0][2]); acc[0][3] = fma(a.x, c.w, acc[0][3]);
+        acc[1][0] = fma(a.y, c.x, acc[1][0]); acc[1][1] = fma(a.y, c.y, acc[1][1]); acc[1][2] = fma(a.y, c.z, acc[1][2]); acc[1][3] = fma(a.y, c.w, acc[1][3]);
+        acc[2][0] = fma(a.z, c.x, acc[2][0]); acc[2][1] = fma(a.z, c.y, acc[2][1]); acc[2][2] = fma(a.z, c.z, acc[2][2]); acc[2][3] = fma(a.z, c.w, acc[2][3]);
+        acc[3][0] = fma(a.w, c.x, acc[3][0]); acc[3][1] = fma(a.w, c.y, acc[3][1]); acc[3][2] = fma(a.w, c.z, acc[3][2]); acc[3][3] = fma(a.w, c.w, acc[3][3]);
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const double v = acc[x][y] + __shfl_xor_sync(0xffffffffu, acc[x][y], 16);
+      const int a = 4 * bi + x, c = 4 * bj + y;
+      if (half == 0 && bi >= 0 && a <= c && c < L) Hrow[(size_t)(row0 + row) * NP + pair_index(a, c, L)] = v;
+    }
+}
+
 // c[k][l] = sum_i F[i][k] P[i][l]    (one block per (k,l), fixed-order tree)
 __global__ void nmtf_reduce_c_kernel(const double* __restrict__ F, const double* __restrict__ P, int64_t I, int K, int L,
                                      double* __restrict__ c) {
