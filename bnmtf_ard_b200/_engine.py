@@ -231,6 +231,21 @@ class NMFEngine(object):
         return {"MSE": float(mse), "R^2": float(r2), "Rp": float(rp)}
 
 
+    def performances_all(self, stats):
+        """performances() of every row of a (iterations, NSTATS) block; element for element the same
+        float64 expressions, evaluated by numpy over the iteration axis."""
+        stats = np.asarray(stats, dtype=np.float64).reshape(-1, NSTATS)
+        rss, se, srce = stats[:, _lib.ST_RSS], stats[:, _lib.ST_SUM_E], stats[:, _lib.ST_SUM_RCE]
+        n, sst = self.size_Omega, self.ss_total
+        mse = rss / n
+        r2 = 1.0 - rss / sst if sst != 0.0 else np.full(len(rss), np.inf)
+        cov = sst - srce
+        var_pred = sst - 2.0 * srce + (rss - se * se / n)
+        with np.errstate(all="ignore"):
+            rp = cov / (np.sqrt(sst) * np.sqrt(var_pred))
+        return {"MSE": [float(v) for v in mse], "R^2": [float(v) for v in r2], "Rp": [float(v) for v in rp]}
+
+
 class NMTFEngine(NMFEngine):
     """Handle for the tri-factorisation R ~ F S G^T: side U is F (I x K), side V is G (J x L)."""
 

@@ -89,10 +89,9 @@ class NMFCommon(object):
             eng.set_hyper(False, self.alphatau, self.betatau, 1., 1., self.lambdaU, self.lambdaV)
 
     def _fill_performances(self, eng, stats):
-        for row in stats:
-            perf = eng.performances(row)
-            for metric in ALL_METRICS:
-                self.all_performances[metric].append(perf[metric])
+        perf = eng.performances_all(stats)      # all iterations at once (same expressions as eng.performances)
+        for metric in ALL_METRICS:
+            self.all_performances[metric].extend(perf[metric])
 
     # -- metrics (bnmf_gibbs.py:252-270; identical in all eight models) --------
     def compute_MSE(self, M, R, R_pred):

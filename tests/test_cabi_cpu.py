@@ -194,3 +194,23 @@ def test_nmtf_np_constructor_and_guards():
     m.initialise('ones', 'ones')
     assert m.F.shape == (2, 2) and m.S.shape == (2, 1) and m.G.shape == (2, 1)
     np.testing.assert_array_equal(m.triple_dot(m.F, m.S, m.G.T), 2. * np.ones((2, 2)))
+
+
+def test_performances_all_equals_rowwise():
+    """The vectorised per-iteration metrics are element for element the row-wise ones."""
+    import numpy as np
+    from bnmtf_ard_b200 import _lib
+    from bnmtf_ard_b200._engine import NMFEngine
+    eng = NMFEngine.__new__(NMFEngine)
+    eng.size_Omega, eng.ss_total = 1234.0, 987.654321
+    rng = np.random.default_rng(0)
+    stats = np.zeros((50, _lib.NSTATS))
+    stats[:, _lib.ST_RSS] = rng.uniform(1, 2000, 50)
+    stats[:, _lib.ST_SUM_E] = rng.normal(0, 30, 50)
+    stats[:, _lib.ST_SUM_RCE] = rng.normal(0, 300, 50)
+    allp = eng.performances_all(stats)
+    for i, row in enumerate(stats):
+        one = eng.performances(row)
+        for key in ("MSE", "R^2", "Rp"):
+            assert one[key] == allp[key][i] or (np.isnan(one[key]) and np.isnan(allp[key][i]))
+    eng.h = None
