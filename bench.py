@@ -304,8 +304,10 @@ def main():
         eng.set_factor(_lib.SIDE_U, _lib.F_VALUE, U_h)
         eng.set_factor(_lib.SIDE_V, _lib.F_VALUE, V_h)
         eng.set_scalars(1.0, np.ones(K))
-        r2 = eng.run(_lib.GIBBS, e2e_steps, seed=3, traces=True)
-        _ = float(r2["all_U"][-1, 0, 0]) + float(r2["stats"][-1, 0])
+        # every rank holds the same chain: the draws are delivered to host memory once, by rank 0 (the other
+        # ranks read back their per-iteration statistics only)
+        r2 = eng.run(_lib.GIBBS, e2e_steps, seed=3, traces=(rank == 0))
+        _ = (float(r2["all_U"][-1, 0, 0]) if rank == 0 else 0.0) + float(r2["stats"][-1, 0])
         barrier()
         e2e_s = time.perf_counter() - t0
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -315,7 +317,9 @@ def main():
         e2e = {"value": e2e_steps / e2e_s, "unit": "iterations/s", "steps": e2e_steps,
                "h2d_bytes_per_step": int(((I + J) * K * 8 + (K + 1) * 8) / e2e_steps),
                "d2h_bytes_per_step": int((I + J) * K * 8 + K * 8 + 16 * 8),
-               "note": "engine.run() through the C ABI with host numpy state and host trace buffers (pageable)"}
+               "note": "engine.run() through the C ABI with host numpy state and host trace buffers (pageable)" +
+                       ("" if world == 1 else "; the draws go to host memory on rank 0 only (all ranks hold the same chain; "
+                        "with every rank storing its own copy the 8-GPU rate is host-memory bound: profiles/r01_final_bench_n8.json)")}
         # same call with the posterior means accumulated on the device (summarise_on_device):
         # no all_U / all_V; the means of the second half of the chain are read back at the end
         eng.set_summary(e2e_steps // 2, 1)

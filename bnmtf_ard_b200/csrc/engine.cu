@@ -1203,10 +1203,10 @@ class TraceDrain {
 
  private:
   struct Job { const char* src[3]; char* dst[3]; size_t bytes[3]; int n; };
-  // the destination pages are usually untouched: four threads take the page faults side by side
+  // the destination pages are usually untouched: six threads take the page faults side by side
   static void spread_memcpy(char* dst, const char* src, size_t bytes) {
-    constexpr int NT = 4;
-    if (bytes < ((size_t)8 << 20)) { memcpy(dst, src, bytes); return; }
+    constexpr int NT = 6;
+    if (bytes < ((size_t)4 << 20)) { memcpy(dst, src, bytes); return; }
     const size_t piece = (bytes / NT + 4095) & ~(size_t)4095;
     std::thread th[NT - 1];
     for (int q = 1; q < NT; ++q) {
