@@ -109,6 +109,7 @@ struct Side {
   // v2 (cluster) layout
   bool v2 = false;
   int cs = 8, tw = 0, rs = 0, npt2 = 0, v2div = 1;
+  bool v2tm = false;                     // residual segments in tensor memory (kernels_v2.cuh, TM variant)
   int64_t nsets = 0, tslots = 0;
   double* tvals = nullptr;
   uint16_t* tcols = nullptr;
@@ -258,12 +259,16 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   int div = 2;                                                     // CTAs (of different clusters) per SM
   if (getenv("BNMTF_V2_DIV")) div = std::max(1, std::min(3, atoi(getenv("BNMTF_V2_DIV"))));
   if (npt2 == 18 && div == 3) div = 2;                             // 28 warps do not split in three
-  const int rs = wpc_full / div - 1;                               // rows per set (warp 0 is the control warp)
+  const int rs = wpc_full / div - 1;                                   // rows per set (warp 0 is the control warp)
   sd.v2div = div;
   sd.v3B = getenv("BNMTF_V3_B") ? atoi(getenv("BNMTF_V3_B")) : 0;   // blocked variant (kernels_v3.cuh): opt-in, the B = 1 sweep is faster since both use st.async exchanges
   if (sd.v3B != 2) sd.v3B = 0;
+  // 20 entries per lane, opt-in (BNMTF_V2_TM=1): the TM variant parks the gathered values of a column in tensor memory
+  // instead of gathering them again for the rank-1 correction (same packed layout, bitwise the same results; measured
+  // equal in speed at 20000 x 20000: the sweep is bound by its per-column exchange, not by the gathers)
+  sd.v2tm = npt2 == 20 && div == 2 && sd.v3B == 0 && getenv("BNMTF_V2_TM") && atoi(getenv("BNMTF_V2_TM")) == 1;
   const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, V2_CS) * sizeof(double);
-  sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && sd.kf >= 3 && smem_vb <= 200 * 1024 && sd.tw * 2 < 65535;
+  sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && sd.kf >= 3 && smem_vb <= 200 * 1024 && (sd.tw + V2_PAD) * 16 < 65536;
   if (sd.v2 && n > 0) {
     sd.cs = V2_CS; sd.npt2 = npt2; sd.rs = rs;
     sd.nsets = (n + rs - 1) / rs;
@@ -759,10 +764,10 @@ static int launch_sweep_m(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int n
   FAIL("unsupported entries-per-thread %d", npt);
 }
 
-template <int NPT, int MODE, int DIV>
+template <int NPT, int MODE, int DIV, int TMW = 0>
 static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  auto kern = sweep2_kernel<NPT, MODE, V2_CS, DIV>;
+  auto kern = sweep2_kernel<NPT, MODE, V2_CS, DIV, TMW>;
   const size_t smem = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS, p.K2, MODE == M_GIBBS) * sizeof(double);
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3((p.rs + 1) * 32);
@@ -777,8 +782,15 @@ static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     cfg.gridDim = dim3(V2_CS * 128);
     int ncl = 0;
-    CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
+    // the occupancy query places one CTA per SM for a kernel that allocates tensor memory (15 clusters instead of 33);
+    // the TM variant has the block size, registers and shared memory of the register variant and takes 128 of the 512
+    // TMEM columns per CTA, so the register variant's answer holds for it
+    auto occ_kern = sweep2_kernel<NPT, MODE, V2_CS, DIV, 0>;
+    if (TMW > 0) CK(cudaFuncSetAttribute(occ_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaOccupancyMaxActiveClusters(&ncl, occ_kern, &cfg));
     if (ncl < 1) FAIL("cluster sweep kernel does not fit (smem %zu bytes, %d threads)", smem, (p.rs + 1) * 32);
+    if (getenv("BNMTF_V2_NCL")) ncl = std::max(1, atoi(getenv("BNMTF_V2_NCL")));   // experiments: clusters are independent, a larger grid queues
+    if (getenv("BNMTF_V2_DBG")) fprintf(stderr, "sweep2<%d,%d,%d,%d>: %d clusters of %d x %d threads, %zu bytes of shared memory\n", NPT, MODE, DIV, TMW, ncl, V2_CS, (p.rs + 1) * 32, smem);
     sd.nclusters[method] = ncl;
   }
   const int ncl = (int)std::min<int64_t>(sd.nclusters[method], p.nsets);
@@ -804,6 +816,7 @@ static int launch_sweep2_d(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
 
 template <int MODE>
 static int launch_sweep2_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
+  if (sd.v2tm) return launch_sweep2_t<20, MODE, 2, V2_TM_WARPS>(h, p, sd, method);
   switch (sd.v2div) {
     case 1: return launch_sweep2_d<MODE, 1>(h, p, sd, method);
     case 2: return launch_sweep2_d<MODE, 2>(h, p, sd, method);
@@ -1463,7 +1476,7 @@ int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {  // out8: 16 values
   out8[4] = h->s[0].nslots; out8[5] = h->s[1].nslots; out8[6] = h->s[0].nnz; out8[7] = h->s[1].nnz;
   for (int q = 0; q < 2; ++q) {
     const Side& sd = h->s[q];
-    out8[8 + 4 * q] = sd.v2 ? ((sd.v3B > 0 && !h->nmtf) ? 3 : 1) : 0;   // 1: cluster sweep, 3: blocked cluster sweep
+    out8[8 + 4 * q] = sd.v2 ? (sd.v2tm ? 4 : (sd.v3B > 0 && !h->nmtf) ? 3 : 1) : 0;   // 1: cluster sweep, 3: blocked cluster sweep, 4: cluster sweep with the segments in tensor memory
     out8[9 + 4 * q] = sd.v2 ? sd.npt2 : 0;
     out8[10 + 4 * q] = sd.v2 ? sd.rs : 0; out8[11 + 4 * q] = sd.v2 ? sd.tslots : 0;
   }

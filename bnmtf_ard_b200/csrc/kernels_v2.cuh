@@ -74,10 +74,15 @@ __global__ void count_rows_tiles_kernel(const uint8_t* __restrict__ M, int64_t n
   if (lane == 0) { rowlen[row] = total; atomicMax(maxseg, best); }
 }
 
+// Padded slots read a zero behind the tile.  There are V2_PAD zero entries and the pad of lane l points at
+// entry padcol + l % 16, i.e. at the bank class the lane's real entries have: pads never collide with the
+// gathers of the other lanes (a single shared zero sat in one bank class and cost every mixed half-warp a
+// replay: 25 % extra shared-memory wavefronts at the 20000 x 20000 size, 4 % with per-class zeros).
+constexpr int V2_PAD = 16;
 __global__ void fill_pads_kernel(double* __restrict__ tvals, uint16_t* __restrict__ tcols, int64_t nslots, uint16_t padcol) {
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nslots; q += (int64_t)gridDim.x * blockDim.x) {
     tvals[q] = 0.0;
-    tcols[q] = padcol;
+    tcols[q] = (uint16_t)(padcol + (q & 15));   // slot index = ... * 32 + lane
   }
 }
 
@@ -184,7 +189,7 @@ struct Sweep2Params {
 // columns of prepared random material kept in shared memory (Gibbs): one round of 32/rs columns ahead of the updates
 __host__ __device__ constexpr int sweep2_rnd_window(int rs) { return (1 + 2 * ((32 / rs) < 1 ? 1 : (32 / rs))) <= 8 ? 8 : 16; }
 __host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs, int K2 = 0, bool gibbs = false) {
-  return (size_t)3 * (tw + 2) * nv + 6 /*mbarriers: 3 tile stages, 2 record buffers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ +
+  return (size_t)3 * (tw + V2_PAD) * nv + 6 /*mbarriers: 3 tile stages, 2 record buffers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ +
          (size_t)2 * cs * rs * 4 /*part, double buffered*/ + (size_t)cs * rs * K2 /*projection partials*/ +
          (size_t)cs * rs * 4 /*row-statistics partials*/ + (gibbs ? (size_t)sweep2_rnd_window(rs) * rs * 6 : 0) /*random material*/;
 }
@@ -226,17 +231,224 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int NPT, int MODE, int CS, int DIV>
-__global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_kernel(const Sweep2Params p) {
+
+// ---- tensor memory (TMEM) as a per-warp scratch area -------------------------------------------------------------
+// The TM variant of the cluster sweep keeps the residual segments in tensor memory instead of registers: TMEM is a
+// second 256 KB on-chip array per SM that only tcgen05 instructions reach, idle in a kernel without MMAs.  A warp may
+// touch the 32 TMEM lanes of its quarter (warp % 4); its segment is NPT fp64 values per lane = 2 * NPT 32-bit columns.
+// Measured (tools/ubench/tmem.cu): a 20-double-per-lane round trip (tcgen05.ld + tcgen05.st) of 12 warps takes ~300
+// cycles per SM, i.e. ~200 B/cycle/SM each way, next to the shared-memory pipe the gathers use.
+struct TmChunk {          // 8 columns = 4 doubles per lane
+  uint32_t r[8];
+  __device__ __forceinline__ double get(int i) const { return __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]); }
+  __device__ __forceinline__ void set(int i, double v) { r[2 * i] = (uint32_t)__double2loint(v); r[2 * i + 1] = (uint32_t)__double2hiint(v); }
+};
+__device__ __forceinline__ void tm_ld8(uint32_t taddr, TmChunk& ch) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(ch.r[0]), "=r"(ch.r[1]), "=r"(ch.r[2]), "=r"(ch.r[3]), "=r"(ch.r[4]), "=r"(ch.r[5]), "=r"(ch.r[6]), "=r"(ch.r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t taddr, const TmChunk& ch) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(ch.r[0]), "r"(ch.r[1]),
+               "r"(ch.r[2]), "r"(ch.r[3]), "r"(ch.r[4]), "r"(ch.r[5]), "r"(ch.r[6]), "r"(ch.r[7])
+               : "memory");
+}
+// the chunk is an in/out operand so that no use of its registers is scheduled above the wait
+__device__ __forceinline__ void tm_wait_ld(TmChunk& ch) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(ch.r[0]), "+r"(ch.r[1]), "+r"(ch.r[2]), "+r"(ch.r[3]), "+r"(ch.r[4]), "+r"(ch.r[5]), "+r"(ch.r[6]), "+r"(ch.r[7])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+constexpr int V2_TM_COLS = 128;   // TMEM columns per CTA: 3 warps per lane quarter x 40 columns (two CTAs per SM: 256 of 512)
+constexpr int V2_TM_WARPS = 12;   // warps per CTA of the TM variant = Sweep2Cfg<20>::WPC / 2 (same packed layout)
+#ifndef BNMTF_V2_TM_DB
+#define BNMTF_V2_TM_DB 1            // 1: the next chunk's tcgen05.ld is in flight while the current chunk is used
+#endif
+
+// Compute warps of the TM variant.  The register variant gathers column k-1 of the other factor a second time when it
+// folds the rank-1 correction of column k-1 into the pass of column k (the values cannot stay in registers: 40 more
+// per thread).  Here the gathered values of a column are parked in tensor memory (one tcgen05.st per 4 entries) and
+// read back in the next pass (tcgen05.ld, the next chunk's load in flight while the current chunk is used): one
+// shared-memory gather per entry and column in the update passes instead of two.  The residual stays in registers;
+// entries, operands and the order of every sum are those of the register variant, so the results are bitwise equal.
+template <int NPT, int MODE, int CS, int RS>
+__device__ __forceinline__ void sweep2_compute_tm(const Sweep2Params& p, cg::cluster_group& cluster, int c, int cid, int nclusters,
+                                                  int warp, int lane, double* tiles, uint64_t* mbar, const double* delta, double* xs,
+                                                  double* part, double* proj, double* statp, uint32_t tm_base) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  constexpr int RS = Sweep2Cfg<NPT>::WPC / DIV - 1;
+  constexpr int NCH = NPT / 4;
+  static_assert(NPT % 4 == 0, "TMEM chunks hold 4 entries");
+  const int K = p.K, tw = p.tw, K2 = p.K2;
+  const int tile_doubles = (tw + V2_PAD) * NV;
+  const int total = 2 * K + K2;
+  const int r = warp - 1;                                 // row of the set owned by this warp
+  const uint32_t tm = tm_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)(NPT * 2);
+  double* stat0 = cluster.map_shared_rank(statp, 0);      // CTA 0's copy, through DSMEM
+  const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[3]);
+  uint32_t gseq = 0;
+  for (int set = cid; set < p.nsets; set += nclusters) {
+    const int rows_here = min(RS, p.n_loc - set * RS);
+    const int64_t seg = ((int64_t)(set * CS + c) * NPT) * RS * 32 + (int64_t)r * 32 + lane;
+    double e[NPT];
+    uint32_t cp[NPT / 2];
+#pragma unroll
+    for (int n = 0; n < NPT; ++n) e[n] = p.tvals[seg + (int64_t)n * RS * 32];
+#pragma unroll
+    for (int n = 0; n < NPT; n += 2) {
+      const uint32_t a = p.tcols[seg + (int64_t)n * RS * 32], b = p.tcols[seg + (int64_t)(n + 1) * RS * 32];
+      cp[n / 2] = (a * (NV * 8)) | ((b * (NV * 8)) << 16);   // byte offsets inside a tile stage
+    }
+    {                                                        // "column -1" of the parked values: zeros (delta is 0 too)
+      TmChunk z;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z.r[i] = 0u;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) tm_st8(tm + 8 * ch, z);
+    }
+    for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
+      const size_t g = (size_t)(p.row0 + set * RS) * K + q;
+      xs[q] = p.Xval[g];
+    }
+    cluster_sync_all();   // xs visible; CTA 0 has finished with `part` of the previous set
+
+    // ---- residual of the segment: e = r - sum_k x_k y_k   (tile sequence 0 .. K-1)
+    for (int q = 0; q < K; ++q) {
+      const uint32_t g = gseq + q;
+      mbar_wait(&mbar[g % 3], (g / 3) & 1u);
+      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+      const double xk = (r < rows_here) ? xs[r * K + q] : 0.0;
+#pragma unroll
+      for (int n = 0; n < NPT; ++n) {
+        const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+        e[n] = fma(-xk, *reinterpret_cast<const double*>(T + off), e[n]);
+      }
+      __syncthreads();
+    }
+
+    // ---- the K column updates   (tile sequence K .. 2K-1)
+    double dprev = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const uint32_t g = gseq + K + k;
+      TmChunk b[2];
+      tm_wait_st();                        // the parked values of column k-1 (stored before the exchange) are in place
+      tm_ld8(tm, b[0]);
+      mbar_wait(&mbar[g % 3], (g / 3) & 1u);
+      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        TmChunk& cur = b[BNMTF_V2_TM_DB ? (ch & 1) : 0];
+        if (!BNMTF_V2_TM_DB && ch > 0) tm_ld8(tm + 8 * ch, cur);
+        tm_wait_ld(cur);
+        if (BNMTF_V2_TM_DB && ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = 4 * ch + i;
+          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+          e[n] = fma(-dprev, cur.get(i), e[n]);          // k == 0: 0 * 0
+          double v;
+          if (MODE == M_VB) { const double2 vv = *reinterpret_cast<const double2*>(T + off); v = vv.x; s1 += vv.y; }
+          else v = *reinterpret_cast<const double*>(T + off);
+          s0 = fma(v, v, s0);
+          s2 = fma(e[n], v, s2);
+          cur.set(i, v);
+        }
+        tm_st8(tm + 8 * ch, cur);
+      }
+      named_arrive(1, (RS + 1) * 32);      // this warp has finished its pass of column k
+      s0 = warp_sum(s0); s2 = warp_sum(s2);
+      if (MODE == M_VB) s1 = warp_sum(s1);
+      if (lane < CS) {   // lane cc sends this warp's partial sums to CTA cc (every CTA updates redundantly)
+        const uint32_t dst = map_to_cta(part_u32 + (uint32_t)(((k & 1) * CS + c) * RS + r) * 32u, lane);
+        const uint32_t bar = map_to_cta(rbar_u32 + (uint32_t)(k & 1) * 8u, lane);
+        st_async_f64(dst, s0, bar); st_async_f64(dst + 8, s1, bar); st_async_f64(dst + 16, s2, bar);
+      }
+      __syncthreads();                     // the control warp of this CTA has written the deltas
+      dprev = (r < rows_here) ? delta[r] : 0.0;
+    }
+
+    // ---- last correction, then the row statistics of the final residual
+    {
+      double st0 = 0.0, st1 = 0.0, st2 = 0.0;
+      TmChunk b[2];
+      tm_wait_st();
+      tm_ld8(tm, b[0]);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        TmChunk& cur = b[BNMTF_V2_TM_DB ? (ch & 1) : 0];
+        if (!BNMTF_V2_TM_DB && ch > 0) tm_ld8(tm + 8 * ch, cur);
+        tm_wait_ld(cur);
+        if (BNMTF_V2_TM_DB && ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = 4 * ch + i;
+          e[n] = fma(-dprev, cur.get(i), e[n]);
+          const double rr = p.tvals[seg + (int64_t)n * RS * 32];
+          st0 = fma(e[n], e[n], st0);
+          st1 += e[n];
+          st2 = fma(rr - p.rmean, e[n], st2);   // padded slots hold e == 0
+        }
+      }
+      st0 = warp_sum(st0); st1 = warp_sum(st1); st2 = warp_sum(st2);
+      if (lane == 0) {
+        double* dst = stat0 + ((size_t)c * RS + r) * 4;
+        dst[0] = st0; dst[1] = st1; dst[2] = st2;
+      }
+    }
+    if (K2 > 0) {
+      // ---- projection epilogue: sum_j e_j Y2[l][j] over this segment, partials to CTA 0   (tiles 2K .. 2K+K2-1)
+      double* proj0 = cluster.map_shared_rank(proj, 0);
+      __syncthreads();
+      for (int q = 0; q < K2; ++q) {
+        const uint32_t g = gseq + 2 * K + q;
+        mbar_wait(&mbar[g % 3], (g / 3) & 1u);
+        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+        double s = 0.0;
+#pragma unroll
+        for (int n = 0; n < NPT; ++n) {
+          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+          s = fma(e[n], *reinterpret_cast<const double*>(T + off), s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) proj0[((size_t)c * RS + r) * K2 + q] = s;
+        __syncthreads();
+      }
+    }
+    cluster_sync_all();
+    if (c == 0) {
+      __syncthreads();
+      for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
+        const size_t g = (size_t)(p.row0 + set * RS) * K + q;
+        p.Xval[g] = xs[q];
+        if (MODE == M_VB) p.Xvar[g] = xs[(size_t)RS * K + q];
+        if (p.Xmu != nullptr) { p.Xmu[g] = xs[(size_t)2 * RS * K + q]; p.Xtau[g] = xs[(size_t)3 * RS * K + q]; }
+      }
+      for (int q = threadIdx.x; q < rows_here * K2; q += blockDim.x) {   // fixed-order sum of the CS projection partials
+        const int rr = q / K2, l = q - rr * K2;
+        double t = 0.0;
+        for (int cc = 0; cc < CS; ++cc) t += proj[((size_t)cc * RS + rr) * K2 + l];
+        p.proj_out[(size_t)(p.row0 + set * RS + rr) * K2 + l] = t;
+      }
+    }
+    gseq += total;
+    __syncthreads();   // xs / tiles are reused by the next set
+  }
+}
+
+template <int NPT, int MODE, int CS, int DIV, int TMW = 0>
+__global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 32, DIV) sweep2_kernel(const Sweep2Params p) {
+  constexpr int NV = (MODE == M_VB) ? 2 : 1;
+  constexpr int RS = (TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) - 1;
   static_assert(MODE != M_NP, "the NP updates run on the v1 kernel");
   cg::cluster_group cluster = cg::this_cluster();
   const int c = (int)cluster.block_rank();
   const int cid = blockIdx.x / CS, nclusters = gridDim.x / CS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = p.K, tw = p.tw;
-  const int tile_doubles = (tw + 2) * NV;
+  const int tile_doubles = (tw + V2_PAD) * NV;
   const uint32_t tile_bytes = (uint32_t)tw * NV * 8u;
 
   extern __shared__ __align__(128) double smem2[];
@@ -260,9 +472,19 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
     fence_mbar_init();
   }
   for (int s = threadIdx.x; s < 3; s += blockDim.x) {     // the zero slots read by padded entries
-    for (int z = 0; z < 2 * NV; ++z) tiles[s * tile_doubles + tw * NV + z] = 0.0;
+    for (int z = 0; z < V2_PAD * NV; ++z) tiles[s * tile_doubles + tw * NV + z] = 0.0;
+  }
+  uint32_t& tm_base_sh = *reinterpret_cast<uint32_t*>(&mbar[5]);   // the sixth mbarrier slot is spare
+  if (TMW > 0) {                                          // tensor memory for the residual segments of this CTA
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm_base_sh)), "n"(V2_TM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
+  if (TMW > 0) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm_base = TMW > 0 ? tm_base_sh : 0u;
 
   const double* ybase = p.Ykm + (size_t)c * tw * NV;      // this CTA's tile of column 0
   const size_t ystride = (size_t)p.ldy * NV;
@@ -422,6 +644,9 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
       gseq += total;
       __syncthreads();
     }
+  } else if (TMW > 0) {
+    if constexpr (TMW > 0)
+      sweep2_compute_tm<NPT, MODE, CS, RS>(p, cluster, c, cid, nclusters, warp, lane, tiles, mbar, delta, xs, part, proj, statp, tm_base);
   } else {
     // =========================== compute warps ===========================
     const int r = warp - 1;                                 // row of the set owned by this warp
@@ -560,6 +785,11 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_ke
       gseq += total;
       __syncthreads();   // xs / tiles are reused by the next set
     }
+  }
+  if (TMW > 0) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "n"(V2_TM_COLS) : "memory");
   }
   cluster_sync_all();    // no CTA may exit while its shared memory can still be written remotely
 }

@@ -43,7 +43,7 @@ __host__ __device__ inline Sweep3Layout sweep3_layout(int tw, int nv, int rs, in
                                                       bool want_mu, bool gibbs) {
   Sweep3Layout L;
   size_t o = 0;
-  L.tiles = o; o += (size_t)2 * (tw + 1) * B * nv;   // 2 slots x (tw + 1 zero entry) x B*NV interleaved doubles
+  L.tiles = o; o += (size_t)2 * (tw + V2_PAD) * B * nv;   // 2 slots x (tw + V2_PAD zero entries) x B*NV interleaved doubles
   L.mbar = o; o += 4;   // 2 tile mbarriers + 2 record mbarriers
   L.delta = o; o += (size_t)B * rs + (((size_t)B * rs) & 1);
   L.xs = o; o += (size_t)rs * K;
@@ -121,14 +121,14 @@ __global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep3_ke
   const int K = p.K, tw = p.tw;
   const int NBK = (K + B - 1) / B;                        // blocks per pass
   constexpr int EW = B * NV;                              // doubles per tile entry: the block's columns interleaved
-  const int slot_doubles = (tw + 1) * EW;                 // one stage: tw entries + the zero entry padded slots read
+  const int slot_doubles = (tw + V2_PAD) * EW;            // one stage: tw entries + the zero entries padded slots read
   const uint32_t block_bytes = (uint32_t)tw * EW * 8u;
   const bool want_mu = p.Xmu != nullptr;
   const bool prof_on = (p.dbg & 2) && blockIdx.x == 0 && (warp == 0 || warp == 1);
 
   extern __shared__ __align__(128) double smem3[];
   const Sweep3Layout L = sweep3_layout(tw, NV, RS, K, CS, B, NVAL, MODE == M_VB, want_mu, MODE == M_GIBBS);
-  double* tiles = smem3 + L.tiles;                        // [2 slots][tw + 1][EW]
+  double* tiles = smem3 + L.tiles;                        // [2 slots][tw + V2_PAD][EW]
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem3 + L.mbar);
   double* delta = smem3 + L.delta;                        // [B][RS]
   double* xs = smem3 + L.xs;                              // [RS][K]

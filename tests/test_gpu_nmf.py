@@ -155,7 +155,8 @@ def test_np_golden(golden):
 # tail row sets, both sides tiled, and spill placement of crowded bank classes.
 SHAPES = [(37, 23, 3, 0.8), (120, 150, 5, 0.9), (90, 400, 4, 0.55), (64, 3000, 6, 0.7), (700, 140, 7, 0.8),
           (33, 9000, 3, 0.9), (100, 4096, 5, 0.5), (2300, 2500, 4, 0.3), (41, 5000, 3, 0.45), (70, 2049, 8, 0.95),
-          (9, 17500, 3, 0.97)]     # the last one: rows of ~17000 observed entries, streamed from global memory (kernels_long.cuh)
+          (9, 17500, 3, 0.97),     # rows of ~17000 observed entries, streamed from global memory (kernels_long.cuh)
+          (36, 5120, 4, 0.92)]     # row segments of ~590 entries (20 per lane): cluster sweep with the tensor-memory park
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -200,6 +201,35 @@ def test_cluster_kernel_is_selected():
     info = eng.layout_info()
     assert info["v2_U"] in (1, 3) and info["v2_V"] == 0 and info["v2_npt_U"] in (8, 12)
     eng.close()
+
+
+@pytest.mark.parametrize("cls_name", ["bnmf_gibbs", "nmf_icm", "bnmf_vb"])
+def test_tensor_memory_sweep_is_bitwise_the_register_sweep(cls_name, monkeypatch):
+    """Row segments of 20 entries per lane run the cluster sweep that parks the gathered values of a column in tensor
+    memory (tcgen05.st / tcgen05.ld) instead of gathering them a second time for the rank-1 correction.  Same entries,
+    operands and summation orders: with BNMTF_V2_TM=0 (register variant) the same seeded run must end in the same bits."""
+    import bnmtf_ard_b200 as pkg
+    I, J, K, dens = SHAPES[11]
+    R, M, _ = make_problem(99, I, J, K, dens, nonneg=True)
+    hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0}
+    outs = []
+    for tm in ("1", "0"):
+        monkeypatch.setenv("BNMTF_V2_TM", tm)
+        m = getattr(pkg, cls_name)(R, M, K, True, hyper)
+        m.verbose = False
+        np.random.seed(3)
+        m.initialise("random")
+        m.run(4)
+        info = m._engine().layout_info()
+        assert info["v2_U"] == (4 if tm == "1" else 1) and info["v2_npt_U"] == 20 and info["v2_rows_per_set_U"] == 11
+        if cls_name == "bnmf_gibbs":
+            outs.append((m.all_U.copy(), m.all_V.copy(), np.asarray(m.all_tau).copy(), np.asarray(m.all_performances["MSE"])))
+        elif cls_name == "nmf_icm":
+            outs.append((m.U.copy(), m.V.copy(), np.asarray(m.tau), np.asarray(m.all_performances["MSE"])))
+        else:
+            outs.append((m.exp_U.copy(), m.exp_V.copy(), m.var_U.copy(), np.asarray(m.all_elbo)))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
 
 
 def test_streamed_rows_are_selected_and_column_params_match():
