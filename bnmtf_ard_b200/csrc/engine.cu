@@ -765,10 +765,18 @@ static int launch_sweep_m(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int n
 }
 
 template <int NPT, int MODE, int DIV, int TMW = 0>
-static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
+static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p_in, Side& sd, int method) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
   auto kern = sweep2_kernel<NPT, MODE, V2_CS, DIV, TMW>;
-  const size_t smem = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS, p.K2, MODE == M_GIBBS) * sizeof(double);
+  // tile ring: a fourth stage when it does not cost a resident CTA (228 KB per SM, 1 KB reserved per CTA, 227 KB per CTA)
+  Sweep2Params p = p_in;
+  const size_t smem3 = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS, p.K2, MODE == M_GIBBS, 3) * sizeof(double);
+  const size_t smem4 = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS, p.K2, MODE == M_GIBBS, 4) * sizeof(double);
+  const size_t per_sm = 228 * 1024;
+  const int ctas3 = (int)std::min<size_t>(DIV, per_sm / (smem3 + 1024)), ctas4 = (int)std::min<size_t>(DIV, per_sm / (smem4 + 1024));
+  p.nst = (smem4 <= 227 * 1024 && ctas4 >= ctas3) ? 4 : 3;
+  if (getenv("BNMTF_V2_NST")) p.nst = atoi(getenv("BNMTF_V2_NST")) == 4 && smem4 <= 227 * 1024 ? 4 : 3;
+  const size_t smem = p.nst == 4 ? smem4 : smem3;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3((p.rs + 1) * 32);
   cfg.dynamicSmemBytes = smem;
@@ -790,7 +798,7 @@ static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
     CK(cudaOccupancyMaxActiveClusters(&ncl, occ_kern, &cfg));
     if (ncl < 1) FAIL("cluster sweep kernel does not fit (smem %zu bytes, %d threads)", smem, (p.rs + 1) * 32);
     if (getenv("BNMTF_V2_NCL")) ncl = std::max(1, atoi(getenv("BNMTF_V2_NCL")));   // experiments: clusters are independent, a larger grid queues
-    if (getenv("BNMTF_V2_DBG")) fprintf(stderr, "sweep2<%d,%d,%d,%d>: %d clusters of %d x %d threads, %zu bytes of shared memory\n", NPT, MODE, DIV, TMW, ncl, V2_CS, (p.rs + 1) * 32, smem);
+    if (getenv("BNMTF_V2_DBG")) fprintf(stderr, "sweep2<%d,%d,%d,%d>: %d clusters of %d x %d threads, %zu bytes of shared memory, %d tile stages\n", NPT, MODE, DIV, TMW, ncl, V2_CS, (p.rs + 1) * 32, smem, p.nst);
     sd.nclusters[method] = ncl;
   }
   const int ncl = (int)std::min<int64_t>(sd.nclusters[method], p.nsets);

@@ -75,6 +75,18 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Two warp sums for the price of one: afterwards lanes 0..15 hold the total of a, lanes 16..31 the total of b.
+// The first exchange hands each half the value it keeps; the remaining rounds are those of warp_sum on a single value,
+// pairing the same partial sums in the same order, so the totals are bitwise warp_sum(a) and warp_sum(b).
+// (Shuffles share the shared-memory pipe with the gathers of the sweeps: 10 SHFL instead of 20.)
+__device__ __forceinline__ double warp_sum_pair(double a, double b, int lane) {
+  const bool up = (lane & 16) != 0;
+  double v = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // Team-wide sum of NR values, result valid on the team leader warp (all of its
 // lanes).  Fixed order => bitwise reproducible.  Non-leader warps only arrive.
 template <int NR>

@@ -181,6 +181,7 @@ struct Sweep2Params {
   int64_t ldy2;
   int K2;
   double* proj_out;
+  int nst;                               // stages of the tile ring (3 or 4)
   int dbg;                               // timing experiments only: 1 = no update math, 2 = phase clocks into prof
   unsigned long long* prof;              // [32] clock64 sums of cluster 0 / CTA 0 (dbg & 2)
 };
@@ -188,8 +189,8 @@ struct Sweep2Params {
 // dynamic shared memory of sweep2_kernel, in doubles
 // columns of prepared random material kept in shared memory (Gibbs): one round of 32/rs columns ahead of the updates
 __host__ __device__ constexpr int sweep2_rnd_window(int rs) { return (1 + 2 * ((32 / rs) < 1 ? 1 : (32 / rs))) <= 8 ? 8 : 16; }
-__host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs, int K2 = 0, bool gibbs = false) {
-  return (size_t)3 * (tw + V2_PAD) * nv + 6 /*mbarriers: 3 tile stages, 2 record buffers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ +
+__host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs, int K2 = 0, bool gibbs = false, int nst = 3) {
+  return (size_t)nst * (tw + V2_PAD) * nv + 8 /*mbarrier slots: 0-3 tile stages, 4-5 record buffers, 7 TMEM base*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ +
          (size_t)2 * cs * rs * 4 /*part, double buffered*/ + (size_t)cs * rs * K2 /*projection partials*/ +
          (size_t)cs * rs * 4 /*row-statistics partials*/ + (gibbs ? (size_t)sweep2_rnd_window(rs) * rs * 6 : 0) /*random material*/;
 }
@@ -284,10 +285,13 @@ __device__ __forceinline__ void sweep2_compute_tm(const Sweep2Params& p, cg::clu
   const int K = p.K, tw = p.tw, K2 = p.K2;
   const int tile_doubles = (tw + V2_PAD) * NV;
   const int total = 2 * K + K2;
+  const int NST = p.nst;
+  auto stg = [&](uint32_t g) -> uint32_t { return NST == 4 ? (g & 3u) : (g % 3u); };
+  auto phs = [&](uint32_t g) -> uint32_t { return (NST == 4 ? (g >> 2) : (g / 3u)) & 1u; };
   const int r = warp - 1;                                 // row of the set owned by this warp
   const uint32_t tm = tm_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)(NPT * 2);
   double* stat0 = cluster.map_shared_rank(statp, 0);      // CTA 0's copy, through DSMEM
-  const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[3]);
+  const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[4]);
   uint32_t gseq = 0;
   for (int set = cid; set < p.nsets; set += nclusters) {
     const int rows_here = min(RS, p.n_loc - set * RS);
@@ -317,8 +321,8 @@ __device__ __forceinline__ void sweep2_compute_tm(const Sweep2Params& p, cg::clu
     // ---- residual of the segment: e = r - sum_k x_k y_k   (tile sequence 0 .. K-1)
     for (int q = 0; q < K; ++q) {
       const uint32_t g = gseq + q;
-      mbar_wait(&mbar[g % 3], (g / 3) & 1u);
-      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+      mbar_wait(&mbar[stg(g)], phs(g));
+      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
       const double xk = (r < rows_here) ? xs[r * K + q] : 0.0;
 #pragma unroll
       for (int n = 0; n < NPT; ++n) {
@@ -335,8 +339,8 @@ __device__ __forceinline__ void sweep2_compute_tm(const Sweep2Params& p, cg::clu
       TmChunk b[2];
       tm_wait_st();                        // the parked values of column k-1 (stored before the exchange) are in place
       tm_ld8(tm, b[0]);
-      mbar_wait(&mbar[g % 3], (g / 3) & 1u);
-      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+      mbar_wait(&mbar[stg(g)], phs(g));
+      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
       double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
@@ -359,12 +363,13 @@ __device__ __forceinline__ void sweep2_compute_tm(const Sweep2Params& p, cg::clu
         tm_st8(tm + 8 * ch, cur);
       }
       named_arrive(1, (RS + 1) * 32);      // this warp has finished its pass of column k
-      s0 = warp_sum(s0); s2 = warp_sum(s2);
+      const double s02 = warp_sum_pair(s0, s2, lane);   // lanes 0..15: sum of s0, lanes 16..31: sum of s2
       if (MODE == M_VB) s1 = warp_sum(s1);
-      if (lane < CS) {   // lane cc sends this warp's partial sums to CTA cc (every CTA updates redundantly)
-        const uint32_t dst = map_to_cta(part_u32 + (uint32_t)(((k & 1) * CS + c) * RS + r) * 32u, lane);
-        const uint32_t bar = map_to_cta(rbar_u32 + (uint32_t)(k & 1) * 8u, lane);
-        st_async_f64(dst, s0, bar); st_async_f64(dst + 8, s1, bar); st_async_f64(dst + 16, s2, bar);
+      if ((lane & 15) < CS) {   // lanes cc / 16 + cc send this warp's partial sums to CTA cc (every CTA updates redundantly)
+        const uint32_t dst = map_to_cta(part_u32 + (uint32_t)(((k & 1) * CS + c) * RS + r) * 32u, lane & 15);
+        const uint32_t bar = map_to_cta(rbar_u32 + (uint32_t)(k & 1) * 8u, lane & 15);
+        st_async_f64(dst + ((lane & 16) ? 16u : 0u), s02, bar);
+        if (MODE == M_VB && lane < 16) st_async_f64(dst + 8, s1, bar);
       }
       __syncthreads();                     // the control warp of this CTA has written the deltas
       dprev = (r < rows_here) ? delta[r] : 0.0;
@@ -404,8 +409,8 @@ __device__ __forceinline__ void sweep2_compute_tm(const Sweep2Params& p, cg::clu
       __syncthreads();
       for (int q = 0; q < K2; ++q) {
         const uint32_t g = gseq + 2 * K + q;
-        mbar_wait(&mbar[g % 3], (g / 3) & 1u);
-        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+        mbar_wait(&mbar[stg(g)], phs(g));
+        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
         double s = 0.0;
 #pragma unroll
         for (int n = 0; n < NPT; ++n) {
@@ -438,6 +443,22 @@ __device__ __forceinline__ void sweep2_compute_tm(const Sweep2Params& p, cg::clu
   }
 }
 
+// phase clocks of cluster 0 / CTA 0 (timing experiments: build with -DBNMTF_V2_PROF, run with BNMTF_V2_DBG=2)
+#ifdef BNMTF_V2_PROF
+#define P2_T0() long long t_prof = prof_on ? clock64() : 0
+#define P2_ADD(slot)                                                       \
+  do {                                                                     \
+    if (prof_on) {                                                         \
+      const long long t_now = clock64();                                   \
+      if (lane == 0) p.prof[slot] += (unsigned long long)(t_now - t_prof); \
+      t_prof = t_now;                                                      \
+    }                                                                      \
+  } while (0)
+#else
+#define P2_T0() do { } while (0)
+#define P2_ADD(slot) do { } while (0)
+#endif
+
 template <int NPT, int MODE, int CS, int DIV, int TMW = 0>
 __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 32, DIV) sweep2_kernel(const Sweep2Params p) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
@@ -452,9 +473,12 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
   const uint32_t tile_bytes = (uint32_t)tw * NV * 8u;
 
   extern __shared__ __align__(128) double smem2[];
-  double* tiles = smem2;                                  // 3 stages
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(tiles + 3 * tile_doubles);
-  double* delta = reinterpret_cast<double*>(mbar + 6);    // [RS]
+  double* tiles = smem2;                                  // NST stages
+  const int NST = p.nst;                                  // stages of the tile ring
+  auto stg = [&](uint32_t g) -> uint32_t { return NST == 4 ? (g & 3u) : (g % 3u); };
+  auto phs = [&](uint32_t g) -> uint32_t { return (NST == 4 ? (g >> 2) : (g / 3u)) & 1u; };
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(tiles + NST * tile_doubles);
+  double* delta = reinterpret_cast<double*>(mbar + 8);    // [RS]
   double* xs = delta + RS + 1;                            // [RS][K]
   double* xvar = xs + (size_t)RS * K;
   double* xmu = xvar + (size_t)RS * K;
@@ -468,13 +492,13 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
   const int total = 2 * K + K2;                           // tiles per set: residual pass, update pass, projection epilogue
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 5; ++s) mbar_init(&mbar[s], 1);   // 0-2: tile stages, 3-4: records of even / odd columns
+    for (int s = 0; s < 6; ++s) mbar_init(&mbar[s], 1);   // 0-3: tile stages, 4-5: records of even / odd columns
     fence_mbar_init();
   }
-  for (int s = threadIdx.x; s < 3; s += blockDim.x) {     // the zero slots read by padded entries
+  for (int s = threadIdx.x; s < NST; s += blockDim.x) {   // the zero slots read by padded entries
     for (int z = 0; z < V2_PAD * NV; ++z) tiles[s * tile_doubles + tw * NV + z] = 0.0;
   }
-  uint32_t& tm_base_sh = *reinterpret_cast<uint32_t*>(&mbar[5]);   // the sixth mbarrier slot is spare
+  uint32_t& tm_base_sh = *reinterpret_cast<uint32_t*>(&mbar[7]);   // a spare mbarrier slot
   if (TMW > 0) {                                          // tensor memory for the residual segments of this CTA
     if (warp == 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm_base_sh)), "n"(V2_TM_COLS) : "memory");
@@ -506,6 +530,9 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
     constexpr int CPR = (32 / RS) < 1 ? 1 : (32 / RS);
     static_assert(1 + 2 * CPR <= RW || MODE != M_GIBBS, "random-material window too small");
     int gen = 0;
+#ifdef BNMTF_V2_PROF
+    const bool prof_on = (p.dbg & 2) && cid == 0 && c == 0 && p.prof != nullptr;
+#endif
     auto gen_round = [&](int rows_here, int64_t row_base) {
       const int cj = lane / RS, rr = lane - cj * RS;
       const int k = gen + cj;
@@ -517,6 +544,7 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
     };
     for (int set = cid; set < p.nsets; set += nclusters) {
       const int rows_here = min(RS, p.n_loc - set * RS);
+      P2_T0();
       for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
         const size_t g = (size_t)(p.row0 + set * RS) * K + q;
         xs[q] = p.Xval[g];
@@ -525,25 +553,26 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
         gen = 0;
         while (gen < min(K, 1 + CPR)) gen_round(rows_here, p.row0 + (int64_t)set * RS);
       }
-      if (lane == 0) {   // prime the ring: first three tiles of this set's sequence (K init + K sweep)
+      if (lane == 0) {   // prime the ring: first NST tiles of this set's sequence (K init + K sweep)
         fence_proxy_async();
-        for (int q = 0; q < 3 && q < total; ++q) {
+        for (int q = 0; q < NST && q < total; ++q) {
           const uint32_t g = gseq + q;
-          mbar_expect_tx(&mbar[g % 3], tile_bytes);
-          tma_load_1d(tiles + (g % 3) * tile_doubles, tile_src(q), tile_bytes, &mbar[g % 3]);
+          mbar_expect_tx(&mbar[stg(g)], tile_bytes);
+          tma_load_1d(tiles + stg(g) * tile_doubles, tile_src(q), tile_bytes, &mbar[stg(g)]);
         }
       }
       cluster_sync_all();
       for (int q = 0; q < K; ++q) {          // residual pass: refill the stage each tile leaves
         __syncthreads();
-        if (lane == 0 && q + 3 < total) {
+        if (lane == 0 && q + NST < total) {
           const uint32_t g = gseq + q;
           fence_proxy_async();
-          mbar_expect_tx(&mbar[g % 3], tile_bytes);
-          tma_load_1d(tiles + (g % 3) * tile_doubles, tile_src(q + 3), tile_bytes, &mbar[g % 3]);
+          mbar_expect_tx(&mbar[stg(g)], tile_bytes);
+          tma_load_1d(tiles + stg(g) * tile_doubles, tile_src(q + NST), tile_bytes, &mbar[stg(g)]);
         }
       }
       double acc_esd = 0.0, acc_q = 0.0, acc_prior = 0.0;
+      P2_ADD(0);                             // set start + residual pass (control side)
       const int64_t grow = p.row0 + (int64_t)set * RS + lane;
       const bool sampler = (lane < rows_here);   // every CTA updates the RS rows redundantly (bitwise identical)
       for (int k = 0; k < K; ++k) {
@@ -560,23 +589,27 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
           __syncwarp();
           while (gen < min(K, k + 1 + CPR)) gen_round(rows_here, p.row0 + (int64_t)set * RS);
         }
+        P2_ADD(0);                           // preparation + random material
         named_sync(1, (RS + 1) * 32);        // the compute warps of this CTA have finished their pass of column k
-        if (lane == 0 && k >= 1 && K + k + 2 < total) {   // tile of column k-1 is dead
-          const uint32_t gn = gseq + K + k + 2;
+        P2_ADD(1);
+        if (lane == 0 && k >= 1 && K + k - 1 + NST < total) {   // tile of column k-1 is dead: its stage takes tile k-1+NST
+          const uint32_t gn = gseq + K + k - 1 + NST;
           fence_proxy_async();
-          mbar_expect_tx(&mbar[gn % 3], tile_bytes);
-          tma_load_1d(tiles + (gn % 3) * tile_doubles, tile_src(K + k + 2), tile_bytes, &mbar[gn % 3]);
+          mbar_expect_tx(&mbar[stg(gn)], tile_bytes);
+          tma_load_1d(tiles + stg(gn) * tile_doubles, tile_src(K + k - 1 + NST), tile_bytes, &mbar[stg(gn)]);
         }
-        // the partial sums of column k: CS x RS warps each send 3 doubles by st.async; they complete this CTA's mbarrier
-        if (lane == 0) mbar_expect_tx(&mbar[3 + (k & 1)], (uint32_t)(CS * RS * 3 * 8));
-        mbar_wait(&mbar[3 + (k & 1)], rec_phase[k & 1] & 1u);
+        // the partial sums of column k: CS x RS warps each send 2 (VB: 3) doubles by st.async; they complete this CTA's mbarrier
+        if (lane == 0) mbar_expect_tx(&mbar[4 + (k & 1)], (uint32_t)(CS * RS * (MODE == M_VB ? 3 : 2) * 8));
+        mbar_wait(&mbar[4 + (k & 1)], rec_phase[k & 1] & 1u);
         rec_phase[k & 1]++;
+        P2_ADD(2);                           // waiting for the records of all CTAs
         if (sampler) {
           double t3[3] = {0.0, 0.0, 0.0};
 #pragma unroll
           for (int cc = 0; cc < CS; ++cc) {
             const double* src = part + ((size_t)((k & 1) * CS + cc) * RS + lane) * 4;
-            t3[0] += src[0]; t3[1] += src[1]; t3[2] += src[2];
+            t3[0] += src[0]; t3[2] += src[2];
+            if (MODE == M_VB) t3[1] += src[1];   // only the VB sweeps send the second sum
           }
           double ct, cm, vn = 0.0, x_new;
           if (p.dbg & 1) { x_new = x_old + 1e-3 * t3[0]; ct = cm = 0.0; }
@@ -594,23 +627,25 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
           if (MODE == M_VB) xvar[lane * K + k] = vn;
           delta[lane] = x_new - x_old;
         }
+        P2_ADD(3);                           // record sums + conditional
         __syncthreads();                     // deltas of column k are in this CTA's shared memory
+        P2_ADD(4);
       }
       if (K2 > 0) {                          // projection epilogue: keep the ring fed (tiles 2K .. 2K+K2-1)
         __syncthreads();                     // every warp has applied the last correction: the stage of tile 2K-1 is free
-        if (lane == 0 && 2 * K + 2 < total && K >= 2) {
-          const uint32_t gn = gseq + 2 * K + 2;
+        if (lane == 0 && 2 * K - 1 + NST < total && K >= 2) {
+          const uint32_t gn = gseq + 2 * K - 1 + NST;
           fence_proxy_async();
-          mbar_expect_tx(&mbar[gn % 3], tile_bytes);
-          tma_load_1d(tiles + (gn % 3) * tile_doubles, tile_src(2 * K + 2), tile_bytes, &mbar[gn % 3]);
+          mbar_expect_tx(&mbar[stg(gn)], tile_bytes);
+          tma_load_1d(tiles + stg(gn) * tile_doubles, tile_src(2 * K - 1 + NST), tile_bytes, &mbar[stg(gn)]);
         }
         for (int q = 0; q < K2; ++q) {
           __syncthreads();
-          if (lane == 0 && 2 * K + q + 3 < total) {
-            const uint32_t gn = gseq + 2 * K + q + 3;
+          if (lane == 0 && 2 * K + q + NST < total) {
+            const uint32_t gn = gseq + 2 * K + q + NST;
             fence_proxy_async();
-            mbar_expect_tx(&mbar[gn % 3], tile_bytes);
-            tma_load_1d(tiles + (gn % 3) * tile_doubles, tile_src(2 * K + q + 3), tile_bytes, &mbar[gn % 3]);
+            mbar_expect_tx(&mbar[stg(gn)], tile_bytes);
+            tma_load_1d(tiles + stg(gn) * tile_doubles, tile_src(2 * K + q + NST), tile_bytes, &mbar[stg(gn)]);
           }
         }
       }
@@ -651,11 +686,18 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
     // =========================== compute warps ===========================
     const int r = warp - 1;                                 // row of the set owned by this warp
     double* stat0 = cluster.map_shared_rank(statp, 0);      // CTA 0's copy, through DSMEM
-    const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[3]);
+    const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[4]);
     uint32_t gseq = 0;
+#ifdef BNMTF_V2_PROF
+    const bool prof_on = (p.dbg & 2) && cid == 0 && c == 0 && warp == 1 && p.prof != nullptr;
+#endif
     for (int set = cid; set < p.nsets; set += nclusters) {
       const int rows_here = min(RS, p.n_loc - set * RS);
       const int64_t seg = ((int64_t)(set * CS + c) * NPT) * RS * 32 + (int64_t)r * 32 + lane;
+      P2_T0();
+#ifdef BNMTF_V2_PROF
+      if (prof_on && lane == 0) p.prof[16] += 1;
+#endif
       double e[NPT];
       uint32_t cp[NPT / 2];
 #pragma unroll
@@ -670,12 +712,13 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
         xs[q] = p.Xval[g];
       }
       cluster_sync_all();   // xs visible; CTA 0 has finished with `part` of the previous set
+      P2_ADD(8);            // segment loads + set start barrier
 
       // ---- residual of the segment: e = r - sum_k x_k y_k   (tile sequence 0 .. K-1)
       for (int q = 0; q < K; ++q) {
         const uint32_t g = gseq + q;
-        mbar_wait(&mbar[g % 3], (g / 3) & 1u);
-        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+        mbar_wait(&mbar[stg(g)], phs(g));
+        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
         const double xk = (r < rows_here) ? xs[r * K + q] : 0.0;
 #pragma unroll
         for (int n = 0; n < NPT; ++n) {
@@ -685,13 +728,15 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
         __syncthreads();
       }
 
+      P2_ADD(9);            // residual pass
       // ---- the K column updates   (tile sequence K .. 2K-1)
       double dprev = 0.0;
       for (int k = 0; k < K; ++k) {
         const uint32_t g = gseq + K + k;
-        mbar_wait(&mbar[g % 3], (g / 3) & 1u);
-        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
-        const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + ((g + 2) % 3) * tile_doubles);   // tile g-1
+        mbar_wait(&mbar[stg(g)], phs(g));
+        P2_ADD(10);                          // waiting for the tile
+        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
+        const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + stg(g + NST - 1) * tile_doubles);   // tile g-1
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         if (k > 0) {
 #pragma unroll
@@ -715,22 +760,26 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
             s2 = fma(e[n], v, s2);
           }
         }
+        P2_ADD(11);                          // pass
         named_arrive(1, (RS + 1) * 32);      // this warp no longer reads the tile of column k-1
-        s0 = warp_sum(s0); s2 = warp_sum(s2);
+        const double s02 = warp_sum_pair(s0, s2, lane);   // lanes 0..15: sum of s0, lanes 16..31: sum of s2
         if (MODE == M_VB) s1 = warp_sum(s1);
-        if (lane < CS) {   // lane cc sends this warp's partial sums to CTA cc (every CTA updates redundantly)
-          const uint32_t dst = map_to_cta(part_u32 + (uint32_t)(((k & 1) * CS + c) * RS + r) * 32u, lane);
-          const uint32_t bar = map_to_cta(rbar_u32 + (uint32_t)(k & 1) * 8u, lane);
-          st_async_f64(dst, s0, bar); st_async_f64(dst + 8, s1, bar); st_async_f64(dst + 16, s2, bar);
+        if ((lane & 15) < CS) {   // lanes cc / 16 + cc send this warp's partial sums to CTA cc (every CTA updates redundantly)
+          const uint32_t dst = map_to_cta(part_u32 + (uint32_t)(((k & 1) * CS + c) * RS + r) * 32u, lane & 15);
+          const uint32_t bar = map_to_cta(rbar_u32 + (uint32_t)(k & 1) * 8u, lane & 15);
+          st_async_f64(dst + ((lane & 16) ? 16u : 0u), s02, bar);
+          if (MODE == M_VB && lane < 16) st_async_f64(dst + 8, s1, bar);
         }
+        P2_ADD(12);                          // reduction + record stores
         __syncthreads();                     // the control warp of this CTA has written the deltas
         dprev = (r < rows_here) ? delta[r] : 0.0;
+        P2_ADD(14);                          // waiting for the deltas
       }
 
       // ---- last correction, then the row statistics of the final residual
       {
         const uint32_t g = gseq + 2 * K - 1;
-        const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+        const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
         double st0 = 0.0, st1 = 0.0, st2 = 0.0;
 #pragma unroll
         for (int n = 0; n < NPT; ++n) {
@@ -753,8 +802,8 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
         __syncthreads();
         for (int q = 0; q < K2; ++q) {
           const uint32_t g = gseq + 2 * K + q;
-          mbar_wait(&mbar[g % 3], (g / 3) & 1u);
-          const char* __restrict__ T = reinterpret_cast<const char*>(tiles + (g % 3) * tile_doubles);
+          mbar_wait(&mbar[stg(g)], phs(g));
+          const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
           double s = 0.0;
 #pragma unroll
           for (int n = 0; n < NPT; ++n) {
@@ -784,6 +833,7 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
       }
       gseq += total;
       __syncthreads();   // xs / tiles are reused by the next set
+      P2_ADD(15);        // statistics, store, end of set
     }
   }
   if (TMW > 0) {

@@ -198,8 +198,11 @@ __device__ __forceinline__ double tn_draw_fast(double num, double prec, const Tn
     x = m.z1 - a;
     if (!ok) { ok = (m.z2 >= a); x = m.z2 - a; }
   } else {
-    const double alpha = 0.5 * (a + sqrt(a * a + 4.0));
-    const double ia = 1.0 / alpha, am = a - alpha;
+    // alpha = (a + sqrt(a^2 + 4)) / 2 and 1 / alpha = (sqrt(a^2 + 4) - a) / 2: no division on the chain (the
+    // difference loses ~a^2 ulp, so very large bounds keep the division)
+    const double sq = sqrt(a * a + 4.0);
+    const double alpha = 0.5 * (a + sq);
+    const double ia = a < 256.0 ? 0.5 * (sq - a) : 1.0 / alpha, am = a - alpha;
     x = m.e1 * ia;
     double t = am + x;
     ok = (m.l1 >= t * t);
