@@ -4,6 +4,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1351,6 +1352,10 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   const int want_mu = getenv("BNMTF_TRACE_PARAMS") && atoi(getenv("BNMTF_TRACE_PARAMS")) != 0;
   h->sweep_ms[0] = h->sweep_ms[1] = 0; h->sweep_n[0] = h->sweep_n[1] = 0;
   if (iterations == 0) return 0;
+  const bool run_timing = getenv("BNMTF_RUN_TIMING") != nullptr;   // host wall clock of the stages of this call, to stderr
+  const auto wall0 = std::chrono::steady_clock::now();
+  auto wall_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count(); };
+  double t_setup = 0, t_enq = 0, t_sync = 0, t_drain = 0;
 
   // traces are staged on the device in chunks and copied out while the next chunk runs
   const size_t per_it = sizeof(double) * ((size_t)su.n_glob + sv.n_glob) * K;
@@ -1380,6 +1385,7 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   h->km_mode = method == BNMTF_VB ? 2 : 1;
   if (summary_reset(h)) return 1;
   CK(cudaEventRecord(ev[0], h->stream));
+  t_setup = wall_ms();
 
   const int nchunks = (iterations + chunk - 1) / chunk;
   if (tr && nchunks > 1 && !getenv("BNMTF_NO_PINNED_TRACES") && drain.start(h, nchunks, per_it * (size_t)chunk)) return 1;
@@ -1458,17 +1464,25 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
     }
   }
   if (tr && copy_chunk(nchunks - 1)) return 1;
+  t_enq = wall_ms();
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaStreamSynchronize(h->copy_stream));
   CK(cudaGetLastError());
+  t_sync = wall_ms();
   if (iter_stats) CK(cudaMemcpy(iter_stats, h->stats_dev, sizeof(double) * BNMTF_NSTATS * iterations, cudaMemcpyDeviceToHost));
   if (drain.finish()) return 1;
+  t_drain = wall_ms();
   if (all_lambdak) CK(cudaMemcpy(all_lambdak, lam_trace, sizeof(double) * K * iterations, cudaMemcpyDeviceToHost));
   if (iter_seconds) {
     for (int it = 0; it < iterations; ++it) {
       float ms = 0; CK(cudaEventElapsedTime(&ms, ev[0], ev[it + 1]));
       iter_seconds[it] = ms * 1e-3;
     }
+  }
+  if (run_timing) {
+    float dev_ms = 0; cudaEventElapsedTime(&dev_ms, ev[0], ev[iterations]);
+    fprintf(stderr, "[bnmtf_nmf_run] %d iterations, %d trace chunk(s): set-up %.1f ms, loop enqueued at %.1f, streams idle at %.1f, traces delivered at %.1f, "
+            "device loop %.1f ms\n", iterations, tr ? nchunks : 0, t_setup, t_enq, t_sync, t_drain, dev_ms);
   }
   for (auto& e : ev) cudaEventDestroy(e);
   for (int b = 0; b < 2; ++b) { cudaEventDestroy(chunk_done[b]); cudaEventDestroy(chunk_copied[b]); }
