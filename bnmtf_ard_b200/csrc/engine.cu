@@ -110,7 +110,7 @@ struct Side {
   // v2 (cluster) layout
   bool v2 = false;
   int cs = 8, tw = 0, rs = 0, npt2 = 0, v2div = 1;
-  bool v2tm = false;                     // residual segments in tensor memory (kernels_v2.cuh, TM variant)
+  int v2tm = 0;                          // tensor-memory variants of the cluster sweep (kernels_v2.cuh): 1 parked column, 2 residual in TMEM
   int64_t nsets = 0, tslots = 0;
   double* tvals = nullptr;
   uint16_t* tcols = nullptr;
@@ -256,7 +256,7 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   if (npt2 > 4 && npt2 < 8) npt2 = 8;
   if (npt2 > 8 && npt2 < 12) npt2 = 12;
   if (npt2 > 12 && npt2 < 16) npt2 = 16;
-  const int wpc_full = npt2 <= 16 ? 32 : (npt2 <= 18 ? 28 : 24);   // Sweep2Cfg<NPT>::WPC
+  const int wpc_full = npt2 <= 16 ? 32 : (npt2 <= 18 ? 28 : Sweep2Cfg<20>::WPC);   // Sweep2Cfg<NPT>::WPC
   int div = 2;                                                     // CTAs (of different clusters) per SM
   if (getenv("BNMTF_V2_DIV")) div = std::max(1, std::min(3, atoi(getenv("BNMTF_V2_DIV"))));
   if (npt2 == 18 && div == 3) div = 2;                             // 28 warps do not split in three
@@ -267,7 +267,11 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   // 20 entries per lane, opt-in (BNMTF_V2_TM=1): the TM variant parks the gathered values of a column in tensor memory
   // instead of gathering them again for the rank-1 correction (same packed layout, bitwise the same results; measured
   // equal in speed at 20000 x 20000: the sweep is bound by its per-column exchange, not by the gathers)
-  sd.v2tm = npt2 == 20 && div == 2 && sd.v3B == 0 && getenv("BNMTF_V2_TM") && atoi(getenv("BNMTF_V2_TM")) == 1;
+  sd.v2tm = 0;
+  if (npt2 == 20 && div == 2 && rs == V2_TM_WARPS - 1 && sd.v3B == 0 && getenv("BNMTF_V2_TM")) {
+    const int v = atoi(getenv("BNMTF_V2_TM"));
+    if (v == 1 || v == 2) sd.v2tm = v;
+  }
   const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, V2_CS) * sizeof(double);
   sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && sd.kf >= 3 && smem_vb <= 200 * 1024 && (sd.tw + V2_PAD) * 16 < 65536;
   if (sd.v2 && n > 0) {
@@ -765,10 +769,10 @@ static int launch_sweep_m(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int n
   FAIL("unsupported entries-per-thread %d", npt);
 }
 
-template <int NPT, int MODE, int DIV, int TMW = 0>
+template <int NPT, int MODE, int DIV, int TMW = 0, int TMV = 1>
 static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p_in, Side& sd, int method) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  auto kern = sweep2_kernel<NPT, MODE, V2_CS, DIV, TMW>;
+  auto kern = sweep2_kernel<NPT, MODE, V2_CS, DIV, TMW, TMV>;
   // tile ring: a fourth stage when it does not cost a resident CTA (228 KB per SM, 1 KB reserved per CTA, 227 KB per CTA)
   Sweep2Params p = p_in;
   const size_t smem3 = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS, p.K2, MODE == M_GIBBS, 3) * sizeof(double);
@@ -825,7 +829,8 @@ static int launch_sweep2_d(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
 
 template <int MODE>
 static int launch_sweep2_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
-  if (sd.v2tm) return launch_sweep2_t<20, MODE, 2, V2_TM_WARPS>(h, p, sd, method);
+  if (sd.v2tm == 1) return launch_sweep2_t<20, MODE, 2, V2_TM_WARPS, 1>(h, p, sd, method);
+  if (sd.v2tm == 2) return launch_sweep2_t<20, MODE, 2, V2_TM_WARPS, 2>(h, p, sd, method);
   switch (sd.v2div) {
     case 1: return launch_sweep2_d<MODE, 1>(h, p, sd, method);
     case 2: return launch_sweep2_d<MODE, 2>(h, p, sd, method);
@@ -1498,7 +1503,7 @@ int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {  // out8: 16 values
   out8[4] = h->s[0].nslots; out8[5] = h->s[1].nslots; out8[6] = h->s[0].nnz; out8[7] = h->s[1].nnz;
   for (int q = 0; q < 2; ++q) {
     const Side& sd = h->s[q];
-    out8[8 + 4 * q] = sd.v2 ? (sd.v2tm ? 4 : (sd.v3B > 0 && !h->nmtf) ? 3 : 1) : 0;   // 1: cluster sweep, 3: blocked cluster sweep, 4: cluster sweep with the segments in tensor memory
+    out8[8 + 4 * q] = sd.v2 ? (sd.v2tm ? 3 + sd.v2tm : (sd.v3B > 0 && !h->nmtf) ? 3 : 1) : 0;   // 1: cluster sweep, 3: blocked cluster sweep, 4: cluster sweep with the segments in tensor memory
     out8[9 + 4 * q] = sd.v2 ? sd.npt2 : 0;
     out8[10 + 4 * q] = sd.v2 ? sd.rs : 0; out8[11 + 4 * q] = sd.v2 ? sd.tslots : 0;
   }

@@ -203,9 +203,12 @@ __host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, in
 // WPC is the largest block the register file allows (1 CTA per SM); smaller blocks
 // (WPC/2, WPC/3: 2 or 3 CTAs of different clusters per SM) let one cluster's barrier
 // and update latency overlap with another cluster's gathers.
+#ifndef BNMTF_V2_WPC20
+#define BNMTF_V2_WPC20 24   // warps per SM at 20 entries per lane
+#endif
 template <int NPT>
 struct Sweep2Cfg {
-  static constexpr int WPC = NPT <= 16 ? 32 : (NPT <= 18 ? 28 : 24);
+  static constexpr int WPC = NPT <= 16 ? 32 : (NPT <= 18 ? 28 : BNMTF_V2_WPC20);
 };
 
 // Remote (DSMEM) store that signals the destination CTA's mbarrier when it lands: the receiver waits on its own
@@ -443,6 +446,210 @@ __device__ __forceinline__ void sweep2_compute_tm(const Sweep2Params& p, cg::clu
   }
 }
 
+// TM variant 2 (BNMTF_V2_TM=2): the residual segments themselves live in tensor memory.  At one row per warp and 80
+// registers the register variant has room for ONE shared-memory load in flight per warp (ncu source page: every
+// gather of the pass lands in the same register pair, each followed by its FMAs), so a pass is a chain of ~40 load
+// latencies.  With the 40 registers of e[] gone the gathers of a chunk of 4 entries are all in flight together while
+// the next chunk of the residual arrives from TMEM.  Same entries, operands and order of every sum: bitwise equal.
+template <int NPT, int MODE, int CS, int RS>
+__device__ __forceinline__ void sweep2_compute_tme(const Sweep2Params& p, cg::cluster_group& cluster, int c, int cid, int nclusters,
+                                                   int warp, int lane, double* tiles, uint64_t* mbar, const double* delta, double* xs,
+                                                   double* part, double* proj, double* statp, uint32_t tm_base) {
+  constexpr int NV = (MODE == M_VB) ? 2 : 1;
+  constexpr int NCH = NPT / 4;
+  static_assert(NPT % 4 == 0, "TMEM chunks hold 4 entries");
+  const int K = p.K, tw = p.tw, K2 = p.K2;
+  const int tile_doubles = (tw + V2_PAD) * NV;
+  const int total = 2 * K + K2;
+  const int NST = p.nst;
+  auto stg = [&](uint32_t g) -> uint32_t { return NST == 4 ? (g & 3u) : (g % 3u); };
+  auto phs = [&](uint32_t g) -> uint32_t { return (NST == 4 ? (g >> 2) : (g / 3u)) & 1u; };
+  const int r = warp - 1;                                 // row of the set owned by this warp
+  const uint32_t tm = tm_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)(NPT * 2);
+  double* stat0 = cluster.map_shared_rank(statp, 0);      // CTA 0's copy, through DSMEM
+  const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[4]);
+  uint32_t gseq = 0;
+  for (int set = cid; set < p.nsets; set += nclusters) {
+    const int rows_here = min(RS, p.n_loc - set * RS);
+    const int64_t seg = ((int64_t)(set * CS + c) * NPT) * RS * 32 + (int64_t)r * 32 + lane;
+    uint32_t cp[NPT / 2];
+#pragma unroll
+    for (int n = 0; n < NPT; n += 2) {
+      const uint32_t a = p.tcols[seg + (int64_t)n * RS * 32], b = p.tcols[seg + (int64_t)(n + 1) * RS * 32];
+      cp[n / 2] = (a * (NV * 8)) | ((b * (NV * 8)) << 16);   // byte offsets inside a tile stage
+    }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {                       // R values of the segment -> TMEM
+      TmChunk b;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b.set(i, p.tvals[seg + (int64_t)(4 * ch + i) * RS * 32]);
+      tm_st8(tm + 8 * ch, b);
+    }
+    for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
+      const size_t g = (size_t)(p.row0 + set * RS) * K + q;
+      xs[q] = p.Xval[g];
+    }
+    cluster_sync_all();   // xs visible; CTA 0 has finished with `part` of the previous set
+
+    // ---- residual of the segment: e = r - sum_k x_k y_k   (tile sequence 0 .. K-1)
+    for (int q = 0; q < K; ++q) {
+      const uint32_t g = gseq + q;
+      TmChunk b[2];
+      tm_wait_st();
+      tm_ld8(tm, b[0]);
+      mbar_wait(&mbar[stg(g)], phs(g));
+      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
+      const double xk = (r < rows_here) ? xs[r * K + q] : 0.0;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        TmChunk& cur = b[ch & 1];
+        double y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = 4 * ch + i;
+          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+          y[i] = *reinterpret_cast<const double*>(T + off);
+        }
+        tm_wait_ld(cur);
+        if (ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur.set(i, fma(-xk, y[i], cur.get(i)));
+        tm_st8(tm + 8 * ch, cur);
+      }
+      __syncthreads();
+    }
+
+    // ---- the K column updates   (tile sequence K .. 2K-1)
+    double dprev = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const uint32_t g = gseq + K + k;
+      TmChunk b[2];
+      tm_wait_st();
+      tm_ld8(tm, b[0]);
+      mbar_wait(&mbar[stg(g)], phs(g));
+      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
+      const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + stg(g + NST - 1) * tile_doubles);   // tile g-1
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        TmChunk& cur = b[ch & 1];
+        double yp[4], v[4], w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = 4 * ch + i;
+          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+          yp[i] = *reinterpret_cast<const double*>(Tp + off);   // k == 0: the last tile of the residual pass, times dprev == 0
+          if (MODE == M_VB) { const double2 vv = *reinterpret_cast<const double2*>(T + off); v[i] = vv.x; w[i] = vv.y; }
+          else { v[i] = *reinterpret_cast<const double*>(T + off); w[i] = 0.0; }
+        }
+        tm_wait_ld(cur);
+        if (ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const double e = fma(-dprev, yp[i], cur.get(i));
+          if (MODE == M_VB) s1 += w[i];
+          s0 = fma(v[i], v[i], s0);
+          s2 = fma(e, v[i], s2);
+          cur.set(i, e);
+        }
+        tm_st8(tm + 8 * ch, cur);
+      }
+      named_arrive(1, (RS + 1) * 32);      // this warp no longer reads the tile of column k-1
+      const double s02 = warp_sum_pair(s0, s2, lane);   // lanes 0..15: sum of s0, lanes 16..31: sum of s2
+      if (MODE == M_VB) s1 = warp_sum(s1);
+      if ((lane & 15) < CS) {   // lanes cc / 16 + cc send this warp's partial sums to CTA cc (every CTA updates redundantly)
+        const uint32_t dst = map_to_cta(part_u32 + (uint32_t)(((k & 1) * CS + c) * RS + r) * 32u, lane & 15);
+        const uint32_t bar = map_to_cta(rbar_u32 + (uint32_t)(k & 1) * 8u, lane & 15);
+        st_async_f64(dst + ((lane & 16) ? 16u : 0u), s02, bar);
+        if (MODE == M_VB && lane < 16) st_async_f64(dst + 8, s1, bar);
+      }
+      __syncthreads();                     // the control warp of this CTA has written the deltas
+      dprev = (r < rows_here) ? delta[r] : 0.0;
+    }
+
+    // ---- last correction, then the row statistics of the final residual
+    {
+      const uint32_t g = gseq + 2 * K - 1;
+      const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
+      double st0 = 0.0, st1 = 0.0, st2 = 0.0;
+      TmChunk b[2];
+      tm_wait_st();
+      tm_ld8(tm, b[0]);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        TmChunk& cur = b[ch & 1];
+        tm_wait_ld(cur);
+        if (ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = 4 * ch + i;
+          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+          const double e = fma(-dprev, *reinterpret_cast<const double*>(Tp + off), cur.get(i));
+          const double rr = p.tvals[seg + (int64_t)n * RS * 32];
+          st0 = fma(e, e, st0);
+          st1 += e;
+          st2 = fma(rr - p.rmean, e, st2);   // padded slots hold e == 0
+          cur.set(i, e);
+        }
+        if (K2 > 0) tm_st8(tm + 8 * ch, cur);
+      }
+      st0 = warp_sum(st0); st1 = warp_sum(st1); st2 = warp_sum(st2);
+      if (lane == 0) {
+        double* dst = stat0 + ((size_t)c * RS + r) * 4;
+        dst[0] = st0; dst[1] = st1; dst[2] = st2;
+      }
+    }
+    if (K2 > 0) {
+      // ---- projection epilogue: sum_j e_j Y2[l][j] over this segment, partials to CTA 0   (tiles 2K .. 2K+K2-1)
+      double* proj0 = cluster.map_shared_rank(proj, 0);
+      tm_wait_st();
+      __syncthreads();
+      for (int q = 0; q < K2; ++q) {
+        const uint32_t g = gseq + 2 * K + q;
+        mbar_wait(&mbar[stg(g)], phs(g));
+        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
+        double s = 0.0;
+        TmChunk b[2];
+        tm_ld8(tm, b[0]);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          TmChunk& cur = b[ch & 1];
+          tm_wait_ld(cur);
+          if (ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = 4 * ch + i;
+            const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
+            s = fma(cur.get(i), *reinterpret_cast<const double*>(T + off), s);
+          }
+        }
+        s = warp_sum(s);
+        if (lane == 0) proj0[((size_t)c * RS + r) * K2 + q] = s;
+        __syncthreads();
+      }
+    }
+    tm_wait_st();
+    cluster_sync_all();
+    if (c == 0) {
+      __syncthreads();
+      for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
+        const size_t g = (size_t)(p.row0 + set * RS) * K + q;
+        p.Xval[g] = xs[q];
+        if (MODE == M_VB) p.Xvar[g] = xs[(size_t)RS * K + q];
+        if (p.Xmu != nullptr) { p.Xmu[g] = xs[(size_t)2 * RS * K + q]; p.Xtau[g] = xs[(size_t)3 * RS * K + q]; }
+      }
+      for (int q = threadIdx.x; q < rows_here * K2; q += blockDim.x) {   // fixed-order sum of the CS projection partials
+        const int rr = q / K2, l = q - rr * K2;
+        double t = 0.0;
+        for (int cc = 0; cc < CS; ++cc) t += proj[((size_t)cc * RS + rr) * K2 + l];
+        p.proj_out[(size_t)(p.row0 + set * RS + rr) * K2 + l] = t;
+      }
+    }
+    gseq += total;
+    __syncthreads();   // xs / tiles are reused by the next set
+  }
+}
+
 // phase clocks of cluster 0 / CTA 0 (timing experiments: build with -DBNMTF_V2_PROF, run with BNMTF_V2_DBG=2)
 #ifdef BNMTF_V2_PROF
 #define P2_T0() long long t_prof = prof_on ? clock64() : 0
@@ -459,10 +666,12 @@ __device__ __forceinline__ void sweep2_compute_tm(const Sweep2Params& p, cg::clu
 #define P2_ADD(slot) do { } while (0)
 #endif
 
-template <int NPT, int MODE, int CS, int DIV, int TMW = 0>
+// TMW > 0: tensor-memory variants (TMW warps per CTA); TMV = 1: the gathered column is parked in TMEM, 2: the residual
+template <int NPT, int MODE, int CS, int DIV, int TMW = 0, int TMV = 1>
 __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 32, DIV) sweep2_kernel(const Sweep2Params p) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
   constexpr int RS = (TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) - 1;
+  constexpr int NTHR = (RS + 1) * 32;                     // threads of the CTA
   static_assert(MODE != M_NP, "the NP updates run on the v1 kernel");
   cg::cluster_group cluster = cg::this_cluster();
   const int c = (int)cluster.block_rank();
@@ -590,7 +799,7 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
           while (gen < min(K, k + 1 + CPR)) gen_round(rows_here, p.row0 + (int64_t)set * RS);
         }
         P2_ADD(0);                           // preparation + random material
-        named_sync(1, (RS + 1) * 32);        // the compute warps of this CTA have finished their pass of column k
+        named_sync(1, NTHR);                 // the compute warps of this CTA have finished their pass of column k
         P2_ADD(1);
         if (lane == 0 && k >= 1 && K + k - 1 + NST < total) {   // tile of column k-1 is dead: its stage takes tile k-1+NST
           const uint32_t gn = gseq + K + k - 1 + NST;
@@ -680,8 +889,10 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
       __syncthreads();
     }
   } else if (TMW > 0) {
-    if constexpr (TMW > 0)
+    if constexpr (TMW > 0 && TMV == 1)
       sweep2_compute_tm<NPT, MODE, CS, RS>(p, cluster, c, cid, nclusters, warp, lane, tiles, mbar, delta, xs, part, proj, statp, tm_base);
+    if constexpr (TMW > 0 && TMV == 2)
+      sweep2_compute_tme<NPT, MODE, CS, RS>(p, cluster, c, cid, nclusters, warp, lane, tiles, mbar, delta, xs, part, proj, statp, tm_base);
   } else {
     // =========================== compute warps ===========================
     const int r = warp - 1;                                 // row of the set owned by this warp
