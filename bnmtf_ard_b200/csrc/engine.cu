@@ -129,6 +129,12 @@ struct Side {
   double* lamk = nullptr;    // ARD prior of this side's columns (not owned for NMF)
 };
 constexpr int V2_CS = 8;
+// experiments: BNMTF_V2_CS=16 runs the cluster sweep on (non-portable) clusters of 16 CTAs -- tiles half as wide, segments
+// of 12 entries per lane, 15 rows per CTA; only the 12-entry instantiation exists for it
+static int v2_cs() {
+  static const int cs = (getenv("BNMTF_V2_CS") && atoi(getenv("BNMTF_V2_CS")) == 16) ? 16 : V2_CS;
+  return cs;
+}
 }  // namespace
 
 struct bnmtf_nmf_s {
@@ -200,7 +206,7 @@ static void choose_team(int64_t maxlen, int* tpr, int* npt) {
   *npt = n;
 }
 
-static int v2_tile_width(int64_t m) { return (int)roundup((m + V2_CS - 1) / V2_CS, 32); }
+static int v2_tile_width(int64_t m) { return (int)roundup((m + v2_cs() - 1) / v2_cs(), 32); }
 
 // phase 1: observed entries per row and the longest (row, tile) segment of a dense block
 static int count_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld) {
@@ -272,16 +278,18 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
     const int v = atoi(getenv("BNMTF_V2_TM"));
     if (v == 1 || v == 2) sd.v2tm = v;
   }
-  const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, V2_CS) * sizeof(double);
+  const int cs = v2_cs();
+  if (cs != V2_CS) { sd.v3B = 0; sd.v2tm = 0; }
+  const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, cs) * sizeof(double);
   sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && sd.kf >= 3 && smem_vb <= 200 * 1024 && (sd.tw + V2_PAD) * 16 < 65536;
   if (sd.v2 && n > 0) {
-    sd.cs = V2_CS; sd.npt2 = npt2; sd.rs = rs;
+    sd.cs = cs; sd.npt2 = npt2; sd.rs = rs;
     sd.nsets = (n + rs - 1) / rs;
-    sd.tslots = sd.nsets * V2_CS * (int64_t)npt2 * rs * 32;
+    sd.tslots = sd.nsets * cs * (int64_t)npt2 * rs * 32;
     CK(cudaMalloc(&sd.tvals, sizeof(double) * sd.tslots));
     CK(cudaMalloc(&sd.tcols, sizeof(uint16_t) * sd.tslots));
     fill_pads_kernel<<<1024, 256, 0, h->stream>>>(sd.tvals, sd.tcols, sd.tslots, (uint16_t)sd.tw);
-    pack_tiles_kernel<<<(unsigned)((n * V2_CS + 7) / 8), 256, 0, h->stream>>>(sd.dR, sd.dM, n, m, ld, V2_CS, sd.tw, rs, npt2,
+    pack_tiles_kernel<<<(unsigned)((n * cs + 7) / 8), 256, 0, h->stream>>>(sd.dR, sd.dM, n, m, ld, cs, sd.tw, rs, npt2,
                                                                              sd.tvals, sd.tcols);
     h->launches += 2;
   } else {
@@ -302,7 +310,7 @@ static int alloc_side_state(bnmtf_nmf_s* h, Side& sd, int K) {
   CK(cudaMalloc(&sd.val, nb)); CK(cudaMalloc(&sd.var, nb)); CK(cudaMalloc(&sd.mu, nb)); CK(cudaMalloc(&sd.tau, nb));
   CK(cudaMemsetAsync(sd.val, 0, nb, h->stream)); CK(cudaMemsetAsync(sd.var, 0, nb, h->stream));
   CK(cudaMemsetAsync(sd.mu, 0, nb, h->stream)); CK(cudaMemsetAsync(sd.tau, 0, nb, h->stream));
-  sd.ld = roundup(std::max(sd.n_padglob, sd.n_glob + 1) + V2_CS * 32, 16);  // >= CS * tile width
+  sd.ld = roundup(std::max(sd.n_padglob, sd.n_glob + 1) + 16 * 32, 16);  // >= CS * tile width (CS <= 16)
   CK(cudaMalloc(&sd.km, sizeof(double) * 2 * sd.ld * K));
   CK(cudaMemsetAsync(sd.km, 0, sizeof(double) * 2 * sd.ld * K, h->stream));
   CK(cudaMalloc(&sd.km3, sizeof(double) * 2 * sd.ld * (K + 3)));
@@ -769,14 +777,14 @@ static int launch_sweep_m(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int n
   FAIL("unsupported entries-per-thread %d", npt);
 }
 
-template <int NPT, int MODE, int DIV, int TMW = 0, int TMV = 1>
+template <int NPT, int MODE, int DIV, int TMW = 0, int TMV = 1, int CS = V2_CS>
 static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p_in, Side& sd, int method) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  auto kern = sweep2_kernel<NPT, MODE, V2_CS, DIV, TMW, TMV>;
+  auto kern = sweep2_kernel<NPT, MODE, CS, DIV, TMW, TMV>;
   // tile ring: a fourth stage when it does not cost a resident CTA (228 KB per SM, 1 KB reserved per CTA, 227 KB per CTA)
   Sweep2Params p = p_in;
-  const size_t smem3 = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS, p.K2, MODE == M_GIBBS, 3) * sizeof(double);
-  const size_t smem4 = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, V2_CS, p.K2, MODE == M_GIBBS, 4) * sizeof(double);
+  const size_t smem3 = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, CS, p.K2, MODE == M_GIBBS, 3) * sizeof(double);
+  const size_t smem4 = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, CS, p.K2, MODE == M_GIBBS, 4) * sizeof(double);
   const size_t per_sm = 228 * 1024;
   const int ctas3 = (int)std::min<size_t>(DIV, per_sm / (smem3 + 1024)), ctas4 = (int)std::min<size_t>(DIV, per_sm / (smem4 + 1024));
   p.nst = (smem4 <= 227 * 1024 && ctas4 >= ctas3) ? 4 : 3;
@@ -788,27 +796,28 @@ static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p_in, Side& sd, i
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = V2_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (sd.nclusters[method] == 0) {
     // one fixed opt-in limit per instantiation: both sides (and other handles) share the kernel
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    cfg.gridDim = dim3(V2_CS * 128);
+    if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cfg.gridDim = dim3(CS * 64);
     int ncl = 0;
     // the occupancy query places one CTA per SM for a kernel that allocates tensor memory (15 clusters instead of 33);
     // the TM variant has the block size, registers and shared memory of the register variant and takes 128 of the 512
     // TMEM columns per CTA, so the register variant's answer holds for it
-    auto occ_kern = sweep2_kernel<NPT, MODE, V2_CS, DIV, 0>;
+    auto occ_kern = sweep2_kernel<NPT, MODE, CS, DIV, 0>;
     if (TMW > 0) CK(cudaFuncSetAttribute(occ_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaOccupancyMaxActiveClusters(&ncl, occ_kern, &cfg));
     if (ncl < 1) FAIL("cluster sweep kernel does not fit (smem %zu bytes, %d threads)", smem, (p.rs + 1) * 32);
     if (getenv("BNMTF_V2_NCL")) ncl = std::max(1, atoi(getenv("BNMTF_V2_NCL")));   // experiments: clusters are independent, a larger grid queues
-    if (getenv("BNMTF_V2_DBG")) fprintf(stderr, "sweep2<%d,%d,%d,%d>: %d clusters of %d x %d threads, %zu bytes of shared memory, %d tile stages\n", NPT, MODE, DIV, TMW, ncl, V2_CS, (p.rs + 1) * 32, smem, p.nst);
+    if (getenv("BNMTF_V2_DBG")) fprintf(stderr, "sweep2<%d,%d,%d,%d>: %d clusters of %d x %d threads, %zu bytes of shared memory, %d tile stages\n", NPT, MODE, DIV, TMW, ncl, CS, (p.rs + 1) * 32, smem, p.nst);
     sd.nclusters[method] = ncl;
   }
   const int ncl = (int)std::min<int64_t>(sd.nclusters[method], p.nsets);
   if (ncl < 1) return 0;
-  cfg.gridDim = dim3(V2_CS * ncl);
+  cfg.gridDim = dim3(CS * ncl);
   CK(cudaLaunchKernelEx(&cfg, kern, p));
   h->launches++;
   return 0;
@@ -829,6 +838,10 @@ static int launch_sweep2_d(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
 
 template <int MODE>
 static int launch_sweep2_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
+  if (sd.cs == 16) {
+    if (sd.npt2 != 12 || sd.v2div != 2) FAIL("BNMTF_V2_CS=16 serves 12 entries per lane and two CTAs per SM only (this side: %d, %d)", sd.npt2, sd.v2div);
+    return launch_sweep2_t<12, MODE, 2, 0, 1, 16>(h, p, sd, method);
+  }
   if (sd.v2tm == 1) return launch_sweep2_t<20, MODE, 2, V2_TM_WARPS, 1>(h, p, sd, method);
   if (sd.v2tm == 2) return launch_sweep2_t<20, MODE, 2, V2_TM_WARPS, 2>(h, p, sd, method);
   switch (sd.v2div) {
