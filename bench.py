@@ -369,6 +369,19 @@ def main():
                                 "kernel_ms": ms, "kernel_share_of_step": (sweeps["ms_U"] + sweeps["ms_V"]) / (1e3 * dev_s),
                                 "north_star_equiv_gbs": northstar_bytes * value / 1e9,
                                 "north_star_equiv_frac": northstar_bytes * value / 1e9 / peak}
+            if info.get("v2_U") and info.get("v2_V") and int(info["v2_U"]) == 1:
+                # what the cluster sweep actually leans on: the shared-memory pipe.  Algorithmic 8-byte gathers per launch
+                # (residual pass K + update passes 2K per slot) at 128 B per wavefront, against one wavefront per SM and
+                # clock at the SM clock sampled during the run (ncu counts 1.08e9 load wavefronts incl. 8 % replays).
+                slots = 0.5 * (info["v2_slots_U"] + info["v2_slots_V"])
+                wf = slots * 3 * K * 8.0 / 128.0
+                sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+                wf_peak = sm_count * float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+                line["roofline"]["onchip"] = {"bound": "shared-memory wavefronts", "achieved": wf / (ms * 1e-3) / 1e9,
+                                              "peak": wf_peak / 1e9, "unit": "Gwavefronts/s",
+                                              "frac": wf / (ms * 1e-3) / wf_peak,
+                                              "note": "algorithmic gathers only; the sweep is bound by its per-column "
+                                                      "dependency chain (profiles/r01_final_sweep_ncu.md)"}
         line["e2e"] = e2e
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
