@@ -110,6 +110,7 @@ struct Side {
   // v2 (cluster) layout
   bool v2 = false;
   int cs = 8, tw = 0, rs = 0, npt2 = 0, v2div = 1;
+  int v2rpw = 1;                         // rows per compute warp of the cluster sweep (2: opt-in variant)
   int v2tm = 0;                          // tensor-memory variants of the cluster sweep (kernels_v2.cuh): 1 parked column, 2 residual in TMEM
   int64_t nsets = 0, tslots = 0;
   double* tvals = nullptr;
@@ -266,7 +267,7 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   int div = 2;                                                     // CTAs (of different clusters) per SM
   if (getenv("BNMTF_V2_DIV")) div = std::max(1, std::min(3, atoi(getenv("BNMTF_V2_DIV"))));
   if (npt2 == 18 && div == 3) div = 2;                             // 28 warps do not split in three
-  const int rs = wpc_full / div - 1;                                   // rows per set (warp 0 is the control warp)
+  int rs = wpc_full / div - 1;                                         // rows per set (warp 0 is the control warp)
   sd.v2div = div;
   sd.v3B = getenv("BNMTF_V3_B") ? atoi(getenv("BNMTF_V3_B")) : 0;   // blocked variant (kernels_v3.cuh): opt-in, the B = 1 sweep is faster since both use st.async exchanges
   if (sd.v3B != 2) sd.v3B = 0;
@@ -280,6 +281,10 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   }
   const int cs = v2_cs();
   if (cs != V2_CS) { sd.v3B = 0; sd.v2tm = 0; }
+  sd.v2rpw = 1;
+  if (npt2 == 20 && div == 2 && cs == V2_CS && sd.v3B == 0 && sd.v2tm == 0 && getenv("BNMTF_V2_RPW") && atoi(getenv("BNMTF_V2_RPW")) == 2) {
+    sd.v2rpw = 2; rs = (V2_RPW2_WARPS - 1) * 2;   // two rows per warp: 14 rows per CTA of 8 warps
+  }
   const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, cs) * sizeof(double);
   sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && sd.kf >= 3 && smem_vb <= 200 * 1024 && (sd.tw + V2_PAD) * 16 < 65536;
   if (sd.v2 && n > 0) {
@@ -777,10 +782,10 @@ static int launch_sweep_m(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int n
   FAIL("unsupported entries-per-thread %d", npt);
 }
 
-template <int NPT, int MODE, int DIV, int TMW = 0, int TMV = 1, int CS = V2_CS>
+template <int NPT, int MODE, int DIV, int TMW = 0, int TMV = 1, int CS = V2_CS, int RPW = 1>
 static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p_in, Side& sd, int method) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  auto kern = sweep2_kernel<NPT, MODE, CS, DIV, TMW, TMV>;
+  auto kern = sweep2_kernel<NPT, MODE, CS, DIV, TMW, TMV, RPW>;
   // tile ring: a fourth stage when it does not cost a resident CTA (228 KB per SM, 1 KB reserved per CTA, 227 KB per CTA)
   Sweep2Params p = p_in;
   const size_t smem3 = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, CS, p.K2, MODE == M_GIBBS, 3) * sizeof(double);
@@ -791,7 +796,7 @@ static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p_in, Side& sd, i
   if (getenv("BNMTF_V2_NST")) p.nst = atoi(getenv("BNMTF_V2_NST")) == 4 && smem4 <= 227 * 1024 ? 4 : 3;
   const size_t smem = p.nst == 4 ? smem4 : smem3;
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3((p.rs + 1) * 32);
+  cfg.blockDim = dim3((p.rs / RPW + 1) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
@@ -807,12 +812,12 @@ static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p_in, Side& sd, i
     // the occupancy query places one CTA per SM for a kernel that allocates tensor memory (15 clusters instead of 33);
     // the TM variant has the block size, registers and shared memory of the register variant and takes 128 of the 512
     // TMEM columns per CTA, so the register variant's answer holds for it
-    auto occ_kern = sweep2_kernel<NPT, MODE, CS, DIV, 0>;
+    auto occ_kern = sweep2_kernel<NPT, MODE, CS, DIV, 0, 1, RPW>;
     if (TMW > 0) CK(cudaFuncSetAttribute(occ_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaOccupancyMaxActiveClusters(&ncl, occ_kern, &cfg));
-    if (ncl < 1) FAIL("cluster sweep kernel does not fit (smem %zu bytes, %d threads)", smem, (p.rs + 1) * 32);
+    if (ncl < 1) FAIL("cluster sweep kernel does not fit (smem %zu bytes, %d threads)", smem, (p.rs / RPW + 1) * 32);
     if (getenv("BNMTF_V2_NCL")) ncl = std::max(1, atoi(getenv("BNMTF_V2_NCL")));   // experiments: clusters are independent, a larger grid queues
-    if (getenv("BNMTF_V2_DBG")) fprintf(stderr, "sweep2<%d,%d,%d,%d>: %d clusters of %d x %d threads, %zu bytes of shared memory, %d tile stages\n", NPT, MODE, DIV, TMW, ncl, CS, (p.rs + 1) * 32, smem, p.nst);
+    if (getenv("BNMTF_V2_DBG")) fprintf(stderr, "sweep2<%d,%d,%d,%d>: %d clusters of %d x %d threads, %zu bytes of shared memory, %d tile stages\n", NPT, MODE, DIV, TMW, ncl, CS, (p.rs / RPW + 1) * 32, smem, p.nst);
     sd.nclusters[method] = ncl;
   }
   const int ncl = (int)std::min<int64_t>(sd.nclusters[method], p.nsets);
@@ -842,6 +847,7 @@ static int launch_sweep2_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
     if (sd.npt2 != 12 || sd.v2div != 2) FAIL("BNMTF_V2_CS=16 serves 12 entries per lane and two CTAs per SM only (this side: %d, %d)", sd.npt2, sd.v2div);
     return launch_sweep2_t<12, MODE, 2, 0, 1, 16>(h, p, sd, method);
   }
+  if (sd.v2rpw == 2) return launch_sweep2_t<20, MODE, 2, 0, 1, V2_CS, 2>(h, p, sd, method);
   if (sd.v2tm == 1) return launch_sweep2_t<20, MODE, 2, V2_TM_WARPS, 1>(h, p, sd, method);
   if (sd.v2tm == 2) return launch_sweep2_t<20, MODE, 2, V2_TM_WARPS, 2>(h, p, sd, method);
   switch (sd.v2div) {
@@ -1516,7 +1522,7 @@ int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {  // out8: 16 values
   out8[4] = h->s[0].nslots; out8[5] = h->s[1].nslots; out8[6] = h->s[0].nnz; out8[7] = h->s[1].nnz;
   for (int q = 0; q < 2; ++q) {
     const Side& sd = h->s[q];
-    out8[8 + 4 * q] = sd.v2 ? (sd.v2tm ? 3 + sd.v2tm : (sd.v3B > 0 && !h->nmtf) ? 3 : 1) : 0;   // 1: cluster sweep, 3: blocked cluster sweep, 4: cluster sweep with the segments in tensor memory
+    out8[8 + 4 * q] = sd.v2 ? (sd.v2rpw == 2 ? 6 : sd.v2tm ? 3 + sd.v2tm : (sd.v3B > 0 && !h->nmtf) ? 3 : 1) : 0;   // 1: cluster sweep, 3: blocked cluster sweep, 4: cluster sweep with the segments in tensor memory
     out8[9 + 4 * q] = sd.v2 ? sd.npt2 : 0;
     out8[10 + 4 * q] = sd.v2 ? sd.rs : 0; out8[11 + 4 * q] = sd.v2 ? sd.tslots : 0;
   }

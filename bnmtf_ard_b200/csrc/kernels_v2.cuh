@@ -650,6 +650,191 @@ __device__ __forceinline__ void sweep2_compute_tme(const Sweep2Params& p, cg::cl
   }
 }
 
+// Compute warps owning RPW rows each (opt-in, BNMTF_V2_RPW=2 at 20 entries per lane).  Throughput of the sweep is rows
+// in flight per column time, and the rows in flight are bounded by the register file, a third of which goes to the ~30
+// registers every thread needs besides its residual entries.  Two rows per warp halve that overhead per row: 8 warps per
+// CTA at 128 registers carry 14 rows (12 warps at 80 registers: 11) and the two rows give the scheduler independent
+// load / FMA chains.  Same entries, operands and order of every sum per row: bitwise the results of one row per warp.
+template <int NPT, int MODE, int CS, int RS, int RPW>
+__device__ __forceinline__ void sweep2_compute_rows(const Sweep2Params& p, cg::cluster_group& cluster, int c, int cid, int nclusters,
+                                                    int warp, int lane, double* tiles, uint64_t* mbar, const double* delta, double* xs,
+                                                    double* part, double* proj, double* statp) {
+  constexpr int NV = (MODE == M_VB) ? 2 : 1;
+  constexpr int NTHR = (RS / RPW + 1) * 32;               // threads of the CTA
+  const int K = p.K, tw = p.tw, K2 = p.K2;
+  const int tile_doubles = (tw + V2_PAD) * NV;
+  const int total = 2 * K + K2;
+  const int NST = p.nst;
+  auto stg = [&](uint32_t g) -> uint32_t { return NST == 4 ? (g & 3u) : (g % 3u); };
+  auto phs = [&](uint32_t g) -> uint32_t { return (NST == 4 ? (g >> 2) : (g / 3u)) & 1u; };
+  const int r0 = (warp - 1) * RPW;                        // first row of the set owned by this warp
+  const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[4]);
+  uint32_t gseq = 0;
+  for (int set = cid; set < p.nsets; set += nclusters) {
+    const int rows_here = min(RS, p.n_loc - set * RS);
+    const int64_t seg0 = ((int64_t)(set * CS + c) * NPT) * RS * 32 + (int64_t)r0 * 32 + lane;
+    double e[RPW][NPT];
+    uint32_t cp[RPW][NPT / 2];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int64_t seg = seg0 + rr * 32;
+#pragma unroll
+      for (int n = 0; n < NPT; ++n) e[rr][n] = p.tvals[seg + (int64_t)n * RS * 32];
+#pragma unroll
+      for (int n = 0; n < NPT; n += 2) {
+        const uint32_t a = p.tcols[seg + (int64_t)n * RS * 32], b = p.tcols[seg + (int64_t)(n + 1) * RS * 32];
+        cp[rr][n / 2] = (a * (NV * 8)) | ((b * (NV * 8)) << 16);   // byte offsets inside a tile stage
+      }
+    }
+    for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
+      const size_t g = (size_t)(p.row0 + set * RS) * K + q;
+      xs[q] = p.Xval[g];
+    }
+    cluster_sync_all();   // xs visible; CTA 0 has finished with `part` of the previous set
+
+    // ---- residual of the segments: e = r - sum_k x_k y_k   (tile sequence 0 .. K-1)
+    for (int q = 0; q < K; ++q) {
+      const uint32_t g = gseq + q;
+      mbar_wait(&mbar[stg(g)], phs(g));
+      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
+      double xk[RPW];
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) xk[rr] = (r0 + rr < rows_here) ? xs[(r0 + rr) * K + q] : 0.0;
+#pragma unroll
+      for (int n = 0; n < NPT; ++n) {
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+          const uint32_t off = (n & 1) ? (cp[rr][n / 2] >> 16) : (cp[rr][n / 2] & 0xFFFFu);
+          e[rr][n] = fma(-xk[rr], *reinterpret_cast<const double*>(T + off), e[rr][n]);
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- the K column updates   (tile sequence K .. 2K-1)
+    double dprev[RPW];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) dprev[rr] = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const uint32_t g = gseq + K + k;
+      mbar_wait(&mbar[stg(g)], phs(g));
+      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
+      const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + stg(g + NST - 1) * tile_doubles);   // tile g-1
+      double s0[RPW], s1[RPW], s2[RPW];
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) s0[rr] = s1[rr] = s2[rr] = 0.0;
+      if (k > 0) {
+#pragma unroll
+        for (int n = 0; n < NPT; ++n) {
+#pragma unroll
+          for (int rr = 0; rr < RPW; ++rr) {
+            const uint32_t off = (n & 1) ? (cp[rr][n / 2] >> 16) : (cp[rr][n / 2] & 0xFFFFu);
+            e[rr][n] = fma(-dprev[rr], *reinterpret_cast<const double*>(Tp + off), e[rr][n]);
+            double v;
+            if (MODE == M_VB) { const double2 vv = *reinterpret_cast<const double2*>(T + off); v = vv.x; s1[rr] += vv.y; }
+            else v = *reinterpret_cast<const double*>(T + off);
+            s0[rr] = fma(v, v, s0[rr]);
+            s2[rr] = fma(e[rr][n], v, s2[rr]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < NPT; ++n) {
+#pragma unroll
+          for (int rr = 0; rr < RPW; ++rr) {
+            const uint32_t off = (n & 1) ? (cp[rr][n / 2] >> 16) : (cp[rr][n / 2] & 0xFFFFu);
+            double v;
+            if (MODE == M_VB) { const double2 vv = *reinterpret_cast<const double2*>(T + off); v = vv.x; s1[rr] += vv.y; }
+            else v = *reinterpret_cast<const double*>(T + off);
+            s0[rr] = fma(v, v, s0[rr]);
+            s2[rr] = fma(e[rr][n], v, s2[rr]);
+          }
+        }
+      }
+      named_arrive(1, NTHR);               // this warp no longer reads the tile of column k-1
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        const double s02 = warp_sum_pair(s0[rr], s2[rr], lane);   // lanes 0..15: sum of s0, lanes 16..31: sum of s2
+        if (MODE == M_VB) s1[rr] = warp_sum(s1[rr]);
+        if ((lane & 15) < CS) {   // lanes cc / 16 + cc send this row's partial sums to CTA cc (every CTA updates redundantly)
+          const uint32_t dst = map_to_cta(part_u32 + (uint32_t)(((k & 1) * CS + c) * RS + r0 + rr) * 32u, lane & 15);
+          const uint32_t bar = map_to_cta(rbar_u32 + (uint32_t)(k & 1) * 8u, lane & 15);
+          st_async_f64(dst + ((lane & 16) ? 16u : 0u), s02, bar);
+          if (MODE == M_VB && lane < 16) st_async_f64(dst + 8, s1[rr], bar);
+        }
+      }
+      __syncthreads();                     // the control warp of this CTA has written the deltas
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) dprev[rr] = (r0 + rr < rows_here) ? delta[r0 + rr] : 0.0;
+    }
+
+    // ---- last correction, then the row statistics of the final residual
+    {
+      const uint32_t g = gseq + 2 * K - 1;
+      const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
+      double* stat0 = cluster.map_shared_rank(statp, 0);      // CTA 0's copy, through DSMEM
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        double st0 = 0.0, st1 = 0.0, st2 = 0.0;
+#pragma unroll
+        for (int n = 0; n < NPT; ++n) {
+          const uint32_t off = (n & 1) ? (cp[rr][n / 2] >> 16) : (cp[rr][n / 2] & 0xFFFFu);
+          e[rr][n] = fma(-dprev[rr], *reinterpret_cast<const double*>(Tp + off), e[rr][n]);
+          const double rv = p.tvals[seg0 + rr * 32 + (int64_t)n * RS * 32];
+          st0 = fma(e[rr][n], e[rr][n], st0);
+          st1 += e[rr][n];
+          st2 = fma(rv - p.rmean, e[rr][n], st2);   // padded slots hold e == 0
+        }
+        st0 = warp_sum(st0); st1 = warp_sum(st1); st2 = warp_sum(st2);
+        if (lane == 0) {
+          double* dst = stat0 + ((size_t)c * RS + r0 + rr) * 4;
+          dst[0] = st0; dst[1] = st1; dst[2] = st2;
+        }
+      }
+    }
+    if (K2 > 0) {
+      // ---- projection epilogue: sum_j e_j Y2[l][j] over the segments, partials to CTA 0   (tiles 2K .. 2K+K2-1)
+      double* proj0 = cluster.map_shared_rank(proj, 0);
+      __syncthreads();
+      for (int q = 0; q < K2; ++q) {
+        const uint32_t g = gseq + 2 * K + q;
+        mbar_wait(&mbar[stg(g)], phs(g));
+        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+          double s = 0.0;
+#pragma unroll
+          for (int n = 0; n < NPT; ++n) {
+            const uint32_t off = (n & 1) ? (cp[rr][n / 2] >> 16) : (cp[rr][n / 2] & 0xFFFFu);
+            s = fma(e[rr][n], *reinterpret_cast<const double*>(T + off), s);
+          }
+          s = warp_sum(s);
+          if (lane == 0) proj0[((size_t)c * RS + r0 + rr) * K2 + q] = s;
+        }
+        __syncthreads();
+      }
+    }
+    cluster_sync_all();
+    if (c == 0) {
+      __syncthreads();
+      for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
+        const size_t g = (size_t)(p.row0 + set * RS) * K + q;
+        p.Xval[g] = xs[q];
+        if (MODE == M_VB) p.Xvar[g] = xs[(size_t)RS * K + q];
+        if (p.Xmu != nullptr) { p.Xmu[g] = xs[(size_t)2 * RS * K + q]; p.Xtau[g] = xs[(size_t)3 * RS * K + q]; }
+      }
+      for (int q = threadIdx.x; q < rows_here * K2; q += blockDim.x) {   // fixed-order sum of the CS projection partials
+        const int rr = q / K2, l = q - rr * K2;
+        double t = 0.0;
+        for (int cc = 0; cc < CS; ++cc) t += proj[((size_t)cc * RS + rr) * K2 + l];
+        p.proj_out[(size_t)(p.row0 + set * RS + rr) * K2 + l] = t;
+      }
+    }
+    gseq += total;
+    __syncthreads();   // xs / tiles are reused by the next set
+  }
+}
+
 // phase clocks of cluster 0 / CTA 0 (timing experiments: build with -DBNMTF_V2_PROF, run with BNMTF_V2_DBG=2)
 #ifdef BNMTF_V2_PROF
 #define P2_T0() long long t_prof = prof_on ? clock64() : 0
@@ -667,11 +852,12 @@ __device__ __forceinline__ void sweep2_compute_tme(const Sweep2Params& p, cg::cl
 #endif
 
 // TMW > 0: tensor-memory variants (TMW warps per CTA); TMV = 1: the gathered column is parked in TMEM, 2: the residual
-template <int NPT, int MODE, int CS, int DIV, int TMW = 0, int TMV = 1>
-__global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 32, DIV) sweep2_kernel(const Sweep2Params p) {
+constexpr int V2_RPW2_WARPS = 8;   // warps per CTA of the two-rows-per-warp variant (control warp + 7 x 2 rows)
+template <int NPT, int MODE, int CS, int DIV, int TMW = 0, int TMV = 1, int RPW = 1>
+__global__ void __launch_bounds__((TMW > 0 ? TMW : RPW > 1 ? V2_RPW2_WARPS : Sweep2Cfg<NPT>::WPC / DIV) * 32, DIV) sweep2_kernel(const Sweep2Params p) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  constexpr int RS = (TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) - 1;
-  constexpr int NTHR = (RS + 1) * 32;                     // threads of the CTA
+  constexpr int RS = ((TMW > 0 ? TMW : RPW > 1 ? V2_RPW2_WARPS : Sweep2Cfg<NPT>::WPC / DIV) - 1) * RPW;
+  constexpr int NTHR = (RS / RPW + 1) * 32;               // threads of the CTA
   static_assert(MODE != M_NP, "the NP updates run on the v1 kernel");
   cg::cluster_group cluster = cg::this_cluster();
   const int c = (int)cluster.block_rank();
@@ -893,6 +1079,9 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : Sweep2Cfg<NPT>::WPC / DIV) * 
       sweep2_compute_tm<NPT, MODE, CS, RS>(p, cluster, c, cid, nclusters, warp, lane, tiles, mbar, delta, xs, part, proj, statp, tm_base);
     if constexpr (TMW > 0 && TMV == 2)
       sweep2_compute_tme<NPT, MODE, CS, RS>(p, cluster, c, cid, nclusters, warp, lane, tiles, mbar, delta, xs, part, proj, statp, tm_base);
+  } else if (RPW > 1) {
+    if constexpr (RPW > 1)
+      sweep2_compute_rows<NPT, MODE, CS, RS, RPW>(p, cluster, c, cid, nclusters, warp, lane, tiles, mbar, delta, xs, part, proj, statp);
   } else {
     // =========================== compute warps ===========================
     const int r = warp - 1;                                 // row of the set owned by this warp

@@ -206,22 +206,25 @@ def test_cluster_kernel_is_selected():
 @pytest.mark.parametrize("cls_name", ["bnmf_gibbs", "nmf_icm", "bnmf_vb"])
 def test_tensor_memory_sweep_is_bitwise_the_register_sweep(cls_name, monkeypatch):
     """Row segments of 20 entries per lane run the cluster sweep that parks the gathered values of a column in tensor
-    memory (tcgen05.st / tcgen05.ld) instead of gathering them a second time for the rank-1 correction.  Same entries,
-    operands and summation orders: with BNMTF_V2_TM=0 (register variant) the same seeded run must end in the same bits."""
+    memory (tcgen05.st / tcgen05.ld) instead of gathering them a second time for the rank-1 correction (variant 1), keeps
+    the residual itself there (variant 2), or gives every warp two rows (BNMTF_V2_RPW=2, 14 rows per CTA).  Same entries,
+    operands and summation orders per row: the same seeded run must end in the bits of the default register variant."""
     import bnmtf_ard_b200 as pkg
     I, J, K, dens = SHAPES[11]
     R, M, _ = make_problem(99, I, J, K, dens, nonneg=True)
     hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0}
     outs = []
-    for tm in ("1", "2", "0"):
+    for tm, rpw in (("1", "1"), ("2", "1"), ("0", "2"), ("0", "1")):   # the last one is the default register variant
         monkeypatch.setenv("BNMTF_V2_TM", tm)
+        monkeypatch.setenv("BNMTF_V2_RPW", rpw)
         m = getattr(pkg, cls_name)(R, M, K, True, hyper)
         m.verbose = False
         np.random.seed(3)
         m.initialise("random")
         m.run(4)
         info = m._engine().layout_info()
-        assert info["v2_U"] == {"1": 4, "2": 5, "0": 1}[tm] and info["v2_npt_U"] == 20 and info["v2_rows_per_set_U"] == 11
+        assert info["v2_U"] == (6 if rpw == "2" else {"1": 4, "2": 5, "0": 1}[tm]) and info["v2_npt_U"] == 20
+        assert info["v2_rows_per_set_U"] == (14 if rpw == "2" else 11)
         if cls_name == "bnmf_gibbs":
             outs.append((m.all_U.copy(), m.all_V.copy(), np.asarray(m.all_tau).copy(), np.asarray(m.all_performances["MSE"])))
         elif cls_name == "nmf_icm":
