@@ -7,17 +7,20 @@
 //   * the residual of the RS x TW block (observed entries only) lives in registers,
 //     one warp per row segment;
 //   * column k of the other factor, restricted to the tile, is staged in shared
-//     memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier) through a 3-stage ring
-//     and gathered from there (entries are placed so that a half-warp hits 16
-//     distinct 8-byte banks);
-//   * the per-row partial sums of the CS tiles meet in CTA 0's shared memory through
-//     DSMEM stores; one warp of CTA 0 computes the RS updates of the column in
-//     parallel (lane = row) and pushes the RS deltas back into every CTA's shared
-//     memory; cluster barriers order the two exchanges;
+//     memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier) through a 3- or 4-stage
+//     ring and gathered from there (entries are placed so that a half-warp hits 16
+//     distinct 8-byte banks; padded slots read a zero of their own bank class);
+//   * the two per-row partial sums of a warp are reduced together (warp_sum_pair) and
+//     sent to EVERY CTA's record buffer by st.async with mbarrier completion; the
+//     control warp of each CTA sums the CS records in a fixed order and updates the RS
+//     rows redundantly (lane = row, bitwise identical in all CTAs) -- no cluster
+//     barrier and no cluster-scope fence per column;
 //   * the rank-1 correction of column k is folded into the accumulation loop of
 //     column k+1 ("lazy"), so nothing but e[] has to stay in registers.
-// L2 -> SM traffic drops from 192 GB to ~10 GB per sweep; the kernel becomes
-// shared-memory-gather bound.
+// L2 -> SM traffic drops from 192 GB to ~31 GB per sweep.  What bounds the kernel is
+// the per-column dependency chain (profiles/r01_final_sweep_ncu.md).  Opt-in variants
+// kept for reference, all bitwise equal to the default: tensor memory as a scratch
+// area (sweep2_compute_tm / _tme) and two rows per warp (sweep2_compute_rows).
 #pragma once
 #include <cooperative_groups.h>
 #include <cstdint>
