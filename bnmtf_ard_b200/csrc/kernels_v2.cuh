@@ -1012,11 +1012,9 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : RPW > 1 ? V2_RPW2_WARPS : Swe
           double ct, cm, vn = 0.0, x_new;
           if (p.dbg & 1) { x_new = x_old + 1e-3 * t3[0]; ct = cm = 0.0; }
           else if (MODE == M_GIBBS) {
-            Rng rng(uc.seed, uc.purpose, (uint64_t)grow, (uint32_t)k, uc.iteration);
-            rng.draw = 2;                    // Philox blocks 0 and 1 of this stream made the material
             ct = tau * t3[0];                                            // tauU, bnmf_gibbs.py:205
             const double num = -lam + tau * (t3[2] + x_old * t3[0]);     // numerator of muU, bnmf_gibbs.py:210
-            x_new = tn_draw_fast(num, ct, mat, rng, cm);
+            x_new = tn_draw_lazy(num, ct, mat, uc.seed, uc.purpose, (uint64_t)grow, (uint32_t)k, uc.iteration, cm);
           }
           else x_new = conditional_update<MODE>(t3, x_old, lam, tau, uc, (uint64_t)grow, k, 0.0, 0.0, 0.0, ct, cm, vn, acc_esd,
                                                 acc_q, acc_prior);

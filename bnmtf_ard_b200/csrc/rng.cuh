@@ -214,6 +214,52 @@ __device__ __forceinline__ double tn_draw_fast(double num, double prec, const Tn
   return (d >= 0.0 && isfinite(d)) ? d : 0.0;
 }
 
+// Out-of-line fallback of tn_draw_lazy: opens the row's Philox stream behind the prepared material (draw = 2) and
+// draws by the inverse CDF.  Everything it needs travels by value, so the caller keeps its state in registers.
+__device__ __noinline__ double2 tn_draw_fallback(double num, double prec, uint64_t seed, uint32_t purpose, uint64_t index,
+                                                 uint32_t k, uint32_t iteration) {
+  Rng rng(seed, purpose, index, k, iteration);
+  rng.draw = 2;                      // Philox blocks 0 and 1 of this stream made the material
+  double mu;
+  const double x = tn_draw_pre(num, prec, rng.u01(), rng, mu);
+  return make_double2(x, mu);
+}
+
+// tn_draw_fast for the cluster sweep's control warp, where the conditional sits on the per-column dependency chain:
+// the same draws bit for bit, but the fallback stream is only built when both proposals were rejected and neither it nor
+// the mean are ever addressed (tn_draw_fast hands `Rng&` / `double&` to an out-of-line function, which pins both in local
+// memory: five stores and a dependent load per conditional).
+__device__ __forceinline__ double tn_draw_lazy(double num, double prec, const TnPre& m, uint64_t seed, uint32_t purpose,
+                                               uint64_t index, uint32_t k, uint32_t iteration, double& mu_out) {
+  if (prec == 0.0) { mu_out = num / prec; return 0.0; }
+  const double sigma = rsqrt(prec);
+  double mu = num * sigma * sigma;
+  const double a = -num * sigma;
+  double x;      // z - a >= 0
+  bool ok;
+  if (!(a > TN_FAST_A0)) {
+    ok = (m.z1 >= a);
+    x = m.z1 - a;
+    if (!ok) { ok = (m.z2 >= a); x = m.z2 - a; }
+  } else {
+    const double sq = sqrt(a * a + 4.0);
+    const double alpha = 0.5 * (a + sq);
+    const double ia = a < 256.0 ? 0.5 * (sq - a) : 1.0 / alpha, am = a - alpha;
+    x = m.e1 * ia;
+    double t = am + x;
+    ok = (m.l1 >= t * t);
+    if (!ok) { x = m.e2 * ia; t = am + x; ok = (m.l2 >= t * t); }
+  }
+  double d = sigma * x;
+  d = (d >= 0.0 && isfinite(d)) ? d : 0.0;
+  if (!ok) {
+    const double2 fb = tn_draw_fallback(num, prec, seed, purpose, index, k, iteration);
+    d = fb.x; mu = fb.y;
+  }
+  mu_out = mu;
+  return d;
+}
+
 // ---- TN_vector_expectation / TN_vector_variance -----------------------------
 // truncated_normal_vector.py:53-73 (same operation order as the reference so
 // that the results agree to rounding): sigma = 1/sqrt(tau); x = -mu/sigma;
