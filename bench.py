@@ -365,7 +365,7 @@ def main():
             northstar_bytes = 2 * K * 16.125 * I * J
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                 "traffic": load_traffic(), "peak_source": peak_src,
-                                "kernel": {0: "sweep_kernel", 1: "sweep2_kernel", 3: "sweep3_kernel", 4: "sweep2_kernel (column parked in tensor memory)", 5: "sweep2_kernel (residual in tensor memory)", 6: "sweep2_kernel (two rows per warp)"}[int(info.get("v2_U", 0))],
+                                "kernel": {0: "sweep_kernel", 1: "sweep2_kernel", 3: "sweep3_kernel", 4: "sweep2_kernel (column parked in tensor memory)", 5: "sweep2_kernel (residual in tensor memory)", 6: "sweep2_kernel (two rows per warp)", 7: "sweep2la_kernel (pass one column ahead)"}[int(info.get("v2_U", 0))],
                                 "kernel_ms": ms, "kernel_share_of_step": (sweeps["ms_U"] + sweeps["ms_V"]) / (1e3 * dev_s),
                                 "north_star_equiv_gbs": northstar_bytes * value / 1e9,
                                 "north_star_equiv_frac": northstar_bytes * value / 1e9 / peak}

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
 #include "kernels_v3.cuh"
+#include "kernels_v2la.cuh"
 #include "kernels_nmtf.cuh"
 #include "kernels_kmeans.cuh"
 #include "kernels_summary.cuh"
@@ -110,6 +111,8 @@ struct Side {
   // v2 (cluster) layout
   bool v2 = false;
   int cs = 8, tw = 0, rs = 0, npt2 = 0, v2div = 1;
+  bool v2la = false;                     // look-ahead cluster sweep (kernels_v2la.cuh), opt-in
+  int ncl_la[4] = {0, 0, 0, 0};
   int v2rpw = 1;                         // rows per compute warp of the cluster sweep (2: opt-in variant)
   int v2tm = 0;                          // tensor-memory variants of the cluster sweep (kernels_v2.cuh): 1 parked column, 2 residual in TMEM
   int64_t nsets = 0, tslots = 0;
@@ -281,8 +284,9 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   }
   const int cs = v2_cs();
   if (cs != V2_CS) { sd.v3B = 0; sd.v2tm = 0; }
+  sd.v2la = npt2 == 20 && div == 2 && cs == V2_CS && sd.v3B == 0 && sd.v2tm == 0 && getenv("BNMTF_V2_LA") && atoi(getenv("BNMTF_V2_LA")) == 1;
   sd.v2rpw = 1;
-  if (npt2 == 20 && div == 2 && cs == V2_CS && sd.v3B == 0 && sd.v2tm == 0 && getenv("BNMTF_V2_RPW") && atoi(getenv("BNMTF_V2_RPW")) == 2) {
+  if (!sd.v2la && npt2 == 20 && div == 2 && cs == V2_CS && sd.v3B == 0 && sd.v2tm == 0 && getenv("BNMTF_V2_RPW") && atoi(getenv("BNMTF_V2_RPW")) == 2) {
     sd.v2rpw = 2; rs = (V2_RPW2_WARPS - 1) * 2;   // two rows per warp: 14 rows per CTA of 8 warps
   }
   const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, cs) * sizeof(double);
@@ -828,6 +832,36 @@ static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p_in, Side& sd, i
   return 0;
 }
 
+// look-ahead cluster sweep (kernels_v2la.cuh): 20 entries per lane, Gibbs / ICM, no projection epilogue
+template <int MODE>
+static int launch_sweep2la(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
+  auto kern = sweep2la_kernel<20, MODE, V2_CS>;
+  const size_t smem = sweep2la_smem_doubles(p.tw, p.rs, p.K, V2_CS, MODE == M_GIBBS) * sizeof(double);
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3((p.rs + 1) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = V2_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (sd.ncl_la[method] == 0) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg.gridDim = dim3(V2_CS * 128);
+    int ncl = 0;
+    CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
+    if (ncl < 1) FAIL("look-ahead cluster sweep does not fit (smem %zu bytes, %d threads)", smem, (p.rs + 1) * 32);
+    if (getenv("BNMTF_V2_DBG")) fprintf(stderr, "sweep2la<20,%d>: %d clusters of %d x %d threads, %zu bytes of shared memory\n", MODE, ncl, V2_CS, (p.rs + 1) * 32, smem);
+    sd.ncl_la[method] = ncl;
+  }
+  const int ncl = (int)std::min<int64_t>(sd.ncl_la[method], p.nsets);
+  if (ncl < 1) return 0;
+  cfg.gridDim = dim3(V2_CS * ncl);
+  CK(cudaLaunchKernelEx(&cfg, kern, p));
+  h->launches++;
+  return 0;
+}
+
 template <int MODE, int DIV>
 static int launch_sweep2_d(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
   switch (sd.npt2) {
@@ -1011,6 +1045,11 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
         case BNMTF_VB: rc = launch_sweep3_m<M_VB>(h, p, sd, method, &done3); break;
         default: FAIL("unknown method %d", method);
       }
+    }
+    if (!done3 && rc == 0 && sd.v2la && p.K2 == 0 && !h->nmtf && (method == BNMTF_GIBBS || method == BNMTF_ICM)) {
+      p.Ykm = sd.ysrc;
+      rc = method == BNMTF_GIBBS ? launch_sweep2la<M_GIBBS>(h, p, sd, method) : launch_sweep2la<M_ICM>(h, p, sd, method);
+      done3 = true;
     }
     if (!done3 && rc == 0) {
       p.Ykm = sd.ysrc;
@@ -1522,7 +1561,7 @@ int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {  // out8: 16 values
   out8[4] = h->s[0].nslots; out8[5] = h->s[1].nslots; out8[6] = h->s[0].nnz; out8[7] = h->s[1].nnz;
   for (int q = 0; q < 2; ++q) {
     const Side& sd = h->s[q];
-    out8[8 + 4 * q] = sd.v2 ? (sd.v2rpw == 2 ? 6 : sd.v2tm ? 3 + sd.v2tm : (sd.v3B > 0 && !h->nmtf) ? 3 : 1) : 0;   // 1: cluster sweep, 3: blocked cluster sweep, 4: cluster sweep with the segments in tensor memory
+    out8[8 + 4 * q] = sd.v2 ? (sd.v2la ? 7 : sd.v2rpw == 2 ? 6 : sd.v2tm ? 3 + sd.v2tm : (sd.v3B > 0 && !h->nmtf) ? 3 : 1) : 0;   // 1: cluster sweep, 3: blocked cluster sweep, 4: cluster sweep with the segments in tensor memory
     out8[9 + 4 * q] = sd.v2 ? sd.npt2 : 0;
     out8[10 + 4 * q] = sd.v2 ? sd.rs : 0; out8[11 + 4 * q] = sd.v2 ? sd.tslots : 0;
   }

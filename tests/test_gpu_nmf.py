@@ -236,6 +236,21 @@ def test_tensor_memory_sweep_is_bitwise_the_register_sweep(cls_name, monkeypatch
             assert np.array_equal(a, b)
 
 
+def test_lookahead_sweep_vs_oracle(monkeypatch):
+    """BNMTF_V2_LA=1: the cluster sweep whose pass runs one column ahead of the conditionals (kernels_v2la.cuh: the pass of
+    column k needs delta_{k-2} only, the control warp forms sum e y_k = h_k - delta_{k-1} g_k).  Same conditionals in the
+    same order: the Gibbs replay and the ICM trajectory must match the oracle like the default sweep does."""
+    from bnmtf_ard_b200._engine import NMFEngine
+    monkeypatch.setenv("BNMTF_V2_LA", "1")
+    I, J, K, dens = SHAPES[11]
+    R, M, _ = make_problem(1, I, J, K, dens)
+    eng = NMFEngine(R, M, K)
+    assert eng.layout_info()["v2_U"] == 7
+    eng.close()
+    test_gibbs_iteration_vs_oracle(SHAPES[11], monkeypatch)
+    test_icm_vb_np_iterations_vs_oracle(SHAPES[11])
+
+
 def test_streamed_rows_are_selected_and_column_params_match():
     """Rows beyond 16384 observed entries: the row sweep streams the residual from global memory; the single-column
     conditionals (tauU / muU of the class API) go through the same kernel and must match the oracle."""
