@@ -6,12 +6,20 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SRC = os.path.join(PKG, "csrc", "engine.cu")
-DEPS = [SRC] + [os.path.join(PKG, "csrc", f) for f in ("kernels.cuh", "kernels_v2.cuh", "kernels_v3.cuh", "kernels_nmtf.cuh", "kernels_kmeans.cuh", "kernels_summary.cuh", "kernels_batch.cuh", "kernels_long.cuh", "rng.cuh",
-                                                        "engine_nmtf.inc", "engine_summary.inc", "engine_batch.inc")] + [os.path.join(ROOT, "include", "bnmtf_b200.h")]
+
+
+def deps():
+    """Every header / include file of the engine, globbed so that a new one cannot be forgotten."""
+    import glob
+    csrc = os.path.join(PKG, "csrc")
+    return sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh")) + glob.glob(os.path.join(csrc, "*.inc"))
+                  + glob.glob(os.path.join(ROOT, "include", "*.h")))
+
+
 LIB = os.path.join(PKG, "libbnmtf_b200.so")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-split-compile", "0"]
 
 
 def find_nvcc():
@@ -25,7 +33,7 @@ def up_to_date():
     if not os.path.exists(LIB):
         return False
     t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(d) <= t for d in DEPS if os.path.exists(d))
+    return all(os.path.getmtime(d) <= t for d in deps())
 
 
 def build(force=False, verbose=False):

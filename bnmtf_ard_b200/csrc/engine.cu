@@ -15,8 +15,6 @@
 #include "../../include/bnmtf_b200.h"
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
-#include "kernels_v3.cuh"
-#include "kernels_v2la.cuh"
 #include "kernels_nmtf.cuh"
 #include "kernels_kmeans.cuh"
 #include "kernels_summary.cuh"
@@ -111,10 +109,6 @@ struct Side {
   // v2 (cluster) layout
   bool v2 = false;
   int cs = 8, tw = 0, rs = 0, npt2 = 0, v2div = 1;
-  bool v2la = false;                     // look-ahead cluster sweep (kernels_v2la.cuh), opt-in
-  int ncl_la[4] = {0, 0, 0, 0};
-  int v2rpw = 1;                         // rows per compute warp of the cluster sweep (2: opt-in variant)
-  int v2tm = 0;                          // tensor-memory variants of the cluster sweep (kernels_v2.cuh): 1 parked column, 2 residual in TMEM
   int64_t nsets = 0, tslots = 0;
   double* tvals = nullptr;
   uint16_t* tcols = nullptr;
@@ -122,9 +116,6 @@ struct Side {
   bool long_rows = false;      // rows beyond the register-resident configurations: residual in global scratch (kernels_long.cuh)
   double* escr = nullptr;      // [nslots]
   int occ_long[4] = {0, 0, 0, 0};
-  int v3B = 0;                 // columns per cluster exchange of the blocked sweep (0: v2 kernel)
-  int nclusters3[4] = {0, 0, 0, 0};
-  bool v3fit[4] = {false, false, false, false};
   // factor geometry: kf columns; sweeps on this side gather from ysrc ([kf][ysrc_ld][NV])
   int kf = 0;
   const double* ysrc = nullptr;
@@ -133,12 +124,6 @@ struct Side {
   double* lamk = nullptr;    // ARD prior of this side's columns (not owned for NMF)
 };
 constexpr int V2_CS = 8;
-// experiments: BNMTF_V2_CS=16 runs the cluster sweep on (non-portable) clusters of 16 CTAs -- tiles half as wide, segments
-// of 12 entries per lane, 15 rows per CTA; only the 12-entry instantiation exists for it
-static int v2_cs() {
-  static const int cs = (getenv("BNMTF_V2_CS") && atoi(getenv("BNMTF_V2_CS")) == 16) ? 16 : V2_CS;
-  return cs;
-}
 }  // namespace
 
 struct bnmtf_nmf_s {
@@ -210,7 +195,7 @@ static void choose_team(int64_t maxlen, int* tpr, int* npt) {
   *npt = n;
 }
 
-static int v2_tile_width(int64_t m) { return (int)roundup((m + v2_cs() - 1) / v2_cs(), 32); }
+static int v2_tile_width(int64_t m) { return (int)roundup((m + V2_CS - 1) / V2_CS, 32); }
 
 // phase 1: observed entries per row and the longest (row, tile) segment of a dense block
 static int count_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld) {
@@ -267,28 +252,10 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   if (npt2 > 8 && npt2 < 12) npt2 = 12;
   if (npt2 > 12 && npt2 < 16) npt2 = 16;
   const int wpc_full = npt2 <= 16 ? 32 : (npt2 <= 18 ? 28 : Sweep2Cfg<20>::WPC);   // Sweep2Cfg<NPT>::WPC
-  int div = 2;                                                     // CTAs (of different clusters) per SM
-  if (getenv("BNMTF_V2_DIV")) div = std::max(1, std::min(3, atoi(getenv("BNMTF_V2_DIV"))));
-  if (npt2 == 18 && div == 3) div = 2;                             // 28 warps do not split in three
+  const int div = 2;                                               // CTAs (of different clusters) per SM: measured best (1 and 3: r01 profiles)
   int rs = wpc_full / div - 1;                                         // rows per set (warp 0 is the control warp)
   sd.v2div = div;
-  sd.v3B = getenv("BNMTF_V3_B") ? atoi(getenv("BNMTF_V3_B")) : 0;   // blocked variant (kernels_v3.cuh): opt-in, the B = 1 sweep is faster since both use st.async exchanges
-  if (sd.v3B != 2) sd.v3B = 0;
-  // 20 entries per lane, opt-in (BNMTF_V2_TM=1): the TM variant parks the gathered values of a column in tensor memory
-  // instead of gathering them again for the rank-1 correction (same packed layout, bitwise the same results; measured
-  // equal in speed at 20000 x 20000: the sweep is bound by its per-column exchange, not by the gathers)
-  sd.v2tm = 0;
-  if (npt2 == 20 && div == 2 && rs == V2_TM_WARPS - 1 && sd.v3B == 0 && getenv("BNMTF_V2_TM")) {
-    const int v = atoi(getenv("BNMTF_V2_TM"));
-    if (v == 1 || v == 2) sd.v2tm = v;
-  }
-  const int cs = v2_cs();
-  if (cs != V2_CS) { sd.v3B = 0; sd.v2tm = 0; }
-  sd.v2la = npt2 == 20 && div == 2 && cs == V2_CS && sd.v3B == 0 && sd.v2tm == 0 && getenv("BNMTF_V2_LA") && atoi(getenv("BNMTF_V2_LA")) == 1;
-  sd.v2rpw = 1;
-  if (!sd.v2la && npt2 == 20 && div == 2 && cs == V2_CS && sd.v3B == 0 && sd.v2tm == 0 && getenv("BNMTF_V2_RPW") && atoi(getenv("BNMTF_V2_RPW")) == 2) {
-    sd.v2rpw = 2; rs = (V2_RPW2_WARPS - 1) * 2;   // two rows per warp: 14 rows per CTA of 8 warps
-  }
+  const int cs = V2_CS;
   const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, cs) * sizeof(double);
   sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && sd.kf >= 3 && smem_vb <= 200 * 1024 && (sd.tw + V2_PAD) * 16 < 65536;
   if (sd.v2 && n > 0) {
@@ -739,15 +706,6 @@ static int refresh_km(bnmtf_nmf_s* h, int side, int method) {
   else
     rm_to_km_kernel<1><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, sd.kf, sd.ld);
   h->launches++;
-  // the blocked cluster sweep of the other side reads the block-major copy
-  const Side& consumer = h->s[1 - side];
-  if (consumer.v2 && consumer.v3B > 0 && !h->nmtf && method != BNMTF_NP) {
-    const int B = consumer.v3B;
-    dim3 g3((unsigned)((sd.ld + 255) / 256), (unsigned)((sd.kf + B - 1) / B));
-    if (method == BNMTF_VB && B == 2) rm_to_kmB_kernel<2, 2><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.km3, sd.n_glob, sd.kf, sd.ld);
-    else if (B == 2) rm_to_kmB_kernel<1, 2><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.km3, sd.n_glob, sd.kf, sd.ld);
-    h->launches++;
-  }
   return 0;
 }
 
@@ -786,10 +744,10 @@ static int launch_sweep_m(bnmtf_nmf_s* h, const SweepParams& p, int n_loc, int n
   FAIL("unsupported entries-per-thread %d", npt);
 }
 
-template <int NPT, int MODE, int DIV, int TMW = 0, int TMV = 1, int CS = V2_CS, int RPW = 1>
+template <int NPT, int MODE, int DIV, int CS = V2_CS>
 static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p_in, Side& sd, int method) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  auto kern = sweep2_kernel<NPT, MODE, CS, DIV, TMW, TMV, RPW>;
+  auto kern = sweep2_kernel<NPT, MODE, CS, DIV>;
   // tile ring: a fourth stage when it does not cost a resident CTA (228 KB per SM, 1 KB reserved per CTA, 227 KB per CTA)
   Sweep2Params p = p_in;
   const size_t smem3 = sweep2_smem_doubles(p.tw, NV, p.rs, p.K, CS, p.K2, MODE == M_GIBBS, 3) * sizeof(double);
@@ -800,7 +758,7 @@ static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p_in, Side& sd, i
   if (getenv("BNMTF_V2_NST")) p.nst = atoi(getenv("BNMTF_V2_NST")) == 4 && smem4 <= 227 * 1024 ? 4 : 3;
   const size_t smem = p.nst == 4 ? smem4 : smem3;
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3((p.rs / RPW + 1) * 32);
+  cfg.blockDim = dim3((p.rs + 1) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
@@ -813,50 +771,15 @@ static int launch_sweep2_t(bnmtf_nmf_s* h, const Sweep2Params& p_in, Side& sd, i
     if (CS > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cfg.gridDim = dim3(CS * 64);
     int ncl = 0;
-    // the occupancy query places one CTA per SM for a kernel that allocates tensor memory (15 clusters instead of 33);
-    // the TM variant has the block size, registers and shared memory of the register variant and takes 128 of the 512
-    // TMEM columns per CTA, so the register variant's answer holds for it
-    auto occ_kern = sweep2_kernel<NPT, MODE, CS, DIV, 0, 1, RPW>;
-    if (TMW > 0) CK(cudaFuncSetAttribute(occ_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaOccupancyMaxActiveClusters(&ncl, occ_kern, &cfg));
-    if (ncl < 1) FAIL("cluster sweep kernel does not fit (smem %zu bytes, %d threads)", smem, (p.rs / RPW + 1) * 32);
+    CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
+    if (ncl < 1) FAIL("cluster sweep kernel does not fit (smem %zu bytes, %d threads)", smem, (p.rs + 1) * 32);
     if (getenv("BNMTF_V2_NCL")) ncl = std::max(1, atoi(getenv("BNMTF_V2_NCL")));   // experiments: clusters are independent, a larger grid queues
-    if (getenv("BNMTF_V2_DBG")) fprintf(stderr, "sweep2<%d,%d,%d,%d>: %d clusters of %d x %d threads, %zu bytes of shared memory, %d tile stages\n", NPT, MODE, DIV, TMW, ncl, CS, (p.rs / RPW + 1) * 32, smem, p.nst);
+    if (getenv("BNMTF_V2_DBG")) fprintf(stderr, "sweep2<%d,%d,%d>: %d clusters of %d x %d threads, %zu bytes of shared memory, %d tile stages\n", NPT, MODE, DIV, ncl, CS, (p.rs + 1) * 32, smem, p.nst);
     sd.nclusters[method] = ncl;
   }
   const int ncl = (int)std::min<int64_t>(sd.nclusters[method], p.nsets);
   if (ncl < 1) return 0;
   cfg.gridDim = dim3(CS * ncl);
-  CK(cudaLaunchKernelEx(&cfg, kern, p));
-  h->launches++;
-  return 0;
-}
-
-// look-ahead cluster sweep (kernels_v2la.cuh): 20 entries per lane, Gibbs / ICM, no projection epilogue
-template <int MODE>
-static int launch_sweep2la(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
-  auto kern = sweep2la_kernel<20, MODE, V2_CS>;
-  const size_t smem = sweep2la_smem_doubles(p.tw, p.rs, p.K, V2_CS, MODE == M_GIBBS) * sizeof(double);
-  cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3((p.rs + 1) * 32);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = h->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = V2_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  if (sd.ncl_la[method] == 0) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    cfg.gridDim = dim3(V2_CS * 128);
-    int ncl = 0;
-    CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
-    if (ncl < 1) FAIL("look-ahead cluster sweep does not fit (smem %zu bytes, %d threads)", smem, (p.rs + 1) * 32);
-    if (getenv("BNMTF_V2_DBG")) fprintf(stderr, "sweep2la<20,%d>: %d clusters of %d x %d threads, %zu bytes of shared memory\n", MODE, ncl, V2_CS, (p.rs + 1) * 32, smem);
-    sd.ncl_la[method] = ncl;
-  }
-  const int ncl = (int)std::min<int64_t>(sd.ncl_la[method], p.nsets);
-  if (ncl < 1) return 0;
-  cfg.gridDim = dim3(V2_CS * ncl);
   CK(cudaLaunchKernelEx(&cfg, kern, p));
   h->launches++;
   return 0;
@@ -869,7 +792,7 @@ static int launch_sweep2_d(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
     case 8: return launch_sweep2_t<8, MODE, DIV>(h, p, sd, method);
     case 12: return launch_sweep2_t<12, MODE, DIV>(h, p, sd, method);
     case 16: return launch_sweep2_t<16, MODE, DIV>(h, p, sd, method);
-    case 18: return launch_sweep2_t<18, MODE, (DIV == 3 ? 2 : DIV)>(h, p, sd, method);
+    case 18: return launch_sweep2_t<18, MODE, DIV>(h, p, sd, method);
     case 20: return launch_sweep2_t<20, MODE, DIV>(h, p, sd, method);
   }
   FAIL("unsupported v2 entries-per-lane %d", sd.npt2);
@@ -877,74 +800,7 @@ static int launch_sweep2_d(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
 
 template <int MODE>
 static int launch_sweep2_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method) {
-  if (sd.cs == 16) {
-    if (sd.npt2 != 12 || sd.v2div != 2) FAIL("BNMTF_V2_CS=16 serves 12 entries per lane and two CTAs per SM only (this side: %d, %d)", sd.npt2, sd.v2div);
-    return launch_sweep2_t<12, MODE, 2, 0, 1, 16>(h, p, sd, method);
-  }
-  if (sd.v2rpw == 2) return launch_sweep2_t<20, MODE, 2, 0, 1, V2_CS, 2>(h, p, sd, method);
-  if (sd.v2tm == 1) return launch_sweep2_t<20, MODE, 2, V2_TM_WARPS, 1>(h, p, sd, method);
-  if (sd.v2tm == 2) return launch_sweep2_t<20, MODE, 2, V2_TM_WARPS, 2>(h, p, sd, method);
-  switch (sd.v2div) {
-    case 1: return launch_sweep2_d<MODE, 1>(h, p, sd, method);
-    case 2: return launch_sweep2_d<MODE, 2>(h, p, sd, method);
-    case 3: return launch_sweep2_d<MODE, 3>(h, p, sd, method);
-  }
-  FAIL("bad v2 block divisor %d", sd.v2div);
-}
-
-template <int NPT, int MODE, int DIV, int B>
-static int launch_sweep3_t(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method, bool* fits) {
-  constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  auto kern = sweep3_kernel<NPT, MODE, V2_CS, DIV, B>;
-  const size_t smem = sweep3_layout(p.tw, NV, p.rs, p.K, V2_CS, B, Sweep3Rec<B, MODE>::NVAL, MODE == M_VB, p.Xmu != nullptr, MODE == M_GIBBS).total *
-                      sizeof(double);
-  *fits = smem <= (size_t)(227 * 1024) / DIV - 1024;
-  if (!*fits) return 0;
-  cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3((p.rs + 1) * 32);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = h->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = V2_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  if (sd.nclusters3[method] == 0) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    cfg.gridDim = dim3(V2_CS * 128);
-    int ncl = 0;
-    CK(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
-    if (ncl < 1) { *fits = false; return 0; }
-    sd.nclusters3[method] = ncl;
-  }
-  const int ncl = (int)std::min<int64_t>(sd.nclusters3[method], p.nsets);
-  if (ncl < 1) return 0;
-  cfg.gridDim = dim3(V2_CS * ncl);
-  CK(cudaLaunchKernelEx(&cfg, kern, p));
-  h->launches++;
-  return 0;
-}
-
-template <int MODE, int DIV, int B>
-static int launch_sweep3_d(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method, bool* fits) {
-  switch (sd.npt2) {
-    case 4: return launch_sweep3_t<4, MODE, DIV, B>(h, p, sd, method, fits);
-    case 8: return launch_sweep3_t<8, MODE, DIV, B>(h, p, sd, method, fits);
-    case 12: return launch_sweep3_t<12, MODE, DIV, B>(h, p, sd, method, fits);
-    case 16: return launch_sweep3_t<16, MODE, DIV, B>(h, p, sd, method, fits);
-    case 18: return launch_sweep3_t<18, MODE, DIV, B>(h, p, sd, method, fits);
-    case 20: return launch_sweep3_t<20, MODE, DIV, B>(h, p, sd, method, fits);
-  }
-  *fits = false;
-  return 0;
-}
-
-// blocked cluster sweep; *fits = false (and nothing launched) when the configuration does not fit
-template <int MODE>
-static int launch_sweep3_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int method, bool* fits) {
-  *fits = false;
-  if (sd.v3B == 2 && sd.v2div == 2) return launch_sweep3_d<MODE, 2, 2>(h, p, sd, method, fits);
-  if (sd.v3B == 2 && sd.v2div == 1) return launch_sweep3_d<MODE, 1, 2>(h, p, sd, method, fits);
-  return 0;
+  return launch_sweep2_d<MODE, 2>(h, p, sd, method);
 }
 
 // argument block of the row-team sweep (v1 layout) on `side`
@@ -1035,30 +891,12 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
       p.prof = prof_buf;
       bnmtf_prof_last = prof_buf;
     }
-    bool done3 = false;
     rc = 0;
-    if (sd.v3B > 0 && !h->nmtf) {
-      p.Ykm = h->s[1 - side].km3;
-      switch (method) {
-        case BNMTF_GIBBS: rc = launch_sweep3_m<M_GIBBS>(h, p, sd, method, &done3); break;
-        case BNMTF_ICM: rc = launch_sweep3_m<M_ICM>(h, p, sd, method, &done3); break;
-        case BNMTF_VB: rc = launch_sweep3_m<M_VB>(h, p, sd, method, &done3); break;
-        default: FAIL("unknown method %d", method);
-      }
-    }
-    if (!done3 && rc == 0 && sd.v2la && p.K2 == 0 && !h->nmtf && (method == BNMTF_GIBBS || method == BNMTF_ICM)) {
-      p.Ykm = sd.ysrc;
-      rc = method == BNMTF_GIBBS ? launch_sweep2la<M_GIBBS>(h, p, sd, method) : launch_sweep2la<M_ICM>(h, p, sd, method);
-      done3 = true;
-    }
-    if (!done3 && rc == 0) {
-      p.Ykm = sd.ysrc;
-      switch (method) {
-        case BNMTF_GIBBS: rc = launch_sweep2_m<M_GIBBS>(h, p, sd, method); break;
-        case BNMTF_ICM: rc = launch_sweep2_m<M_ICM>(h, p, sd, method); break;
-        case BNMTF_VB: rc = launch_sweep2_m<M_VB>(h, p, sd, method); break;
-        default: FAIL("unknown method %d", method);
-      }
+    switch (method) {
+      case BNMTF_GIBBS: rc = launch_sweep2_m<M_GIBBS>(h, p, sd, method); break;
+      case BNMTF_ICM: rc = launch_sweep2_m<M_ICM>(h, p, sd, method); break;
+      case BNMTF_VB: rc = launch_sweep2_m<M_VB>(h, p, sd, method); break;
+      default: FAIL("unknown method %d", method);
     }
   } else {
     SweepParams p{};
@@ -1561,7 +1399,7 @@ int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {  // out8: 16 values
   out8[4] = h->s[0].nslots; out8[5] = h->s[1].nslots; out8[6] = h->s[0].nnz; out8[7] = h->s[1].nnz;
   for (int q = 0; q < 2; ++q) {
     const Side& sd = h->s[q];
-    out8[8 + 4 * q] = sd.v2 ? (sd.v2la ? 7 : sd.v2rpw == 2 ? 6 : sd.v2tm ? 3 + sd.v2tm : (sd.v3B > 0 && !h->nmtf) ? 3 : 1) : 0;   // 1: cluster sweep, 3: blocked cluster sweep, 4: cluster sweep with the segments in tensor memory
+    out8[8 + 4 * q] = sd.v2 ? 1 : 0;   // 1: cluster sweep
     out8[9 + 4 * q] = sd.v2 ? sd.npt2 : 0;
     out8[10 + 4 * q] = sd.v2 ? sd.rs : 0; out8[11 + 4 * q] = sd.v2 ? sd.tslots : 0;
   }

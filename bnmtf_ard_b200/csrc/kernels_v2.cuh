@@ -18,9 +18,9 @@
 //   * the rank-1 correction of column k is folded into the accumulation loop of
 //     column k+1 ("lazy"), so nothing but e[] has to stay in registers.
 // L2 -> SM traffic drops from 192 GB to ~31 GB per sweep.  What bounds the kernel is
-// the per-column dependency chain (profiles/r01_final_sweep_ncu.md).  Opt-in variants
-// kept for reference, all bitwise equal to the default: tensor memory as a scratch
-// area (sweep2_compute_tm / _tme) and two rows per warp (sweep2_compute_rows).
+// the per-column dependency chain (profiles/r01_final_sweep_ncu.md).  The variants measured
+// slower in round 1 (tensor memory as a scratch area, two rows per warp, clusters of 16,
+// the look-ahead pass) are recorded in profiles/r01_final_sweep_ncu.md and were removed.
 #pragma once
 #include <cooperative_groups.h>
 #include <cstdint>
@@ -193,7 +193,7 @@ struct Sweep2Params {
 // columns of prepared random material kept in shared memory (Gibbs): one round of 32/rs columns ahead of the updates
 __host__ __device__ constexpr int sweep2_rnd_window(int rs) { return (1 + 2 * ((32 / rs) < 1 ? 1 : (32 / rs))) <= 8 ? 8 : 16; }
 __host__ __device__ inline size_t sweep2_smem_doubles(int tw, int nv, int rs, int K, int cs, int K2 = 0, bool gibbs = false, int nst = 3) {
-  return (size_t)nst * (tw + V2_PAD) * nv + 8 /*mbarrier slots: 0-3 tile stages, 4-5 record buffers, 7 TMEM base*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ +
+  return (size_t)nst * (tw + V2_PAD) * nv + 8 /*mbarrier slots: 0-3 tile stages, 4-5 record buffers*/ + rs + 1 /*delta*/ + (size_t)4 * rs * K /*xs,xvar,xmu,xtau*/ +
          (size_t)2 * cs * rs * 4 /*part, double buffered*/ + (size_t)cs * rs * K2 /*projection partials*/ +
          (size_t)cs * rs * 4 /*row-statistics partials*/ + (gibbs ? (size_t)sweep2_rnd_window(rs) * rs * 6 : 0) /*random material*/;
 }
@@ -239,605 +239,6 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 
-// ---- tensor memory (TMEM) as a per-warp scratch area -------------------------------------------------------------
-// The TM variant of the cluster sweep keeps the residual segments in tensor memory instead of registers: TMEM is a
-// second 256 KB on-chip array per SM that only tcgen05 instructions reach, idle in a kernel without MMAs.  A warp may
-// touch the 32 TMEM lanes of its quarter (warp % 4); its segment is NPT fp64 values per lane = 2 * NPT 32-bit columns.
-// Measured (tools/ubench/tmem.cu): a 20-double-per-lane round trip (tcgen05.ld + tcgen05.st) of 12 warps takes ~300
-// cycles per SM, i.e. ~200 B/cycle/SM each way, next to the shared-memory pipe the gathers use.
-struct TmChunk {          // 8 columns = 4 doubles per lane
-  uint32_t r[8];
-  __device__ __forceinline__ double get(int i) const { return __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]); }
-  __device__ __forceinline__ void set(int i, double v) { r[2 * i] = (uint32_t)__double2loint(v); r[2 * i + 1] = (uint32_t)__double2hiint(v); }
-};
-__device__ __forceinline__ void tm_ld8(uint32_t taddr, TmChunk& ch) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(ch.r[0]), "=r"(ch.r[1]), "=r"(ch.r[2]), "=r"(ch.r[3]), "=r"(ch.r[4]), "=r"(ch.r[5]), "=r"(ch.r[6]), "=r"(ch.r[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tm_st8(uint32_t taddr, const TmChunk& ch) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(ch.r[0]), "r"(ch.r[1]),
-               "r"(ch.r[2]), "r"(ch.r[3]), "r"(ch.r[4]), "r"(ch.r[5]), "r"(ch.r[6]), "r"(ch.r[7])
-               : "memory");
-}
-// the chunk is an in/out operand so that no use of its registers is scheduled above the wait
-__device__ __forceinline__ void tm_wait_ld(TmChunk& ch) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(ch.r[0]), "+r"(ch.r[1]), "+r"(ch.r[2]), "+r"(ch.r[3]), "+r"(ch.r[4]), "+r"(ch.r[5]), "+r"(ch.r[6]), "+r"(ch.r[7])
-               :
-               : "memory");
-}
-__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-constexpr int V2_TM_COLS = 128;   // TMEM columns per CTA: 3 warps per lane quarter x 40 columns (two CTAs per SM: 256 of 512)
-constexpr int V2_TM_WARPS = 12;   // warps per CTA of the TM variant = Sweep2Cfg<20>::WPC / 2 (same packed layout)
-#ifndef BNMTF_V2_TM_DB
-#define BNMTF_V2_TM_DB 1            // 1: the next chunk's tcgen05.ld is in flight while the current chunk is used
-#endif
-
-// Compute warps of the TM variant.  The register variant gathers column k-1 of the other factor a second time when it
-// folds the rank-1 correction of column k-1 into the pass of column k (the values cannot stay in registers: 40 more
-// per thread).  Here the gathered values of a column are parked in tensor memory (one tcgen05.st per 4 entries) and
-// read back in the next pass (tcgen05.ld, the next chunk's load in flight while the current chunk is used): one
-// shared-memory gather per entry and column in the update passes instead of two.  The residual stays in registers;
-// entries, operands and the order of every sum are those of the register variant, so the results are bitwise equal.
-template <int NPT, int MODE, int CS, int RS>
-__device__ __forceinline__ void sweep2_compute_tm(const Sweep2Params& p, cg::cluster_group& cluster, int c, int cid, int nclusters,
-                                                  int warp, int lane, double* tiles, uint64_t* mbar, const double* delta, double* xs,
-                                                  double* part, double* proj, double* statp, uint32_t tm_base) {
-  constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  constexpr int NCH = NPT / 4;
-  static_assert(NPT % 4 == 0, "TMEM chunks hold 4 entries");
-  const int K = p.K, tw = p.tw, K2 = p.K2;
-  const int tile_doubles = (tw + V2_PAD) * NV;
-  const int total = 2 * K + K2;
-  const int NST = p.nst;
-  auto stg = [&](uint32_t g) -> uint32_t { return NST == 4 ? (g & 3u) : (g % 3u); };
-  auto phs = [&](uint32_t g) -> uint32_t { return (NST == 4 ? (g >> 2) : (g / 3u)) & 1u; };
-  const int r = warp - 1;                                 // row of the set owned by this warp
-  const uint32_t tm = tm_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)(NPT * 2);
-  double* stat0 = cluster.map_shared_rank(statp, 0);      // CTA 0's copy, through DSMEM
-  const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[4]);
-  uint32_t gseq = 0;
-  for (int set = cid; set < p.nsets; set += nclusters) {
-    const int rows_here = min(RS, p.n_loc - set * RS);
-    const int64_t seg = ((int64_t)(set * CS + c) * NPT) * RS * 32 + (int64_t)r * 32 + lane;
-    double e[NPT];
-    uint32_t cp[NPT / 2];
-#pragma unroll
-    for (int n = 0; n < NPT; ++n) e[n] = p.tvals[seg + (int64_t)n * RS * 32];
-#pragma unroll
-    for (int n = 0; n < NPT; n += 2) {
-      const uint32_t a = p.tcols[seg + (int64_t)n * RS * 32], b = p.tcols[seg + (int64_t)(n + 1) * RS * 32];
-      cp[n / 2] = (a * (NV * 8)) | ((b * (NV * 8)) << 16);   // byte offsets inside a tile stage
-    }
-    {                                                        // "column -1" of the parked values: zeros (delta is 0 too)
-      TmChunk z;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) z.r[i] = 0u;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) tm_st8(tm + 8 * ch, z);
-    }
-    for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
-      const size_t g = (size_t)(p.row0 + set * RS) * K + q;
-      xs[q] = p.Xval[g];
-    }
-    cluster_sync_all();   // xs visible; CTA 0 has finished with `part` of the previous set
-
-    // ---- residual of the segment: e = r - sum_k x_k y_k   (tile sequence 0 .. K-1)
-    for (int q = 0; q < K; ++q) {
-      const uint32_t g = gseq + q;
-      mbar_wait(&mbar[stg(g)], phs(g));
-      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
-      const double xk = (r < rows_here) ? xs[r * K + q] : 0.0;
-#pragma unroll
-      for (int n = 0; n < NPT; ++n) {
-        const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
-        e[n] = fma(-xk, *reinterpret_cast<const double*>(T + off), e[n]);
-      }
-      __syncthreads();
-    }
-
-    // ---- the K column updates   (tile sequence K .. 2K-1)
-    double dprev = 0.0;
-    for (int k = 0; k < K; ++k) {
-      const uint32_t g = gseq + K + k;
-      TmChunk b[2];
-      tm_wait_st();                        // the parked values of column k-1 (stored before the exchange) are in place
-      tm_ld8(tm, b[0]);
-      mbar_wait(&mbar[stg(g)], phs(g));
-      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        TmChunk& cur = b[BNMTF_V2_TM_DB ? (ch & 1) : 0];
-        if (!BNMTF_V2_TM_DB && ch > 0) tm_ld8(tm + 8 * ch, cur);
-        tm_wait_ld(cur);
-        if (BNMTF_V2_TM_DB && ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = 4 * ch + i;
-          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
-          e[n] = fma(-dprev, cur.get(i), e[n]);          // k == 0: 0 * 0
-          double v;
-          if (MODE == M_VB) { const double2 vv = *reinterpret_cast<const double2*>(T + off); v = vv.x; s1 += vv.y; }
-          else v = *reinterpret_cast<const double*>(T + off);
-          s0 = fma(v, v, s0);
-          s2 = fma(e[n], v, s2);
-          cur.set(i, v);
-        }
-        tm_st8(tm + 8 * ch, cur);
-      }
-      named_arrive(1, (RS + 1) * 32);      // this warp has finished its pass of column k
-      const double s02 = warp_sum_pair(s0, s2, lane);   // lanes 0..15: sum of s0, lanes 16..31: sum of s2
-      if (MODE == M_VB) s1 = warp_sum(s1);
-      if ((lane & 15) < CS) {   // lanes cc / 16 + cc send this warp's partial sums to CTA cc (every CTA updates redundantly)
-        const uint32_t dst = map_to_cta(part_u32 + (uint32_t)(((k & 1) * CS + c) * RS + r) * 32u, lane & 15);
-        const uint32_t bar = map_to_cta(rbar_u32 + (uint32_t)(k & 1) * 8u, lane & 15);
-        st_async_f64(dst + ((lane & 16) ? 16u : 0u), s02, bar);
-        if (MODE == M_VB && lane < 16) st_async_f64(dst + 8, s1, bar);
-      }
-      __syncthreads();                     // the control warp of this CTA has written the deltas
-      dprev = (r < rows_here) ? delta[r] : 0.0;
-    }
-
-    // ---- last correction, then the row statistics of the final residual
-    {
-      double st0 = 0.0, st1 = 0.0, st2 = 0.0;
-      TmChunk b[2];
-      tm_wait_st();
-      tm_ld8(tm, b[0]);
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        TmChunk& cur = b[BNMTF_V2_TM_DB ? (ch & 1) : 0];
-        if (!BNMTF_V2_TM_DB && ch > 0) tm_ld8(tm + 8 * ch, cur);
-        tm_wait_ld(cur);
-        if (BNMTF_V2_TM_DB && ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = 4 * ch + i;
-          e[n] = fma(-dprev, cur.get(i), e[n]);
-          const double rr = p.tvals[seg + (int64_t)n * RS * 32];
-          st0 = fma(e[n], e[n], st0);
-          st1 += e[n];
-          st2 = fma(rr - p.rmean, e[n], st2);   // padded slots hold e == 0
-        }
-      }
-      st0 = warp_sum(st0); st1 = warp_sum(st1); st2 = warp_sum(st2);
-      if (lane == 0) {
-        double* dst = stat0 + ((size_t)c * RS + r) * 4;
-        dst[0] = st0; dst[1] = st1; dst[2] = st2;
-      }
-    }
-    if (K2 > 0) {
-      // ---- projection epilogue: sum_j e_j Y2[l][j] over this segment, partials to CTA 0   (tiles 2K .. 2K+K2-1)
-      double* proj0 = cluster.map_shared_rank(proj, 0);
-      __syncthreads();
-      for (int q = 0; q < K2; ++q) {
-        const uint32_t g = gseq + 2 * K + q;
-        mbar_wait(&mbar[stg(g)], phs(g));
-        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
-        double s = 0.0;
-#pragma unroll
-        for (int n = 0; n < NPT; ++n) {
-          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
-          s = fma(e[n], *reinterpret_cast<const double*>(T + off), s);
-        }
-        s = warp_sum(s);
-        if (lane == 0) proj0[((size_t)c * RS + r) * K2 + q] = s;
-        __syncthreads();
-      }
-    }
-    cluster_sync_all();
-    if (c == 0) {
-      __syncthreads();
-      for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
-        const size_t g = (size_t)(p.row0 + set * RS) * K + q;
-        p.Xval[g] = xs[q];
-        if (MODE == M_VB) p.Xvar[g] = xs[(size_t)RS * K + q];
-        if (p.Xmu != nullptr) { p.Xmu[g] = xs[(size_t)2 * RS * K + q]; p.Xtau[g] = xs[(size_t)3 * RS * K + q]; }
-      }
-      for (int q = threadIdx.x; q < rows_here * K2; q += blockDim.x) {   // fixed-order sum of the CS projection partials
-        const int rr = q / K2, l = q - rr * K2;
-        double t = 0.0;
-        for (int cc = 0; cc < CS; ++cc) t += proj[((size_t)cc * RS + rr) * K2 + l];
-        p.proj_out[(size_t)(p.row0 + set * RS + rr) * K2 + l] = t;
-      }
-    }
-    gseq += total;
-    __syncthreads();   // xs / tiles are reused by the next set
-  }
-}
-
-// TM variant 2 (BNMTF_V2_TM=2): the residual segments themselves live in tensor memory.  At one row per warp and 80
-// registers the register variant has room for ONE shared-memory load in flight per warp (ncu source page: every
-// gather of the pass lands in the same register pair, each followed by its FMAs), so a pass is a chain of ~40 load
-// latencies.  With the 40 registers of e[] gone the gathers of a chunk of 4 entries are all in flight together while
-// the next chunk of the residual arrives from TMEM.  Same entries, operands and order of every sum: bitwise equal.
-template <int NPT, int MODE, int CS, int RS>
-__device__ __forceinline__ void sweep2_compute_tme(const Sweep2Params& p, cg::cluster_group& cluster, int c, int cid, int nclusters,
-                                                   int warp, int lane, double* tiles, uint64_t* mbar, const double* delta, double* xs,
-                                                   double* part, double* proj, double* statp, uint32_t tm_base) {
-  constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  constexpr int NCH = NPT / 4;
-  static_assert(NPT % 4 == 0, "TMEM chunks hold 4 entries");
-  const int K = p.K, tw = p.tw, K2 = p.K2;
-  const int tile_doubles = (tw + V2_PAD) * NV;
-  const int total = 2 * K + K2;
-  const int NST = p.nst;
-  auto stg = [&](uint32_t g) -> uint32_t { return NST == 4 ? (g & 3u) : (g % 3u); };
-  auto phs = [&](uint32_t g) -> uint32_t { return (NST == 4 ? (g >> 2) : (g / 3u)) & 1u; };
-  const int r = warp - 1;                                 // row of the set owned by this warp
-  const uint32_t tm = tm_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)(NPT * 2);
-  double* stat0 = cluster.map_shared_rank(statp, 0);      // CTA 0's copy, through DSMEM
-  const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[4]);
-  uint32_t gseq = 0;
-  for (int set = cid; set < p.nsets; set += nclusters) {
-    const int rows_here = min(RS, p.n_loc - set * RS);
-    const int64_t seg = ((int64_t)(set * CS + c) * NPT) * RS * 32 + (int64_t)r * 32 + lane;
-    uint32_t cp[NPT / 2];
-#pragma unroll
-    for (int n = 0; n < NPT; n += 2) {
-      const uint32_t a = p.tcols[seg + (int64_t)n * RS * 32], b = p.tcols[seg + (int64_t)(n + 1) * RS * 32];
-      cp[n / 2] = (a * (NV * 8)) | ((b * (NV * 8)) << 16);   // byte offsets inside a tile stage
-    }
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {                       // R values of the segment -> TMEM
-      TmChunk b;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) b.set(i, p.tvals[seg + (int64_t)(4 * ch + i) * RS * 32]);
-      tm_st8(tm + 8 * ch, b);
-    }
-    for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
-      const size_t g = (size_t)(p.row0 + set * RS) * K + q;
-      xs[q] = p.Xval[g];
-    }
-    cluster_sync_all();   // xs visible; CTA 0 has finished with `part` of the previous set
-
-    // ---- residual of the segment: e = r - sum_k x_k y_k   (tile sequence 0 .. K-1)
-    for (int q = 0; q < K; ++q) {
-      const uint32_t g = gseq + q;
-      TmChunk b[2];
-      tm_wait_st();
-      tm_ld8(tm, b[0]);
-      mbar_wait(&mbar[stg(g)], phs(g));
-      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
-      const double xk = (r < rows_here) ? xs[r * K + q] : 0.0;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        TmChunk& cur = b[ch & 1];
-        double y[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = 4 * ch + i;
-          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
-          y[i] = *reinterpret_cast<const double*>(T + off);
-        }
-        tm_wait_ld(cur);
-        if (ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cur.set(i, fma(-xk, y[i], cur.get(i)));
-        tm_st8(tm + 8 * ch, cur);
-      }
-      __syncthreads();
-    }
-
-    // ---- the K column updates   (tile sequence K .. 2K-1)
-    double dprev = 0.0;
-    for (int k = 0; k < K; ++k) {
-      const uint32_t g = gseq + K + k;
-      TmChunk b[2];
-      tm_wait_st();
-      tm_ld8(tm, b[0]);
-      mbar_wait(&mbar[stg(g)], phs(g));
-      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
-      const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + stg(g + NST - 1) * tile_doubles);   // tile g-1
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        TmChunk& cur = b[ch & 1];
-        double yp[4], v[4], w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = 4 * ch + i;
-          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
-          yp[i] = *reinterpret_cast<const double*>(Tp + off);   // k == 0: the last tile of the residual pass, times dprev == 0
-          if (MODE == M_VB) { const double2 vv = *reinterpret_cast<const double2*>(T + off); v[i] = vv.x; w[i] = vv.y; }
-          else { v[i] = *reinterpret_cast<const double*>(T + off); w[i] = 0.0; }
-        }
-        tm_wait_ld(cur);
-        if (ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const double e = fma(-dprev, yp[i], cur.get(i));
-          if (MODE == M_VB) s1 += w[i];
-          s0 = fma(v[i], v[i], s0);
-          s2 = fma(e, v[i], s2);
-          cur.set(i, e);
-        }
-        tm_st8(tm + 8 * ch, cur);
-      }
-      named_arrive(1, (RS + 1) * 32);      // this warp no longer reads the tile of column k-1
-      const double s02 = warp_sum_pair(s0, s2, lane);   // lanes 0..15: sum of s0, lanes 16..31: sum of s2
-      if (MODE == M_VB) s1 = warp_sum(s1);
-      if ((lane & 15) < CS) {   // lanes cc / 16 + cc send this warp's partial sums to CTA cc (every CTA updates redundantly)
-        const uint32_t dst = map_to_cta(part_u32 + (uint32_t)(((k & 1) * CS + c) * RS + r) * 32u, lane & 15);
-        const uint32_t bar = map_to_cta(rbar_u32 + (uint32_t)(k & 1) * 8u, lane & 15);
-        st_async_f64(dst + ((lane & 16) ? 16u : 0u), s02, bar);
-        if (MODE == M_VB && lane < 16) st_async_f64(dst + 8, s1, bar);
-      }
-      __syncthreads();                     // the control warp of this CTA has written the deltas
-      dprev = (r < rows_here) ? delta[r] : 0.0;
-    }
-
-    // ---- last correction, then the row statistics of the final residual
-    {
-      const uint32_t g = gseq + 2 * K - 1;
-      const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
-      double st0 = 0.0, st1 = 0.0, st2 = 0.0;
-      TmChunk b[2];
-      tm_wait_st();
-      tm_ld8(tm, b[0]);
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        TmChunk& cur = b[ch & 1];
-        tm_wait_ld(cur);
-        if (ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = 4 * ch + i;
-          const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
-          const double e = fma(-dprev, *reinterpret_cast<const double*>(Tp + off), cur.get(i));
-          const double rr = p.tvals[seg + (int64_t)n * RS * 32];
-          st0 = fma(e, e, st0);
-          st1 += e;
-          st2 = fma(rr - p.rmean, e, st2);   // padded slots hold e == 0
-          cur.set(i, e);
-        }
-        if (K2 > 0) tm_st8(tm + 8 * ch, cur);
-      }
-      st0 = warp_sum(st0); st1 = warp_sum(st1); st2 = warp_sum(st2);
-      if (lane == 0) {
-        double* dst = stat0 + ((size_t)c * RS + r) * 4;
-        dst[0] = st0; dst[1] = st1; dst[2] = st2;
-      }
-    }
-    if (K2 > 0) {
-      // ---- projection epilogue: sum_j e_j Y2[l][j] over this segment, partials to CTA 0   (tiles 2K .. 2K+K2-1)
-      double* proj0 = cluster.map_shared_rank(proj, 0);
-      tm_wait_st();
-      __syncthreads();
-      for (int q = 0; q < K2; ++q) {
-        const uint32_t g = gseq + 2 * K + q;
-        mbar_wait(&mbar[stg(g)], phs(g));
-        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
-        double s = 0.0;
-        TmChunk b[2];
-        tm_ld8(tm, b[0]);
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          TmChunk& cur = b[ch & 1];
-          tm_wait_ld(cur);
-          if (ch + 1 < NCH) tm_ld8(tm + 8 * (ch + 1), b[(ch + 1) & 1]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = 4 * ch + i;
-            const uint32_t off = (n & 1) ? (cp[n / 2] >> 16) : (cp[n / 2] & 0xFFFFu);
-            s = fma(cur.get(i), *reinterpret_cast<const double*>(T + off), s);
-          }
-        }
-        s = warp_sum(s);
-        if (lane == 0) proj0[((size_t)c * RS + r) * K2 + q] = s;
-        __syncthreads();
-      }
-    }
-    tm_wait_st();
-    cluster_sync_all();
-    if (c == 0) {
-      __syncthreads();
-      for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
-        const size_t g = (size_t)(p.row0 + set * RS) * K + q;
-        p.Xval[g] = xs[q];
-        if (MODE == M_VB) p.Xvar[g] = xs[(size_t)RS * K + q];
-        if (p.Xmu != nullptr) { p.Xmu[g] = xs[(size_t)2 * RS * K + q]; p.Xtau[g] = xs[(size_t)3 * RS * K + q]; }
-      }
-      for (int q = threadIdx.x; q < rows_here * K2; q += blockDim.x) {   // fixed-order sum of the CS projection partials
-        const int rr = q / K2, l = q - rr * K2;
-        double t = 0.0;
-        for (int cc = 0; cc < CS; ++cc) t += proj[((size_t)cc * RS + rr) * K2 + l];
-        p.proj_out[(size_t)(p.row0 + set * RS + rr) * K2 + l] = t;
-      }
-    }
-    gseq += total;
-    __syncthreads();   // xs / tiles are reused by the next set
-  }
-}
-
-// Compute warps owning RPW rows each (opt-in, BNMTF_V2_RPW=2 at 20 entries per lane).  Throughput of the sweep is rows
-// in flight per column time, and the rows in flight are bounded by the register file, a third of which goes to the ~30
-// registers every thread needs besides its residual entries.  Two rows per warp halve that overhead per row: 8 warps per
-// CTA at 128 registers carry 14 rows (12 warps at 80 registers: 11) and the two rows give the scheduler independent
-// load / FMA chains.  Same entries, operands and order of every sum per row: bitwise the results of one row per warp.
-template <int NPT, int MODE, int CS, int RS, int RPW>
-__device__ __forceinline__ void sweep2_compute_rows(const Sweep2Params& p, cg::cluster_group& cluster, int c, int cid, int nclusters,
-                                                    int warp, int lane, double* tiles, uint64_t* mbar, const double* delta, double* xs,
-                                                    double* part, double* proj, double* statp) {
-  constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  constexpr int NTHR = (RS / RPW + 1) * 32;               // threads of the CTA
-  const int K = p.K, tw = p.tw, K2 = p.K2;
-  const int tile_doubles = (tw + V2_PAD) * NV;
-  const int total = 2 * K + K2;
-  const int NST = p.nst;
-  auto stg = [&](uint32_t g) -> uint32_t { return NST == 4 ? (g & 3u) : (g % 3u); };
-  auto phs = [&](uint32_t g) -> uint32_t { return (NST == 4 ? (g >> 2) : (g / 3u)) & 1u; };
-  const int r0 = (warp - 1) * RPW;                        // first row of the set owned by this warp
-  const uint32_t part_u32 = smem_u32(part), rbar_u32 = smem_u32(&mbar[4]);
-  uint32_t gseq = 0;
-  for (int set = cid; set < p.nsets; set += nclusters) {
-    const int rows_here = min(RS, p.n_loc - set * RS);
-    const int64_t seg0 = ((int64_t)(set * CS + c) * NPT) * RS * 32 + (int64_t)r0 * 32 + lane;
-    double e[RPW][NPT];
-    uint32_t cp[RPW][NPT / 2];
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-      const int64_t seg = seg0 + rr * 32;
-#pragma unroll
-      for (int n = 0; n < NPT; ++n) e[rr][n] = p.tvals[seg + (int64_t)n * RS * 32];
-#pragma unroll
-      for (int n = 0; n < NPT; n += 2) {
-        const uint32_t a = p.tcols[seg + (int64_t)n * RS * 32], b = p.tcols[seg + (int64_t)(n + 1) * RS * 32];
-        cp[rr][n / 2] = (a * (NV * 8)) | ((b * (NV * 8)) << 16);   // byte offsets inside a tile stage
-      }
-    }
-    for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
-      const size_t g = (size_t)(p.row0 + set * RS) * K + q;
-      xs[q] = p.Xval[g];
-    }
-    cluster_sync_all();   // xs visible; CTA 0 has finished with `part` of the previous set
-
-    // ---- residual of the segments: e = r - sum_k x_k y_k   (tile sequence 0 .. K-1)
-    for (int q = 0; q < K; ++q) {
-      const uint32_t g = gseq + q;
-      mbar_wait(&mbar[stg(g)], phs(g));
-      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
-      double xk[RPW];
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) xk[rr] = (r0 + rr < rows_here) ? xs[(r0 + rr) * K + q] : 0.0;
-#pragma unroll
-      for (int n = 0; n < NPT; ++n) {
-#pragma unroll
-        for (int rr = 0; rr < RPW; ++rr) {
-          const uint32_t off = (n & 1) ? (cp[rr][n / 2] >> 16) : (cp[rr][n / 2] & 0xFFFFu);
-          e[rr][n] = fma(-xk[rr], *reinterpret_cast<const double*>(T + off), e[rr][n]);
-        }
-      }
-      __syncthreads();
-    }
-
-    // ---- the K column updates   (tile sequence K .. 2K-1)
-    double dprev[RPW];
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) dprev[rr] = 0.0;
-    for (int k = 0; k < K; ++k) {
-      const uint32_t g = gseq + K + k;
-      mbar_wait(&mbar[stg(g)], phs(g));
-      const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
-      const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + stg(g + NST - 1) * tile_doubles);   // tile g-1
-      double s0[RPW], s1[RPW], s2[RPW];
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) s0[rr] = s1[rr] = s2[rr] = 0.0;
-      if (k > 0) {
-#pragma unroll
-        for (int n = 0; n < NPT; ++n) {
-#pragma unroll
-          for (int rr = 0; rr < RPW; ++rr) {
-            const uint32_t off = (n & 1) ? (cp[rr][n / 2] >> 16) : (cp[rr][n / 2] & 0xFFFFu);
-            e[rr][n] = fma(-dprev[rr], *reinterpret_cast<const double*>(Tp + off), e[rr][n]);
-            double v;
-            if (MODE == M_VB) { const double2 vv = *reinterpret_cast<const double2*>(T + off); v = vv.x; s1[rr] += vv.y; }
-            else v = *reinterpret_cast<const double*>(T + off);
-            s0[rr] = fma(v, v, s0[rr]);
-            s2[rr] = fma(e[rr][n], v, s2[rr]);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int n = 0; n < NPT; ++n) {
-#pragma unroll
-          for (int rr = 0; rr < RPW; ++rr) {
-            const uint32_t off = (n & 1) ? (cp[rr][n / 2] >> 16) : (cp[rr][n / 2] & 0xFFFFu);
-            double v;
-            if (MODE == M_VB) { const double2 vv = *reinterpret_cast<const double2*>(T + off); v = vv.x; s1[rr] += vv.y; }
-            else v = *reinterpret_cast<const double*>(T + off);
-            s0[rr] = fma(v, v, s0[rr]);
-            s2[rr] = fma(e[rr][n], v, s2[rr]);
-          }
-        }
-      }
-      named_arrive(1, NTHR);               // this warp no longer reads the tile of column k-1
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) {
-        const double s02 = warp_sum_pair(s0[rr], s2[rr], lane);   // lanes 0..15: sum of s0, lanes 16..31: sum of s2
-        if (MODE == M_VB) s1[rr] = warp_sum(s1[rr]);
-        if ((lane & 15) < CS) {   // lanes cc / 16 + cc send this row's partial sums to CTA cc (every CTA updates redundantly)
-          const uint32_t dst = map_to_cta(part_u32 + (uint32_t)(((k & 1) * CS + c) * RS + r0 + rr) * 32u, lane & 15);
-          const uint32_t bar = map_to_cta(rbar_u32 + (uint32_t)(k & 1) * 8u, lane & 15);
-          st_async_f64(dst + ((lane & 16) ? 16u : 0u), s02, bar);
-          if (MODE == M_VB && lane < 16) st_async_f64(dst + 8, s1[rr], bar);
-        }
-      }
-      __syncthreads();                     // the control warp of this CTA has written the deltas
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) dprev[rr] = (r0 + rr < rows_here) ? delta[r0 + rr] : 0.0;
-    }
-
-    // ---- last correction, then the row statistics of the final residual
-    {
-      const uint32_t g = gseq + 2 * K - 1;
-      const char* __restrict__ Tp = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
-      double* stat0 = cluster.map_shared_rank(statp, 0);      // CTA 0's copy, through DSMEM
-#pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) {
-        double st0 = 0.0, st1 = 0.0, st2 = 0.0;
-#pragma unroll
-        for (int n = 0; n < NPT; ++n) {
-          const uint32_t off = (n & 1) ? (cp[rr][n / 2] >> 16) : (cp[rr][n / 2] & 0xFFFFu);
-          e[rr][n] = fma(-dprev[rr], *reinterpret_cast<const double*>(Tp + off), e[rr][n]);
-          const double rv = p.tvals[seg0 + rr * 32 + (int64_t)n * RS * 32];
-          st0 = fma(e[rr][n], e[rr][n], st0);
-          st1 += e[rr][n];
-          st2 = fma(rv - p.rmean, e[rr][n], st2);   // padded slots hold e == 0
-        }
-        st0 = warp_sum(st0); st1 = warp_sum(st1); st2 = warp_sum(st2);
-        if (lane == 0) {
-          double* dst = stat0 + ((size_t)c * RS + r0 + rr) * 4;
-          dst[0] = st0; dst[1] = st1; dst[2] = st2;
-        }
-      }
-    }
-    if (K2 > 0) {
-      // ---- projection epilogue: sum_j e_j Y2[l][j] over the segments, partials to CTA 0   (tiles 2K .. 2K+K2-1)
-      double* proj0 = cluster.map_shared_rank(proj, 0);
-      __syncthreads();
-      for (int q = 0; q < K2; ++q) {
-        const uint32_t g = gseq + 2 * K + q;
-        mbar_wait(&mbar[stg(g)], phs(g));
-        const char* __restrict__ T = reinterpret_cast<const char*>(tiles + stg(g) * tile_doubles);
-#pragma unroll
-        for (int rr = 0; rr < RPW; ++rr) {
-          double s = 0.0;
-#pragma unroll
-          for (int n = 0; n < NPT; ++n) {
-            const uint32_t off = (n & 1) ? (cp[rr][n / 2] >> 16) : (cp[rr][n / 2] & 0xFFFFu);
-            s = fma(e[rr][n], *reinterpret_cast<const double*>(T + off), s);
-          }
-          s = warp_sum(s);
-          if (lane == 0) proj0[((size_t)c * RS + r0 + rr) * K2 + q] = s;
-        }
-        __syncthreads();
-      }
-    }
-    cluster_sync_all();
-    if (c == 0) {
-      __syncthreads();
-      for (int q = threadIdx.x; q < rows_here * K; q += blockDim.x) {
-        const size_t g = (size_t)(p.row0 + set * RS) * K + q;
-        p.Xval[g] = xs[q];
-        if (MODE == M_VB) p.Xvar[g] = xs[(size_t)RS * K + q];
-        if (p.Xmu != nullptr) { p.Xmu[g] = xs[(size_t)2 * RS * K + q]; p.Xtau[g] = xs[(size_t)3 * RS * K + q]; }
-      }
-      for (int q = threadIdx.x; q < rows_here * K2; q += blockDim.x) {   // fixed-order sum of the CS projection partials
-        const int rr = q / K2, l = q - rr * K2;
-        double t = 0.0;
-        for (int cc = 0; cc < CS; ++cc) t += proj[((size_t)cc * RS + rr) * K2 + l];
-        p.proj_out[(size_t)(p.row0 + set * RS + rr) * K2 + l] = t;
-      }
-    }
-    gseq += total;
-    __syncthreads();   // xs / tiles are reused by the next set
-  }
-}
-
 // phase clocks of cluster 0 / CTA 0 (timing experiments: build with -DBNMTF_V2_PROF, run with BNMTF_V2_DBG=2)
 #ifdef BNMTF_V2_PROF
 #define P2_T0() long long t_prof = prof_on ? clock64() : 0
@@ -854,13 +255,11 @@ __device__ __forceinline__ void sweep2_compute_rows(const Sweep2Params& p, cg::c
 #define P2_ADD(slot) do { } while (0)
 #endif
 
-// TMW > 0: tensor-memory variants (TMW warps per CTA); TMV = 1: the gathered column is parked in TMEM, 2: the residual
-constexpr int V2_RPW2_WARPS = 8;   // warps per CTA of the two-rows-per-warp variant (control warp + 7 x 2 rows)
-template <int NPT, int MODE, int CS, int DIV, int TMW = 0, int TMV = 1, int RPW = 1>
-__global__ void __launch_bounds__((TMW > 0 ? TMW : RPW > 1 ? V2_RPW2_WARPS : Sweep2Cfg<NPT>::WPC / DIV) * 32, DIV) sweep2_kernel(const Sweep2Params p) {
+template <int NPT, int MODE, int CS, int DIV>
+__global__ void __launch_bounds__(Sweep2Cfg<NPT>::WPC / DIV * 32, DIV) sweep2_kernel(const Sweep2Params p) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
-  constexpr int RS = ((TMW > 0 ? TMW : RPW > 1 ? V2_RPW2_WARPS : Sweep2Cfg<NPT>::WPC / DIV) - 1) * RPW;
-  constexpr int NTHR = (RS / RPW + 1) * 32;               // threads of the CTA
+  constexpr int RS = Sweep2Cfg<NPT>::WPC / DIV - 1;
+  constexpr int NTHR = (RS + 1) * 32;                     // threads of the CTA
   static_assert(MODE != M_NP, "the NP updates run on the v1 kernel");
   cg::cluster_group cluster = cg::this_cluster();
   const int c = (int)cluster.block_rank();
@@ -896,17 +295,7 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : RPW > 1 ? V2_RPW2_WARPS : Swe
   for (int s = threadIdx.x; s < NST; s += blockDim.x) {   // the zero slots read by padded entries
     for (int z = 0; z < V2_PAD * NV; ++z) tiles[s * tile_doubles + tw * NV + z] = 0.0;
   }
-  uint32_t& tm_base_sh = *reinterpret_cast<uint32_t*>(&mbar[7]);   // a spare mbarrier slot
-  if (TMW > 0) {                                          // tensor memory for the residual segments of this CTA
-    if (warp == 0) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm_base_sh)), "n"(V2_TM_COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  }
   __syncthreads();
-  if (TMW > 0) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tm_base = TMW > 0 ? tm_base_sh : 0u;
 
   const double* ybase = p.Ykm + (size_t)c * tw * NV;      // this CTA's tile of column 0
   const size_t ystride = (size_t)p.ldy * NV;
@@ -1075,14 +464,6 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : RPW > 1 ? V2_RPW2_WARPS : Swe
       gseq += total;
       __syncthreads();
     }
-  } else if (TMW > 0) {
-    if constexpr (TMW > 0 && TMV == 1)
-      sweep2_compute_tm<NPT, MODE, CS, RS>(p, cluster, c, cid, nclusters, warp, lane, tiles, mbar, delta, xs, part, proj, statp, tm_base);
-    if constexpr (TMW > 0 && TMV == 2)
-      sweep2_compute_tme<NPT, MODE, CS, RS>(p, cluster, c, cid, nclusters, warp, lane, tiles, mbar, delta, xs, part, proj, statp, tm_base);
-  } else if (RPW > 1) {
-    if constexpr (RPW > 1)
-      sweep2_compute_rows<NPT, MODE, CS, RS, RPW>(p, cluster, c, cid, nclusters, warp, lane, tiles, mbar, delta, xs, part, proj, statp);
   } else {
     // =========================== compute warps ===========================
     const int r = warp - 1;                                 // row of the set owned by this warp
@@ -1236,11 +617,6 @@ __global__ void __launch_bounds__((TMW > 0 ? TMW : RPW > 1 ? V2_RPW2_WARPS : Swe
       __syncthreads();   // xs / tiles are reused by the next set
       P2_ADD(15);        // statistics, store, end of set
     }
-  }
-  if (TMW > 0) {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "n"(V2_TM_COLS) : "memory");
   }
   cluster_sync_all();    // no CTA may exit while its shared memory can still be written remotely
 }

@@ -203,54 +203,6 @@ def test_cluster_kernel_is_selected():
     eng.close()
 
 
-@pytest.mark.parametrize("cls_name", ["bnmf_gibbs", "nmf_icm", "bnmf_vb"])
-def test_tensor_memory_sweep_is_bitwise_the_register_sweep(cls_name, monkeypatch):
-    """Row segments of 20 entries per lane run the cluster sweep that parks the gathered values of a column in tensor
-    memory (tcgen05.st / tcgen05.ld) instead of gathering them a second time for the rank-1 correction (variant 1), keeps
-    the residual itself there (variant 2), or gives every warp two rows (BNMTF_V2_RPW=2, 14 rows per CTA).  Same entries,
-    operands and summation orders per row: the same seeded run must end in the bits of the default register variant."""
-    import bnmtf_ard_b200 as pkg
-    I, J, K, dens = SHAPES[11]
-    R, M, _ = make_problem(99, I, J, K, dens, nonneg=True)
-    hyper = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0}
-    outs = []
-    for tm, rpw in (("1", "1"), ("2", "1"), ("0", "2"), ("0", "1")):   # the last one is the default register variant
-        monkeypatch.setenv("BNMTF_V2_TM", tm)
-        monkeypatch.setenv("BNMTF_V2_RPW", rpw)
-        m = getattr(pkg, cls_name)(R, M, K, True, hyper)
-        m.verbose = False
-        np.random.seed(3)
-        m.initialise("random")
-        m.run(4)
-        info = m._engine().layout_info()
-        assert info["v2_U"] == (6 if rpw == "2" else {"1": 4, "2": 5, "0": 1}[tm]) and info["v2_npt_U"] == 20
-        assert info["v2_rows_per_set_U"] == (14 if rpw == "2" else 11)
-        if cls_name == "bnmf_gibbs":
-            outs.append((m.all_U.copy(), m.all_V.copy(), np.asarray(m.all_tau).copy(), np.asarray(m.all_performances["MSE"])))
-        elif cls_name == "nmf_icm":
-            outs.append((m.U.copy(), m.V.copy(), np.asarray(m.tau), np.asarray(m.all_performances["MSE"])))
-        else:
-            outs.append((m.exp_U.copy(), m.exp_V.copy(), m.var_U.copy(), np.asarray(m.all_elbo)))
-    for other in outs[:-1]:
-        for a, b in zip(other, outs[-1]):
-            assert np.array_equal(a, b)
-
-
-def test_lookahead_sweep_vs_oracle(monkeypatch):
-    """BNMTF_V2_LA=1: the cluster sweep whose pass runs one column ahead of the conditionals (kernels_v2la.cuh: the pass of
-    column k needs delta_{k-2} only, the control warp forms sum e y_k = h_k - delta_{k-1} g_k).  Same conditionals in the
-    same order: the Gibbs replay and the ICM trajectory must match the oracle like the default sweep does."""
-    from bnmtf_ard_b200._engine import NMFEngine
-    monkeypatch.setenv("BNMTF_V2_LA", "1")
-    I, J, K, dens = SHAPES[11]
-    R, M, _ = make_problem(1, I, J, K, dens)
-    eng = NMFEngine(R, M, K)
-    assert eng.layout_info()["v2_U"] == 7
-    eng.close()
-    test_gibbs_iteration_vs_oracle(SHAPES[11], monkeypatch)
-    test_icm_vb_np_iterations_vs_oracle(SHAPES[11])
-
-
 def test_streamed_rows_are_selected_and_column_params_match():
     """Rows beyond 16384 observed entries: the row sweep streams the residual from global memory; the single-column
     conditionals (tauU / muU of the class API) go through the same kernel and must match the oracle."""
