@@ -76,6 +76,31 @@ def broadcast_bytes(payload, src=0):
     return bytes(t.cpu().tolist())
 
 
+def broadcast_int(value, src=0):
+    """A 64-bit integer from rank `src` to every rank (identity when world == 1)."""
+    td = _pg()
+    if td is None or td.get_world_size() == 1:
+        return int(value)
+    import torch
+    t = torch.tensor([int(value)], dtype=torch.int64, device=_device_for_backend(td))
+    td.broadcast(t, src=src)
+    return int(t.item())
+
+
+def same_on_all_ranks(values):
+    """True when every rank holds bitwise the same float64 vector (MAX == MIN of the bit patterns)."""
+    td = _pg()
+    if td is None or td.get_world_size() == 1:
+        return True
+    import torch
+    bits = np.ascontiguousarray(np.asarray(values, dtype=np.float64)).view(np.int64)
+    hi = torch.from_numpy(bits.copy()).to(_device_for_backend(td))
+    lo = hi.clone()
+    td.all_reduce(hi, op=td.ReduceOp.MAX)
+    td.all_reduce(lo, op=td.ReduceOp.MIN)
+    return bool(torch.equal(hi, lo))
+
+
 def barrier():
     td = _pg()
     if td is not None and td.get_world_size() > 1:

@@ -117,6 +117,19 @@ class NMFEngine(object):
     def set_factor(self, side, field, arr):
         a = f64(arr, (self.n_of(side), self.k_of(side)))
         check(self.lib.bnmtf_nmf_set_factor(self.h, side, field, dptr(a)))
+        if self.world > 1:
+            self._uploaded = getattr(self, "_uploaded", 0.0) + float(a.sum()) * (1 + side + 2 * field)
+
+    def _check_replicated_state(self):
+        """One process per GPU: every rank uploads its own host copy of the state and the shards exchanged during the
+        run are conditioned on it, so the copies must be identical -- a cheap fingerprint of what was uploaded since
+        the last run is compared over the ranks before the device loop starts."""
+        if self.world > 1:
+            fp, self._uploaded = getattr(self, "_uploaded", 0.0), 0.0
+            if not _dist.same_on_all_ranks([fp]):
+                raise RuntimeError("multi-GPU run: the ranks hold different initial states (factor fingerprint %r on rank %d); "
+                                   "initialise with the same values on every rank -- initialise() of the model classes does, "
+                                   "its seed is broadcast from rank 0" % (fp, self.rank))
 
     def get_factor(self, side, field):
         out = np.empty((self.n_of(side), self.k_of(side)))
@@ -126,6 +139,8 @@ class NMFEngine(object):
     def set_scalars(self, tau, lambdak=None):
         lk = None if lambdak is None else f64(lambdak, (self.K,))
         check(self.lib.bnmtf_nmf_set_scalars(self.h, float(tau), dptr(lk)))
+        if self.world > 1:
+            self._uploaded = getattr(self, "_uploaded", 0.0) + 7.0 * float(tau) + (0.0 if lk is None else 11.0 * float(lk.sum()))
 
     def get_scalars(self, want_lambdak=True):
         tau = C.c_double()
@@ -161,6 +176,7 @@ class NMFEngine(object):
 
     def run(self, method, iterations, seed=0, traces=True, want_lambdak=True):
         it = int(iterations)
+        self._check_replicated_state()
         res = {
             "all_U": np.zeros((it, self.I, self.K)) if traces else None,
             "all_V": np.zeros((it, self.J, self.K)) if traces else None,
@@ -290,6 +306,7 @@ class NMTFEngine(NMFEngine):
 
     def run(self, method, iterations, seed=0, traces=True):
         it = int(iterations)
+        self._check_replicated_state()
         res = {
             "all_F": np.zeros((it, self.I, self.K)) if traces else None,
             "all_S": np.zeros((it, self.K, self.L)) if traces else None,

@@ -161,5 +161,18 @@ class NMFCommon(object):
         return {'MSE': MSE, 'R^2': R2, 'Rp': Rp}
 
 
+NMTF_MAX_L, NMTF_MAX_KL = 32, 3631      # csrc/engine.cu: NMTF_MAX_L, NMTF_MAX_KL
+
+
+def check_nmtf_limits(K, L):
+    ''' Size limits of the tri-factorisation engine (the reference has none): raised in the constructor, with the
+        same text the C ABI would give at handle creation, never in the middle of run(). '''
+    if int(L) > NMTF_MAX_L:
+        raise ValueError("tri-factorisation: L = %d is not supported by the B200 engine (L <= %d; K is only bound by "
+                         "K*L <= %d)" % (L, NMTF_MAX_L, NMTF_MAX_KL))
+    if int(K) * int(L) > NMTF_MAX_KL:
+        raise ValueError("tri-factorisation: K*L = %d is not supported by the B200 engine (K*L <= %d)" % (int(K) * int(L), NMTF_MAX_KL))
+
+
 def method_id(name):
     return {'gibbs': _lib.GIBBS, 'icm': _lib.ICM, 'vb': _lib.VB, 'np': _lib.NP}[name]

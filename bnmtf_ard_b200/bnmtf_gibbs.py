@@ -14,7 +14,7 @@ import numpy
 from . import _lib
 from ._engine import NMTFEngine
 from ._lib import F_VALUE, SIDE_U, SIDE_V
-from ._nmf_common import ALL_METRICS, ALL_QUALITY, NMFCommon
+from ._nmf_common import ALL_METRICS, ALL_QUALITY, NMFCommon, check_nmtf_limits
 from .distributions._device import next_seed
 from .distributions.gamma import gamma_draw, gamma_mode
 
@@ -29,6 +29,7 @@ class bnmtf_gibbs(NMFCommon):
         ''' Set up the class and do some checks on the values passed.  (bnmtf_gibbs.py:66-99) '''
         self._setup_data(R, M, K)
         self.L = L
+        check_nmtf_limits(K, L)
         self.ARD = ARD
 
         self.alphatau, self.betatau = float(hyperparameters['alphatau']), float(hyperparameters['betatau'])

@@ -297,6 +297,12 @@ static int alloc_side_state(bnmtf_nmf_s* h, Side& sd, int K) {
 }
 
 static int nmtf_alloc(bnmtf_nmf_s* h);
+// Size limits of the tri-factorisation handle (the reference has none; documented in README.md / INTEGRATION.md and
+// checked when the handle is created, never in the middle of run()): the Gram kernel H_i = sum G_j G_j^T keeps an
+// L x L block per warp (L <= 32), the single-CTA S sweeps keep up to 8 K*L doubles in shared memory (227 KB opt-in).
+constexpr int NMTF_MAX_L = 32;
+constexpr size_t NMTF_S_SMEM_MAX = 227 * 1024;
+constexpr int NMTF_MAX_KL = (int)((NMTF_S_SMEM_MAX / sizeof(double) - 2) / (2 + TN_PRE_DOUBLES));   // 3631
 // ---- stream-ordered memory and copies ----------------------------------------------
 // Every allocation comes from the device's stream-ordered pool (cudaMallocAsync) and every
 // "synchronous" copy runs on the calling handle's stream followed by a stream synchronise:
@@ -379,6 +385,8 @@ static int create_dev_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, i
   if (!out) FAIL("out is NULL");
   *out = nullptr;
   if (I <= 0 || J <= 0 || K <= 0 || L <= 0) FAIL("bad shape I=%lld J=%lld K=%d L=%d", (long long)I, (long long)J, K, L);
+  if (nmtf && L > NMTF_MAX_L) FAIL("tri-factorisation: L = %d is not supported (L <= %d; K is only bound by K*L <= %d)", L, NMTF_MAX_L, NMTF_MAX_KL);
+  if (nmtf && (int64_t)K * L > NMTF_MAX_KL) FAIL("tri-factorisation: K*L = %lld is not supported (K*L <= %d)", (long long)K * L, NMTF_MAX_KL);
   if (I >= (int64_t)0xFFFFFFF0ll || J >= (int64_t)0xFFFFFFF0ll) FAIL("dimension too large for 32-bit column indices");
   if (row0 < 0 || row1 < row0 || row1 > I || col0 < 0 || col1 < col0 || col1 > J) FAIL("bad shard bounds");
   if (shard_rows < row1 - row0 || shard_cols < col1 - col0) FAIL("shard size smaller than the owned range");

@@ -13,7 +13,14 @@ def next_seed():
     """One 62-bit Philox key, consuming two draws of numpy's global legacy stream."""
     lo = int(numpy.random.randint(0, 2 ** 31 - 1))
     hi = int(numpy.random.randint(0, 2 ** 31 - 1))
-    return (hi << 31) | lo
+    seed = (hi << 31) | lo
+    # one process per GPU: every rank consumes its own numpy stream, but all of them must key the device
+    # samplers identically (they replicate the lambda / tau draws and the other ranks' shards are conditioned on
+    # them), so rank 0's seed is the seed of the job whether or not the caller seeded numpy alike on every rank
+    from .. import _dist
+    if _dist.info()[1] > 1:
+        seed = _dist.broadcast_int(seed, src=0)
+    return seed
 
 
 def _vec(x):

@@ -10,7 +10,7 @@ import numpy
 from . import _lib
 from ._engine import NMTFEngine
 from ._lib import F_VALUE, SIDE_U, SIDE_V
-from ._nmf_common import ALL_METRICS, NMFCommon
+from ._nmf_common import ALL_METRICS, NMFCommon, check_nmtf_limits
 from .distributions._device import exp_draws
 
 OPTIONS_INIT_FG = ['kmeans', 'ones', 'random', 'exponential']
@@ -25,6 +25,7 @@ class nmtf_np(NMFCommon):
         self.metrics = ['MSE', 'R^2', 'Rp']
         self._setup_data(R, M, K)
         self.L = L
+        check_nmtf_limits(K, L)
         # For computing the I-div it is easier if unknown values are 1's, not 0's, to avoid numerical issues
         self.R_excl_unknown = numpy.where(self.M != 0, self.R, 1.)
 

@@ -28,16 +28,22 @@ def main():
     from bnmtf_ard_b200._lib import F_MU, F_TAU, F_VALUE, F_VAR, SIDE_U, SIDE_V
 
     ok = True
-    for (I, J, K, dens) in [(257, 190, 5, 0.6), (1001, 777, 8, 0.3), (64, 2500, 4, 0.7)]:
+    # the last shape is a strip of the benchmark configuration (K = 50, rho = 0.2) packed with the benchmark's layout
+    # (20 entries per lane, 11 rows per set: the packing floor of the full 20000 x 20000 matrix is handed over)
+    for (I, J, K, dens) in [(257, 190, 5, 0.6), (1001, 777, 8, 0.3), (64, 2500, 4, 0.7), (400, 20000, 50, 0.2)]:
+        floor = [0, 600, 0, 600] if K == 50 else None
         rng = np.random.default_rng(I + J)
         R = np.abs(rng.exponential(1, (I, K)) @ rng.exponential(1, (J, K)).T + rng.normal(0, 1, (I, J))) + 0.05
         M = (rng.random((I, J)) < dens).astype(float)
         M[np.arange(I), rng.integers(0, J, I)] = 1
         M[rng.integers(0, I, J), np.arange(J)] = 1
         U0, V0 = rng.exponential(1, (I, K)), rng.exponential(1, (J, K))
-        engs = [NMFEngine(R, M, K, device=local)]
+        engs = [NMFEngine(R, M, K, device=local, layout_floor=floor)]
         if rank == 0:
-            engs.append(NMFEngine(R, M, K, device=local, distributed=False))
+            engs.append(NMFEngine(R, M, K, device=local, distributed=False, layout_floor=floor))
+        if floor is not None:
+            info = engs[0].layout_info()
+            assert info["v2_U"] >= 1 and info["v2_npt_U"] == 20 and info["v2_rows_per_set_U"] == 11, info
         for method in (_lib.GIBBS, _lib.ICM, _lib.VB, _lib.NP):
             outs = []
             for e in engs:
@@ -105,6 +111,52 @@ def main():
                 ok = ok and same
         for e in engs:
             e.close()
+    # ---- the class API without a common numpy seed (round-1 advice): every rank seeds numpy differently, yet all ranks
+    # must hold the same chain -- initialise() / run() take rank 0's Philox seed -- and it must be the single-GPU chain
+    from bnmtf_ard_b200 import bnmf_gibbs
+    rng = np.random.default_rng(5)
+    I, J, K = 300, 260, 6
+    R = rng.exponential(1, (I, K)) @ rng.exponential(1, (J, K)).T + rng.normal(0, 1, (I, J))
+    M = (rng.random((I, J)) < 0.5).astype(float)
+    M[np.arange(I), rng.integers(0, J, I)] = 1
+    M[rng.integers(0, I, J), np.arange(J)] = 1
+    hyper = {"alphatau": 1., "betatau": 1., "alpha0": 1., "beta0": 1.}
+    np.random.seed(1000 + rank)
+    m = bnmf_gibbs(R, M, K, True, hyper)
+    m.verbose = False
+    m.train("random", 12)
+    digest = torch.tensor([float(m.U.sum()), float(m.V.sum()), float(m.tau), float(m.all_U[3].sum())], dtype=torch.float64, device="cuda")
+    lo, hi = digest.clone(), digest.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same_ranks = bool(torch.equal(lo, hi))
+    if rank == 0:
+        from bnmtf_ard_b200 import _dist
+        real_info = _dist.info
+        _dist.info = lambda: (0, 1)            # a single-GPU model next to the process group
+        try:
+            np.random.seed(1000)
+            s1 = bnmf_gibbs(R, M, K, True, hyper)
+            s1.verbose = False
+            s1.train("random", 12)
+        finally:
+            _dist.info = real_info
+        same_single = np.array_equal(s1.all_U, m.all_U) and np.array_equal(s1.all_V, m.all_V) and np.array_equal(s1.all_tau, m.all_tau)
+        print("class API, numpy seeded per rank, world %d: ranks agree %s, equals the single-GPU chain %s" % (world, same_ranks, same_single))
+        ok = ok and same_ranks and same_single
+    # ranks that upload different states are refused
+    eng = NMFEngine(R, M, K, device=local)
+    eng.set_hyper(True, 1., 1., 1., 1.)
+    eng.set_factor(SIDE_U, F_VALUE, np.full((I, K), 1.0 + rank)); eng.set_factor(SIDE_V, F_VALUE, np.ones((J, K)))
+    eng.set_scalars(1.0, np.ones(K))
+    try:
+        eng.run(_lib.GIBBS, 1, seed=1, traces=False)
+        refused = False
+    except RuntimeError as e:
+        refused = "different initial states" in str(e)
+    if rank == 0:
+        print("ranks with different uploaded states are refused: %s" % refused)
+        ok = ok and refused
+    eng.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()

@@ -42,6 +42,15 @@ def _worker(rank, world, port, q):
     local = np.array([M[r0:r1].sum(), (R * M)[r0:r1].sum()])
     tot = _dist.allreduce_sum(local)
     out["stats_ok"] = bool(np.allclose(tot, [M.sum(), (R * M).sum()]))
+    # seeds: every rank has its own numpy stream; next_seed() hands out rank 0's (ranks drew their own)
+    from bnmtf_ard_b200.distributions._device import next_seed
+    np.random.seed(100 + rank)
+    out["seed"] = next_seed()
+    np.random.seed(100)
+    out["seed_rank0_stream"] = (lambda lo, hi: (hi << 31) | lo)(int(np.random.randint(0, 2 ** 31 - 1)), int(np.random.randint(0, 2 ** 31 - 1)))
+    out["bcast"] = _dist.broadcast_int(12345678901234 + rank)
+    out["same_yes"] = _dist.same_on_all_ranks([1.5, -2.0])
+    out["same_no"] = _dist.same_on_all_ranks([1.5, float(rank)])
     _dist.barrier()
     dist.destroy_process_group()
     q.put((rank, out))
@@ -63,6 +72,9 @@ def test_gloo_world2_plumbing():
         assert res[r]["info"] == (r, 2)
         assert res[r]["sum"] == [3.0, 30.0]
         assert res[r]["bytes_ok"] and res[r]["stats_ok"]
+        assert res[r]["seed"] == res[0]["seed"] == res[r]["seed_rank0_stream"]
+        assert res[r]["bcast"] == 12345678901234
+        assert res[r]["same_yes"] is True and res[r]["same_no"] is False
 
 
 def test_single_process_defaults():
@@ -70,3 +82,4 @@ def test_single_process_defaults():
     assert _dist.info() == (0, 1)
     assert _dist.allreduce_sum([1.0, 2.0]).tolist() == [1.0, 2.0]
     assert _dist.broadcast_bytes(b"abc") == b"abc"
+    assert _dist.broadcast_int(7) == 7 and _dist.same_on_all_ranks([1.0])
