@@ -5,7 +5,6 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-SRC = os.path.join(PKG, "csrc", "engine.cu")
 
 
 def deps():
@@ -18,8 +17,10 @@ def deps():
 
 LIB = os.path.join(PKG, "libbnmtf_b200.so")
 
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-split-compile", "0"]
+# -split-compile speeds the build up but costs the cluster sweep 18 % (measured on the B200: 10.09 ms against 8.49 ms
+# per sweep for the same source), so each translation unit is compiled whole; the units build in parallel instead.
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC"]
+UNITS = ["engine.cu", "sweep4.cu"]
 
 
 def find_nvcc():
@@ -36,17 +37,37 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps())
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/engine.cu for sm_100a.  Returns the path of the shared library."""
-    if not force and up_to_date():
-        return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB, SRC, "-ldl"]
+def build(force=False, verbose=False, defines=(), lib=None):
+    """Compile csrc/*.cu for sm_100a (one nvcc process per translation unit) and link the shared library.
+    Returns its path."""
+    lib = lib or LIB
+    if not force and lib == LIB and up_to_date():
+        return lib
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = find_nvcc()
+    objdir = os.path.join(ROOT, "build", "obj" + ("_" + "_".join(defines) if defines else ""))
+    os.makedirs(objdir, exist_ok=True)
+    dflags = ["-D" + d for d in defines]
+
+    def compile_unit(unit):
+        obj = os.path.join(objdir, unit[:-3] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + dflags + ["-c", "-o", obj, os.path.join(PKG, "csrc", unit)]
+        if verbose:
+            print(" ".join(cmd))
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (unit, res.stdout, res.stderr))
+        return obj
+
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        objs = list(ex.map(compile_unit, UNITS))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-ldl"]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))
-    return LIB
+        raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
+    return lib
 
 
 if __name__ == "__main__":

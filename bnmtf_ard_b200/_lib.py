@@ -93,7 +93,8 @@ _lib = None
 
 
 def lib_path():
-    return _build.LIB
+    # BNMTF_LIB: timing experiments only (an instrumented build of the same sources, e.g. build/libbnmtf_prof.so)
+    return os.environ.get("BNMTF_LIB") or _build.LIB
 
 
 def load():

@@ -153,6 +153,13 @@ class NMFCommon(object):
         self._last_predict = res
         return {'MSE': res['MSE'], 'R^2': res['R^2'], 'Rp': res['Rp']}
 
+    def _shapes_fit_handle(self, **factors):
+        ''' False when a factor was assigned with another number of columns than the constructor's K (L): the
+            reference's own tests do (tests/code/test_bnmf_vb.py:368-393, test_nmf_np.py:222-243) and numpy.dot does
+            not care, but the device handle is built for K (L) columns.  predict() then evaluates the three metrics
+            the way the sampled classes' predict() does -- on the host, off the iteration loop. '''
+        return all(numpy.shape(v) == want for v, want in factors.values())
+
     def _predict_from(self, M_pred, X, Y):
         R_pred = numpy.dot(X, Y.T)
         MSE = self.compute_MSE(M_pred, self.R, R_pred)

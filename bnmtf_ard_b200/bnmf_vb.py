@@ -68,17 +68,27 @@ class bnmf_vb(NMFCommon):
     def _upload_state(self):
         eng = self._engine()
         self._upload_hyper(eng)
-        for side, X in ((SIDE_U, 'U'), (SIDE_V, 'V')):
-            eng.set_factor(side, F_MU, getattr(self, 'mu_' + X))
-            eng.set_factor(side, F_TAU, getattr(self, 'tau_' + X))
-            eng.set_factor(side, F_VALUE, getattr(self, 'exp_' + X))
-            eng.set_factor(side, F_VAR, getattr(self, 'var_' + X))
+        # The state lives in plain attributes that callers -- the reference's tests above all
+        # (tests/code/test_bnmf_vb.py:231-290) -- assign one by one before calling a single update; what has not been
+        # assigned yet does not enter that update and goes up as a neutral value (mu 0, tau 1, moments 0, scalars 1 / 0).
+        for side, X, n in ((SIDE_U, 'U', self.I), (SIDE_V, 'V', self.J)):
+            eng.set_factor(side, F_MU, self._state('mu_' + X, (n, self.K), 0.))
+            eng.set_factor(side, F_TAU, self._state('tau_' + X, (n, self.K), 1.))
+            eng.set_factor(side, F_VALUE, self._state('exp_' + X, (n, self.K), 0.))
+            eng.set_factor(side, F_VAR, self._state('var_' + X, (n, self.K), 0.))
+        sc = [self._state('exp_tau', (), 1.), self._state('exp_logtau', (), 0.), self._state('alpha_s', (), 1.), self._state('beta_s', (), 1.)]
         if self.ARD:
-            eng.set_vb_scalars(self.exp_tau, self.exp_logtau, self.alpha_s, self.beta_s,
-                               self.alphak_s, self.betak_s, self.exp_lambdak, self.exp_loglambdak)
+            eng.set_vb_scalars(*sc, self._state('alphak_s', (self.K,), 1.), self._state('betak_s', (self.K,), 1.),
+                               self._state('exp_lambdak', (self.K,), 1.), self._state('exp_loglambdak', (self.K,), 0.))
         else:
-            eng.set_vb_scalars(self.exp_tau, self.exp_logtau, self.alpha_s, self.beta_s)
+            eng.set_vb_scalars(*sc)
         return eng
+
+    def _state(self, name, shape, default):
+        v = getattr(self, name, None)
+        if v is None or callable(v):        # (alpha_s / beta_s are methods of the sampled parent class until VB assigns them)
+            return default if shape == () else numpy.full(shape, default)
+        return v
 
     _WANT_LAMBDAK = False
 
@@ -159,6 +169,8 @@ class bnmf_vb(NMFCommon):
 
     def predict(self, M_pred):
         ''' Predict missing values in R. '''
+        if not self._shapes_fit_handle(U=(self.exp_U, (self.I, self.K)), V=(self.exp_V, (self.J, self.K))):
+            return self._predict_from(M_pred, numpy.asarray(self.exp_U, dtype=float), numpy.asarray(self.exp_V, dtype=float))
         return self._device_predict(M_pred, _lib.PRED_CURRENT, self._upload_state())
 
     def quality(self, metric):

@@ -79,18 +79,29 @@ class bnmtf_vb(bnmtf_gibbs):
     def _upload_state(self):
         eng = self._engine()
         self._upload_hyper(eng)
-        for side, X in ((SIDE_U, 'F'), (SIDE_V, 'G')):
-            eng.set_factor(side, F_MU, getattr(self, 'mu_' + X)); eng.set_factor(side, F_TAU, getattr(self, 'tau_' + X))
-            eng.set_factor(side, F_VALUE, getattr(self, 'exp_' + X)); eng.set_factor(side, F_VAR, getattr(self, 'var_' + X))
-        eng.set_S(F_MU, self.mu_S); eng.set_S(F_TAU, self.tau_S)
-        eng.set_S(F_VALUE, self.exp_S); eng.set_S(F_VAR, self.var_S)
+        # attributes that the caller has not assigned yet (the reference's tests set only what one update reads,
+        # tests/code/test_bnmtf_vb.py:349-477) go up as neutral values: mu 0, tau 1, moments 0, scalars 1 / 0
+        st = self._state
+        for side, X, n, k in ((SIDE_U, 'F', self.I, self.K), (SIDE_V, 'G', self.J, self.L)):
+            eng.set_factor(side, F_MU, st('mu_' + X, (n, k), 0.)); eng.set_factor(side, F_TAU, st('tau_' + X, (n, k), 1.))
+            eng.set_factor(side, F_VALUE, st('exp_' + X, (n, k), 0.)); eng.set_factor(side, F_VAR, st('var_' + X, (n, k), 0.))
+        kl = (self.K, self.L)
+        eng.set_S(F_MU, st('mu_S', kl, 0.)); eng.set_S(F_TAU, st('tau_S', kl, 1.))
+        eng.set_S(F_VALUE, st('exp_S', kl, 0.)); eng.set_S(F_VAR, st('var_S', kl, 0.))
+        sc = [st('exp_tau', (), 1.), st('exp_logtau', (), 0.), st('alpha_s', (), 1.), st('beta_s', (), 1.)]
         if self.ARD:
-            eng.set_vb_scalars(self.exp_tau, self.exp_logtau, self.alpha_s, self.beta_s,
-                               numpy.array([self.alphaFk_s, self.betaFk_s, self.exp_lambdaFk, self.exp_loglambdaFk]),
-                               numpy.array([self.alphaGl_s, self.betaGl_s, self.exp_lambdaGl, self.exp_loglambdaGl]))
+            eng.set_vb_scalars(*sc,
+                               numpy.array([st('alphaFk_s', (self.K,), 1.), st('betaFk_s', (self.K,), 1.), st('exp_lambdaFk', (self.K,), 1.), st('exp_loglambdaFk', (self.K,), 0.)]),
+                               numpy.array([st('alphaGl_s', (self.L,), 1.), st('betaGl_s', (self.L,), 1.), st('exp_lambdaGl', (self.L,), 1.), st('exp_loglambdaGl', (self.L,), 0.)]))
         else:
-            eng.set_vb_scalars(self.exp_tau, self.exp_logtau, self.alpha_s, self.beta_s)
+            eng.set_vb_scalars(*sc)
         return eng
+
+    def _state(self, name, shape, default):
+        v = getattr(self, name, None)
+        if v is None or callable(v):        # (alpha_s / beta_s are methods of the sampled parent class until VB assigns them)
+            return default if shape == () else numpy.full(shape, default)
+        return v
 
     def run(self, iterations):
         ''' Run the VB updates.  (bnmtf_vb.py:193-245) '''
@@ -189,6 +200,9 @@ class bnmtf_vb(bnmtf_gibbs):
 
     def predict(self, M_pred):
         ''' Predict missing values in R. '''
+        if not self._shapes_fit_handle(F=(self.exp_F, (self.I, self.K)), S=(self.exp_S, (self.K, self.L)), G=(self.exp_G, (self.J, self.L))):
+            FS = numpy.dot(numpy.asarray(self.exp_F, dtype=float), numpy.asarray(self.exp_S, dtype=float))
+            return self._predict_from(M_pred, FS, numpy.asarray(self.exp_G, dtype=float))
         return self._device_predict(M_pred, _lib.PRED_CURRENT, self._upload_state())
 
     def quality(self, metric):

@@ -15,6 +15,7 @@
 #include "../../include/bnmtf_b200.h"
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
+#include "sweep4.h"
 #include "kernels_nmtf.cuh"
 #include "kernels_kmeans.cuh"
 #include "kernels_summary.cuh"
@@ -93,7 +94,8 @@ struct Side {
   int64_t* rowstart = nullptr;
   double *val = nullptr, *var = nullptr, *mu = nullptr, *tau = nullptr;  // [n_padglob][K]
   double* km = nullptr;  // [K][ld][2]
-  double* km3 = nullptr; // [ceil(K/B)][ld][B*NV]: block-major copy read by the blocked cluster sweep of the other side
+  double* kmB = nullptr;  // [ceil(K/2)][ld][2]: block-major copy of the values, read by the blocked cluster sweep of the other side
+  double* kmBq = nullptr; // same layout, Var + E^2 (VB)
   int64_t ld = 0;
   double* lam_rm = nullptr;
   double* rowstats = nullptr;  // [n_padglob][NRS]
@@ -113,6 +115,8 @@ struct Side {
   double* tvals = nullptr;
   uint16_t* tcols = nullptr;
   int nclusters[4] = {0, 0, 0, 0};
+  bool v4 = false;                       // blocked cluster sweep (kernels_v4.cuh) serves this side's Gibbs / ICM / VB sweeps
+  int nclusters4[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};   // resident clusters per method, without / with the parameter outputs
   bool long_rows = false;      // rows beyond the register-resident configurations: residual in global scratch (kernels_long.cuh)
   double* escr = nullptr;      // [nslots]
   int occ_long[4] = {0, 0, 0, 0};
@@ -147,6 +151,8 @@ struct bnmtf_nmf_s {
   double sweep_ms[2] = {0, 0};
   int64_t sweep_n[2] = {0, 0};
   int km_mode = -1;            // NV layout currently held by the km copies
+  double* gmat = nullptr;              // random-material scratch of the blocked cluster sweep (kernels_v4.cuh)
+  size_t gmat_doubles = 0;
   uint32_t* iter_dev = nullptr;        // device-side iteration index (graph replays of the run loop)
   const uint32_t* iter_ptr = nullptr;  // == iter_dev while a graph-mode run is in progress
   // ---- tri-factorisation (R ~ F S G^T): side 0 = F (I x K), side 1 = G (J x L)
@@ -258,6 +264,12 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
   const int cs = V2_CS;
   const size_t smem_vb = sweep2_smem_doubles(sd.tw, 2, rs, sd.kf, cs) * sizeof(double);
   sd.v2 = !force_v1 && m >= 2048 && maxseg >= 64 && npt2 <= 20 && sd.kf >= 3 && smem_vb <= 200 * 1024 && (sd.tw + V2_PAD) * 16 < 65536;
+  {
+    const char* v4env = getenv("BNMTF_V4");
+    const int rs4 = npt2 == 20 ? sweep4_wpc() / 2 - 1 : rs;    // the blocked sweep may trade rows per set for registers (20 entries per lane only)
+    sd.v4 = sd.v2 && !h->nmtf && npt2 % 4 == 0 && sweep4_fits(sd.tw, rs4, sd.kf) && (v4env && atoi(v4env) == 1);   // opt-in: measured 8.1 - 9.2 ms per sweep at C3 against 8.5 for kernels_v2.cuh, depending on the build
+    if (sd.v4) rs = rs4;
+  }
   if (sd.v2 && n > 0) {
     sd.cs = cs; sd.npt2 = npt2; sd.rs = rs;
     sd.nsets = (n + rs - 1) / rs;
@@ -269,7 +281,7 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
                                                                              sd.tvals, sd.tcols);
     h->launches += 2;
   } else {
-    sd.v2 = false;
+    sd.v2 = false; sd.v4 = false;
   }
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -289,8 +301,9 @@ static int alloc_side_state(bnmtf_nmf_s* h, Side& sd, int K) {
   sd.ld = roundup(std::max(sd.n_padglob, sd.n_glob + 1) + 16 * 32, 16);  // >= CS * tile width (CS <= 16)
   CK(cudaMalloc(&sd.km, sizeof(double) * 2 * sd.ld * K));
   CK(cudaMemsetAsync(sd.km, 0, sizeof(double) * 2 * sd.ld * K, h->stream));
-  CK(cudaMalloc(&sd.km3, sizeof(double) * 2 * sd.ld * (K + 3)));
-  CK(cudaMemsetAsync(sd.km3, 0, sizeof(double) * 2 * sd.ld * (K + 3), h->stream));
+  const size_t nbB = sizeof(double) * 2 * sd.ld * ((K + 1) / 2);
+  CK(cudaMalloc(&sd.kmB, nbB)); CK(cudaMalloc(&sd.kmBq, nbB));
+  CK(cudaMemsetAsync(sd.kmB, 0, nbB, h->stream)); CK(cudaMemsetAsync(sd.kmBq, 0, nbB, h->stream));
   CK(cudaMalloc(&sd.rowstats, sizeof(double) * sd.n_padglob * NRS));
   CK(cudaMemsetAsync(sd.rowstats, 0, sizeof(double) * sd.n_padglob * NRS, h->stream));
   return 0;
@@ -525,7 +538,7 @@ static int create_host_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, 
 static void free_side(Side& sd) {
   cudaFree(sd.vals); cudaFree(sd.cols); cudaFree(sd.rowstart);
   cudaFree(sd.val); cudaFree(sd.var); cudaFree(sd.mu); cudaFree(sd.tau);
-  cudaFree(sd.km); cudaFree(sd.km3); cudaFree(sd.lam_rm); cudaFree(sd.rowstats);
+  cudaFree(sd.km); cudaFree(sd.kmB); cudaFree(sd.kmBq); cudaFree(sd.lam_rm); cudaFree(sd.rowstats);
   cudaFree(sd.trace[0]); cudaFree(sd.trace[1]);
   cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev); cudaFree(sd.ycomb); cudaFree(sd.escr);
   if (sd.own_dense) { cudaFree((void*)sd.dR); cudaFree((void*)sd.dM); }
@@ -543,7 +556,7 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   cudaFree(h->S); cudaFree(h->Svar); cudaFree(h->Smu); cudaFree(h->Stau); cudaFree(h->lamS); cudaFree(h->lamG);
   cudaFree(h->Prow); cudaFree(h->Hrow); cudaFree(h->cvec); cudaFree(h->TT); cudaFree(h->Tpart);
   cudaFree(h->Arow); cudaFree(h->Brow); cudaFree(h->Crow); cudaFree(h->BS); cudaFree(h->PA); cudaFree(h->QC);
-  cudaFree(h->lamstateG); cudaFree(h->vbmisc); cudaFree(h->iter_dev);
+  cudaFree(h->lamstateG); cudaFree(h->vbmisc); cudaFree(h->iter_dev); cudaFree(h->gmat);
   summary_free(h);
   for (int b = 0; b < 2; ++b) if (h->pin[b]) cudaFreeHost(h->pin[b]);
   cudaStreamSynchronize(h->stream);
@@ -714,6 +727,13 @@ static int refresh_km(bnmtf_nmf_s* h, int side, int method) {
   else
     rm_to_km_kernel<1><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, sd.kf, sd.ld);
   h->launches++;
+  // the blocked cluster sweep of the other side reads the block-major copies
+  if (h->s[1 - side].v4 && !h->nmtf && method != BNMTF_NP) {
+    dim3 g3((unsigned)((sd.ld + 255) / 256), (unsigned)((sd.kf + 1) / 2));
+    if (method == BNMTF_VB) rm_to_kmB_kernel<true><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
+    else rm_to_kmB_kernel<false><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
+    h->launches++;
+  }
   return 0;
 }
 
@@ -900,6 +920,24 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
       bnmtf_prof_last = prof_buf;
     }
     rc = 0;
+    if (sd.v4 && p.K2 == 0) {
+      p.Ykm = h->s[1 - side].kmB; p.Ykm2 = h->s[1 - side].kmBq; p.ldy = h->s[1 - side].ld;
+      if (method != BNMTF_GIBBS && method != BNMTF_ICM && method != BNMTF_VB) FAIL("unknown method %d", method);
+      if (method == BNMTF_GIBBS) {
+        const size_t need = sweep4_gmat_doubles(sd.rs, sd.kf);
+        if (h->gmat_doubles < need) {
+          CK(cudaStreamSynchronize(h->stream));
+          cudaFree(h->gmat); h->gmat = nullptr; h->gmat_doubles = 0;
+          CK(cudaMalloc(&h->gmat, sizeof(double) * need));
+          h->gmat_doubles = need;
+        }
+        p.gmat = h->gmat;
+      }
+      std::string err;
+      rc = launch_sweep4(sd.npt2, method, p, h->stream, &sd.nclusters4[method][p.Xmu != nullptr ? 1 : 0], &err);
+      if (rc) { g_err = err; return 1; }
+      h->launches++;
+    } else
     switch (method) {
       case BNMTF_GIBBS: rc = launch_sweep2_m<M_GIBBS>(h, p, sd, method); break;
       case BNMTF_ICM: rc = launch_sweep2_m<M_ICM>(h, p, sd, method); break;
@@ -926,6 +964,11 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     // phase clocks of cluster 0 / CTA 0 (control warp: slots 0-4, first compute warp: 8-15), in cycles per set
     cudaStreamSynchronize(h->stream);
     unsigned long long* pb = bnmtf_prof_last;
+    if (pb && pb[16] > 0 && sd.v4) {
+      fprintf(stderr, "[v4 prof side %d] sets %llu | ctrl: start+phaseA %llu prep %llu slotwait %llu recwait %llu cond %llu book %llu tail %llu | comp: start %llu phaseA %llu statx %llu corr %llu tilewait %llu dot %llu reduce %llu deltawait %llu tail %llu (cycles/set)\n",
+              side, pb[16], pb[0] / pb[16], pb[1] / pb[16], pb[2] / pb[16], pb[3] / pb[16], pb[4] / pb[16], pb[5] / pb[16], pb[6] / pb[16], pb[8] / pb[16],
+              pb[9] / pb[16], pb[10] / pb[16], pb[11] / pb[16], pb[12] / pb[16], pb[13] / pb[16], pb[14] / pb[16], pb[15] / pb[16], pb[17] / pb[16]);
+    } else
     if (pb && pb[16] > 0) {
       fprintf(stderr, "[v3 prof side %d] sets %llu | ctrl: pre %llu wait_pass %llu cbar %llu update %llu sync %llu | comp: start %llu resid %llu tilewait %llu pass %llu reduce %llu cbar %llu deltawait %llu tail %llu (cycles/set) | fallback lanes %llu, columns with a fallback %llu of %llu\n",
               side, pb[16], pb[0] / pb[16], pb[1] / pb[16], pb[2] / pb[16], pb[3] / pb[16], pb[4] / pb[16], pb[8] / pb[16],
@@ -1407,7 +1450,7 @@ int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {  // out8: 16 values
   out8[4] = h->s[0].nslots; out8[5] = h->s[1].nslots; out8[6] = h->s[0].nnz; out8[7] = h->s[1].nnz;
   for (int q = 0; q < 2; ++q) {
     const Side& sd = h->s[q];
-    out8[8 + 4 * q] = sd.v2 ? 1 : 0;   // 1: cluster sweep
+    out8[8 + 4 * q] = sd.v2 ? (sd.v4 ? 4 : 1) : 0;   // 1: cluster sweep (kernels_v2.cuh), 4: blocked cluster sweep (kernels_v4.cuh)
     out8[9 + 4 * q] = sd.v2 ? sd.npt2 : 0;
     out8[10 + 4 * q] = sd.v2 ? sd.rs : 0; out8[11 + 4 * q] = sd.v2 ? sd.tslots : 0;
   }

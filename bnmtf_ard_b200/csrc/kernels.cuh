@@ -152,7 +152,7 @@ __device__ __forceinline__ double conditional_update(const double (&s)[3], doubl
     v_new = vn;
     acc_esd += (vn + en * en) * s[1] - (en * en) * s[0];
     if (WITH_Q)
-      acc_q += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951))
+      acc_q += -0.5 * log(ct) + log_half_erfc_ref(-cm * sqrt(ct) / 1.4142135623730951)
                + 0.5 * ct * (vn + (en - cm) * (en - cm));
     acc_prior += lam * en;
   } else {
@@ -178,7 +178,7 @@ __device__ __forceinline__ double vb_row_q(const double* xs, const double* xvar,
   double qq = 0.0;
   for (int kk = lane; kk < K; kk += 32) {
     const double ct = xtau[kk], cm = xmu[kk], en = xs[kk], vn = xvar[kk];
-    qq += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951)) + 0.5 * ct * (vn + (en - cm) * (en - cm));
+    qq += -0.5 * log(ct) + log_half_erfc_ref(-cm * sqrt(ct) / 1.4142135623730951) + 0.5 * ct * (vn + (en - cm) * (en - cm));
   }
   return warp_sum(qq);
 }
@@ -477,27 +477,27 @@ __global__ void __launch_bounds__(SweepCfg<NPT>::MAXT, 1) sweep_kernel(const Swe
 // Row-major factor [n_pad][K]  ->  k-major gather layout [K][ld][NV], zero padded
 // for i >= n.  NV == 2 (VB): (exp, var + exp^2) pairs (bnmf_vb.py:254).
 // -----------------------------------------------------------------------------
-// Block-major copy for the blocked cluster sweep (kernels_v3.cuh): the B columns of a block are
-// interleaved per row, Y[(kb * ld + i) * B * NV + j * NV + v] for column kb * B + j; zero for
-// columns >= K and rows >= n.
-template <int NV, int B>
-__global__ void rm_to_kmB_kernel(const double* __restrict__ Xval, const double* __restrict__ Xvar, double* __restrict__ Y,
-                                 int64_t n, int K, int64_t ld) {
+// Block-major copies for the blocked cluster sweep (kernels_v4.cuh): the two columns of a block are interleaved per
+// row, YE[(kb * ld + i) * 2 + j] = X[i][2 kb + j] and (VB) YQ[...] = Var + X^2 of the same entry (bnmf_vb.py:254);
+// zero for columns >= K and rows >= n.
+template <bool VB>
+__global__ void rm_to_kmB_kernel(const double* __restrict__ Xval, const double* __restrict__ Xvar, double* __restrict__ YE,
+                                 double* __restrict__ YQ, int64_t n, int K, int64_t ld) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int kb = blockIdx.y;
   if (i >= ld) return;
-  double* dst = Y + ((size_t)kb * ld + i) * (B * NV);
-#pragma unroll
-  for (int j = 0; j < B; ++j) {
-    const int k = kb * B + j;
-    double a = 0.0, b = 0.0;
-    if (i < n && k < K) {
-      a = Xval[i * K + k];
-      if (NV == 2) { const double vv = Xvar[i * K + k]; b = vv + a * a; }
+  double2 e = make_double2(0.0, 0.0), q = make_double2(0.0, 0.0);
+  if (i < n) {
+    const int k = 2 * kb;
+    e.x = Xval[i * K + k];
+    if (VB) q.x = Xvar[i * K + k] + e.x * e.x;
+    if (k + 1 < K) {
+      e.y = Xval[i * K + k + 1];
+      if (VB) q.y = Xvar[i * K + k + 1] + e.y * e.y;
     }
-    dst[j * NV] = a;
-    if (NV == 2) dst[j * NV + 1] = b;
   }
+  reinterpret_cast<double2*>(YE)[(size_t)kb * ld + i] = e;
+  if (VB) reinterpret_cast<double2*>(YQ)[(size_t)kb * ld + i] = q;
 }
 
 template <int NV>
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
 
 // Graph replays: copy the draws of the iteration *iter_ptr into the trace staging buffers
 // (all_U[it], all_V[it], all_lambdak[it]); runs before finalize_kernel advances the index.
-__global__ void trace_copy_kernel(double* __restrict__ dstU, const double* __restrict__ srcU, int64_t nU, double* __restrict__ dstV,
+static __global__ void trace_copy_kernel(double* __restrict__ dstU, const double* __restrict__ srcU, int64_t nU, double* __restrict__ dstV,
                                   const double* __restrict__ srcV, int64_t nV, double* __restrict__ dstL,
                                   const double* __restrict__ srcL, int64_t nL, const uint32_t* __restrict__ iter_ptr) {
   const size_t it = *iter_ptr;
@@ -719,7 +719,7 @@ __global__ void trace_copy_kernel(double* __restrict__ dstU, const double* __res
 
 // ---- packing -----------------------------------------------------------------
 // observed entries per row of a dense mask block (n x m, row-major, ld)
-__global__ void count_rows_kernel(const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld, int* __restrict__ rowlen) {
+static __global__ void count_rows_kernel(const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld, int* __restrict__ rowlen) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -730,7 +730,7 @@ __global__ void count_rows_kernel(const uint8_t* __restrict__ M, int64_t n, int6
 }
 
 // compact one row per warp, in column order, then pad the tail of the row
-__global__ void pack_rows_kernel(const double* __restrict__ R, const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld,
+static __global__ void pack_rows_kernel(const double* __restrict__ R, const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld,
                                  const int64_t* __restrict__ rowstart, uint32_t padcol, double* __restrict__ vals,
                                  uint32_t* __restrict__ cols) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -769,7 +769,7 @@ __global__ void transpose_kernel(const T* __restrict__ A, int64_t n, int64_t m, 
 }
 
 // sum of r and of (r-c)^2 over the packed values; padded slots are flagged by cols == padcol
-__global__ void data_stats_kernel(const double* __restrict__ vals, const uint32_t* __restrict__ cols, int64_t nslots,
+static __global__ void data_stats_kernel(const double* __restrict__ vals, const uint32_t* __restrict__ cols, int64_t nslots,
                                   uint32_t padcol, double center, double* __restrict__ partial) {
   __shared__ double sh[32];
   double a = 0.0, b = 0.0, cnt = 0.0;
@@ -781,7 +781,7 @@ __global__ void data_stats_kernel(const double* __restrict__ vals, const uint32_
 }
 
 // ---- initialise(): Exp(rate lambda) draws or 1/lambda -----------------------
-__global__ void init_factor_kernel(double* __restrict__ X, int64_t n, int K, const double* __restrict__ lam_rm,
+static __global__ void init_factor_kernel(double* __restrict__ X, int64_t n, int K, const double* __restrict__ lam_rm,
                                    const double* __restrict__ lamk, int random, uint64_t seed, uint32_t purpose) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * K) return;
@@ -797,7 +797,7 @@ __global__ void init_factor_kernel(double* __restrict__ X, int64_t n, int K, con
 }
 
 // VB initialise: tau_X = 1, moments of TN(mu, 1)  (bnmf_vb.py:118-135)
-__global__ void vb_init_moments_kernel(const double* __restrict__ mu, double* __restrict__ tau, double* __restrict__ ex,
+static __global__ void vb_init_moments_kernel(const double* __restrict__ mu, double* __restrict__ tau, double* __restrict__ ex,
                                        double* __restrict__ var, int64_t n) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
@@ -808,24 +808,24 @@ __global__ void vb_init_moments_kernel(const double* __restrict__ mu, double* __
 }
 
 // ---- distributions API kernels ------------------------------------------------
-__global__ void api_tn_draw_kernel(const double* mu, const double* tau, double* out, int64_t n, uint64_t seed) {
+static __global__ void api_tn_draw_kernel(const double* mu, const double* tau, double* out, int64_t n, uint64_t seed) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Rng rng(seed, RNG_API, (uint64_t)i, 1u, 0u);
   out[i] = tn_draw(mu[i], tau[i], rng);
 }
-__global__ void api_tn_moments_kernel(const double* mu, const double* tau, double* e, double* v, int64_t n) {
+static __global__ void api_tn_moments_kernel(const double* mu, const double* tau, double* e, double* v, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   tn_moments(mu[i], tau[i], e[i], v[i]);
 }
-__global__ void api_gamma_draw_kernel(const double* alpha, const double* beta, double* out, int64_t n, uint64_t seed) {
+static __global__ void api_gamma_draw_kernel(const double* alpha, const double* beta, double* out, int64_t n, uint64_t seed) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Rng rng(seed, RNG_API, (uint64_t)i, 2u, 0u);
   out[i] = gamma_draw(alpha[i], beta[i], rng);
 }
-__global__ void api_exp_draw_kernel(const double* lambda, double* out, int64_t n, uint64_t seed) {
+static __global__ void api_exp_draw_kernel(const double* lambda, double* out, int64_t n, uint64_t seed) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Rng rng(seed, RNG_API, (uint64_t)i, 3u, 0u);

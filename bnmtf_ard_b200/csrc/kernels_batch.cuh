@@ -102,7 +102,7 @@ __global__ void rm_to_km_batch_kernel(const KmArgs* __restrict__ aa) {
 }
 
 // grid (blocks per model, models), 256 threads
-__global__ void summary_accum_batch_kernel(const SumBatchArgs* __restrict__ aa) {
+static __global__ void summary_accum_batch_kernel(const SumBatchArgs* __restrict__ aa) {
   const SumBatchArgs& g = aa[blockIdx.y];
   const int it = (int)*g.iter_ptr - 1;
   if (g.thin <= 0 || it < g.burn || (it - g.burn) % g.thin != 0) return;

@@ -12,7 +12,7 @@ namespace bnmtf {
 // cm = [Kc][ld] pairs (centroid value, centroid mask as 0/1).  The closest cluster is the
 // lowest index among those with the smallest defined MSE; a cluster without overlap has
 // no MSE (None) and is only kept while nothing better has been seen (kmeans.py:112-116).
-__global__ void kmeans_assign_kernel(const double* __restrict__ vals, const uint32_t* __restrict__ cols,
+static __global__ void kmeans_assign_kernel(const double* __restrict__ vals, const uint32_t* __restrict__ cols,
                                      const int64_t* __restrict__ rowstart, int n_loc, int64_t row0, uint32_t padcol,
                                      const double* __restrict__ cm, int64_t ld, int Kc, int* __restrict__ assign,
                                      double* __restrict__ dist) {
@@ -48,7 +48,7 @@ __global__ void kmeans_assign_kernel(const double* __restrict__ vals, const uint
 // update_cluster() (kmeans.py:131-170): one warp per coordinate of the transposed layout (entries = points that
 // observe the coordinate).  centroid[c][j] = mean of the observed values of the points assigned to c, mask 1;
 // 0 and mask 0 if none.  Only clusters with flag[c] != 0 are written.
-__global__ void kmeans_update_kernel(const double* __restrict__ vals, const uint32_t* __restrict__ cols,
+static __global__ void kmeans_update_kernel(const double* __restrict__ vals, const uint32_t* __restrict__ cols,
                                      const int64_t* __restrict__ rowstart, int n_loc, int64_t row0, uint32_t padcol,
                                      const int* __restrict__ assign, const int* __restrict__ flag, int Kc,
                                      double* __restrict__ cm, int64_t ld) {
@@ -71,7 +71,7 @@ __global__ void kmeans_update_kernel(const double* __restrict__ vals, const uint
 }
 
 // per-coordinate minimum and maximum of the observed values (kmeans.py:50-52)
-__global__ void kmeans_minmax_kernel(const double* __restrict__ vals, const uint32_t* __restrict__ cols,
+static __global__ void kmeans_minmax_kernel(const double* __restrict__ vals, const uint32_t* __restrict__ cols,
                                      const int64_t* __restrict__ rowstart, int n_loc, int64_t row0, uint32_t padcol,
                                      double* __restrict__ mins, double* __restrict__ maxs) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

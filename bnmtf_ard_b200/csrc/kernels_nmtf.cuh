@@ -22,7 +22,7 @@
 namespace bnmtf {
 
 // out_km[c][i] = sum_q X_rm[i][q] * Smat[q*s_q + c*s_c]  (i < n), zero padded to ld
-__global__ void combine_km_kernel(const double* __restrict__ X_rm, int64_t n, int kq, const double* __restrict__ Smat, int s_q,
+static __global__ void combine_km_kernel(const double* __restrict__ X_rm, int64_t n, int kq, const double* __restrict__ Smat, int s_q,
                                   int s_c, double* __restrict__ out_km, int64_t ld) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(WARPS * 32) nmtf_gram44_kernel(const uint32_t*
 }
 
 // c[k][l] = sum_i F[i][k] P[i][l]    (one block per (k,l), fixed-order tree)
-__global__ void nmtf_reduce_c_kernel(const double* __restrict__ F, const double* __restrict__ P, int64_t I, int K, int L,
+static __global__ void nmtf_reduce_c_kernel(const double* __restrict__ F, const double* __restrict__ P, int64_t I, int K, int L,
                                      double* __restrict__ c) {
   __shared__ double sh[32];
   const int k = blockIdx.x / L, l = blockIdx.x % L;
@@ -227,7 +227,7 @@ __global__ void nmtf_reduce_c_kernel(const double* __restrict__ F, const double*
 constexpr int RT_PKT = 14;   // pairs per block
 constexpr int RT_RC = 32;    // row chunks
 constexpr int RT_ROWS = 64;  // rows of F products staged at a time
-__global__ void __launch_bounds__(256) nmtf_reduce_T_kernel(const double* __restrict__ F, const double* __restrict__ H, int64_t I, int K,
+static __global__ void __launch_bounds__(256) nmtf_reduce_T_kernel(const double* __restrict__ F, const double* __restrict__ H, int64_t I, int K,
                                                             int NPK, int W, double* __restrict__ part) {
   __shared__ double ff[RT_ROWS][RT_PKT];
   __shared__ double red[8][RT_PKT][33];
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) nmtf_reduce_T_kernel(const double* __rest
     }
   }
 }
-__global__ void nmtf_reduce_T_fold_kernel(const double* __restrict__ part, int64_t n, double* __restrict__ TT) {
+static __global__ void nmtf_reduce_T_fold_kernel(const double* __restrict__ part, int64_t n, double* __restrict__ TT) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
   double t = 0.0;
@@ -381,7 +381,7 @@ __global__ void nmtf_lambda_kernel(const double* __restrict__ F, int64_t I, int 
 // Pair-layout gather source of update_F / update_G (bnmtf_vb.py:337-339,365-366):
 //   out[c][i] = ( w, var + w^2 ),  w = sum_q EX[i][q] ES(q,c),
 //   var = sum_q (VX+EX^2)[i][q] (VS+ES^2)(q,c) - sum_q EX[i][q]^2 ES(q,c)^2      (var_SkG / var_FSl)
-__global__ void vb_combine_km_kernel(const double* __restrict__ EX, const double* __restrict__ VX, int64_t n, int kq,
+static __global__ void vb_combine_km_kernel(const double* __restrict__ EX, const double* __restrict__ VX, int64_t n, int kq,
                                      const double* __restrict__ ES, const double* __restrict__ VS, int s_q, int s_c,
                                      double* __restrict__ out_km, int64_t ld) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -401,7 +401,7 @@ __global__ void vb_combine_km_kernel(const double* __restrict__ EX, const double
 }
 
 // out[k][l] = sum_i f(i,k) P[i][l]  with f = F (Fvar == nullptr) or Fvar + F^2
-__global__ void nmtf_reduce_c2_kernel(const double* __restrict__ F, const double* __restrict__ Fvar, const double* __restrict__ P,
+static __global__ void nmtf_reduce_c2_kernel(const double* __restrict__ F, const double* __restrict__ Fvar, const double* __restrict__ P,
                                       int64_t I, int K, int L, double* __restrict__ out) {
   __shared__ double sh[32];
   const int k = blockIdx.x / L, l = blockIdx.x % L;
@@ -423,7 +423,7 @@ __device__ __forceinline__ double tmat(const double* TT, int k, int l, int k2, i
 //   covG = sum_{k'!=k} ES(k',l) PA[pair(k,k')][l],  covF = sum_{l'!=l} ES(k,l') QC[pair(l,l')][k]
 // mode: -1 full sweep, -2 dry (ELBO terms of the stored state), d >= 0 report (tau, mu) of entry d.
 // misc[0] = sum_d q-terms of S for the ELBO (bnmtf_vb.py:290-292), misc[1] = sum lambdaS*ES (:268).
-__global__ void __launch_bounds__(512) nmtf_s_sweep_vb_kernel(const double* __restrict__ c_in, const double* __restrict__ TT, const double* __restrict__ BS,
+static __global__ void __launch_bounds__(512) nmtf_s_sweep_vb_kernel(const double* __restrict__ c_in, const double* __restrict__ TT, const double* __restrict__ BS,
                                        const double* __restrict__ PA, const double* __restrict__ QC, int K, int L, double* Sexp,
                                        double* Svar, double* Smu, double* Stau, const double* __restrict__ lamS,
                                        const double* __restrict__ scal, int mode, double* out_tau, double* out_mu, double* misc) {
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_vb_kernel(const double* __re
         out_tau[0] = ct; out_mu[0] = cm;
         bc[0] = 0.0;
       } else {
-        acc_q += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951)) + 0.5 * ct * (vn + (en - cm) * (en - cm));
+        acc_q += -0.5 * log(ct) + log_half_erfc_ref(-cm * sqrt(ct) / 1.4142135623730951) + 0.5 * ct * (vn + (en - cm) * (en - cm));
         acc_prior += lamS[d] * en;
         bc[0] = en - es[d];
         if (mode == -1) { Smu[d] = cm; Stau[d] = ct; Svar[d] = vn; es[d] = en; }
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_vb_kernel(const double* __re
 //   * T_dd, BS, lambdaS sit in shared memory; the q(S) terms of the ELBO (two logarithms and an erfc per entry,
 //     bnmtf_vb.py:290-292) and sum lambdaS ES are evaluated by all threads after the sweep (fixed-order block sum).
 // Entry reports (mode >= 0) see exactly the from-scratch sums of the general kernel.
-__global__ void __launch_bounds__(512) nmtf_s_sweep_vb_fast_kernel(const double* __restrict__ c_in, const double* __restrict__ TT,
+static __global__ void __launch_bounds__(512) nmtf_s_sweep_vb_fast_kernel(const double* __restrict__ c_in, const double* __restrict__ TT,
                                        const double* __restrict__ BS, const double* __restrict__ PA, const double* __restrict__ QC,
                                        int K, int L, double* Sexp, double* Svar, double* Smu, double* Stau,
                                        const double* __restrict__ lamS, const double* __restrict__ scal, int mode, double* out_tau,
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_vb_fast_kernel(const double*
     double aq = 0.0, ap = 0.0;
     for (int d = tid; d < KL; d += nt) {
       const double ct = Stau[d], cm = Smu[d], en = es[d], vn = Svar[d];
-      aq += -0.5 * log(ct) + log(0.5 * erfc(-cm * sqrt(ct) / 1.4142135623730951)) + 0.5 * ct * (vn + (en - cm) * (en - cm));
+      aq += -0.5 * log(ct) + log_half_erfc_ref(-cm * sqrt(ct) / 1.4142135623730951) + 0.5 * ct * (vn + (en - cm) * (en - cm));
       ap += lam[d] * en;
     }
     aq = block_sum(aq, red);
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_vb_fast_kernel(const double*
 //   = sum_j sum_k C_jk ((sum_l ES_kl EG_jl)^2 - sum_l ES_kl^2 EG_jl^2),  C = masked column sums of VarF.
 // T3_BLOCKS blocks over contiguous ranges of j, then a fixed-order fold of their partial sums (nmtf_t3_fold_kernel).
 constexpr int T3_BLOCKS = 128;
-__global__ void __launch_bounds__(256) nmtf_t3_kernel(const double* __restrict__ C, const double* __restrict__ EG, const double* __restrict__ ES, int64_t J,
+static __global__ void __launch_bounds__(256) nmtf_t3_kernel(const double* __restrict__ C, const double* __restrict__ EG, const double* __restrict__ ES, int64_t J,
                                int K, int L, double* __restrict__ part) {
   __shared__ double sh[32];
   double a = 0.0;
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(256) nmtf_t3_kernel(const double* __restrict__
   a = block_sum(a, sh);
   if (threadIdx.x == 0) part[blockIdx.x] = a;
 }
-__global__ void nmtf_t3_fold_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+static __global__ void nmtf_t3_fold_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double a = 0.0;
   for (int q = 0; q < n; ++q) a += part[q];
@@ -616,7 +616,7 @@ __global__ void nmtf_t3_fold_kernel(const double* __restrict__ part, int n, doub
 
 // VB lambda updates of both ARD blocks (bnmtf_vb.py:207-213,326-334,383-391): block per column.
 // state[4][K+L]: alpha*, beta*, E[lambda], E[log lambda] (F columns first, then G columns).
-__global__ void nmtf_lambda_vb_kernel(const double* __restrict__ F, int64_t I, int K, const double* __restrict__ G, int64_t J, int L,
+static __global__ void nmtf_lambda_vb_kernel(const double* __restrict__ F, int64_t I, int K, const double* __restrict__ G, int64_t J, int L,
                                       Hyper h, double* colsum, double* state, double* lamF, double* lamG, int update) {
   __shared__ double sh[32];
   const int c = blockIdx.x;
@@ -641,7 +641,7 @@ __global__ void nmtf_lambda_vb_kernel(const double* __restrict__ F, int64_t I, i
 
 // update_tau / update_exp_tau / elbo of bnmtf_vb (bnmtf_vb.py:225-229,248-324).  Single block.
 // misc: [0] q-terms of S, [1] sum lambdaS*ES, [2] T3.
-__global__ void __launch_bounds__(1024) nmtf_vb_finalize_kernel(const double* __restrict__ rsF, int64_t nF, const double* __restrict__ rsG, int64_t nG, int K,
+static __global__ void __launch_bounds__(1024) nmtf_vb_finalize_kernel(const double* __restrict__ rsF, int64_t nF, const double* __restrict__ rsG, int64_t nG, int K,
                                         int L, Hyper h, double sumlog_lamS, const double* __restrict__ colsum,
                                         const double* __restrict__ state, const double* __restrict__ misc, double* scal,
                                         double* stats_out, int update, int64_t I, int64_t J, uint32_t* iter_ctr) {
@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(1024) nmtf_vb_finalize_kernel(const double* __
 
 // nmtf_np.update_S(k,l) (nmtf_np.py:181-188): S_kl <- S_kl * sum_i F_ik num_i / sum_i F_ik den_i with the row parts
 // num_i = sum_j M_ij R_ij/Rhat_ij G_jl, den_i = sum_j M_ij G_jl.  One block; writes S_kl (and the new value to out).
-__global__ void nmtf_np_s_update_kernel(const double* __restrict__ F, const double* __restrict__ num, const double* __restrict__ den,
+static __global__ void nmtf_np_s_update_kernel(const double* __restrict__ F, const double* __restrict__ num, const double* __restrict__ den,
                                         int64_t I, int K, int k, double* S_kl, double* out, int apply) {
   __shared__ double sh[32];
   double a = 0.0, b = 0.0;
@@ -720,7 +720,7 @@ __global__ void nmtf_np_s_update_kernel(const double* __restrict__ F, const doub
   }
 }
 
-__global__ void init_vector_kernel(double* __restrict__ X, int64_t n, const double* __restrict__ lam, int random, uint64_t seed,
+static __global__ void init_vector_kernel(double* __restrict__ X, int64_t n, const double* __restrict__ lam, int random, uint64_t seed,
                                    uint32_t purpose) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;

@@ -10,7 +10,7 @@ struct SumArgs { SumSeg seg[6]; int nseg; };
 
 // dst += src for every segment; summation order over iterations is the launch order, i.e. the
 // order of numpy's axis-0 sum in the reference.
-__global__ void summary_accum_kernel(SumArgs a) {
+static __global__ void summary_accum_kernel(SumArgs a) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int s = 0; s < a.nseg; ++s) {
     double* __restrict__ d = a.seg[s].dst;
@@ -19,7 +19,7 @@ __global__ void summary_accum_kernel(SumArgs a) {
   }
 }
 
-__global__ void summary_mean_kernel(double* __restrict__ dst, const double* __restrict__ sum, int64_t n, double count) {
+static __global__ void summary_mean_kernel(double* __restrict__ dst, const double* __restrict__ sum, int64_t n, double count) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = sum[i] / count;
 }
@@ -52,7 +52,7 @@ __device__ __forceinline__ void pred_block_reduce(double (&v)[NQ], double* __res
 
 // pass 1: prediction of every test entry (A_i . B_j, or A_i S B_j^T when S != nullptr) and the
 // per-block sums of r and p.  A: [nA][ka], B: [nB][kb] row-major.
-__global__ void __launch_bounds__(PRED_THREADS) predict_pass1_kernel(
+static __global__ void __launch_bounds__(PRED_THREADS) predict_pass1_kernel(
     const double* __restrict__ A, int ka, const double* __restrict__ B, int kb, const double* __restrict__ S,
     const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, const double* __restrict__ vals, int64_t n,
     double* __restrict__ pred, double* __restrict__ partial) {
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(PRED_THREADS) predict_pass1_kernel(
 }
 
 // pass 2: centred sums; means[0] = mean of r, means[1] = mean of p
-__global__ void __launch_bounds__(PRED_THREADS) predict_pass2_kernel(
+static __global__ void __launch_bounds__(PRED_THREADS) predict_pass2_kernel(
     const double* __restrict__ vals, const double* __restrict__ pred, int64_t n, const double* __restrict__ means,
     double* __restrict__ partial) {
   const double mr = means[0], mp = means[1];
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(PRED_THREADS) predict_pass2_kernel(
 
 // fixed-order fold of the per-block partials.  stage 0: out[0..1] = means; stage 1: the metrics
 // out[8] = {n, MSE, R^2, Rp, SS_res, SS_tot, mean_real, mean_pred}
-__global__ void predict_fold_kernel(const double* __restrict__ partial, int nblocks, int nq, int stage, double n,
+static __global__ void predict_fold_kernel(const double* __restrict__ partial, int nblocks, int nq, int stage, double n,
                                     double* __restrict__ means, double* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double s[4] = {0, 0, 0, 0};

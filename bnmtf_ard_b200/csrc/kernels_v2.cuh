@@ -60,7 +60,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ---- layout statistics: observed entries per row and the longest (row, tile) segment
-__global__ void count_rows_tiles_kernel(const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld, int tw,
+static __global__ void count_rows_tiles_kernel(const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld, int tw,
                                         int* __restrict__ rowlen, int* __restrict__ maxseg) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -82,7 +82,7 @@ __global__ void count_rows_tiles_kernel(const uint8_t* __restrict__ M, int64_t n
 // gathers of the other lanes (a single shared zero sat in one bank class and cost every mixed half-warp a
 // replay: 25 % extra shared-memory wavefronts at the 20000 x 20000 size, 4 % with per-class zeros).
 constexpr int V2_PAD = 16;
-__global__ void fill_pads_kernel(double* __restrict__ tvals, uint16_t* __restrict__ tcols, int64_t nslots, uint16_t padcol) {
+static __global__ void fill_pads_kernel(double* __restrict__ tvals, uint16_t* __restrict__ tcols, int64_t nslots, uint16_t padcol) {
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nslots; q += (int64_t)gridDim.x * blockDim.x) {
     tvals[q] = 0.0;
     tcols[q] = (uint16_t)(padcol + (q & 15));   // slot index = ... * 32 + lane
@@ -95,7 +95,7 @@ __global__ void fill_pads_kernel(double* __restrict__ tvals, uint16_t* __restric
 // so each half-warp of a gather instruction reads 16 distinct 8-byte banks; classes
 // with more than 2*NPT entries spill, in canonical order, into the slots that
 // shorter classes leave empty.  The placement depends only on the segment and NPT.
-__global__ void pack_tiles_kernel(const double* __restrict__ R, const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld,
+static __global__ void pack_tiles_kernel(const double* __restrict__ R, const uint8_t* __restrict__ M, int64_t n, int64_t m, int64_t ld,
                                   int cs, int tw, int rs, int npt, double* __restrict__ tvals, uint16_t* __restrict__ tcols) {
   const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -184,6 +184,7 @@ struct Sweep2Params {
   int64_t ldy2;
   int K2;
   double* proj_out;
+  double* gmat;                          // blocked cluster sweep (kernels_v4.cuh), Gibbs: scratch for the random material of the resident row sets
   int nst;                               // stages of the tile ring (3 or 4)
   int dbg;                               // timing experiments only: 1 = no update math, 2 = phase clocks into prof
   unsigned long long* prof;              // [32] clock64 sums of cluster 0 / CTA 0 (dbg & 2)

@@ -69,7 +69,7 @@ __device__ __forceinline__ double exp_draw(double lambda, Rng& rng) { return -lo
 
 // ---- gamma_draw(alpha,beta): shape alpha, RATE beta (gamma.py:11-14) --------
 // Marsaglia & Tsang (2000); alpha < 1 boosted by U^(1/alpha).
-__device__ __noinline__ double gamma_draw(double alpha, double beta, Rng& rng) {
+static __device__ __noinline__ double gamma_draw(double alpha, double beta, Rng& rng) {
   double boost = 1.0;
   if (alpha < 1.0) { boost = pow(rng.u01(), 1.0 / alpha); alpha += 1.0; }
   const double d = alpha - 1.0 / 3.0, c = rsqrt(9.0 * d);
@@ -92,7 +92,7 @@ __device__ __noinline__ double gamma_draw(double alpha, double beta, Rng& rng) {
 //   a <= 4 : inverse CDF in the upper tail,  P(Z >= z) = u * P(Z >= a).
 //   a  > 4 : Robert (1995) translated-exponential rejection; the excess z - a
 //            is returned directly so that mu + sigma z never cancels.
-__device__ __noinline__ double tn_draw(double mu, double tau, Rng& rng) {
+static __device__ __noinline__ double tn_draw(double mu, double tau, Rng& rng) {
   if (tau == 0.0) return 0.0;
   const double sigma = 1.0 / sqrt(tau);
   const double a = -mu / sigma;
@@ -119,7 +119,7 @@ __device__ __noinline__ double tn_draw(double mu, double tau, Rng& rng) {
 // Philox rounds run before the row sums arrive).  No division or square root on the
 // critical path: sigma = rsqrt(prec), a = -mu/sigma = -num*sigma, and the draw is
 // sigma*(z - a), which also never cancels.  mu_out returns num/prec (to 1-2 ulp).
-__device__ __noinline__ double tn_draw_pre(double num, double prec, double u1, Rng& rng, double& mu_out) {
+static __device__ __noinline__ double tn_draw_pre(double num, double prec, double u1, Rng& rng, double& mu_out) {
   if (prec == 0.0) { mu_out = num / prec; return 0.0; }
   const double sigma = rsqrt(prec);
   mu_out = num * sigma * sigma;
@@ -172,7 +172,7 @@ __device__ __forceinline__ TnPre tn_pre_material(Rng& rng) {
 }
 
 // out-of-line version for kernels whose registers are busy when the material is prepared
-__device__ __noinline__ void tn_pre_material_store(uint64_t seed, uint32_t purpose, uint64_t index, uint32_t k, uint32_t iteration,
+static __device__ __noinline__ void tn_pre_material_store(uint64_t seed, uint32_t purpose, uint64_t index, uint32_t k, uint32_t iteration,
                                                    double* dst) {
   Rng rng(seed, purpose, index, k, iteration);
   const TnPre m = tn_pre_material(rng);
@@ -216,7 +216,7 @@ __device__ __forceinline__ double tn_draw_fast(double num, double prec, const Tn
 
 // Out-of-line fallback of tn_draw_lazy: opens the row's Philox stream behind the prepared material (draw = 2) and
 // draws by the inverse CDF.  Everything it needs travels by value, so the caller keeps its state in registers.
-__device__ __noinline__ double2 tn_draw_fallback(double num, double prec, uint64_t seed, uint32_t purpose, uint64_t index,
+static __device__ __noinline__ double2 tn_draw_fallback(double num, double prec, uint64_t seed, uint32_t purpose, uint64_t index,
                                                  uint32_t k, uint32_t iteration) {
   Rng rng(seed, purpose, index, k, iteration);
   rng.draw = 2;                      // Philox blocks 0 and 1 of this stream made the material
@@ -266,7 +266,7 @@ __device__ __forceinline__ double tn_draw_lazy(double num, double prec, const Tn
 // lambda(x) = pdf(x) / (0.5 erfc(x/sqrt2)); mean = mu + sigma lambda;
 // var = sigma^2 (1 - lambda (lambda - x)); if mu < -30 sigma: mean = 1/(|mu| tau),
 // var = mean^2; anything negative / inf / NaN -> 0.
-__device__ __noinline__ void tn_moments(double mu, double tau, double& e, double& v) {
+static __device__ __noinline__ void tn_moments(double mu, double tau, double& e, double& v) {
   const double sigma = 1.0 / sqrt(tau);
   if (mu < -30.0 * sigma) {
     e = 1.0 / (fabs(mu) * tau);
@@ -280,6 +280,15 @@ __device__ __noinline__ void tn_moments(double mu, double tau, double& e, double
   }
   if (!(e >= 0.0 && isfinite(e))) e = 0.0;
   if (!(v >= 0.0 && isfinite(v))) v = 0.0;
+}
+
+// log(0.5 erfc(x)) as the reference's ELBO evaluates it (bnmf_vb.py:222,225; bnmtf_vb.py:286-292): scipy.special.erfc is
+// cephes' erfc, which returns exactly 0 once x * x exceeds MAXLOG = 709.78... (x > 26.64) instead of a denormal, so the
+// reference's ELBO is -inf from there on.  CUDA's erfc keeps returning denormals up to x = 27.2; the cut is mirrored so
+// that the ELBO turns -inf in the same iteration as the reference's (tests/test_gpu_configs.py, GDSC matrix).
+__device__ __forceinline__ double log_half_erfc_ref(double x) {
+  const double c = (x > 0.0 && x * x > 7.09782712893383996843e2) ? 0.0 : erfc(x);
+  return log(0.5 * c);
 }
 
 // digamma for x > 0 (scipy.special.psi in gamma.py:22-24): recurrence up to

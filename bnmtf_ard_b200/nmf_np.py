@@ -85,6 +85,8 @@ class nmf_np(NMFCommon):
 
     def predict(self, M_pred):
         ''' Predict missing values in R. '''
+        if not self._shapes_fit_handle(U=(self.U, (self.I, self.K)), V=(self.V, (self.J, self.K))):
+            return self._predict_from(M_pred, numpy.asarray(self.U, dtype=float), numpy.asarray(self.V, dtype=float))
         return self._device_predict(M_pred, _lib.PRED_CURRENT, self._upload_state())
 
     def compute_I_div(self):

@@ -125,6 +125,9 @@ class nmtf_np(NMFCommon):
 
     def predict(self, M_pred):
         ''' Predict missing values in R. '''
+        if not self._shapes_fit_handle(F=(self.F, (self.I, self.K)), S=(self.S, (self.K, self.L)), G=(self.G, (self.J, self.L))):
+            FS = numpy.dot(numpy.asarray(self.F, dtype=float), numpy.asarray(self.S, dtype=float))
+            return self._predict_from(M_pred, FS, numpy.asarray(self.G, dtype=float))
         return self._device_predict(M_pred, _lib.PRED_CURRENT, self._upload_state())
 
     def compute_I_div(self):

@@ -30,6 +30,13 @@ FILES = ["test_bnmf_gibbs.py", "test_bnmf_vb.py", "test_nmf_icm.py", "test_nmf_n
 
 # file::test -> why the literal comparison of the reference cannot be met by a different float64 summation order
 EXPECTED = {
+    # measured on the B200 with tools/refsuite_diffs.py (gpurun_out/r02_refsuite_diffs.log -> profiles/r02_reference_suite.md)
+    "test_bnmf_vb.py::test_exp_square_diff": "`== 172.66666666666666`: the column-sum form gives 172.66666666666669 (1 ulp, rel 1.7e-16)",
+    "test_bnmf_vb.py::test_update_tau": "`beta_s == betatau + 172.66666666666666/2.`: same sum as test_exp_square_diff, 1 ulp",
+    "test_bnmf_vb.py::test_update_U": "`mu_U[i,k] == ...` literal: residual form + FMA differ from numpy's expression by 1 ulp (rel 1.9e-16); tau_U equal",
+    "test_bnmtf_vb.py::test_update_F": "`abs(mu_F - muFik) < 1e-17` on values of order 1: below one ulp of float64, only the identical operation order passes",
+    "test_bnmtf_vb.py::test_update_G": "`abs(mu_G - muGjl) < 1e-17`: as test_update_F",
+    "test_nmtf_np.py::test_compute_I_div": "`I_div == expected` literal: 2344.289361880598 against 2344.2893618805974 (1 ulp, rel 1.9e-16, fixed-order tree sum)",
 }
 
 MODEL_MODULES = ["bnmf_gibbs", "bnmf_vb", "nmf_icm", "nmf_np", "bnmtf_gibbs", "bnmtf_vb", "nmtf_icm", "nmtf_np"]
