@@ -365,23 +365,23 @@ def main():
             northstar_bytes = 2 * K * 16.125 * I * J
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                 "traffic": load_traffic(), "peak_source": peak_src,
-                                "kernel": {0: "sweep_kernel", 1: "sweep2_kernel", 3: "sweep3_kernel", 4: "sweep2_kernel (column parked in tensor memory)", 5: "sweep2_kernel (residual in tensor memory)", 6: "sweep2_kernel (two rows per warp)", 7: "sweep2la_kernel (pass one column ahead)"}[int(info.get("v2_U", 0))],
+                                "kernel": {0: "sweep_kernel", 1: "sweep2_kernel", 4: "sweep4_kernel", 5: "sweep5_kernel"}[int(info.get("v2_U", 0))],
                                 "kernel_ms": ms, "kernel_share_of_step": (sweeps["ms_U"] + sweeps["ms_V"]) / (1e3 * dev_s),
                                 "north_star_equiv_gbs": northstar_bytes * value / 1e9,
                                 "north_star_equiv_frac": northstar_bytes * value / 1e9 / peak}
-            if info.get("v2_U") and info.get("v2_V") and int(info["v2_U"]) == 1:
-                # what the cluster sweep actually leans on: the shared-memory pipe.  Algorithmic 8-byte gathers per launch
-                # (residual pass K + update passes 2K per slot) at 128 B per wavefront, against one wavefront per SM and
-                # clock at the SM clock sampled during the run (ncu counts 1.08e9 load wavefronts incl. 8 % replays).
-                slots = 0.5 * (info["v2_slots_U"] + info["v2_slots_V"])
-                wf = slots * 3 * K * 8.0 / 128.0
+            if info.get("v2_U") and info.get("v2_V"):
+                # what the cluster sweeps actually lean on: the shared-memory pipe.  Algorithmic 8-byte gathers per launch
+                # over the OBSERVED entries (residual pass K + update passes 2K per entry; padded slots are not useful work)
+                # at 128 B per wavefront, against one wavefront per SM and clock at the SM clock sampled during the run.
+                nnz = 0.5 * (info["nnz_U"] + info["nnz_V"])
+                wf = nnz * 3 * K * 8.0 / 128.0
                 sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
                 wf_peak = sm_count * float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
                 line["roofline"]["onchip"] = {"bound": "shared-memory wavefronts", "achieved": wf / (ms * 1e-3) / 1e9,
                                               "peak": wf_peak / 1e9, "unit": "Gwavefronts/s",
                                               "frac": wf / (ms * 1e-3) / wf_peak,
-                                              "note": "algorithmic gathers only; the sweep is bound by its per-column "
-                                                      "dependency chain (profiles/r01_final_sweep_ncu.md)"}
+                                              "padding": 0.5 * (info["v2_slots_U"] + info["v2_slots_V"]) / nnz,
+                                              "note": "algorithmic gathers of the observed entries only (nnz x 3K x 8 B)"}
         line["e2e"] = e2e
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
 #include "sweep4.h"
+#include "sweep5.h"
 #include "kernels_nmtf.cuh"
 #include "kernels_kmeans.cuh"
 #include "kernels_summary.cuh"
@@ -116,6 +117,7 @@ struct Side {
   uint16_t* tcols = nullptr;
   int nclusters[4] = {0, 0, 0, 0};
   bool v4 = false;                       // blocked cluster sweep (kernels_v4.cuh) serves this side's Gibbs / ICM / VB sweeps
+  bool v5 = false;                       // per-row-chain cluster sweep (kernels_v5.cuh) serves them
   int nclusters4[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};   // resident clusters per method, without / with the parameter outputs
   bool long_rows = false;      // rows beyond the register-resident configurations: residual in global scratch (kernels_long.cuh)
   double* escr = nullptr;      // [nslots]
@@ -152,6 +154,7 @@ struct bnmtf_nmf_s {
   int64_t sweep_n[2] = {0, 0};
   int km_mode = -1;            // NV layout currently held by the km copies
   double* gmat = nullptr;              // random-material scratch of the blocked cluster sweep (kernels_v4.cuh)
+  int* set_counter = nullptr;          // kernels_v5.cuh: work queue of row sets
   size_t gmat_doubles = 0;
   uint32_t* iter_dev = nullptr;        // device-side iteration index (graph replays of the run loop)
   const uint32_t* iter_ptr = nullptr;  // == iter_dev while a graph-mode run is in progress
@@ -269,6 +272,11 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
     const int rs4 = npt2 == 20 ? sweep4_wpc() / 2 - 1 : rs;    // the blocked sweep may trade rows per set for registers (20 entries per lane only)
     sd.v4 = sd.v2 && !h->nmtf && npt2 % 4 == 0 && sweep4_fits(sd.tw, rs4, sd.kf) && (v4env && atoi(v4env) == 1);   // opt-in: measured 8.1 - 9.2 ms per sweep at C3 against 8.5 for kernels_v2.cuh, depending on the build
     if (sd.v4) rs = rs4;
+    // per-row-chain cluster sweep (kernels_v5.cuh): the default for the two-factor models when it fits; BNMTF_V5=0 falls back
+    const char* v5env = getenv("BNMTF_V5");
+    const int npt5 = npt2 == 18 ? 20 : npt2;
+    sd.v5 = sd.v2 && !sd.v4 && !h->nmtf && !(v5env && atoi(v5env) == 0) && sweep5_fits(npt5, sd.tw, sd.kf);
+    if (sd.v5) { npt2 = npt5; rs = sweep5_rows_per_set(npt5); }
   }
   if (sd.v2 && n > 0) {
     sd.cs = cs; sd.npt2 = npt2; sd.rs = rs;
@@ -281,7 +289,7 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
                                                                              sd.tvals, sd.tcols);
     h->launches += 2;
   } else {
-    sd.v2 = false; sd.v4 = false;
+    sd.v2 = false; sd.v4 = false; sd.v5 = false;
   }
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -556,7 +564,7 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   cudaFree(h->S); cudaFree(h->Svar); cudaFree(h->Smu); cudaFree(h->Stau); cudaFree(h->lamS); cudaFree(h->lamG);
   cudaFree(h->Prow); cudaFree(h->Hrow); cudaFree(h->cvec); cudaFree(h->TT); cudaFree(h->Tpart);
   cudaFree(h->Arow); cudaFree(h->Brow); cudaFree(h->Crow); cudaFree(h->BS); cudaFree(h->PA); cudaFree(h->QC);
-  cudaFree(h->lamstateG); cudaFree(h->vbmisc); cudaFree(h->iter_dev); cudaFree(h->gmat);
+  cudaFree(h->lamstateG); cudaFree(h->vbmisc); cudaFree(h->iter_dev); cudaFree(h->gmat); cudaFree(h->set_counter);
   summary_free(h);
   for (int b = 0; b < 2; ++b) if (h->pin[b]) cudaFreeHost(h->pin[b]);
   cudaStreamSynchronize(h->stream);
@@ -728,7 +736,7 @@ static int refresh_km(bnmtf_nmf_s* h, int side, int method) {
     rm_to_km_kernel<1><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, sd.kf, sd.ld);
   h->launches++;
   // the blocked cluster sweep of the other side reads the block-major copies
-  if (h->s[1 - side].v4 && !h->nmtf && method != BNMTF_NP) {
+  if ((h->s[1 - side].v4 || h->s[1 - side].v5) && !h->nmtf && method != BNMTF_NP) {
     dim3 g3((unsigned)((sd.ld + 255) / 256), (unsigned)((sd.kf + 1) / 2));
     if (method == BNMTF_VB) rm_to_kmB_kernel<true><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
     else rm_to_kmB_kernel<false><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
@@ -920,11 +928,11 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
       bnmtf_prof_last = prof_buf;
     }
     rc = 0;
-    if (sd.v4 && p.K2 == 0) {
+    if ((sd.v4 || sd.v5) && p.K2 == 0) {
       p.Ykm = h->s[1 - side].kmB; p.Ykm2 = h->s[1 - side].kmBq; p.ldy = h->s[1 - side].ld;
       if (method != BNMTF_GIBBS && method != BNMTF_ICM && method != BNMTF_VB) FAIL("unknown method %d", method);
       if (method == BNMTF_GIBBS) {
-        const size_t need = sweep4_gmat_doubles(sd.rs, sd.kf);
+        const size_t need = sd.v5 ? sweep5_gmat_doubles(sd.rs, sd.kf) : sweep4_gmat_doubles(sd.rs, sd.kf);
         if (h->gmat_doubles < need) {
           CK(cudaStreamSynchronize(h->stream));
           cudaFree(h->gmat); h->gmat = nullptr; h->gmat_doubles = 0;
@@ -933,8 +941,14 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
         }
         p.gmat = h->gmat;
       }
+      if (sd.v5) {
+        if (!h->set_counter) CK(cudaMalloc(&h->set_counter, sizeof(int)));
+        CK(cudaMemsetAsync(h->set_counter, 0, sizeof(int), h->stream));
+        p.set_counter = h->set_counter;
+      }
       std::string err;
-      rc = launch_sweep4(sd.npt2, method, p, h->stream, &sd.nclusters4[method][p.Xmu != nullptr ? 1 : 0], &err);
+      rc = sd.v5 ? launch_sweep5(sd.npt2, method, p, h->stream, &sd.nclusters4[method][p.Xmu != nullptr ? 1 : 0], &err)
+                 : launch_sweep4(sd.npt2, method, p, h->stream, &sd.nclusters4[method][p.Xmu != nullptr ? 1 : 0], &err);
       if (rc) { g_err = err; return 1; }
       h->launches++;
     } else
@@ -964,6 +978,11 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     // phase clocks of cluster 0 / CTA 0 (control warp: slots 0-4, first compute warp: 8-15), in cycles per set
     cudaStreamSynchronize(h->stream);
     unsigned long long* pb = bnmtf_prof_last;
+    if (pb && pb[16] > 0 && sd.v5) {
+      fprintf(stderr, "[v5 prof side %d] rows %llu | start %llu | resid: tilewait %llu pass %llu | meet %llu table %llu | update: tilewait %llu pass %llu reduce+send %llu recwait %llu cond %llu | tail %llu (cycles/row) | warp loop %llu, before it %llu, CTA %llu cycles\n",
+              side, pb[16], pb[0] / pb[16], pb[1] / pb[16], pb[2] / pb[16], pb[3] / pb[16], pb[4] / pb[16], pb[5] / pb[16], pb[6] / pb[16], pb[7] / pb[16],
+              pb[8] / pb[16], pb[9] / pb[16], pb[10] / pb[16], pb[20], pb[21], pb[22]);
+    } else
     if (pb && pb[16] > 0 && sd.v4) {
       fprintf(stderr, "[v4 prof side %d] sets %llu | ctrl: start+phaseA %llu prep %llu slotwait %llu recwait %llu cond %llu book %llu tail %llu | comp: start %llu phaseA %llu statx %llu corr %llu tilewait %llu dot %llu reduce %llu deltawait %llu tail %llu (cycles/set)\n",
               side, pb[16], pb[0] / pb[16], pb[1] / pb[16], pb[2] / pb[16], pb[3] / pb[16], pb[4] / pb[16], pb[5] / pb[16], pb[6] / pb[16], pb[8] / pb[16],
@@ -1450,7 +1469,7 @@ int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {  // out8: 16 values
   out8[4] = h->s[0].nslots; out8[5] = h->s[1].nslots; out8[6] = h->s[0].nnz; out8[7] = h->s[1].nnz;
   for (int q = 0; q < 2; ++q) {
     const Side& sd = h->s[q];
-    out8[8 + 4 * q] = sd.v2 ? (sd.v4 ? 4 : 1) : 0;   // 1: cluster sweep (kernels_v2.cuh), 4: blocked cluster sweep (kernels_v4.cuh)
+    out8[8 + 4 * q] = sd.v2 ? (sd.v5 ? 5 : (sd.v4 ? 4 : 1)) : 0;   // 1: cluster sweep (kernels_v2.cuh), 4: blocked (kernels_v4.cuh), 5: per-row chains (kernels_v5.cuh)
     out8[9 + 4 * q] = sd.v2 ? sd.npt2 : 0;
     out8[10 + 4 * q] = sd.v2 ? sd.rs : 0; out8[11 + 4 * q] = sd.v2 ? sd.tslots : 0;
   }

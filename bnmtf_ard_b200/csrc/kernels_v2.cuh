@@ -185,6 +185,7 @@ struct Sweep2Params {
   int K2;
   double* proj_out;
   double* gmat;                          // blocked cluster sweep (kernels_v4.cuh), Gibbs: scratch for the random material of the resident row sets
+  int* set_counter;                      // kernels_v5.cuh: row sets handed out so far beyond the first round (zeroed before every launch)
   int nst;                               // stages of the tile ring (3 or 4)
   int dbg;                               // timing experiments only: 1 = no update math, 2 = phase clocks into prof
   unsigned long long* prof;              // [32] clock64 sums of cluster 0 / CTA 0 (dbg & 2)

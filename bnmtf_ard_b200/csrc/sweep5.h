@@ -1,0 +1,18 @@
+// Host interface of the per-row-chain cluster sweep (kernels_v5.cuh), compiled in its own translation unit (sweep5.cu).
+#pragma once
+#include <string>
+#include <cuda_runtime.h>
+#include "kernels_v2.cuh"
+
+namespace bnmtf {
+// rows per set (= row warps per CTA) the kernel runs with for `npt` entries per lane; 0 when npt is not served
+int sweep5_rows_per_set(int npt);
+// true when the kernel serves K columns and its shared memory (worst case: VB) fits one CTA
+bool sweep5_fits(int npt, int tw, int K);
+// doubles of random-material scratch a Gibbs launch needs (Sweep2Params::gmat), for the largest grid
+size_t sweep5_gmat_doubles(int rs, int K);
+// Launch one sweep on `stream`; p.rs must be sweep5_rows_per_set(npt) as chosen when the side was packed.  method:
+// BNMTF_GIBBS / ICM / VB (0 / 1 / 2).  *ncl_cache (0 on first use) caches the number of co-resident clusters.
+// Returns 0, or 1 with *err set.
+int launch_sweep5(int npt, int method, const Sweep2Params& p, cudaStream_t stream, int* ncl_cache, std::string* err);
+}  // namespace bnmtf

@@ -1,0 +1,11 @@
+set -x
+timeout 600 python -m pytest tests/test_gpu_configs.py -m gpu -q -x -k "c3" --durations=5 > gpurun_out/r02_v5_c3.log 2>&1; echo "rc=$?" >> gpurun_out/r02_v5_c3.log
+tail -5 gpurun_out/r02_v5_c3.log
+timeout 600 python -m pytest tests/test_gpu_nmf.py tests/test_gpu_batch.py tests/test_gpu_summary.py -m gpu -q -x > gpurun_out/r02_v5_nmf.log 2>&1; echo "rc=$?" >> gpurun_out/r02_v5_nmf.log
+tail -5 gpurun_out/r02_v5_nmf.log
+for rs in 11 10 9; do
+BNMTF_V5_RS=$rs timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r02_bench6_rs$rs.json 2> gpurun_out/r02_bench6_rs$rs.err
+python -c "import json;d=json.load(open('gpurun_out/r02_bench6_rs$rs.json'));print('rs$rs',d['value'],d['roofline']['kernel'],d['roofline']['kernel_ms'],d['config']['train_mse_last'])"
+done
+BNMTF_V5_WIDE=1 timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r02_bench6_wide.json 2> gpurun_out/r02_bench6_wide.err
+python -c "import json;d=json.load(open('gpurun_out/r02_bench6_wide.json'));print('wide',d['value'],d['roofline']['kernel'],d['roofline']['kernel_ms'],d['config']['train_mse_last'])"
