@@ -27,6 +27,13 @@ import numpy as np  # noqa: E402
 
 HYPER = {"alphatau": 1.0, "betatau": 1.0, "alpha0": 1.0, "beta0": 1.0}
 METRIC = "BNMF-ARD Gibbs iters/sec, 20k x 20k K=50"
+CACHE_NOTE = "inputs exceed L2: the packed observed entries of R read by one iteration (>= 1.9 GB) against 126 MB; no flush"
+
+
+def config_of(args):
+    """The same dictionary in both arms (the driver compares them)."""
+    return {"workload": "BNMF Gibbs+ARD %dx%d rho=%.2f K=%d (BASELINE configs[2])" % (args.I, args.J, args.density, args.K),
+            "cache": CACHE_NOTE}
 
 
 def parse_args():
@@ -156,24 +163,43 @@ def load_peaks():
 # --------------------------------------------------------------------------- #
 def run_reference(args):
     """CPU arm: the reference's own bnmf_gibbs (shimmed copy under oracle/_ref) --
-    or the numpy oracle port if the copy is absent -- on a bounded sample of the
-    workload: the top-left s x s block of the same synthetic matrix, one
-    iteration per step; iterations/sec are scaled by (s*s)/(I*J) because the
-    reference's cost per iteration is proportional to I*J."""
+    or the numpy oracle port if the copy is absent -- on bounded samples of the
+    workload: top-left s x s blocks of the same synthetic recipe.  Two raw points
+    are measured (s = 2000 and, when the budget allows, s = 4000) and printed with
+    the exponent they imply; `value` is the larger block's rate scaled by
+    (s*s)/(I*J): the reference's cost per iteration is proportional to I*J
+    (BASELINE.md sections 2-3)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_baseline(args, steps=max(1, args.steps), warmup=min(args.warmup, 1), budget_s=90.0)
+    t_start = time.perf_counter()
+    small = cpu_baseline(args, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1), budget_s=25.0)
+    points = [small["point"]]
+    res = small
+    s_big = min(2 * small["point"]["s"], args.I, args.J)
+    # one iteration on the block of twice the side costs ~4x the small block's iteration (+ its set-up)
+    if s_big > small["point"]["s"] and 6.0 * small["point"]["s_per_iteration"] < 150.0 - (time.perf_counter() - t_start):
+        big = cpu_baseline(args, steps=1, warmup=0, budget_s=0.0, side=s_big)
+        points.append(big["point"])
+        res = big
+    if len(points) == 2:
+        import math
+        expo = math.log(points[1]["s_per_iteration"] / points[0]["s_per_iteration"]) / math.log(points[1]["s"] / float(points[0]["s"]))
+        res["sample"] += "; raw points %s: time per iteration grows as s^%.2f (2.0 = proportional to I*J)" % (
+            ", ".join("%dx%d: %.2f s/iteration" % (q["s"], q["s"], q["s_per_iteration"]) for q in points), expo)
+        res["scaling_exponent"] = expo
+    res["points"] = points
+    res.pop("point", None)
     line = {"metric": METRIC, "value": res["value"], "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "BNMF Gibbs+ARD %dx%d rho=%.2f K=%d (BASELINE configs[2])" % (args.I, args.J, args.density, args.K)},
+            "config": config_of(args),
             "cpu_baseline": res,
             "e2e": {"value": res["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def cpu_baseline(args, steps=1, warmup=0, budget_s=20.0):
+def cpu_baseline(args, steps=1, warmup=0, budget_s=20.0, side=None):
     """Time the reference's CPU implementation on a bounded sample: the s x s block
     (same synthetic recipe, same K, same density), s chosen from a calibration
     iteration so that warmup+steps iterations take about `budget_s` seconds."""
@@ -209,16 +235,54 @@ def cpu_baseline(args, steps=1, warmup=0, budget_s=20.0):
             orc.gibbs_replay_iteration(R, M, U, V, 1.0, lam, lam, np.abs(U), np.abs(V))
         return time.perf_counter() - t0
 
-    s_cal = min(400, args.I, args.J)
-    per_cell = time_block(s_cal, 1, 0) / float(s_cal * s_cal)          # seconds per iteration per matrix cell
-    s = int(min(args.cpu_sample, args.I, args.J, max(200, (budget_s / ((steps + warmup) * per_cell)) ** 0.5)))
+    if side is None:
+        s_cal = min(400, args.I, args.J)
+        per_cell = time_block(s_cal, 1, 0) / float(s_cal * s_cal)          # seconds per iteration per matrix cell
+        s = int(min(args.cpu_sample, args.I, args.J, max(200, (budget_s / ((steps + warmup) * per_cell)) ** 0.5)))
+    else:
+        s = int(side)
     dt = time_block(s, steps, warmup)
     scale = (s * s) / float(args.I * args.J)
     return {"value": steps / dt * scale, "unit": "iterations/s", "cores": int(threads), "kind": kind,
+            "point": {"s": s, "s_per_iteration": dt / steps},
             "sample": "%dx%d block of the same synthetic recipe (rho=%.2f, K=%d), %d timed iteration(s) in %.1f s; "
                       "it/s scaled by (s*s)/(I*J): the reference's cost per iteration is proportional to I*J "
                       "(BASELINE.md section 2)" % (s, s, args.density, args.K, steps, dt),
             "sample_it_per_s": steps / dt}
+
+
+def parity_check(args):
+    """The checker, not the thing measured: one strip of the benchmark matrix in the benchmark's packed layout (20
+    entries per lane, 11 rows per set, K = 50, several persistent waves of row sets) goes through two Gibbs iterations of
+    the class API with the conditional parameters of every draw kept, and the oracle -- fed the same draws -- must
+    reproduce them (tests/test_gpu_configs.py::test_c3_strip_gibbs_replay).  Returns the largest relative deviations."""
+    import nmf_oracle as orc
+    from bnmtf_ard_b200 import bnmf_gibbs
+    from bnmtf_ard_b200._lib import F_MU, F_TAU, SIDE_U, SIDE_V
+    I, J, K = 400, args.J, args.K
+    R, M = synth_host(I, J, K, args.density, seed=77)
+    os.environ["BNMTF_TRACE_PARAMS"] = "1"
+    try:
+        m = bnmf_gibbs(R, M, K, True, dict(HYPER))
+        m.verbose = False
+        m._layout_floor = [0, 600, 0, 600]      # the full matrix's longest (row, tile) segments: same layout as the timed run
+        np.random.seed(5)
+        m.initialise("random")
+        m.run(2)
+        eng = m._engine()
+        info = eng.layout_info()
+        lam = m.all_lambdak[1]
+        tU, mU, tV, mV, _ = orc.gibbs_replay_iteration(R, M, m.all_U[0].copy(), m.all_V[0].copy(), m.all_tau[0], lam, lam,
+                                                       m.all_U[1], m.all_V[1])
+        rel_tau = max(float(np.max(np.abs(eng.get_factor(sd, F_TAU) - t) / t)) for sd, t in ((SIDE_U, tU), (SIDE_V, tV)))
+        rel_mu = max(float(np.max(np.abs(eng.get_factor(sd, F_MU) - mu) / np.maximum(np.abs(mu), 1.0 / np.sqrt(t))))
+                     for sd, mu, t in ((SIDE_U, mU, tU), (SIDE_V, mV, tV)))
+        m._engine().close()
+    finally:
+        del os.environ["BNMTF_TRACE_PARAMS"]
+    return {"max_rel": max(rel_tau, rel_mu), "max_rel_tau": rel_tau, "max_rel_mu": rel_mu, "tolerance": 1e-9,
+            "what": "Gibbs replay of a %dx%d strip, K=%d, against the oracle (conditional tau and mu of every draw of iteration 2)" % (I, J, K),
+            "layout": {"v2_U": int(info["v2_U"]), "v2_npt_U": int(info["v2_npt_U"]), "v2_rows_per_set_U": int(info["v2_rows_per_set_U"])}}
 
 
 # --------------------------------------------------------------------------- #
@@ -250,7 +314,10 @@ def main():
     Rrow, Mrow = R[r0:r1].contiguous(), M[r0:r1].contiguous()
     Rcol, Mcol = R[:, c0:c1].contiguous(), M[:, c0:c1].contiguous()
     torch.cuda.synchronize()
-    os.environ["BNMTF_TIME_SWEEPS"] = "1" if world == 1 else "0"
+    # the same run loop at every N: eager launches (no CUDA graph: multi-GPU runs cannot capture their NCCL calls; at 14 ms
+    # per iteration the launch overhead is not measurable) and no per-sweep event synchronisation inside the timed region
+    os.environ["BNMTF_TIME_SWEEPS"] = "0"
+    os.environ["BNMTF_NO_GRAPH"] = "1"
     eng = NMFEngine.from_device_blocks(I, J, K, Rrow.data_ptr(), Mrow.data_ptr(), Rcol.data_ptr(), Mcol.data_ptr(),
                                        device=local)
     del Rrow, Mrow, Rcol, Mcol
@@ -268,6 +335,9 @@ def main():
     eng.set_scalars(1.0, np.ones(K))
     eng.init_factors(_lib.GIBBS, True, 12345)
 
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        parity = parity_check(args)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -286,9 +356,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s = float(t.item())
     launches = eng.launch_count() - launches0
-    sweeps = eng.sweep_times()
     perf = eng.performances(res["stats"][-1])
     info = eng.layout_info()
+    # roofline leg, outside the timed region: a few more iterations with every sweep launch bracketed by CUDA events
+    eng.time_sweeps(True)
+    eng.run(_lib.GIBBS, max(2, min(5, args.steps)), seed=4, traces=False)
+    sweeps = eng.sweep_times()
+    eng.time_sweeps(False)
+    barrier()
 
     # ---- end to end through the reference-facing call with HOST buffers: the state
     # (U, V, tau, lambda_k) is uploaded from numpy, run() executes on the device and
@@ -348,11 +423,15 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "BNMF Gibbs+ARD %dx%d rho=%.2f K=%d (BASELINE configs[2])" % (I, J, args.density, K),
-                           "cache": "inputs (packed R: %.2f GB/GPU read per iteration) exceed the 126 MB L2" % (
-                               ((info["v2_slots_U"] + info["v2_slots_V"]) * 10 if info.get("v2_U") else
-                                (info["slots_U"] + info["slots_V"]) * 12) / 1e9),
-                           "layout": info, "wall_s": wall, "train_mse_last": perf["MSE"]},
+                "config": config_of(args),
+                "details": {"layout": info, "wall_s": wall, "train_mse_last": perf["MSE"],
+                            "packed_gb_per_iteration": ((info["v2_slots_U"] + info["v2_slots_V"]) * 10 if info.get("v2_U") else
+                                                        (info["slots_U"] + info["slots_V"]) * 12) / 1e9,
+                            "value_covers": "lambda_k draws, U sweep, V sweep, tau draw and statistics of every iteration, on the "
+                                            "device (multi-GPU: plus the all-gathers); the per-iteration copy of the draws into the "
+                                            "trace buffers (a 16 MB device-to-device copy, < 0.1 % of an iteration) and their "
+                                            "delivery to host memory are part of e2e, not of value",
+                            "run_loop": "eager launches at every N (BNMTF_NO_GRAPH=1), no per-sweep synchronisation"},
                 "gpu_launches": launches, "clocks": clocks}
         # roofline of the dominant kernel (row sweep): algorithmic DRAM bytes of OUR formulation
         if sweeps["n_U"] > 0:
@@ -363,10 +442,12 @@ def main():
                 bytes_per_launch = 0.5 * (info["slots_U"] + info["slots_V"]) * 12.0 + (I + J) * K * 8 * 1.5
             ach = bytes_per_launch / (ms * 1e-3) / 1e9
             northstar_bytes = 2 * K * 16.125 * I * J
-            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            line["roofline"] = {"measured_in": "a separate pass of %d iterations after the timed region, each sweep launch bracketed "
+                                               "by CUDA events on the engine's stream" % sweeps["n_U"],
+                                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                 "traffic": load_traffic(), "peak_source": peak_src,
                                 "kernel": {0: "sweep_kernel", 1: "sweep2_kernel", 4: "sweep4_kernel", 5: "sweep5_kernel"}[int(info.get("v2_U", 0))],
-                                "kernel_ms": ms, "kernel_share_of_step": (sweeps["ms_U"] + sweeps["ms_V"]) / (1e3 * dev_s),
+                                "kernel_ms": ms, "kernel_share_of_step": 2.0 * ms / (1e3 * dev_s / args.steps),
                                 "north_star_equiv_gbs": northstar_bytes * value / 1e9,
                                 "north_star_equiv_frac": northstar_bytes * value / 1e9 / peak}
             if info.get("v2_U") and info.get("v2_V"):
@@ -383,6 +464,8 @@ def main():
                                               "padding": 0.5 * (info["v2_slots_U"] + info["v2_slots_V"]) / nnz,
                                               "note": "algorithmic gathers of the observed entries only (nnz x 3K x 8 B)"}
         line["e2e"] = e2e
+        if parity is not None:
+            line["parity_check"] = parity
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))

@@ -227,6 +227,10 @@ class NMFEngine(object):
                  "v2_U", "v2_npt_U", "v2_rows_per_set_U", "v2_slots_U", "v2_V", "v2_npt_V", "v2_rows_per_set_V", "v2_slots_V"]
         return dict(zip(names, out.tolist()))
 
+    def time_sweeps(self, on):
+        """Measurement passes only: bracket every sweep launch by CUDA events (serialises the run loop)."""
+        check(self.lib.bnmtf_nmf_time_sweeps(self.h, int(bool(on))))
+
     def sweep_times(self):
         out = np.zeros(4)
         check(self.lib.bnmtf_nmf_sweep_times(self.h, dptr(out)))

@@ -53,6 +53,7 @@ SIGNATURES = {
     "bnmtf_nmf_launch_count": (C.c_int64, [_h]),
     "bnmtf_nmf_layout_info": (C.c_int, [_h, _i64p]),
     "bnmtf_nmf_sweep_times": (C.c_int, [_h, _dp]),
+    "bnmtf_nmf_time_sweeps": (C.c_int, [_h, C.c_int]),
     "bnmtf_nmtf_create": (C.c_int, [C.POINTER(_h), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, _dp, _u8p,
                                     C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "bnmtf_nmtf_create_dev": (C.c_int, [C.POINTER(_h), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,

@@ -101,6 +101,7 @@ struct Side {
   double* lam_rm = nullptr;
   double* rowstats = nullptr;  // [n_padglob][NRS]
   double* trace[2] = {nullptr, nullptr};
+  size_t trace_cap[2] = {0, 0};
   int occ[4] = {0, 0, 0, 0};  // cached resident blocks/SM of the sweep kernel per method
   // dense block kept between create() and pack()
   const double* dR = nullptr;
@@ -155,6 +156,15 @@ struct bnmtf_nmf_s {
   int km_mode = -1;            // NV layout currently held by the km copies
   double* gmat = nullptr;              // random-material scratch of the blocked cluster sweep (kernels_v4.cuh)
   int* set_counter = nullptr;          // kernels_v5.cuh: work queue of row sets
+  // scratch of run() that stays with the handle between calls (grow-only): a cross-validation fold of 200 iterations no
+  // longer pays cudaMalloc / cudaFree of the trace chunks, the statistics and iterations + 1 cudaEventCreate per call
+  size_t stats_cap = 0, lam_trace_cap = 0, lam_trace2_cap = 0;
+  double* lam_trace = nullptr;         // [iterations][K]
+  double* lam_trace2 = nullptr;        // tri-factorisation: [iterations][L]
+  double* trS[2] = {nullptr, nullptr}; // tri-factorisation: trace chunks of S
+  size_t trS_cap[2] = {0, 0};
+  std::vector<cudaEvent_t> ev_pool;    // per-iteration timing events
+  cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // trace chunks: done[2], copied[2]
   size_t gmat_doubles = 0;
   uint32_t* iter_dev = nullptr;        // device-side iteration index (graph replays of the run loop)
   const uint32_t* iter_ptr = nullptr;  // == iter_dev while a graph-mode run is in progress
@@ -564,7 +574,9 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   cudaFree(h->S); cudaFree(h->Svar); cudaFree(h->Smu); cudaFree(h->Stau); cudaFree(h->lamS); cudaFree(h->lamG);
   cudaFree(h->Prow); cudaFree(h->Hrow); cudaFree(h->cvec); cudaFree(h->TT); cudaFree(h->Tpart);
   cudaFree(h->Arow); cudaFree(h->Brow); cudaFree(h->Crow); cudaFree(h->BS); cudaFree(h->PA); cudaFree(h->QC);
-  cudaFree(h->lamstateG); cudaFree(h->vbmisc); cudaFree(h->iter_dev); cudaFree(h->gmat); cudaFree(h->set_counter);
+  cudaFree(h->lamstateG); cudaFree(h->vbmisc); cudaFree(h->iter_dev); cudaFree(h->gmat); cudaFree(h->set_counter); cudaFree(h->lam_trace); cudaFree(h->lam_trace2); cudaFree(h->trS[0]); cudaFree(h->trS[1]);
+  for (auto& e : h->ev_pool) cudaEventDestroy(e);
+  for (int q = 0; q < 4; ++q) if (h->chunk_ev[q]) cudaEventDestroy(h->chunk_ev[q]);
   summary_free(h);
   for (int b = 0; b < 2; ++b) if (h->pin[b]) cudaFreeHost(h->pin[b]);
   cudaStreamSynchronize(h->stream);
@@ -1266,6 +1278,24 @@ int trace_chunk_iterations(int iterations, size_t per_it) {
 }
 }  // namespace
 
+// grow-only device scratch kept on the handle between runs
+static int ensure_dev(double** ptr, size_t* cap, size_t bytes) {
+  if (*ptr && *cap >= bytes) return 0;
+  cudaFree(*ptr); *ptr = nullptr; *cap = 0;
+  CK(cudaMalloc(ptr, std::max<size_t>(bytes, 8)));
+  *cap = bytes;
+  return 0;
+}
+static int ensure_events(bnmtf_nmf_s* h, size_t n) {
+  while (h->ev_pool.size() < n) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    h->ev_pool.push_back(e);
+  }
+  for (int q = 0; q < 4; ++q) if (!h->chunk_ev[q]) CK(cudaEventCreate(&h->chunk_ev[q]));
+  return 0;
+}
+
 // Launch-bound run loops: iteration 0 eagerly (first-use attribute / occupancy calls happen here), iteration 1 captured
 // into a CUDA graph, the graph replayed for the rest.  While this runs h->iter_ptr is set: kernels read the iteration
 // index (Philox counters, trace and statistics slots) from the device and the finalize kernel advances it.
@@ -1335,22 +1365,19 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   if (tr) chunk = trace_chunk_iterations(iterations, per_it);
   if (tr) {
     for (int b = 0; b < 2; ++b) {
-      cudaFree(su.trace[b]); cudaFree(sv.trace[b]); su.trace[b] = sv.trace[b] = nullptr;
-      CK(cudaMalloc(&su.trace[b], sizeof(double) * su.n_glob * K * chunk));
-      CK(cudaMalloc(&sv.trace[b], sizeof(double) * sv.n_glob * K * chunk));
+      if (ensure_dev(&su.trace[b], &su.trace_cap[b], sizeof(double) * su.n_glob * K * chunk)) return 1;
+      if (ensure_dev(&sv.trace[b], &sv.trace_cap[b], sizeof(double) * sv.n_glob * K * chunk)) return 1;
     }
   }
   TraceDrain drain;   // joins its worker on every way out of this function
-  cudaFree(h->stats_dev); h->stats_dev = nullptr;
-  double* lam_trace = nullptr;
-  CK(cudaMalloc(&h->stats_dev, sizeof(double) * BNMTF_NSTATS * iterations));
-  CK(cudaMalloc(&lam_trace, sizeof(double) * K * iterations));
+  if (ensure_dev(&h->stats_dev, &h->stats_cap, sizeof(double) * BNMTF_NSTATS * iterations)) return 1;
+  if (ensure_dev(&h->lam_trace, &h->lam_trace_cap, sizeof(double) * K * iterations)) return 1;
+  double* lam_trace = h->lam_trace;
   CK(cudaMemsetAsync(lam_trace, 0, sizeof(double) * K * iterations, h->stream));
 
-  std::vector<cudaEvent_t> ev(iterations + 1);
-  for (auto& e : ev) CK(cudaEventCreate(&e));
-  cudaEvent_t chunk_done[2], chunk_copied[2];
-  for (int b = 0; b < 2; ++b) { CK(cudaEventCreate(&chunk_done[b])); CK(cudaEventCreate(&chunk_copied[b])); }
+  if (ensure_events(h, (size_t)iterations + 1)) return 1;
+  std::vector<cudaEvent_t> ev(h->ev_pool.begin(), h->ev_pool.begin() + iterations + 1);
+  cudaEvent_t chunk_done[2] = {h->chunk_ev[0], h->chunk_ev[1]}, chunk_copied[2] = {h->chunk_ev[2], h->chunk_ev[3]};
 
   refresh_km(h, 0, method); refresh_km(h, 1, method);
   h->km_mode = method == BNMTF_VB ? 2 : 1;
@@ -1455,9 +1482,6 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
     fprintf(stderr, "[bnmtf_nmf_run] %d iterations, %d trace chunk(s): set-up %.1f ms, loop enqueued at %.1f, streams idle at %.1f, traces delivered at %.1f, "
             "device loop %.1f ms\n", iterations, tr ? nchunks : 0, t_setup, t_enq, t_sync, t_drain, dev_ms);
   }
-  for (auto& e : ev) cudaEventDestroy(e);
-  for (int b = 0; b < 2; ++b) { cudaEventDestroy(chunk_done[b]); cudaEventDestroy(chunk_copied[b]); }
-  cudaFree(lam_trace);
   return 0;
 }
 
@@ -1473,6 +1497,13 @@ int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out8) {  // out8: 16 values
     out8[9 + 4 * q] = sd.v2 ? sd.npt2 : 0;
     out8[10 + 4 * q] = sd.v2 ? sd.rs : 0; out8[11 + 4 * q] = sd.v2 ? sd.tslots : 0;
   }
+  return 0;
+}
+
+int bnmtf_nmf_time_sweeps(bnmtf_nmf_t h, int on) {
+  if (!h) FAIL("NULL handle");
+  h->time_sweeps = on != 0;
+  h->sweep_ms[0] = h->sweep_ms[1] = 0; h->sweep_n[0] = h->sweep_n[1] = 0;
   return 0;
 }
 

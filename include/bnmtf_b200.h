@@ -181,6 +181,10 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed,
  * per lane, rows per set, padded entries), [12..15] same for the V side. */
 int64_t bnmtf_nmf_launch_count(bnmtf_nmf_t h);
 int bnmtf_nmf_layout_info(bnmtf_nmf_t h, int64_t* out16);
+/* on != 0: every sweep launch is bracketed by CUDA events (and synchronised) so that bnmtf_nmf_sweep_times can report the
+ * kernel time per side -- measurement passes only, it serialises the run loop; resets the accumulated times.  Default: the
+ * environment variable BNMTF_TIME_SWEEPS when the handle is created (bench.py's roofline leg; no reference counterpart). */
+int bnmtf_nmf_time_sweeps(bnmtf_nmf_t h, int on);
 /* device-event milliseconds spent in the U sweep / V sweep kernels of the last
  * bnmtf_nmf_run (sum over iterations), and their launch counts. out[4]. */
 int bnmtf_nmf_sweep_times(bnmtf_nmf_t h, double* out4);
