@@ -290,9 +290,13 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    # NCCL prints its version banner on stdout at VERSION level; stdout carries the one JSON line only
+    # stdout carries the one JSON line only: libraries that print there (NCCL's version banner comes out on stdout at its
+    # default debug level) are sent to stderr for the duration of the run
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -468,7 +472,8 @@ def main():
             line["parity_check"] = parity
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

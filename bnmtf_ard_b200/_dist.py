@@ -76,6 +76,19 @@ def broadcast_bytes(payload, src=0):
     return bytes(t.cpu().tolist())
 
 
+def allgather_bytes(payload):
+    """Every rank's fixed-length bytes object, concatenated in rank order."""
+    td = _pg()
+    if td is None or td.get_world_size() == 1:
+        return payload
+    import torch
+    dev = _device_for_backend(td)
+    mine = torch.tensor(list(payload), dtype=torch.uint8, device=dev)
+    parts = [torch.zeros_like(mine) for _ in range(td.get_world_size())]
+    td.all_gather(parts, mine)
+    return b"".join(bytes(t.cpu().tolist()) for t in parts)
+
+
 def broadcast_int(value, src=0):
     """A 64-bit integer from rank `src` to every rank (identity when world == 1)."""
     td = _pg()

@@ -39,6 +39,8 @@ SIGNATURES = {
     "bnmtf_nmf_set_data_stats": (C.c_int, [_h, C.c_double, C.c_double]),
     "bnmtf_nccl_unique_id": (C.c_int, [_u8p]),
     "bnmtf_nmf_set_comm": (C.c_int, [_h, C.c_int, C.c_int, _u8p]),
+    "bnmtf_nmf_peer_export": (C.c_int, [_h, _u8p, C.c_int64]),
+    "bnmtf_nmf_peer_import": (C.c_int, [_h, _u8p, C.c_int64]),
     "bnmtf_nmf_set_hyper": (C.c_int, [_h, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp]),
     "bnmtf_nmf_set_factor": (C.c_int, [_h, C.c_int, C.c_int, _dp]),
     "bnmtf_nmf_get_factor": (C.c_int, [_h, C.c_int, C.c_int, _dp]),

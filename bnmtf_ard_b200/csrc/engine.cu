@@ -1,6 +1,7 @@
 // Host side of the engine: model handle, packing of R/M, the iteration loop and
 // the C ABI declared in include/bnmtf_b200.h.  No torch types anywhere.
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -102,6 +103,7 @@ struct Side {
   double* rowstats = nullptr;  // [n_padglob][NRS]
   double* trace[2] = {nullptr, nullptr};
   size_t trace_cap[2] = {0, 0};
+  bool ipc_arrays = false;     // val / var / rowstats were re-allocated outside the pool for the peer exchange
   int occ[4] = {0, 0, 0, 0};  // cached resident blocks/SM of the sweep kernel per method
   // dense block kept between create() and pack()
   const double* dR = nullptr;
@@ -156,6 +158,14 @@ struct bnmtf_nmf_s {
   int km_mode = -1;            // NV layout currently held by the km copies
   double* gmat = nullptr;              // random-material scratch of the blocked cluster sweep (kernels_v4.cuh)
   int* set_counter = nullptr;          // kernels_v5.cuh: work queue of row sets
+  // multi-GPU peer exchange (bnmtf_nmf_peer_export / _import): the per-row-chain sweep writes its rows into the other
+  // ranks' arrays; a device-side barrier replaces the all-gathers
+  static constexpr int MAXPEER = 16;
+  bool peer_ok = false;
+  int* peer_flags = nullptr;           // [MAXPEER] this rank's flag array (one slot per source rank)
+  void* peer_open[MAXPEER][7] = {};    // opened IPC pointers of the other ranks: val/var/rowstats of both sides, flags
+  void** peer_tab_dev = nullptr;       // device copy: [7][MAXPEER] (peers compacted: own rank left out) + flags by rank
+  int peer_epoch = 0;
   // scratch of run() that stays with the handle between calls (grow-only): a cross-validation fold of 200 iterations no
   // longer pays cudaMalloc / cudaFree of the trace chunks, the statistics and iterations + 1 cudaEventCreate per call
   size_t stats_cap = 0, lam_trace_cap = 0, lam_trace2_cap = 0;
@@ -356,6 +366,8 @@ static cudaError_t copy2d_sync(void* dst, size_t dpitch, const void* src, size_t
 // keep up to 8 GB of freed blocks cached in the pool (default: released at every synchronise)
 static cudaError_t pool_setup(int device) {
   static bool done[64] = {false};
+  static std::mutex mu;                       // handles are created from several host threads (cross-validation folds)
+  std::lock_guard<std::mutex> lk(mu);
   if (device < 0 || device >= 64 || done[device]) return cudaSuccess;
   cudaMemPool_t pool;
   cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
@@ -385,6 +397,10 @@ int bnmtf_pool_reserve(int device, int64_t bytes) {
   CK(cudaStreamSynchronize(cudaStreamPerThread));
   return 0;
 }
+
+// (arrays shared with other processes through CUDA IPC cannot live in the pool: plain device allocations)
+static cudaError_t ipc_malloc(void** p, size_t bytes) { return cudaMalloc(p, bytes); }
+static cudaError_t ipc_free(void* p) { return p ? cudaFree(p) : cudaSuccess; }
 
 #define cudaMalloc pool_malloc
 #define cudaFree pool_free
@@ -555,8 +571,10 @@ static int create_host_impl(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, 
 
 static void free_side(Side& sd) {
   cudaFree(sd.vals); cudaFree(sd.cols); cudaFree(sd.rowstart);
-  cudaFree(sd.val); cudaFree(sd.var); cudaFree(sd.mu); cudaFree(sd.tau);
-  cudaFree(sd.km); cudaFree(sd.kmB); cudaFree(sd.kmBq); cudaFree(sd.lam_rm); cudaFree(sd.rowstats);
+  if (sd.ipc_arrays) { ipc_free(sd.val); ipc_free(sd.var); ipc_free(sd.rowstats); }
+  else { cudaFree(sd.val); cudaFree(sd.var); cudaFree(sd.rowstats); }
+  cudaFree(sd.mu); cudaFree(sd.tau);
+  cudaFree(sd.km); cudaFree(sd.kmB); cudaFree(sd.kmBq); cudaFree(sd.lam_rm);
   cudaFree(sd.trace[0]); cudaFree(sd.trace[1]);
   cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev); cudaFree(sd.ycomb); cudaFree(sd.escr);
   if (sd.own_dense) { cudaFree((void*)sd.dR); cudaFree((void*)sd.dM); }
@@ -577,6 +595,8 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   cudaFree(h->lamstateG); cudaFree(h->vbmisc); cudaFree(h->iter_dev); cudaFree(h->gmat); cudaFree(h->set_counter); cudaFree(h->lam_trace); cudaFree(h->lam_trace2); cudaFree(h->trS[0]); cudaFree(h->trS[1]);
   for (auto& e : h->ev_pool) cudaEventDestroy(e);
   for (int q = 0; q < 4; ++q) if (h->chunk_ev[q]) cudaEventDestroy(h->chunk_ev[q]);
+  for (int r = 0; r < bnmtf_nmf_s::MAXPEER; ++r) for (int q = 0; q < 7; ++q) if (h->peer_open[r][q]) cudaIpcCloseMemHandle(h->peer_open[r][q]);
+  ipc_free(h->peer_flags); cudaFree(h->peer_tab_dev);
   summary_free(h);
   for (int b = 0; b < 2; ++b) if (h->pin[b]) cudaFreeHost(h->pin[b]);
   cudaStreamSynchronize(h->stream);
@@ -639,6 +659,71 @@ int bnmtf_nmf_set_comm(bnmtf_nmf_t h, int rank, int world, const uint8_t* nccl_i
   int rc = g_nccl.CommInitRank(&h->comm, world, id, rank);
   if (rc != 0) FAIL("ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
   h->rank = rank; h->world = world;
+  return 0;
+}
+
+// ---- peer exchange: CUDA IPC handles of the arrays the sweeps of the other ranks write into
+static constexpr int PEER_NBUF = 7;     // U: val, var, rowstats; V: val, var, rowstats; flags
+int bnmtf_nmf_peer_export(bnmtf_nmf_t h, uint8_t* blob, int64_t blob_bytes) {
+  if (!h || !blob) FAIL("bad argument");
+  if (blob_bytes < (int64_t)(PEER_NBUF * sizeof(cudaIpcMemHandle_t))) FAIL("peer blob too small");
+  if (h->nmtf) FAIL("the peer exchange serves the two-factor models");
+  ENTER(h);
+  if (!h->peer_flags) {
+    CK(ipc_malloc((void**)&h->peer_flags, sizeof(int) * bnmtf_nmf_s::MAXPEER));
+    CK(cudaMemsetAsync(h->peer_flags, 0, sizeof(int) * bnmtf_nmf_s::MAXPEER, h->stream));
+  }
+  for (int sidx = 0; sidx < 2; ++sidx) {   // move the shared arrays out of the stream-ordered pool
+    Side& sd = h->s[sidx];
+    if (sd.ipc_arrays) continue;
+    if (!sd.val || !sd.var || !sd.rowstats) FAIL("peer export before the factors were allocated");
+    double** arr[3] = {&sd.val, &sd.var, &sd.rowstats};
+    const size_t bytes[3] = {sizeof(double) * sd.n_padglob * sd.kf, sizeof(double) * sd.n_padglob * sd.kf, sizeof(double) * sd.n_padglob * NRS};
+    for (int q = 0; q < 3; ++q) {
+      void* fresh = nullptr;
+      CK(ipc_malloc(&fresh, bytes[q]));
+      CK(cudaMemcpyAsync(fresh, *arr[q], bytes[q], cudaMemcpyDeviceToDevice, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      cudaFree(*arr[q]);
+      *arr[q] = (double*)fresh;
+    }
+    sd.ipc_arrays = true;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  void* bufs[PEER_NBUF] = {h->s[0].val, h->s[0].var, h->s[0].rowstats, h->s[1].val, h->s[1].var, h->s[1].rowstats, h->peer_flags};
+  cudaIpcMemHandle_t* out = reinterpret_cast<cudaIpcMemHandle_t*>(blob);
+  for (int q = 0; q < PEER_NBUF; ++q) {
+    if (!bufs[q]) FAIL("peer export before the factors were allocated");
+    CK(cudaIpcGetMemHandle(&out[q], bufs[q]));
+  }
+  return 0;
+}
+
+int bnmtf_nmf_peer_import(bnmtf_nmf_t h, const uint8_t* blobs, int64_t blob_bytes) {
+  if (!h || !blobs) FAIL("bad argument");
+  if (h->world <= 1) return 0;
+  if (h->world > bnmtf_nmf_s::MAXPEER) FAIL("at most %d ranks", bnmtf_nmf_s::MAXPEER);
+  if (blob_bytes < (int64_t)(PEER_NBUF * sizeof(cudaIpcMemHandle_t))) FAIL("peer blob too small");
+  ENTER(h);
+  // table on the device: rows 0..5 = val/var/rowstats of U, V with the peers compacted (own rank left out); row 6 = the
+  // flag arrays indexed by rank (own slot unused)
+  std::vector<void*> tab((size_t)PEER_NBUF * bnmtf_nmf_s::MAXPEER, nullptr);
+  int np = 0;
+  for (int r = 0; r < h->world; ++r) {
+    if (r == h->rank) continue;
+    const cudaIpcMemHandle_t* hd = reinterpret_cast<const cudaIpcMemHandle_t*>(blobs + (size_t)r * blob_bytes);
+    for (int q = 0; q < PEER_NBUF; ++q) {
+      void* ptr = nullptr;
+      CK(cudaIpcOpenMemHandle(&ptr, hd[q], cudaIpcMemLazyEnablePeerAccess));
+      h->peer_open[r][q] = ptr;
+      if (q < 6) tab[(size_t)q * bnmtf_nmf_s::MAXPEER + np] = ptr;
+      else tab[(size_t)q * bnmtf_nmf_s::MAXPEER + r] = ptr;
+    }
+    ++np;
+  }
+  if (!h->peer_tab_dev) CK(cudaMalloc(&h->peer_tab_dev, sizeof(void*) * tab.size()));
+  CK(cudaMemcpy(h->peer_tab_dev, tab.data(), sizeof(void*) * tab.size(), cudaMemcpyHostToDevice));
+  h->peer_ok = true;
   return 0;
 }
 
@@ -953,6 +1038,12 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
         }
         p.gmat = h->gmat;
       }
+      if (sd.v5 && h->peer_ok && h->world > 1) {
+        p.peer_val = reinterpret_cast<double* const*>(h->peer_tab_dev + (size_t)(side * 3 + 0) * bnmtf_nmf_s::MAXPEER);
+        p.peer_var = reinterpret_cast<double* const*>(h->peer_tab_dev + (size_t)(side * 3 + 1) * bnmtf_nmf_s::MAXPEER);
+        p.peer_rowstats = reinterpret_cast<double* const*>(h->peer_tab_dev + (size_t)(side * 3 + 2) * bnmtf_nmf_s::MAXPEER);
+        p.npeers = h->world - 1;
+      }
       if (sd.v5) {
         if (!h->set_counter) CK(cudaMalloc(&h->set_counter, sizeof(int)));
         CK(cudaMemsetAsync(h->set_counter, 0, sizeof(int), h->stream));
@@ -1020,7 +1111,7 @@ static int launch_lambda(bnmtf_nmf_s* h, int method, uint64_t seed, uint32_t ite
   Side& su = h->s[0]; Side& sv = h->s[1];
   const int K = h->K;
 #define LK(MODE)                                                                                                      \
-  lambda_kernel<MODE><<<K, 256, 0, h->stream>>>(su.km, su.ld, h->I, sv.km, sv.ld, h->J, K, h->hyper, h->colsum,       \
+  lambda_kernel<MODE><<<K, 1024, 0, h->stream>>>(su.km, su.ld, h->I, sv.km, sv.ld, h->J, K, h->hyper, h->colsum,       \
                                                 h->lamstate, h->lamk, seed, iteration, update, h->iter_ptr)
   switch (method) {
     case BNMTF_GIBBS: LK(M_GIBBS); break;
@@ -1052,9 +1143,26 @@ static int launch_finalize(bnmtf_nmf_s* h, int method, double* stats_out, uint64
 }
 
 // after a sweep on `side`: make every rank hold the whole factor (and row stats)
+static int peer_sync_end_of_iteration(bnmtf_nmf_s* h) {
+  if (h->world <= 1 || !h->peer_ok || !(h->s[0].v5 || h->s[1].v5)) return 0;
+  std::string err;
+  if (launch_peer_barrier(reinterpret_cast<int* const*>(h->peer_tab_dev + (size_t)6 * bnmtf_nmf_s::MAXPEER), h->peer_flags, h->rank,
+                          h->world, ++h->peer_epoch, h->stream, &err)) { g_err = err; return 1; }
+  h->launches++;
+  return 0;
+}
+
 static int allgather_side(bnmtf_nmf_s* h, int method, int side, bool stats) {
   if (h->world <= 1) return 0;
   Side& sd = h->s[side];
+  if (sd.v5 && h->peer_ok && method != BNMTF_NP) {
+    // the sweep wrote its rows (values, VB variances, row statistics) into every rank's arrays: only the barrier is left
+    std::string err;
+    if (launch_peer_barrier(reinterpret_cast<int* const*>(h->peer_tab_dev + (size_t)6 * bnmtf_nmf_s::MAXPEER), h->peer_flags, h->rank,
+                            h->world, ++h->peer_epoch, h->stream, &err)) { g_err = err; return 1; }
+    h->launches++;
+    return 0;
+  }
   const size_t cnt = (size_t)sd.n_shard * sd.kf;
   double* fields[4] = {sd.val, method == BNMTF_VB ? sd.var : nullptr, nullptr, nullptr};
   for (double* f : fields) {
@@ -1164,7 +1272,7 @@ class TraceDrain {
       std::unique_lock<std::mutex> lk(mu_);
       cv_.wait(lk, [&] { return slots_ready_ && done_ >= c - 1; });
     }
-    if (failed_) FAIL("pinned host memory for the draw traces: %s", cudaGetErrorString(err_));
+    if (failed_) FAIL("pinned host memory for the draw traces: %s", cudaGetErrorString((cudaError_t)err_.load()));
     cudaStream_t cs = h_->copy_stream;
     CK(cudaStreamWaitEvent(cs, dev_ready, 0));
     Job j{};
@@ -1200,7 +1308,7 @@ class TraceDrain {
     for (auto& e : ready_) if (e) cudaEventDestroy(e);
     ready_.clear();
     active = false;
-    if (failed_) FAIL("copying the draw traces to host memory failed: %s", cudaGetErrorString(err_));
+    if (failed_) FAIL("copying the draw traces to host memory failed: %s", cudaGetErrorString((cudaError_t)err_.load()));
     return 0;
   }
 
@@ -1228,7 +1336,7 @@ class TraceDrain {
       h_->pin_bytes = 0;
       cudaError_t e = cudaSuccess;
       for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaHostAlloc((void**)&h_->pin[b], slot_bytes_, cudaHostAllocDefault);
-      if (e == cudaSuccess) h_->pin_bytes = slot_bytes_; else { failed_ = true; err_ = e; }
+      if (e == cudaSuccess) h_->pin_bytes = slot_bytes_; else { err_ = (int)e; failed_ = true; }
     }
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -1244,7 +1352,7 @@ class TraceDrain {
         j = jobs_[i];
       }
       cudaError_t e = cudaEventSynchronize(ready_[i]);
-      if (e != cudaSuccess) { failed_ = true; err_ = e; }
+      if (e != cudaSuccess) { err_ = (int)e; failed_ = true; }
       else for (int q = 0; q < j.n; ++q) spread_memcpy(j.dst[q], j.src[q], j.bytes[q]);
       {
         std::lock_guard<std::mutex> lk(mu_);
@@ -1262,8 +1370,9 @@ class TraceDrain {
   int submitted_ = 0, done_ = 0;
   size_t slot_bytes_ = 0;
   bool slots_ready_ = false;
-  bool stop_ = false, failed_ = false;
-  cudaError_t err_ = cudaSuccess;
+  bool stop_ = false;                        // guarded by mu_
+  std::atomic<bool> failed_{false};          // written by the worker, read by submit() / finish() on the caller's thread
+  std::atomic<int> err_{(int)cudaSuccess};
 };
 
 // iterations per device-side trace chunk: everything at once while it fits 256 MB (the run loop can then be
@@ -1331,6 +1440,16 @@ static int run_graph_replays(bnmtf_nmf_s* h, int iterations, std::vector<cudaEve
       }
       h->launches += per_it * (int64_t)(iterations - 2);
     }
+    if (!rc && ce != cudaSuccess && gexec == nullptr) {
+      // capture or instantiation failed (nothing of the captured iteration has run): the eager loop serves the rest;
+      // the iteration index stays on the device, so the chain is the same
+      cudaGetLastError();
+      ce = cudaSuccess;
+      for (int it = 1; it < iterations && !rc && ce == cudaSuccess; ++it) {
+        rc = one_iteration();
+        if (!rc) ce = cudaEventRecord(ev[it + 1], h->stream);
+      }
+    }
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
   }
@@ -1379,6 +1498,9 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   std::vector<cudaEvent_t> ev(h->ev_pool.begin(), h->ev_pool.begin() + iterations + 1);
   cudaEvent_t chunk_done[2] = {h->chunk_ev[0], h->chunk_ev[1]}, chunk_copied[2] = {h->chunk_ev[2], h->chunk_ev[3]};
 
+  // peer exchange: no rank's first sweep may write into another rank's arrays before that rank has set up its own state
+  // for this run (the uploads of set_factor are complete when the caller gets here)
+  if (peer_sync_end_of_iteration(h)) return 1;
   refresh_km(h, 0, method); refresh_km(h, 1, method);
   h->km_mode = method == BNMTF_VB ? 2 : 1;
   if (summary_reset(h)) return 1;
@@ -1454,6 +1576,9 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
         CK(cudaMemcpyAsync(su.trace[b] + (size_t)slot * su.n_glob * K, su.val, sizeof(double) * su.n_glob * K, cudaMemcpyDeviceToDevice, h->stream));
         CK(cudaMemcpyAsync(sv.trace[b] + (size_t)slot * sv.n_glob * K, sv.val, sizeof(double) * sv.n_glob * K, cudaMemcpyDeviceToDevice, h->stream));
       }
+      // peer exchange: the other ranks' next U sweep writes into this rank's arrays -- not before everything that reads
+      // this iteration's factors here (trace copy, posterior sums, statistics) has run
+      if (peer_sync_end_of_iteration(h)) return 1;
       CK(cudaEventRecord(ev[it + 1], h->stream));
     }
     if (tr) {

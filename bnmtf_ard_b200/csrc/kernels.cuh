@@ -633,15 +633,26 @@ __device__ __forceinline__ void finalize_body(const double* __restrict__ rsU, in
   for (int sidx = 0; sidx < 2; ++sidx) {
     const double* rs = sidx == 0 ? rsU : rsV;
     const int64_t n = sidx == 0 ? nU : nV;
-    for (int f = 0; f < NRS; ++f) {
-      // only VB consumes the U-side statistics and the ELBO/ESD columns
-      const bool needed = (MODE == M_VB) ? (f <= RS_PRIOR)
-                                         : (sidx == 1 && (f <= RS_SUM_RCE || (MODE == M_NP && f == RS_IDIV)));
-      double a = 0.0;
-      if (rs != nullptr && needed) {
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a += rs[i * NRS + f];
-        a = block_sum(a, sh);
+    // only VB consumes the U-side statistics and the ELBO/ESD columns
+    auto needed = [&](int f) -> bool {
+      return (MODE == M_VB) ? (f <= RS_PRIOR) : (sidx == 1 && (f <= RS_SUM_RCE || (MODE == M_NP && f == RS_IDIV)));
+    };
+    // one walk over the rows for all fields (the loads of a row are independent; per field the order of the sum is
+    // the one of a walk per field)
+    double acc[NRS];
+#pragma unroll
+    for (int f = 0; f < NRS; ++f) acc[f] = 0.0;
+    if (rs != nullptr) {
+      for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+        for (int f = 0; f < NRS; ++f)
+          if (needed(f)) acc[f] += rs[i * NRS + f];
       }
+    }
+#pragma unroll
+    for (int f = 0; f < NRS; ++f) {
+      double a = 0.0;
+      if (rs != nullptr && needed(f)) a = block_sum(acc[f], sh);
       if (threadIdx.x == 0) tot[sidx * NRS + f] = a;
     }
   }

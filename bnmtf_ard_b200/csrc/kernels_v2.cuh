@@ -186,6 +186,12 @@ struct Sweep2Params {
   double* proj_out;
   double* gmat;                          // blocked cluster sweep (kernels_v4.cuh), Gibbs: scratch for the random material of the resident row sets
   int* set_counter;                      // kernels_v5.cuh: row sets handed out so far beyond the first round (zeroed before every launch)
+  // multi-GPU, kernels_v5.cuh: the rows this rank updates are also written straight into the factor / statistics arrays of
+  // the other ranks (peer memory over NVLink) -- the all-gather of the sweep's output rides on the sweep itself
+  double* const* peer_val;               // [npeers] the other ranks' Xval
+  double* const* peer_var;               // [npeers] Xvar (VB)
+  double* const* peer_rowstats;          // [npeers] row statistics, indexed by GLOBAL row
+  int npeers;
   int nst;                               // stages of the tile ring (3 or 4)
   int dbg;                               // timing experiments only: 1 = no update math, 2 = phase clocks into prof
   unsigned long long* prof;              // [32] clock64 sums of cluster 0 / CTA 0 (dbg & 2)

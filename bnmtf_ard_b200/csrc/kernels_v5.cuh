@@ -725,8 +725,10 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
             double v0, v1;
             lds_pair5(tab_r + (uint32_t)(kk * TABW) * 8u, v0, v1);
             p.Xval[(size_t)grow * K + kk] = v0;
+            for (int pr = 0; pr < p.npeers; ++pr) p.peer_val[pr][(size_t)grow * K + kk] = v0;   // the other GPUs' copies
             if (VB) {
               p.Xvar[(size_t)grow * K + kk] = v1;
+              for (int pr = 0; pr < p.npeers; ++pr) p.peer_var[pr][(size_t)grow * K + kk] = v1;
               if (want_mu) p.Xmu[(size_t)grow * K + kk] = lds5(tab_r + (uint32_t)(kk * TABW + 3) * 8u);
             } else if (want_mu) {
               p.Xmu[(size_t)grow * K + kk] = v1;
@@ -742,6 +744,11 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
             rs[RS_RSS] = t3[0]; rs[RS_SUM_E] = t3[1]; rs[RS_SUM_RCE] = t3[2];
             rs[RS_ESDVAR] = VB ? acc_esd1 / lds5(misc_a) - acc_esd2 : 0.0; rs[RS_ELBOQ] = acc_q; rs[RS_PRIOR] = acc_prior;
             rs[RS_IDIV] = 0.0; rs[RS_SPARE] = 0.0;
+            for (int pr = 0; pr < p.npeers; ++pr) {
+              double* prs = p.peer_rowstats[pr] + (size_t)grow * NRS;
+#pragma unroll
+              for (int f = 0; f < NRS; ++f) prs[f] = rs[f];
+            }
           }
         }
       }
@@ -765,6 +772,22 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "n"(TMCOLS) : "memory");
   cluster_sync_all();
+}
+
+// Device-side barrier of the ranks after a sweep whose output went to the peers directly: every rank tells every other
+// rank "my sweep number `epoch` and all its writes are done" (a system-scope release store into the peer's flag array)
+// and waits until it has heard the same from all of them.  One warp; launched on the sweep's stream right behind it, so
+// the sweep's peer writes are complete when the flags go out, and whatever follows on the stream sees the peers' rows.
+static __global__ void peer_barrier_kernel(int* const* peer_flags, volatile int* my_flags, int rank, int world, int epoch) {
+  const int r = threadIdx.x;
+  if (r < world && r != rank) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peer_flags[r] + rank), "r"(epoch) : "memory");
+    int seen;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(my_flags + r) : "memory");
+    } while (seen - epoch < 0);
+  }
 }
 
 }  // namespace bnmtf

@@ -116,6 +116,12 @@ static int launch_m(int npt, const Sweep2Params& p, cudaStream_t stream, int* nc
   return 1;
 }
 
+int launch_peer_barrier(int* const* peer_flags_dev, int* my_flags, int rank, int world, int epoch, cudaStream_t stream, std::string* err) {
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(peer_flags_dev, my_flags, rank, world, epoch);
+  CK5(cudaGetLastError());
+  return 0;
+}
+
 int launch_sweep5(int npt, int method, const Sweep2Params& p, cudaStream_t stream, int* ncl_cache, std::string* err) {
   switch (method) {
     case 0: return launch_m<M_GIBBS>(npt, p, stream, ncl_cache, err);

@@ -15,4 +15,6 @@ size_t sweep5_gmat_doubles(int rs, int K);
 // BNMTF_GIBBS / ICM / VB (0 / 1 / 2).  *ncl_cache (0 on first use) caches the number of co-resident clusters.
 // Returns 0, or 1 with *err set.
 int launch_sweep5(int npt, int method, const Sweep2Params& p, cudaStream_t stream, int* ncl_cache, std::string* err);
+// device-side barrier of the ranks behind a sweep that wrote its rows to the peers (kernels_v5.cuh: peer_barrier_kernel)
+int launch_peer_barrier(int* const* peer_flags_dev, int* my_flags, int rank, int world, int epoch, cudaStream_t stream, std::string* err);
 }  // namespace bnmtf

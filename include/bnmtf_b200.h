@@ -120,6 +120,16 @@ int bnmtf_nmf_set_data_stats(bnmtf_nmf_t h, double size_Omega, double mean_R);
 int bnmtf_nccl_unique_id(uint8_t* id128);
 int bnmtf_nmf_set_comm(bnmtf_nmf_t h, int rank, int world, const uint8_t* nccl_id128);
 
+/* Multi-GPU peer exchange (optional, after bnmtf_nmf_set_comm and before the first run; two-factor models): every rank
+ * exports the CUDA IPC handles of its factor / statistics arrays (`blob`, BNMTF_PEER_BLOB_BYTES bytes), the caller
+ * all-gathers the blobs (torch.distributed) and hands all of them -- world x blob_bytes, in rank order -- to every rank.
+ * From then on the cluster sweeps write the rows they update straight into the other ranks' arrays over NVLink and a
+ * device-side barrier replaces the NCCL all-gathers of the iteration.  Same chains, bit for bit.  No reference
+ * counterpart (the reference is single-process numpy). */
+#define BNMTF_PEER_BLOB_BYTES 448
+int bnmtf_nmf_peer_export(bnmtf_nmf_t h, uint8_t* blob, int64_t blob_bytes);
+int bnmtf_nmf_peer_import(bnmtf_nmf_t h, const uint8_t* blobs, int64_t blob_bytes);
+
 /* Hyper-parameters (bnmf_gibbs.py:76-89).  lambdaU (I x K) / lambdaV (J x K)
  * are used when ARD == 0 and may be NULL when ARD != 0. */
 int bnmtf_nmf_set_hyper(bnmtf_nmf_t h, int ARD, double alphatau, double betatau,

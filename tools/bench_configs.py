@@ -4,7 +4,9 @@
   C2  BNMF VB+ARD, GDSC-shaped 707 x 139, 81 % observed, K=20
   C4  BNMTF Gibbs and VB, 10000 x 8000, 30 % observed, K=L=20
 Synthetic data of each shape; iterations/s from CUDA events inside the engine.
-Usage: python tools/bench_configs.py [--out profiles/rNN_configs.json]"""
+Usage: python tools/bench_configs.py [--out profiles/rNN_configs.json]
+C4 also runs sharded: python -m torch.distributed.run --nproc-per-node N ... tools/bench_configs.py --only C4
+(one rank per GPU: rows of R for the F sweep, columns for the G sweep, as bench.py does for configs[2])."""
 import argparse
 import json
 import os
@@ -37,10 +39,19 @@ def main():
     ap.add_argument("--its", type=int, default=0, help="override the iteration counts (profiling)")
     args = ap.parse_args()
     import torch
-    from bnmtf_ard_b200 import _lib
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        args.only = args.only or "C4"
+        assert "C4" in args.only, "only the C4 configurations run sharded"
+    from bnmtf_ard_b200 import _dist, _lib
     from bnmtf_ard_b200._engine import NMFEngine, NMTFEngine
     from bnmtf_ard_b200._lib import F_MU, F_TAU, F_VALUE, F_VAR, SIDE_U, SIDE_V
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", local)
     out = {}
 
     def nmf_engine(I, J, K, dens):
@@ -51,10 +62,15 @@ def main():
 
     def record(name, seconds, its, extra=None):
         s = float(seconds[-1] - seconds[max(0, len(seconds) - its - 1)]) if len(seconds) > its else float(seconds[-1])
-        d = {"iterations_per_s": its / s, "ms_per_iteration": 1e3 * s / its, "timed_iterations": its}
+        if world > 1:      # the slowest rank
+            t = torch.tensor([s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            s = float(t.item())
+        d = {"iterations_per_s": its / s, "ms_per_iteration": 1e3 * s / its, "timed_iterations": its, "n_gpus": world}
         d.update(extra or {})
         out[name] = d
-        print(name, json.dumps(d))
+        if rank == 0:
+            print(name, json.dumps(d))
 
     want = lambda tag: (not args.only) or (tag in args.only)  # noqa: E731
     n = lambda default: args.its if args.its > 0 else default  # noqa: E731
@@ -75,8 +91,12 @@ def main():
     if want("C4"):   # BNMTF Gibbs and VB
         I, J, K, L = 10000, 8000, 20, 20
         R, M = synth(I, J, K, L, 0.3, dev)
-        e = NMTFEngine.from_device_blocks(I, J, K, R.data_ptr(), M.data_ptr(), R.data_ptr(), M.data_ptr(), device=0, L=L)
-        del R, M
+        r0, r1, _ = _dist.shard_bounds(I, rank, world)
+        c0, c1, _ = _dist.shard_bounds(J, rank, world)
+        Rrow, Mrow = R[r0:r1].contiguous(), M[r0:r1].contiguous()
+        Rcol, Mcol = R[:, c0:c1].contiguous(), M[:, c0:c1].contiguous()
+        e = NMTFEngine.from_device_blocks(I, J, K, Rrow.data_ptr(), Mrow.data_ptr(), Rcol.data_ptr(), Mcol.data_ptr(), device=local, L=L)
+        del R, M, Rrow, Mrow, Rcol, Mcol
         torch.cuda.empty_cache()
         lamS = 0.1 * np.ones((K, L))
         e.set_hyper(True, 1., 1., 1., 1., None, None, lamS)
@@ -152,9 +172,12 @@ def main():
             out[key] = {"seconds": dtb, "fits": fits, "fits_per_s": fits / dtb, "best_K": bestb['K'], "best_mse": perfb,
                         "phases_s": cvb.timing, "launches": cvb.launches}
             print("C5b", json.dumps(out[key]))
-    if args.out:
+    if args.out and rank == 0:
         with open(args.out, "w") as f:
             json.dump(out, f, indent=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
