@@ -122,6 +122,7 @@ struct Side {
   bool v4 = false;                       // blocked cluster sweep (kernels_v4.cuh) serves this side's Gibbs / ICM / VB sweeps
   bool v5 = false;                       // per-row-chain cluster sweep (kernels_v5.cuh) serves them
   int nclusters4[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};   // resident clusters per method, without / with the parameter outputs
+  int nclusters5p[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // the same for the kernel with the projection epilogue
   bool long_rows = false;      // rows beyond the register-resident configurations: residual in global scratch (kernels_long.cuh)
   double* escr = nullptr;      // [nslots]
   int occ_long[4] = {0, 0, 0, 0};
@@ -130,6 +131,7 @@ struct Side {
   const double* ysrc = nullptr;
   int64_t ysrc_ld = 0;
   double* ycomb = nullptr;   // NMTF: W = G S^T (F side) / Z = F S (G side), owned
+  double* ycombB = nullptr;  // the same in the block-major layout [ceil(kf/2)][ysrc_ld][2] the per-row-chain cluster sweep reads
   double* lamk = nullptr;    // ARD prior of this side's columns (not owned for NMF)
 };
 constexpr int V2_CS = 8;
@@ -295,7 +297,9 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
     // per-row-chain cluster sweep (kernels_v5.cuh): the default for the two-factor models when it fits; BNMTF_V5=0 falls back
     const char* v5env = getenv("BNMTF_V5");
     const int npt5 = npt2 == 18 ? 20 : npt2;
-    sd.v5 = sd.v2 && !sd.v4 && !h->nmtf && !(v5env && atoi(v5env) == 0) && sweep5_fits(npt5, sd.tw, sd.kf);
+    // (tri-factorisation: the Gibbs / ICM sweeps of F and G; the F sweep carries the projection onto the L columns of G)
+    const int proj_k2 = (h->nmtf && &sd == &h->s[0]) ? h->L : 0;
+    sd.v5 = sd.v2 && !sd.v4 && !(v5env && atoi(v5env) == 0) && sweep5_fits(npt5, sd.tw, sd.kf, proj_k2);
     if (sd.v5) { npt2 = npt5; rs = sweep5_rows_per_set(npt5); }
   }
   if (sd.v2 && n > 0) {
@@ -576,7 +580,7 @@ static void free_side(Side& sd) {
   cudaFree(sd.mu); cudaFree(sd.tau);
   cudaFree(sd.km); cudaFree(sd.kmB); cudaFree(sd.kmBq); cudaFree(sd.lam_rm);
   cudaFree(sd.trace[0]); cudaFree(sd.trace[1]);
-  cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev); cudaFree(sd.ycomb); cudaFree(sd.escr);
+  cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev); cudaFree(sd.ycomb); cudaFree(sd.ycombB); cudaFree(sd.escr);
   if (sd.own_dense) { cudaFree((void*)sd.dR); cudaFree((void*)sd.dM); }
 }
 
@@ -833,7 +837,8 @@ static int refresh_km(bnmtf_nmf_s* h, int side, int method) {
     rm_to_km_kernel<1><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, sd.kf, sd.ld);
   h->launches++;
   // the blocked cluster sweep of the other side reads the block-major copies
-  if ((h->s[1 - side].v4 || h->s[1 - side].v5) && !h->nmtf && method != BNMTF_NP) {
+  // (tri-factorisation: only the projection epilogue of the F sweep reads a factor directly, G)
+  if ((h->s[1 - side].v4 || h->s[1 - side].v5) && (h->nmtf ? (side == 1 && method != BNMTF_VB) : true) && method != BNMTF_NP) {
     dim3 g3((unsigned)((sd.ld + 255) / 256), (unsigned)((sd.kf + 1) / 2));
     if (method == BNMTF_VB) rm_to_kmB_kernel<true><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
     else rm_to_kmB_kernel<false><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
@@ -1013,7 +1018,7 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     p.rmean = h->rmean; p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
     p.iter_ptr = h->iter_ptr;
     if (h->fuse_proj && side == 0 && h->nmtf) {   // NMTF: P_il = sum_j e_ij G_jl from the residual the F sweep ends with
-      p.Ykm2 = h->s[1].km; p.ldy2 = h->s[1].ld; p.K2 = h->L; p.proj_out = h->Prow;
+      p.Ykm2 = sd.v5 ? h->s[1].kmB : h->s[1].km; p.ldy2 = h->s[1].ld; p.K2 = h->L; p.proj_out = h->Prow;
     }
     p.dbg = getenv("BNMTF_V2_DBG") ? atoi(getenv("BNMTF_V2_DBG")) : 0;
     static unsigned long long* prof_buf = nullptr;   // timing experiments only
@@ -1025,8 +1030,9 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
       bnmtf_prof_last = prof_buf;
     }
     rc = 0;
-    if ((sd.v4 || sd.v5) && p.K2 == 0) {
-      p.Ykm = h->s[1 - side].kmB; p.Ykm2 = h->s[1 - side].kmBq; p.ldy = h->s[1 - side].ld;
+    if (sd.v4 || sd.v5) {
+      if (h->nmtf) { p.Ykm = sd.ycombB; p.ldy = sd.ysrc_ld; }       // W = G S^T / Z = F S, block-major (nmtf_make_W / nmtf_make_Z)
+      else { p.Ykm = h->s[1 - side].kmB; p.Ykm2 = h->s[1 - side].kmBq; p.ldy = h->s[1 - side].ld; }
       if (method != BNMTF_GIBBS && method != BNMTF_ICM && method != BNMTF_VB) FAIL("unknown method %d", method);
       if (method == BNMTF_GIBBS) {
         const size_t need = sd.v5 ? sweep5_gmat_doubles(sd.rs, sd.kf) : sweep4_gmat_doubles(sd.rs, sd.kf);
@@ -1050,7 +1056,8 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
         p.set_counter = h->set_counter;
       }
       std::string err;
-      rc = sd.v5 ? launch_sweep5(sd.npt2, method, p, h->stream, &sd.nclusters4[method][p.Xmu != nullptr ? 1 : 0], &err)
+      rc = sd.v5 ? launch_sweep5(sd.npt2, method, p, h->stream,
+                                 p.K2 > 0 ? &sd.nclusters5p[method][p.Xmu != nullptr ? 1 : 0] : &sd.nclusters4[method][p.Xmu != nullptr ? 1 : 0], &err)
                  : launch_sweep4(sd.npt2, method, p, h->stream, &sd.nclusters4[method][p.Xmu != nullptr ? 1 : 0], &err);
       if (rc) { g_err = err; return 1; }
       h->launches++;

@@ -21,9 +21,10 @@
 
 namespace bnmtf {
 
-// out_km[c][i] = sum_q X_rm[i][q] * Smat[q*s_q + c*s_c]  (i < n), zero padded to ld
+// out_km[c][i] = sum_q X_rm[i][q] * Smat[q*s_q + c*s_c]  (i < n), zero padded to ld; out_kmB (optional): the same values in
+// the block-major layout of the per-row-chain cluster sweep, out_kmB[((c / 2) * ld + i) * 2 + (c & 1)]
 static __global__ void combine_km_kernel(const double* __restrict__ X_rm, int64_t n, int kq, const double* __restrict__ Smat, int s_q,
-                                  int s_c, double* __restrict__ out_km, int64_t ld) {
+                                  int s_c, double* __restrict__ out_km, int64_t ld, double* __restrict__ out_kmB) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   if (i >= ld) return;
@@ -31,6 +32,63 @@ static __global__ void combine_km_kernel(const double* __restrict__ X_rm, int64_
   if (i < n)
     for (int q = 0; q < kq; ++q) acc = fma(X_rm[i * kq + q], Smat[q * s_q + c * s_c], acc);
   out_km[(size_t)c * ld + i] = acc;
+  if (out_kmB) out_kmB[((size_t)(c >> 1) * ld + i) * 2 + (c & 1)] = acc;
+}
+
+// Masked row sums of the other factor's variational moments (bnmtf_vb.py:343,352-357,371):
+//   outA[row][w] = sum_{j in Omega_row} Var[j][w],   outB[row][w] = sum_{j in Omega_row} (Var[j][w] + E[j][w]^2)   (WITH_B)
+// One warp per row of the row layout, lane = column w (+ 32 for W > 32).  The rows of the ROW-MAJOR factor are gathered whole
+// (W contiguous doubles per observed entry: every 32-byte sector fetched is used), where the projection mode of the row-team
+// sweep gathers 8 bytes per sector from the k-major copy, once per column.  The 32 column indices of a step are one
+// coalesced load, handed round by shuffles; eight entries are in flight per lane; fixed summation order per row.
+template <int NC, bool WITH_B>
+__global__ void __launch_bounds__(256) nmtf_masked_sums_kernel(const uint32_t* __restrict__ cols, const int64_t* __restrict__ rowstart,
+                                                               int n_loc, int64_t row0, uint32_t padcol, const double* __restrict__ E_rm,
+                                                               const double* __restrict__ V_rm, int W, double* __restrict__ outA,
+                                                               double* __restrict__ outB) {
+  const int row = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row >= n_loc) return;
+  constexpr int U = 8;
+  double a[NC][U], b[NC][U];
+#pragma unroll
+  for (int q = 0; q < NC; ++q)
+#pragma unroll
+    for (int u = 0; u < U; ++u) { a[q][u] = 0.0; b[q][u] = 0.0; }
+  const int64_t beg = rowstart[row], end = rowstart[row + 1];
+  for (int64_t q0 = beg; q0 < end; q0 += 32) {
+    const uint32_t mycol = (q0 + lane < end) ? cols[q0 + lane] : padcol;
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += U) {
+      double v[NC][U], x[NC][U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t j = __shfl_sync(0xffffffffu, mycol, r0 + u);
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+          const int w = lane + 32 * q;
+          const bool on = (j != padcol) && (w < W);
+          v[q][u] = on ? __ldg(V_rm + (size_t)j * W + w) : 0.0;
+          x[q][u] = (WITH_B && on) ? __ldg(E_rm + (size_t)j * W + w) : 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+          a[q][u] += v[q][u];
+          if (WITH_B) b[q][u] += fma(x[q][u], x[q][u], v[q][u]);
+        }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NC; ++q) {
+    const int w = lane + 32 * q;
+    if (w < W) {
+      const size_t o = (size_t)(row0 + row) * W + w;
+      outA[o] = ((a[q][0] + a[q][1]) + (a[q][2] + a[q][3])) + ((a[q][4] + a[q][5]) + (a[q][6] + a[q][7]));
+      if (WITH_B) outB[o] = ((b[q][0] + b[q][1]) + (b[q][2] + b[q][3])) + ((b[q][4] + b[q][5]) + (b[q][6] + b[q][7]));
+    }
+  }
 }
 
 __device__ __forceinline__ void pair_decode(int p, int L, int& a, int& b) {

@@ -41,12 +41,17 @@ struct Sweep5Layout {
   int sstride;                   // doubles per row of the statistics area
 };
 
-__host__ __device__ inline Sweep5Layout sweep5_layout(int tw, int rs, int K, int cs, int nslot, int tabw, bool vb) {
+// doubles per CTA of the record a row's warps send to CTA 0 at the row's end: 3 statistics of the final residual (+ 1 pad) and,
+// with the projection epilogue, the partial sums sum_j e_j Y2[l][j] of the K2 columns of the second factor (in blocks of two)
+__host__ __device__ constexpr int sweep5_rec_width(int K2) { return 4 + 2 * ((K2 + V5_B - 1) / V5_B); }
+
+__host__ __device__ inline Sweep5Layout sweep5_layout(int tw, int rs, int K, int cs, int nslot, int tabw, bool vb, int K2 = 0) {
   Sweep5Layout L;
   const int NBK = (K + V5_B - 1) / V5_B, KP = NBK * V5_B;
   L.nstat = KP + NBK + (vb ? KP : 0);
-  // the row's area also receives the statistics of the final residual ([CS][4], CTA 0 only) once the row's table is built
-  L.sstride = (L.nstat > cs * 4 ? L.nstat : cs * 4) + ((L.nstat > cs * 4 ? L.nstat : cs * 4) & 1);
+  // the row's area also receives the records of the final residual ([CS][sweep5_rec_width], CTA 0 only) once the row's table is built
+  const int recw = cs * sweep5_rec_width(K2);
+  L.sstride = (L.nstat > recw ? L.nstat : recw) + ((L.nstat > recw ? L.nstat : recw) & 1);
   size_t o = 0;
   L.tiles = o; o += (size_t)nslot * (tw + V2_PAD) * V5_B;
   L.mbar = o; o += (size_t)2 * nslot + 4 * rs;          // full[nslot], empty[nslot], rec[rs][2], statbar[rs], rowbar[rs]
@@ -251,10 +256,14 @@ __host__ __device__ constexpr int sweep5_regs(int rs, int minb) {
 #define P5_ADD(slot) do { } while (0)
 #endif
 
-template <int NPT, int MODE, int CS, int RS, int NSLOT, int MINB>
+// PROJ (tri-factorisation F sweep, Gibbs / ICM): an epilogue projects the residual the row ends with onto the K2 columns of
+// a second block-major factor, proj_out[global row][l] = sum_j e_j Y2[l][j] (the row part of the S_kl numerators,
+// bnmtf_gibbs.py:277-283): ceil(K2 / 2) more tiles per row set, the partial sums of the 8 segments meet in CTA 0.
+template <int NPT, int MODE, int CS, int RS, int NSLOT, int MINB, bool PROJ = false>
 __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Params p) {
   constexpr int B = V5_B;
   constexpr bool VB = (MODE == M_VB), GIBBS = (MODE == M_GIBBS);
+  static_assert(!(PROJ && VB), "the projection epilogue serves the Gibbs / ICM sweeps (VB: Ykm2 holds the second moments)");
   constexpr int TABW = 4;                                 // Gibbs: c1, sigma, z1, x_old; ICM: c1, c2, -, x_old; VB: c1, c2, precision, x_old
   constexpr int NCH = NPT / 4;                            // chunks of 4 entries
   constexpr int TMCOLS = sweep5_tm_cols(NPT, RS + 1);
@@ -269,7 +278,9 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
   const int K = p.K, tw = p.tw;
   const int NBK = (K + B - 1) / B, KP = NBK * B;
   const int TA = VB ? 2 * NBK : NBK;                      // tiles of the residual pass (VB: values and second moments alternate)
-  const int total = TA + NBK;                             // tiles per row set
+  const int K2 = PROJ ? p.K2 : 0, NBL = (K2 + B - 1) / B; // projection epilogue: blocks of the second factor
+  const int RECW = sweep5_rec_width(K2);                  // doubles per CTA of a row's final record
+  const int total = TA + NBK + NBL;                       // tiles per row set
   const uint32_t slot_bytes = (uint32_t)(tw + V2_PAD) * B * 8u;
   const uint32_t tile_bytes = (uint32_t)tw * B * 8u;
   const bool want_mu = p.Xmu != nullptr;
@@ -278,7 +289,7 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
   const long long t_entry = clock64();
 #endif
   extern __shared__ __align__(128) double smem5[];
-  const Sweep5Layout L = sweep5_layout(tw, RS, K, CS, NSLOT, TABW, VB);
+  const Sweep5Layout L = sweep5_layout(tw, RS, K, CS, NSLOT, TABW, VB, K2);
   const uint32_t sm = smem_u32(smem5);
   const uint32_t tiles_a = sm + (uint32_t)L.tiles * 8u, mbar_a = sm + (uint32_t)L.mbar * 8u;
   const uint32_t full_a = mbar_a, empty_a = mbar_a + NSLOT * 8u, rec_a = mbar_a + 2 * NSLOT * 8u;
@@ -335,12 +346,14 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
     if (lane == 0) {
       const double* ybase = p.Ykm + (size_t)c * tw * B;   // this CTA's tile of block 0
       const double* qbase = VB ? p.Ykm2 + (size_t)c * tw * B : nullptr;
-      const size_t ystride = (size_t)p.ldy * B;
+      const double* pbase = PROJ ? p.Ykm2 + (size_t)c * tw * B : nullptr;   // this CTA's tile of the second factor's block 0
+      const size_t ystride = (size_t)p.ldy * B, pstride = (size_t)p.ldy2 * B;
       uint32_t g = 0, it = 0;
       for (int set = cid; set < p.nsets; set = next_set(++it)) {
         for (int t = 0; t < total; ++t, ++g) {
-          const double* src = t >= TA ? ybase + (size_t)(t - TA) * ystride
-                                      : (!VB ? ybase + (size_t)t * ystride : ((t & 1) ? qbase : ybase) + (size_t)(t >> 1) * ystride);
+          const double* src = (PROJ && t >= TA + NBK) ? pbase + (size_t)(t - TA - NBK) * pstride
+                              : t >= TA ? ybase + (size_t)(t - TA) * ystride
+                                        : (!VB ? ybase + (size_t)t * ystride : ((t & 1) ? qbase : ybase) + (size_t)(t >> 1) * ystride);
           const uint32_t slot = slot_of(g);
           mbar_wait_a(empty_a + slot * 8u, phase_of(g) ^ 1u);   // all row warps have released the slot's previous tile
           fence_proxy_async();
@@ -687,21 +700,55 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
             for (int i = 0; i < 2; ++i) {
               const double ee = fma(-d1, p1[i], fma(-d0, p0[i], cur.get(h2 + i)));
               const double rr = tv[(size_t)(4 * ch + h2 + i) * RS * 32];
+              if (PROJ) cur.set(h2 + i, ee);
               st0 = fma(ee, ee, st0);
               st1 += ee;
               st2 = fma(rr - p.rmean, ee, st2);   // padded slots hold e == 0
             }
             V5_CHAIN(Tp, p1[1]);
           }
+          if (PROJ) tm5_st8(tm + 8u * ch, cur);   // the projection reads the final residual
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_local(empty_a + slot_of(g - 1u) * 8u);
         st0 = warp_sum_mma(st0); st1 = warp_sum_mma(st1); st2 = warp_sum_mma(st2);
         const uint32_t rowbar = rowbar_a + (uint32_t)r * 8u;
-        if (c == 0 && lane == 0) mbar_expect_tx_a(rowbar, (uint32_t)(CS * 3 * 8));
+        if (c == 0 && lane == 0) mbar_expect_tx_a(rowbar, (uint32_t)(CS * (3 + B * NBL) * 8));
         if (lane < 3)
-          st_async_f64(map_to_cta(stat_r + (uint32_t)(c * 4 + lane) * 8u, 0u), lane == 0 ? st0 : (lane == 1 ? st1 : st2),
+          st_async_f64(map_to_cta(stat_r + (uint32_t)(c * RECW + lane) * 8u, 0u), lane == 0 ? st0 : (lane == 1 ? st1 : st2),
                        map_to_cta(rowbar, 0u));
+        if (PROJ) {
+          // ---- projection epilogue: sum_j e_j Y2[l][j] over this segment, two columns per tile, partial sums to CTA 0
+          for (int m = 0; m < NBL; ++m) {
+            const uint32_t slot = slot_of(g);
+            mbar_wait_a(full_a + slot * 8u, phase_of(g));
+            uint32_t T = tiles_a + slot * slot_bytes;
+            double h0 = 0.0, h1 = 0.0;
+            tm5_wait_st();
+            tm5_ld8(tm, b[0]);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+              TmChunk5& cur = b[ch & 1];
+              tm5_wait_ld(cur);
+              if (ch + 1 < NCH) tm5_ld8(tm + 8u * (ch + 1), b[(ch + 1) & 1]);
+#pragma unroll
+              for (int h2 = 0; h2 < 4; h2 += 2) {
+                double y0[2], y1[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) lds_pair5(T + V5_OFF(4 * ch + h2 + i), y0[i], y1[i]);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) { h0 = fma(cur.get(h2 + i), y0[i], h0); h1 = fma(cur.get(h2 + i), y1[i], h1); }
+                V5_CHAIN(T, y1[1]);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_local(empty_a + slot * 8u);
+            ++g;
+            h0 = warp_sum_mma(h0); h1 = warp_sum_mma(h1);
+            if (lane < 2)
+              st_async_f64(map_to_cta(stat_r + (uint32_t)(c * RECW + 4 + B * m + lane) * 8u, 0u), lane ? h1 : h0, map_to_cta(rowbar, 0u));
+          }
+        }
         if (c == 0) {
           double acc_q = 0.0, acc_prior = 0.0, acc_esd1 = 0.0, acc_esd2 = 0.0;
           __syncwarp();
@@ -734,10 +781,17 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
               p.Xmu[(size_t)grow * K + kk] = v1;
             }
           }
+          if (PROJ) {          // fixed-order sum of the 8 segments' partial sums
+            for (int l = lane; l < K2; l += 32) {
+              double t = 0.0;
+              for (int cc = 0; cc < CS; ++cc) t += lds5(stat_r + (uint32_t)(cc * RECW + 4 + l) * 8u);
+              p.proj_out[(size_t)grow * K2 + l] = t;
+            }
+          }
           if (lane == 0 && p.rowstats != nullptr) {
             double t3[3] = {0.0, 0.0, 0.0};
             for (int cc = 0; cc < CS; ++cc) {
-              const uint32_t src = stat_r + (uint32_t)(cc * 4) * 8u;
+              const uint32_t src = stat_r + (uint32_t)(cc * RECW) * 8u;
               t3[0] += lds5(src); t3[1] += lds5(src + 8); t3[2] += lds5(src + 16);
             }
             double* rs = p.rowstats + (size_t)(set * RS + r) * NRS;

@@ -243,6 +243,7 @@ def test_c4_strip_bnmtf_gibbs_replay(shape, monkeypatch):
     m.initialise("random", "random")
     m.run(2)
     eng = m._engine()
+    assert eng.layout_info()["v2_U" if J >= I else "v2_V"] == 5, eng.layout_info()   # the per-row-chain cluster sweep
     lamF, lamG = m.all_lambdaFk[1], m.all_lambdaGl[1]
     F, S, G = m.all_F[0].copy(), m.all_S[0].copy(), m.all_G[0].copy()
     tF, mF, tS, mS, tG, mG, rss = torc.gibbs_replay_iteration(R, M, F, S, G, m.all_tau[0], lamF, m.lambdaS, lamG,

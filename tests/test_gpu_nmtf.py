@@ -93,7 +93,9 @@ def test_icm_trajectory_golden(gold, ard):
     close(np.asarray(m.all_performances["Rp"])[ok], g[p + "Rp"][ok], RTOL_TRAJ)
 
 
-SHAPES = [(40, 30, 3, 4, 0.7), (150, 220, 5, 3, 0.5), (64, 3000, 4, 6, 0.6), (700, 90, 7, 2, 0.8)]
+# the last two: odd K and L on the per-row-chain cluster sweep (F side with the projection epilogue; G side)
+SHAPES = [(40, 30, 3, 4, 0.7), (150, 220, 5, 3, 0.5), (64, 3000, 4, 6, 0.6), (700, 90, 7, 2, 0.8), (48, 2600, 5, 7, 0.5),
+          (3100, 70, 5, 3, 0.6)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -114,6 +116,8 @@ def test_gibbs_iteration_vs_oracle(shape, monkeypatch):
     assert (F0 >= 0).all() and (S0 >= 0).all() and (G0 >= 0).all() and tau0 > 0
     m.run(1)
     eng = m._engine()
+    if max(I, J) >= 2048:      # the side with >= 2048 columns runs on the per-row-chain cluster sweep (kernels_v5.cuh)
+        assert eng.layout_info()["v2_U" if J >= I else "v2_V"] == 5, eng.layout_info()
     lamF, lamG = m.all_lambdaFk[0], m.all_lambdaGl[0]
     F, S, G = F0.copy(), S0.copy(), G0.copy()
     tF, mF, tS, mS, tG, mG, rss = orc.gibbs_replay_iteration(R, M, F, S, G, tau0, lamF, m.lambdaS, lamG,
@@ -126,7 +130,7 @@ def test_gibbs_iteration_vs_oracle(shape, monkeypatch):
     assert (lamF > 0).all() and (lamG > 0).all() and m.all_tau[0] > 0
 
 
-@pytest.mark.parametrize("shape", SHAPES[:3])
+@pytest.mark.parametrize("shape", SHAPES[:3] + SHAPES[4:])
 def test_icm_iterations_vs_oracle(shape):
     from bnmtf_ard_b200 import nmtf_icm
     I, J, K, L, dens = shape
