@@ -132,6 +132,7 @@ struct Side {
   int64_t ysrc_ld = 0;
   double* ycomb = nullptr;   // NMTF: W = G S^T (F side) / Z = F S (G side), owned
   double* ycombB = nullptr;  // the same in the block-major layout [ceil(kf/2)][ysrc_ld][2] the per-row-chain cluster sweep reads
+  double* ycombBq = nullptr; // VB: the second moments of W / Z, block-major
   double* lamk = nullptr;    // ARD prior of this side's columns (not owned for NMF)
 };
 constexpr int V2_CS = 8;
@@ -299,7 +300,8 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
     const int npt5 = npt2 == 18 ? 20 : npt2;
     // (tri-factorisation: the Gibbs / ICM sweeps of F and G; the F sweep carries the projection onto the L columns of G)
     const int proj_k2 = (h->nmtf && &sd == &h->s[0]) ? h->L : 0;
-    sd.v5 = sd.v2 && !sd.v4 && !(v5env && atoi(v5env) == 0) && sweep5_fits(npt5, sd.tw, sd.kf, proj_k2);
+    const int cov_l = h->nmtf ? (&sd == &h->s[0] ? h->L : h->K) : 0;      // VB covariance term (bnmtf_vb.py:343,371)
+    sd.v5 = sd.v2 && !sd.v4 && !(v5env && atoi(v5env) == 0) && sweep5_fits(npt5, sd.tw, sd.kf, proj_k2, cov_l);
     if (sd.v5) { npt2 = npt5; rs = sweep5_rows_per_set(npt5); }
   }
   if (sd.v2 && n > 0) {
@@ -580,7 +582,7 @@ static void free_side(Side& sd) {
   cudaFree(sd.mu); cudaFree(sd.tau);
   cudaFree(sd.km); cudaFree(sd.kmB); cudaFree(sd.kmBq); cudaFree(sd.lam_rm);
   cudaFree(sd.trace[0]); cudaFree(sd.trace[1]);
-  cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev); cudaFree(sd.ycomb); cudaFree(sd.ycombB); cudaFree(sd.escr);
+  cudaFree(sd.tvals); cudaFree(sd.tcols); cudaFree(sd.rowlen_dev); cudaFree(sd.ycomb); cudaFree(sd.ycombB); cudaFree(sd.ycombBq); cudaFree(sd.escr);
   if (sd.own_dense) { cudaFree((void*)sd.dR); cudaFree((void*)sd.dM); }
 }
 
@@ -838,7 +840,7 @@ static int refresh_km(bnmtf_nmf_s* h, int side, int method) {
   h->launches++;
   // the blocked cluster sweep of the other side reads the block-major copies
   // (tri-factorisation: only the projection epilogue of the F sweep reads a factor directly, G)
-  if ((h->s[1 - side].v4 || h->s[1 - side].v5) && (h->nmtf ? (side == 1 && method != BNMTF_VB) : true) && method != BNMTF_NP) {
+  if ((h->s[1 - side].v4 || h->s[1 - side].v5) && (h->nmtf ? side == 1 : true) && method != BNMTF_NP) {
     dim3 g3((unsigned)((sd.ld + 255) / 256), (unsigned)((sd.kf + 1) / 2));
     if (method == BNMTF_VB) rm_to_kmB_kernel<true><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
     else rm_to_kmB_kernel<false><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
@@ -1006,7 +1008,9 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
   const bool timed = h->time_sweeps && single_k == -1;
   if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
   int rc;
-  if (sd.v2 && single_k == -1 && method != BNMTF_NP && !(h->nmtf && method == BNMTF_VB)) {
+  // (tri-factorisation VB: the per-row-chain kernel carries the covariance term; the lockstep cluster kernel does not)
+  const bool nmtf_vb = h->nmtf && method == BNMTF_VB;
+  if (sd.v2 && single_k == -1 && method != BNMTF_NP && (!nmtf_vb || (sd.v5 && h->cov_side == side && !getenv("BNMTF_VB_V1")))) {
     Sweep2Params p{};
     p.tvals = sd.tvals; p.tcols = sd.tcols; p.nsets = (int)sd.nsets; p.n_loc = (int)sd.n_loc; p.row0 = sd.row0;
     p.K = sd.kf; p.tw = sd.tw; p.rs = sd.rs; p.Ykm = sd.ysrc; p.ldy = sd.ysrc_ld;
@@ -1018,7 +1022,11 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     p.rmean = h->rmean; p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
     p.iter_ptr = h->iter_ptr;
     if (h->fuse_proj && side == 0 && h->nmtf) {   // NMTF: P_il = sum_j e_ij G_jl from the residual the F sweep ends with
-      p.Ykm2 = sd.v5 ? h->s[1].kmB : h->s[1].km; p.ldy2 = h->s[1].ld; p.K2 = h->L; p.proj_out = h->Prow;
+      p.Ykm2 = h->s[1].km; p.ldy2 = h->s[1].ld; p.Yproj = h->s[1].kmB; p.ldp = h->s[1].ld; p.K2 = h->L; p.proj_out = h->Prow;
+    }
+    if (nmtf_vb) {                                // the VB F sweep asks for P through the projection arguments of the call
+      if (proj_y2 != nullptr) { p.Yproj = h->s[1].kmB; p.ldp = h->s[1].ld; p.K2 = proj_k2; p.proj_out = out_mu; }
+      p.covA = h->covA; p.covS = h->covS; p.covL = h->covL; p.cov_sk = h->cov_sk; p.cov_sl = h->cov_sl;
     }
     p.dbg = getenv("BNMTF_V2_DBG") ? atoi(getenv("BNMTF_V2_DBG")) : 0;
     static unsigned long long* prof_buf = nullptr;   // timing experiments only
@@ -1031,7 +1039,7 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     }
     rc = 0;
     if (sd.v4 || sd.v5) {
-      if (h->nmtf) { p.Ykm = sd.ycombB; p.ldy = sd.ysrc_ld; }       // W = G S^T / Z = F S, block-major (nmtf_make_W / nmtf_make_Z)
+      if (h->nmtf) { p.Ykm = sd.ycombB; p.Ykm2 = sd.ycombBq; p.ldy = sd.ysrc_ld; }   // W = G S^T / Z = F S, block-major (nmtf_make_W / nmtf_make_Z)
       else { p.Ykm = h->s[1 - side].kmB; p.Ykm2 = h->s[1 - side].kmBq; p.ldy = h->s[1 - side].ld; }
       if (method != BNMTF_GIBBS && method != BNMTF_ICM && method != BNMTF_VB) FAIL("unknown method %d", method);
       if (method == BNMTF_GIBBS) {
@@ -1057,7 +1065,7 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
       }
       std::string err;
       rc = sd.v5 ? launch_sweep5(sd.npt2, method, p, h->stream,
-                                 p.K2 > 0 ? &sd.nclusters5p[method][p.Xmu != nullptr ? 1 : 0] : &sd.nclusters4[method][p.Xmu != nullptr ? 1 : 0], &err)
+                                 p.K2 > 0 ? &sd.nclusters5p[method][p.Xmu != nullptr ? 1 : 0] : &sd.nclusters4[method][p.Xmu != nullptr ? 1 : 0], &err)   // (one kernel per slot: VB sweeps of a tri-factorisation side always carry the covariance term)
                  : launch_sweep4(sd.npt2, method, p, h->stream, &sd.nclusters4[method][p.Xmu != nullptr ? 1 : 0], &err);
       if (rc) { g_err = err; return 1; }
       h->launches++;

@@ -193,6 +193,66 @@ __global__ void __launch_bounds__(WARPS * 32) nmtf_gram_kernel(const uint32_t* _
   }
 }
 
+// H_i on the FP64 tensor core.  H_i = G_Omega^T G_Omega is a small GEMM per row (L x n_i times n_i x L): with
+// mma.sync.m8n8k4 (DMMA) a step takes FOUR observed entries j_0..j_3 and one 8 x 8 block (bi, bj) of H_i,
+//   A[r][k] = G[j_k][8 bi + r],  B[k][c] = G[j_k][8 bj + c],  D += A B,
+// and the fragment layouts (A: lane holds [lane / 4][lane % 4]; B: [lane % 4][lane / 4]) make both operands of lane
+// (g, t) = (lane / 4, lane % 4) the SAME kind of element, x_b = G[j_t][8 b + g]: a lane loads ceil(L / 8) doubles per step
+// -- straight from the row-major factor, eight lanes reading 64 contiguous bytes of one row, no shared memory -- and the
+// warp issues one DMMA per block of the upper triangle (6 for L <= 24, 10 for L <= 32).  The 4 x 4-block FMA kernel
+// below spends two 32-byte shared loads per 16 FMAs and is bound by them (1.2 ms at 10000 x 8000, 30 % observed, L = 20).
+// One warp per row; the column indices of 8 steps are one coalesced load handed round by shuffles, the 8 steps' loads are
+// issued before their DMMAs.  Fixed summation order per row (independent of the sharding).
+__device__ __forceinline__ void dmma_acc_884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+template <int NB>     // NB = ceil(L / 8) column blocks
+__global__ void __launch_bounds__(128) nmtf_gram_mma_kernel(const uint32_t* __restrict__ cols, const int64_t* __restrict__ rowstart,
+                                                            int n_loc, int64_t row0, uint32_t padcol, const double* __restrict__ G_rm,
+                                                            int L, double* __restrict__ Hrow, int NP) {
+  const int row = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row >= n_loc) return;
+  const int g = lane >> 2, t = lane & 3;
+  constexpr int NBLK = NB * (NB + 1) / 2;
+  double acc[NBLK][2];
+#pragma unroll
+  for (int q = 0; q < NBLK; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+  bool colok[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) colok[b] = (8 * b + g) < L;
+  const int64_t beg = rowstart[row], end = rowstart[row + 1];
+  for (int64_t q0 = beg; q0 < end; q0 += 32) {
+    const uint32_t mycol = (q0 + lane < end) ? cols[q0 + lane] : padcol;
+    double x[8][NB];
+#pragma unroll
+    for (int s8 = 0; s8 < 8; ++s8) {
+      const uint32_t j = __shfl_sync(0xffffffffu, mycol, 4 * s8 + t);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) x[s8][b] = (j != padcol && colok[b]) ? __ldg(G_rm + (size_t)j * L + 8 * b + g) : 0.0;
+    }
+#pragma unroll
+    for (int s8 = 0; s8 < 8; ++s8) {
+      int q = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB; ++bj, ++q) dmma_acc_884(acc[q][0], acc[q][1], x[s8][bi], x[s8][bj]);
+    }
+  }
+  // lane (g, t) holds D[g][2 t], D[g][2 t + 1] of every block
+  int q = 0;
+#pragma unroll
+  for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+    for (int bj = bi; bj < NB; ++bj, ++q) {
+#pragma unroll
+      for (int y = 0; y < 2; ++y) {
+        const int a = 8 * bi + g, c = 8 * bj + 2 * t + y;
+        if (a <= c && c < L) Hrow[(size_t)(row0 + row) * NP + pair_index(a, c, L)] = acc[q][y];
+      }
+    }
+}
+
 // L <= 20: the two half-warps of the row's warp take alternate entries; lane h of a half-warp owns a 4 x 4 block
 // (bi <= bj) of the 5 x 5 block grid of H_i's upper triangle (15 blocks): two 32-byte shared loads and 16 FMAs per
 // entry and lane, i.e. half the shared-memory traffic per FMA of the 4 x 2 mapping above (which was bound by it).
@@ -441,7 +501,7 @@ __global__ void nmtf_lambda_kernel(const double* __restrict__ F, int64_t I, int 
 //   var = sum_q (VX+EX^2)[i][q] (VS+ES^2)(q,c) - sum_q EX[i][q]^2 ES(q,c)^2      (var_SkG / var_FSl)
 static __global__ void vb_combine_km_kernel(const double* __restrict__ EX, const double* __restrict__ VX, int64_t n, int kq,
                                      const double* __restrict__ ES, const double* __restrict__ VS, int s_q, int s_c,
-                                     double* __restrict__ out_km, int64_t ld) {
+                                     double* __restrict__ out_km, int64_t ld, double* __restrict__ outB_e, double* __restrict__ outB_q) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   if (i >= ld) return;
@@ -456,6 +516,10 @@ static __global__ void vb_combine_km_kernel(const double* __restrict__ EX, const
     }
   }
   reinterpret_cast<double2*>(out_km)[(size_t)c * ld + i] = make_double2(w, (a2 - b2) + w * w);
+  if (outB_e) {              // block-major copies for the per-row-chain cluster sweep (kernels_v5.cuh)
+    const size_t o = ((size_t)(c >> 1) * ld + i) * 2 + (c & 1);
+    outB_e[o] = w; outB_q[o] = (a2 - b2) + w * w;
+  }
 }
 
 // out[k][l] = sum_i f(i,k) P[i][l]  with f = F (Fvar == nullptr) or Fvar + F^2

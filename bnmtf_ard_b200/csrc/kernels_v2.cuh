@@ -184,6 +184,15 @@ struct Sweep2Params {
   int64_t ldy2;
   int K2;
   double* proj_out;
+  // kernels_v5.cuh: the second factor of the projection epilogue in the BLOCK-major layout [ceil(K2/2)][ldp][2] (the k-major
+  // Ykm2 above belongs to kernels_v2.cuh; in VB mode Ykm2 holds the second moments of the other factor)
+  const double* __restrict__ Yproj;
+  int64_t ldp;
+  // kernels_v5.cuh, BNMTF VB covariance term of update_F / update_G (bnmtf_vb.py:343,371), as SweepParams (kernels.cuh):
+  //   cov_i = sum_l S(k,l) A_il ((X S)_il - x_ik S(k,l))
+  const double* __restrict__ covA;       // [global row][covL] or nullptr
+  const double* __restrict__ covS;       // S(k,l) = covS[k*cov_sk + l*cov_sl]
+  int covL, cov_sk, cov_sl;
   double* gmat;                          // blocked cluster sweep (kernels_v4.cuh), Gibbs: scratch for the random material of the resident row sets
   int* set_counter;                      // kernels_v5.cuh: row sets handed out so far beyond the first round (zeroed before every launch)
   // multi-GPU, kernels_v5.cuh: the rows this rank updates are also written straight into the factor / statistics arrays of

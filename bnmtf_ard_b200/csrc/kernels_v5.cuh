@@ -36,7 +36,8 @@ constexpr int V5_B = 2;          // columns per block
 #endif
 
 struct Sweep5Layout {
-  size_t tiles, mbar, misc, stat_own, tab, gsum, part, prof, total;   // offsets in doubles
+  size_t tiles, mbar, misc, stat_own, tab, gsum, part, cov, prof, total;   // offsets in doubles
+  int covstride;                 // doubles per row of the covariance area: (fsv_l, A_l) pairs
   int nstat;                     // statistics per row: a[KP], g[NBK], (VB) q[KP]
   int sstride;                   // doubles per row of the statistics area
 };
@@ -45,7 +46,7 @@ struct Sweep5Layout {
 // with the projection epilogue, the partial sums sum_j e_j Y2[l][j] of the K2 columns of the second factor (in blocks of two)
 __host__ __device__ constexpr int sweep5_rec_width(int K2) { return 4 + 2 * ((K2 + V5_B - 1) / V5_B); }
 
-__host__ __device__ inline Sweep5Layout sweep5_layout(int tw, int rs, int K, int cs, int nslot, int tabw, bool vb, int K2 = 0) {
+__host__ __device__ inline Sweep5Layout sweep5_layout(int tw, int rs, int K, int cs, int nslot, int tabw, bool vb, int K2 = 0, int covL = 0) {
   Sweep5Layout L;
   const int NBK = (K + V5_B - 1) / V5_B, KP = NBK * V5_B;
   L.nstat = KP + NBK + (vb ? KP : 0);
@@ -60,6 +61,8 @@ __host__ __device__ inline Sweep5Layout sweep5_layout(int tw, int rs, int K, int
   L.tab = o; o += (size_t)rs * KP * tabw;               // per (row, column): what the conditional needs besides the row sums
   L.gsum = o; o += (size_t)rs * NBK + ((rs * NBK) & 1); // cross terms of the blocks (cluster totals)
   L.part = o; o += (size_t)rs * 2 * cs * V5_B;          // [RS][2][CS][B] records of h, double buffered by exchange parity
+  L.covstride = 2 * covL;
+  L.cov = o; o += (size_t)rs * L.covstride;             // BNMTF VB: per row (fsv_l, A_il), l < covL
   L.prof = o;
 #ifdef BNMTF_V2_PROF
   o += 32;                                              // phase clocks (timing experiments)
@@ -259,11 +262,16 @@ __host__ __device__ constexpr int sweep5_regs(int rs, int minb) {
 // PROJ (tri-factorisation F sweep, Gibbs / ICM): an epilogue projects the residual the row ends with onto the K2 columns of
 // a second block-major factor, proj_out[global row][l] = sum_j e_j Y2[l][j] (the row part of the S_kl numerators,
 // bnmtf_gibbs.py:277-283): ceil(K2 / 2) more tiles per row set, the partial sums of the 8 segments meet in CTA 0.
-template <int NPT, int MODE, int CS, int RS, int NSLOT, int MINB, bool PROJ = false>
+// COV (tri-factorisation VB sweeps of F and G): the covariance term of update_F / update_G (bnmtf_vb.py:343,371),
+//   cov_ik = sum_l S(k,l) A_il ((X S)_il - x_ik S(k,l)),   A = masked sums of the other factor's variances,
+// is subtracted from the row's dot product.  The row's warp keeps (X S)_il and A_il in shared memory, one l per lane, and
+// forms cov of both columns of a block -- plus the cross term that carries the first column's move into the second's
+// cov -- by three tensor-core warp sums while the records of the block travel; (X S)_i is rank-1 updated after each block.
+template <int NPT, int MODE, int CS, int RS, int NSLOT, int MINB, bool PROJ = false, bool COV = false>
 __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Params p) {
   constexpr int B = V5_B;
   constexpr bool VB = (MODE == M_VB), GIBBS = (MODE == M_GIBBS);
-  static_assert(!(PROJ && VB), "the projection epilogue serves the Gibbs / ICM sweeps (VB: Ykm2 holds the second moments)");
+  static_assert(!COV || VB, "the covariance term belongs to the VB updates");
   constexpr int TABW = 4;                                 // Gibbs: c1, sigma, z1, x_old; ICM: c1, c2, -, x_old; VB: c1, c2, precision, x_old
   constexpr int NCH = NPT / 4;                            // chunks of 4 entries
   constexpr int TMCOLS = sweep5_tm_cols(NPT, RS + 1);
@@ -289,7 +297,8 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
   const long long t_entry = clock64();
 #endif
   extern __shared__ __align__(128) double smem5[];
-  const Sweep5Layout L = sweep5_layout(tw, RS, K, CS, NSLOT, TABW, VB, K2);
+  const int covL = COV ? p.covL : 0;
+  const Sweep5Layout L = sweep5_layout(tw, RS, K, CS, NSLOT, TABW, VB, K2, covL);
   const uint32_t sm = smem_u32(smem5);
   const uint32_t tiles_a = sm + (uint32_t)L.tiles * 8u, mbar_a = sm + (uint32_t)L.mbar * 8u;
   const uint32_t full_a = mbar_a, empty_a = mbar_a + NSLOT * 8u, rec_a = mbar_a + 2 * NSLOT * 8u;
@@ -346,8 +355,8 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
     if (lane == 0) {
       const double* ybase = p.Ykm + (size_t)c * tw * B;   // this CTA's tile of block 0
       const double* qbase = VB ? p.Ykm2 + (size_t)c * tw * B : nullptr;
-      const double* pbase = PROJ ? p.Ykm2 + (size_t)c * tw * B : nullptr;   // this CTA's tile of the second factor's block 0
-      const size_t ystride = (size_t)p.ldy * B, pstride = (size_t)p.ldy2 * B;
+      const double* pbase = PROJ ? p.Yproj + (size_t)c * tw * B : nullptr;   // this CTA's tile of the second factor's block 0
+      const size_t ystride = (size_t)p.ldy * B, pstride = (size_t)p.ldp * B;
       uint32_t g = 0, it = 0;
       for (int set = cid; set < p.nsets; set = next_set(++it)) {
         for (int t = 0; t < total; ++t, ++g) {
@@ -381,6 +390,7 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
     const uint32_t tab_r = tab_a + (uint32_t)(r * KP * TABW) * 8u;
     const uint32_t stat_r = stat_own_a + (uint32_t)(r * L.sstride) * 8u;
     const uint32_t gsum_r = gsum_a + (uint32_t)(r * NBK) * 8u;
+    const uint32_t cov_r = sm + (uint32_t)(L.cov + (size_t)r * L.covstride) * 8u;
     const uint32_t tm = tm_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)(NPT * 2);
     double* gmat_row = GIBBS ? p.gmat + ((size_t)blockIdx.x * RS + r) * KP * TN_PRE_DOUBLES : nullptr;
     // The gathers of a chunk are issued two entries at a time: the address of the next pair is made to depend on the last
@@ -550,6 +560,14 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
         sts5(gsum_r + (uint32_t)lane * 8u, gt);
       }
       __syncwarp();
+      if (COV) {               // (X S)_il from the row's current values, and A_il
+        for (int l = lane; l < covL; l += 32) {
+          double a = 0.0;
+          for (int kk = 0; kk < K; ++kk) a = fma(lds5(tab_r + (uint32_t)(kk * TABW + 3) * 8u), __ldg(p.covS + kk * p.cov_sk + l * p.cov_sl), a);
+          sts_pair5(cov_r + (uint32_t)l * 16u, a, __ldg(p.covA + (size_t)grow * covL + l));
+        }
+        __syncwarp();
+      }
 
       // ---- the K column updates, B columns per exchange.  The pass of block n applies the rank-1 corrections of block
       //      n - 1 (tile n - 1) and takes the dot products with block n (tile n) in one walk over the segment.
@@ -628,6 +646,20 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
 #pragma unroll
           for (int w = 0; w < TABW; w += 2) lds_pair5(tab_r + (uint32_t)((k0 + j) * TABW + w) * 8u, tt[j][w], tt[j][w + 1]);
         }
+        double cov0 = 0.0, cov1 = 0.0, ccx = 0.0;
+        if (COV) {             // cov of the block's two columns from (X S)_i as it stands, and the cross term
+          const double xo0 = tt[0][3], xo1 = tt[1][3];
+          for (int l = lane; l < covL; l += 32) {
+            double f, a;
+            lds_pair5(cov_r + (uint32_t)l * 16u, f, a);
+            const double s0 = __ldg(p.covS + k0 * p.cov_sk + l * p.cov_sl);
+            const double s1 = nb > 1 ? __ldg(p.covS + (k0 + 1) * p.cov_sk + l * p.cov_sl) : 0.0;
+            cov0 = fma(s0 * a, f - xo0 * s0, cov0);
+            cov1 = fma(s1 * a, f - xo1 * s1, cov1);
+            ccx = fma(s1 * a, s0, ccx);
+          }
+          cov0 = warp_sum_mma(cov0); cov1 = warp_sum_mma(cov1); ccx = warp_sum_mma(ccx);
+        }
         P5_ADD(7);          // reduction, records sent
         mbar_wait_a(recbar, (xseq >> 1) & 1u);
         P5_ADD(8);          // waiting for the records
@@ -643,7 +675,8 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
             const int k = k0 + j;
             const double* tj = tt[j];
             const double x_old = tj[3];
-            const double h = j ? fma(-d0, g01, hs1) : hs0;     // column k0 + 1 sees the residual after column k0 moved
+            double h = j ? fma(-d0, g01, hs1) : hs0;           // column k0 + 1 sees the residual after column k0 moved
+            if (COV) h -= j ? fma(d0, ccx, cov1) : cov0;       // ... and (X S)_i after column k0 moved
             double x_new, vn = 0.0, mu;
             if (GIBBS) {
               const double sg = tj[1];
@@ -673,6 +706,15 @@ __global__ void __maxnreg__(sweep5_regs(RS, MINB)) sweep5_kernel(const Sweep2Par
               }
             }
           }
+        }
+        if (COV) {             // (X S)_il += delta_k S(k,l)
+          for (int l = lane; l < covL; l += 32) {
+            double f = lds5(cov_r + (uint32_t)l * 16u);
+            f = fma(d0, __ldg(p.covS + k0 * p.cov_sk + l * p.cov_sl), f);
+            if (nb > 1) f = fma(d1, __ldg(p.covS + (k0 + 1) * p.cov_sk + l * p.cov_sl), f);
+            sts5(cov_r + (uint32_t)l * 16u, f);
+          }
+          __syncwarp();
         }
         ++g;
         P5_ADD(9);          // conditionals

@@ -32,7 +32,7 @@ static int v5_nslot(int npt) { return (npt == 20 && v5_wide()) ? 3 : 2; }
 constexpr int V5_MAX_CLUSTERS = 64;   // upper bound of co-resident clusters (148 SMs x 2 CTAs / 8 = 37)
 size_t sweep5_gmat_doubles(int rs, int K) { return (size_t)V5_MAX_CLUSTERS * 8 * rs * (size_t)(2 * ((K + 1) / 2)) * TN_PRE_DOUBLES; }
 
-bool sweep5_fits(int npt, int tw, int K, int K2) {
+bool sweep5_fits(int npt, int tw, int K, int K2, int covL) {
   const int rs = sweep5_rows_per_set(npt);
   if (rs == 0 || K < 2 || K > 64) return false;          // a lane keeps the row's values of columns lane and lane + 32
   const size_t per_cta = (npt == 20 && v5_wide()) ? (size_t)227 * 1024 : ((size_t)228 * 1024 - 2 * 1024) / 2;
@@ -41,9 +41,8 @@ bool sweep5_fits(int npt, int tw, int K, int K2) {
 #else
   const bool vb = true;
 #endif
-  if (K2 < 0 || K2 > 64) return false;
-  return sweep5_layout(tw, rs, K, 8, v5_nslot(npt), 4, vb, 0).total * sizeof(double) <= per_cta &&
-         sweep5_layout(tw, rs, K, 8, v5_nslot(npt), 4, false, K2).total * sizeof(double) <= per_cta;
+  if (K2 < 0 || K2 > 64 || covL < 0 || covL > 64) return false;
+  return sweep5_layout(tw, rs, K, 8, v5_nslot(npt), 4, vb, K2, covL).total * sizeof(double) <= per_cta;
 }
 
 #define CK5(call)                                                                                     \
@@ -66,15 +65,17 @@ __global__ void __launch_bounds__((RS + 1) * 32, MINB) sweep5_occupancy_probe(in
   if (out && threadIdx.x == 0) out[blockIdx.x] = (int)probe_sm[0];
 }
 
-template <int NPT, int MODE, int RS, int NSLOT, int MINB, bool PROJ = false>
+template <int NPT, int MODE, int RS, int NSLOT, int MINB, bool PROJ = false, bool COV = false>
 static int launch_w(const Sweep2Params& p, cudaStream_t stream, int* ncl_cache, std::string* err) {
   constexpr int CS = 8;
-  if (PROJ && (p.K2 < 1 || p.K2 > 64 || p.Ykm2 == nullptr || p.proj_out == nullptr)) { *err = "per-row cluster sweep: bad projection arguments"; return 1; }
-  if (!PROJ && MODE != M_VB && p.K2 != 0) { *err = "per-row cluster sweep: projection requested from a kernel without the epilogue"; return 1; }
+  if (PROJ && (p.K2 < 1 || p.K2 > 64 || p.Yproj == nullptr || p.proj_out == nullptr)) { *err = "per-row cluster sweep: bad projection arguments"; return 1; }
+  if (!PROJ && p.K2 != 0) { *err = "per-row cluster sweep: projection requested from a kernel without the epilogue"; return 1; }
+  if (COV && (p.covL < 1 || p.covL > 64 || p.covA == nullptr || p.covS == nullptr)) { *err = "per-row cluster sweep: bad covariance arguments"; return 1; }
+  if (!COV && p.covA != nullptr) { *err = "per-row cluster sweep: covariance term requested from a kernel without it"; return 1; }
   if (p.rs != RS) { *err = "per-row cluster sweep: the side was packed for another number of rows per set"; return 1; }
   if (MODE == M_GIBBS && p.gmat == nullptr) { *err = "per-row cluster sweep: no random-material scratch"; return 1; }
-  auto kern = sweep5_kernel<NPT, MODE, CS, RS, NSLOT, MINB, PROJ>;
-  const size_t smem = sweep5_layout(p.tw, RS, p.K, CS, NSLOT, 4, MODE == M_VB, PROJ ? p.K2 : 0).total * sizeof(double);
+  auto kern = sweep5_kernel<NPT, MODE, CS, RS, NSLOT, MINB, PROJ, COV>;
+  const size_t smem = sweep5_layout(p.tw, RS, p.K, CS, NSLOT, 4, MODE == M_VB, PROJ ? p.K2 : 0, COV ? p.covL : 0).total * sizeof(double);
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3((RS + 1) * 32);
   cfg.dynamicSmemBytes = smem;
@@ -103,19 +104,19 @@ static int launch_w(const Sweep2Params& p, cudaStream_t stream, int* ncl_cache, 
   return 0;
 }
 
-// the tri-factorisation F sweep with the projection epilogue (Gibbs / ICM)
-template <int MODE>
+// the tri-factorisation sweeps: projection epilogue (F sweep) and / or the VB covariance term
+template <int MODE, bool PROJ, bool COV>
 static int launch_p(int npt, const Sweep2Params& p, cudaStream_t stream, int* ncl_cache, std::string* err) {
   switch (npt) {
-    case 4: return launch_w<4, MODE, 15, 2, 2, true>(p, stream, ncl_cache, err);
-    case 8: return launch_w<8, MODE, 15, 2, 2, true>(p, stream, ncl_cache, err);
-    case 12: return launch_w<12, MODE, 15, 2, 2, true>(p, stream, ncl_cache, err);
-    case 16: return launch_w<16, MODE, 11, 2, 2, true>(p, stream, ncl_cache, err);
+    case 4: return launch_w<4, MODE, 15, 2, 2, PROJ, COV>(p, stream, ncl_cache, err);
+    case 8: return launch_w<8, MODE, 15, 2, 2, PROJ, COV>(p, stream, ncl_cache, err);
+    case 12: return launch_w<12, MODE, 15, 2, 2, PROJ, COV>(p, stream, ncl_cache, err);
+    case 16: return launch_w<16, MODE, 11, 2, 2, PROJ, COV>(p, stream, ncl_cache, err);
     case 20:
       if (v5_wide() || v5_rs20() != 11) break;
-      return launch_w<20, MODE, 11, 2, 2, true>(p, stream, ncl_cache, err);
+      return launch_w<20, MODE, 11, 2, 2, PROJ, COV>(p, stream, ncl_cache, err);
   }
-  *err = "unsupported entries per lane for the per-row cluster sweep with projection";
+  *err = "unsupported entries per lane for the per-row cluster sweep of the tri-factorisation";
   return 1;
 }
 
@@ -144,9 +145,11 @@ int launch_peer_barrier(int* const* peer_flags_dev, int* my_flags, int rank, int
 
 int launch_sweep5(int npt, int method, const Sweep2Params& p, cudaStream_t stream, int* ncl_cache, std::string* err) {
   if (p.K2 > 0 && method != 2) {
-    if (method == 0) return launch_p<M_GIBBS>(npt, p, stream, ncl_cache, err);
-    if (method == 1) return launch_p<M_ICM>(npt, p, stream, ncl_cache, err);
+    if (method == 0) return launch_p<M_GIBBS, true, false>(npt, p, stream, ncl_cache, err);
+    if (method == 1) return launch_p<M_ICM, true, false>(npt, p, stream, ncl_cache, err);
   }
+  if (method == 2 && p.covA != nullptr)
+    return p.K2 > 0 ? launch_p<M_VB, true, true>(npt, p, stream, ncl_cache, err) : launch_p<M_VB, false, true>(npt, p, stream, ncl_cache, err);
   switch (method) {
     case 0: return launch_m<M_GIBBS>(npt, p, stream, ncl_cache, err);
     case 1: return launch_m<M_ICM>(npt, p, stream, ncl_cache, err);

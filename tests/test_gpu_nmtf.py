@@ -215,7 +215,8 @@ def test_vb_trajectory_golden(gold, ard):
     close(m.quality("ELBO"), g[p + "elbo"][-1], RTOL_TRAJ)
 
 
-@pytest.mark.parametrize("shape", [(150, 220, 5, 3, 0.5), (64, 3000, 4, 6, 0.6)])
+# (the shapes with >= 2048 columns on one side: F / G sweep on the per-row-chain cluster kernel with the covariance term)
+@pytest.mark.parametrize("shape", [(150, 220, 5, 3, 0.5), (64, 3000, 4, 6, 0.6)] + SHAPES[4:])
 def test_vb_iterations_vs_oracle(shape):
     from bnmtf_ard_b200 import bnmtf_vb
     I, J, K, L, dens = shape
