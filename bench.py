@@ -383,12 +383,17 @@ def main():
         eng.set_factor(_lib.SIDE_U, _lib.F_VALUE, U_h)
         eng.set_factor(_lib.SIDE_V, _lib.F_VALUE, V_h)
         eng.set_scalars(1.0, np.ones(K))
+        t_up = time.perf_counter() - t0
         # every rank holds the same chain: the draws are delivered to host memory once, by rank 0 (the other
         # ranks read back their per-iteration statistics only)
         r2 = eng.run(_lib.GIBBS, e2e_steps, seed=3, traces=(rank == 0))
         _ = (float(r2["all_U"][-1, 0, 0]) if rank == 0 else 0.0) + float(r2["stats"][-1, 0])
+        t_run = time.perf_counter() - t0
         barrier()
         e2e_s = time.perf_counter() - t0
+        if os.environ.get("BNMTF_RUN_TIMING"):
+            print("[e2e-probe rank %d] state upload %.1f ms, run() returned at %.1f ms, barrier passed at %.1f ms"
+                  % (rank, 1e3 * t_up, 1e3 * t_run, 1e3 * e2e_s), file=sys.stderr)
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

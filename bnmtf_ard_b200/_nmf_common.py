@@ -168,7 +168,7 @@ class NMFCommon(object):
         return {'MSE': MSE, 'R^2': R2, 'Rp': Rp}
 
 
-NMTF_MAX_L, NMTF_MAX_KL = 32, 3631      # csrc/engine.cu: NMTF_MAX_L, NMTF_MAX_KL
+NMTF_MAX_L, NMTF_MAX_KL = 48, 3631      # csrc/engine.cu: NMTF_MAX_L, NMTF_MAX_KL
 
 
 def check_nmtf_limits(K, L):

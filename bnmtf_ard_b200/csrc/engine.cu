@@ -187,6 +187,7 @@ struct bnmtf_nmf_s {
   double *S = nullptr, *Svar = nullptr, *Smu = nullptr, *Stau = nullptr, *lamS = nullptr;   // [K][L]
   double* lamG = nullptr;      // [L] (lamk holds lambdaFk)
   double *Prow = nullptr, *Hrow = nullptr;   // [I_pad][L], [I_pad][L(L+1)/2]
+  double* np_delta = nullptr;                // NMTF NP: the move of the S entry updated last (device scalar)
   double *cvec = nullptr, *TT = nullptr;     // [K*L], [K(K+1)/2][L(L+1)/2]
   double* Tpart = nullptr;                   // [RT_RC][max tensor]: partial tiles of nmtf_reduce_T
   double* sumlog_lamS_dev = nullptr;
@@ -347,7 +348,7 @@ static int nmtf_alloc(bnmtf_nmf_s* h);
 // Size limits of the tri-factorisation handle (the reference has none; documented in README.md / INTEGRATION.md and
 // checked when the handle is created, never in the middle of run()): the Gram kernel H_i = sum G_j G_j^T keeps an
 // L x L block per warp (L <= 32), the single-CTA S sweeps keep up to 8 K*L doubles in shared memory (227 KB opt-in).
-constexpr int NMTF_MAX_L = 32;
+constexpr int NMTF_MAX_L = 48;      // Gram kernel on the FP64 tensor core: up to six 8-column blocks
 constexpr size_t NMTF_S_SMEM_MAX = 227 * 1024;
 constexpr int NMTF_MAX_KL = (int)((NMTF_S_SMEM_MAX / sizeof(double) - 2) / (2 + TN_PRE_DOUBLES));   // 3631
 // ---- stream-ordered memory and copies ----------------------------------------------
@@ -596,7 +597,7 @@ int bnmtf_nmf_destroy(bnmtf_nmf_t h) {
   free_side(h->s[0]); free_side(h->s[1]);
   cudaFree(h->scal); cudaFree(h->colsum); cudaFree(h->lamstate); cudaFree(h->lamk); cudaFree(h->stats_dev);
   cudaFree(h->S); cudaFree(h->Svar); cudaFree(h->Smu); cudaFree(h->Stau); cudaFree(h->lamS); cudaFree(h->lamG);
-  cudaFree(h->Prow); cudaFree(h->Hrow); cudaFree(h->cvec); cudaFree(h->TT); cudaFree(h->Tpart);
+  cudaFree(h->Prow); cudaFree(h->Hrow); cudaFree(h->np_delta); cudaFree(h->cvec); cudaFree(h->TT); cudaFree(h->Tpart);
   cudaFree(h->Arow); cudaFree(h->Brow); cudaFree(h->Crow); cudaFree(h->BS); cudaFree(h->PA); cudaFree(h->QC);
   cudaFree(h->lamstateG); cudaFree(h->vbmisc); cudaFree(h->iter_dev); cudaFree(h->gmat); cudaFree(h->set_counter); cudaFree(h->lam_trace); cudaFree(h->lam_trace2); cudaFree(h->trS[0]); cudaFree(h->trS[1]);
   for (auto& e : h->ev_pool) cudaEventDestroy(e);

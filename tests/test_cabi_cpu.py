@@ -175,6 +175,24 @@ def test_nmtf_constructor_messages(clsname):
     assert m.number_parameters() == 3 * 2 + 2 * 3 + 2 * 3 + 1
 
 
+@pytest.mark.parametrize("clsname", ["bnmtf_gibbs", "nmtf_icm", "bnmtf_vb", "nmtf_np"])
+def test_nmtf_size_limits_are_raised_in_the_constructor(clsname):
+    """The engine's limits ("Limits": L <= 48, K*L <= 3631) surface at construction with a clear
+    message, never in the middle of run(); the reference's largest model-selection setting K = L = 40 is inside them."""
+    import bnmtf_ard_b200 as pkg
+    from bnmtf_ard_b200._nmf_common import NMTF_MAX_KL, NMTF_MAX_L
+    assert (NMTF_MAX_L, NMTF_MAX_KL) == (48, 3631)
+    cls = getattr(pkg, clsname)
+    R, M = np.ones((4, 5)), np.ones((4, 5))
+    hp = {'alphatau': 1., 'betatau': 1., 'alpha0': 1., 'beta0': 1., 'lambdaS': 1.}
+    make = (lambda K, L: cls(R, M, K, L)) if clsname == "nmtf_np" else (lambda K, L: cls(R, M, K, L, True, hp))
+    make(40, 40)
+    with pytest.raises(ValueError, match="L = 49 is not supported"):
+        make(2, 49)
+    with pytest.raises(ValueError, match=r"K\*L = 3640 is not supported"):
+        make(91, 40)
+
+
 def test_nmtf_np_constructor_and_guards():
     from bnmtf_ard_b200 import nmtf_np
     with pytest.raises(AssertionError) as error:

@@ -95,7 +95,7 @@ def test_icm_trajectory_golden(gold, ard):
 
 # the last two: odd K and L on the per-row-chain cluster sweep (F side with the projection epilogue; G side)
 SHAPES = [(40, 30, 3, 4, 0.7), (150, 220, 5, 3, 0.5), (64, 3000, 4, 6, 0.6), (700, 90, 7, 2, 0.8), (48, 2600, 5, 7, 0.5),
-          (3100, 70, 5, 3, 0.6)]
+          (3100, 70, 5, 3, 0.6), (70, 60, 3, 40, 0.8)]      # the last: L = 40, the reference's largest model-selection setting
 
 
 @pytest.mark.parametrize("shape", SHAPES)

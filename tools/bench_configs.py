@@ -111,6 +111,11 @@ def main():
             e.set_vb_scalars(1.0, 0.0, 1.0, 1.0, np.ones((4, K)), np.ones((4, L)))
             r = e.vb_run(n(10) + 3)
             record("C4 BNMTF VB+ARD 10000x8000 K=L=20", r["seconds"], n(10), {"elbo_last": float(r["stats"][-1, _lib.ST_ELBO]), "train_mse_last": e.performances(r["stats"][-1])["MSE"]})
+        if want("np") or args.only in ("", "C4"):     # nmtf_np: F sweep, the K*L update_S in one pass each, G sweep (needs R >= 0)
+            e.set_scalars(1.0, np.ones(K), np.ones(L))
+            e.init(_lib.GIBBS, True, True, 9, 10)       # positive random factors
+            r = e.np_run(n(4) + 2)
+            record("C4-shaped NMTF NP 10000x8000 K=L=20", r["seconds"], n(4), {"i_div_last": float(r["stats"][-1, _lib.ST_IDIV]) if hasattr(_lib, "ST_IDIV") else None})
         e.close()
     if want("C5"):   # nested-CV-shaped workload: 10 folds x K in {1..30} of BNMF VB (200 it) on a CTRP-shaped 887 x 545 matrix
         import contextlib, io, time
