@@ -531,6 +531,23 @@ int bnmtf_nmf_pack(bnmtf_nmf_t h, const int64_t* global4) {
   if (global4) for (int q = 0; q < 4; ++q) g[q] = std::max(g[q], global4[q]);
   if (pack_block(h, su, su.n_loc, h->J, h->J, (uint32_t)h->J, g[0], g[1])) return 1;
   if (pack_block(h, sv, sv.n_loc, h->I, h->I, (uint32_t)h->I, g[2], g[3])) return 1;
+  // Models whose draws are megabytes per iteration deliver their traces through two pinned staging slots (TraceDrain).
+  // cudaHostAlloc takes milliseconds per slot and stalls the launches of the run that first needs them (measured: 8 ms
+  // of idle GPU in a 20-iteration run at 20000 x 20000, K = 50), so such handles get their slots here, at set-up time.
+  {
+    const size_t per_it = sizeof(double) * ((size_t)su.n_glob * su.kf + (size_t)sv.n_glob * sv.kf + (h->nmtf ? (size_t)h->K * h->L : 0));
+    if (per_it >= ((size_t)2 << 20) && !getenv("BNMTF_NO_PINNED_TRACES") && !getenv("BNMTF_TRACE_CHUNK_BYTES")) {
+      const size_t slot = std::max<size_t>((size_t)16 << 20, per_it);
+      if (h->pin_bytes < slot) {
+        for (int b = 0; b < 2; ++b) { if (h->pin[b]) cudaFreeHost(h->pin[b]); h->pin[b] = nullptr; }
+        h->pin_bytes = 0;
+        cudaError_t e = cudaSuccess;
+        for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaHostAlloc((void**)&h->pin[b], slot, cudaHostAllocDefault);
+        if (e == cudaSuccess) h->pin_bytes = slot;
+        else { for (int b = 0; b < 2; ++b) { if (h->pin[b]) cudaFreeHost(h->pin[b]); h->pin[b] = nullptr; } cudaGetLastError(); }   // the run allocates (and reports) later
+      }
+    }
+  }
   return 0;
 }
 
@@ -833,20 +850,22 @@ int bnmtf_nmf_get_vb_scalars(bnmtf_nmf_t h, double* scal4, double* lamstate4K) {
 // ---- launches --------------------------------------------------------------------
 static int refresh_km(bnmtf_nmf_s* h, int side, int method) {
   Side& sd = h->s[side];
+  // the blocked cluster sweep of the other side reads the block-major copies: both layouts from one launch
+  // (tri-factorisation: only the projection epilogue of the F sweep reads a factor directly, G)
+  const bool blockmajor = (h->s[1 - side].v4 || h->s[1 - side].v5) && (h->nmtf ? side == 1 : true) && method != BNMTF_NP;
+  if (blockmajor) {
+    dim3 g3((unsigned)((sd.ld + 255) / 256), (unsigned)((sd.kf + 1) / 2));
+    if (method == BNMTF_VB) rm_to_km_both_kernel<true><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
+    else rm_to_km_both_kernel<false><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
+    h->launches++;
+    return 0;
+  }
   dim3 blk(32, 8), grd((unsigned)((sd.ld + 31) / 32), (unsigned)((sd.kf + 31) / 32));
   if (method == BNMTF_VB)
     rm_to_km_kernel<2><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, sd.kf, sd.ld);
   else
     rm_to_km_kernel<1><<<grd, blk, 0, h->stream>>>(sd.val, sd.var, sd.km, sd.n_glob, sd.kf, sd.ld);
   h->launches++;
-  // the blocked cluster sweep of the other side reads the block-major copies
-  // (tri-factorisation: only the projection epilogue of the F sweep reads a factor directly, G)
-  if ((h->s[1 - side].v4 || h->s[1 - side].v5) && (h->nmtf ? side == 1 : true) && method != BNMTF_NP) {
-    dim3 g3((unsigned)((sd.ld + 255) / 256), (unsigned)((sd.kf + 1) / 2));
-    if (method == BNMTF_VB) rm_to_kmB_kernel<true><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
-    else rm_to_kmB_kernel<false><<<g3, 256, 0, h->stream>>>(sd.val, sd.var, sd.kmB, sd.kmBq, sd.n_glob, sd.kf, sd.ld);
-    h->launches++;
-  }
   return 0;
 }
 

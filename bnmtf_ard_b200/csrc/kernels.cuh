@@ -500,6 +500,36 @@ __global__ void rm_to_kmB_kernel(const double* __restrict__ Xval, const double* 
   if (VB) reinterpret_cast<double2*>(YQ)[(size_t)kb * ld + i] = q;
 }
 
+// Both gather copies in one launch (sides whose other side runs the per-row-chain cluster sweep need the two of them after
+// every sweep): the block-major copies as above plus the k-major copy of rm_to_km_kernel, [K][ld][NV] (NV == 2: the
+// (E, Var + E^2) pairs) -- the same values, bit for bit.
+template <bool VB>
+__global__ void rm_to_km_both_kernel(const double* __restrict__ Xval, const double* __restrict__ Xvar, double* __restrict__ Ykm,
+                                     double* __restrict__ YE, double* __restrict__ YQ, int64_t n, int K, int64_t ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int kb = blockIdx.y;
+  if (i >= ld) return;
+  double2 e = make_double2(0.0, 0.0), q = make_double2(0.0, 0.0);
+  const int k = 2 * kb;
+  if (i < n) {
+    e.x = Xval[i * K + k];
+    if (VB) q.x = Xvar[i * K + k] + e.x * e.x;
+    if (k + 1 < K) {
+      e.y = Xval[i * K + k + 1];
+      if (VB) q.y = Xvar[i * K + k + 1] + e.y * e.y;
+    }
+  }
+  reinterpret_cast<double2*>(YE)[(size_t)kb * ld + i] = e;
+  if (VB) {
+    reinterpret_cast<double2*>(YQ)[(size_t)kb * ld + i] = q;
+    reinterpret_cast<double2*>(Ykm)[(size_t)k * ld + i] = make_double2(e.x, q.x);
+    if (k + 1 < K) reinterpret_cast<double2*>(Ykm)[(size_t)(k + 1) * ld + i] = make_double2(e.y, q.y);
+  } else {
+    Ykm[(size_t)k * ld + i] = e.x;
+    if (k + 1 < K) Ykm[(size_t)(k + 1) * ld + i] = e.y;
+  }
+}
+
 template <int NV>
 __device__ __forceinline__ void rm_to_km_body(const double* __restrict__ Xval, const double* __restrict__ Xvar,
                                               double* __restrict__ Ykm, int64_t n, int K, int64_t ld, int bx, int by) {
@@ -577,7 +607,10 @@ __device__ __forceinline__ void lambda_body(const double* __restrict__ Ukm, int6
   __shared__ double sh[32];
   if (iter_ptr) iteration = *iter_ptr;
   double a = 0.0, b = 0.0;
+  // (unrolled: the loads of eight steps are in flight together; the order of the additions is the loop's)
+#pragma unroll 8
   for (int64_t i = threadIdx.x; i < I; i += blockDim.x) a += Ukm[((size_t)k * ldu + i) * NV];
+#pragma unroll 8
   for (int64_t j = threadIdx.x; j < J; j += blockDim.x) b += Vkm[((size_t)k * ldv + j) * NV];
   a = block_sum(a, sh);
   b = block_sum(b, sh);
@@ -643,6 +676,7 @@ __device__ __forceinline__ void finalize_body(const double* __restrict__ rsU, in
 #pragma unroll
     for (int f = 0; f < NRS; ++f) acc[f] = 0.0;
     if (rs != nullptr) {
+#pragma unroll 4
       for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
 #pragma unroll
         for (int f = 0; f < NRS; ++f)
