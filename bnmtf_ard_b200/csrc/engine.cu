@@ -159,6 +159,9 @@ struct bnmtf_nmf_s {
   double sweep_ms[2] = {0, 0};
   int64_t sweep_n[2] = {0, 0};
   int km_mode = -1;            // NV layout currently held by the km copies
+  // launch-bound runs: the row-team sweeps leave the gather copy / trace slot of the factor they update themselves
+  double* fold_trace[2] = {nullptr, nullptr};   // graph replays with traces: staging buffers the sweeps write their slot of
+  double* fold_lam_trace = nullptr;             // ... and the lambda kernel its slot of all_lambdak
   double* gmat = nullptr;              // random-material scratch of the blocked cluster sweep (kernels_v4.cuh)
   int* set_counter = nullptr;          // kernels_v5.cuh: work queue of row sets
   // multi-GPU peer exchange (bnmtf_nmf_peer_export / _import): the per-row-chain sweep writes its rows into the other
@@ -964,9 +967,16 @@ static int launch_sweep2_m(bnmtf_nmf_s* h, const Sweep2Params& p, Side& sd, int 
 }
 
 // argument block of the row-team sweep (v1 layout) on `side`
+// Both sides on the row-team kernel, one GPU, no streamed rows: the sweeps write the gather copies themselves
+// (SweepParams::km_out) and the run loops skip the transposes behind them.  BNMTF_NO_FOLD=1 keeps the separate launches.
+static bool fold_ok(const bnmtf_nmf_s* h) {
+  static const bool off = [] { const char* e = getenv("BNMTF_NO_FOLD"); return e && atoi(e) != 0; }();
+  return !off && !h->nmtf && h->world <= 1 && !h->s[0].v2 && !h->s[1].v2 && !h->s[0].long_rows && !h->s[1].long_rows;
+}
+
 static void fill_sweep_params(bnmtf_nmf_s* h, int method, int side, int single_k, uint64_t seed, uint32_t iteration,
                               double* out_tau, double* out_mu, bool want_mu, const double* proj_y2, int64_t proj_ld2,
-                              int proj_k2, SweepParams& p) {
+                              int proj_k2, SweepParams& p, bool fold) {
   Side& sd = h->s[side];
   const bool mu_out = (method == BNMTF_VB) || want_mu;
   p.vals = sd.vals; p.cols = sd.cols; p.rowstart = sd.rowstart;
@@ -987,6 +997,10 @@ static void fill_sweep_params(bnmtf_nmf_s* h, int method, int side, int single_k
   p.seed = seed; p.iteration = iteration; p.purpose = side == 0 ? RNG_TN_U : RNG_TN_V;
   p.iter_ptr = h->iter_ptr;
   p.single_k = single_k;
+  if (single_k == -1 && fold) {
+    p.km_out = sd.km; p.km_ld = sd.ld;
+    p.trace_out = h->fold_trace[side]; p.trace_n = sd.n_glob;
+  }
 }
 
 // streamed rows (kernels_long.cuh): one CTA per row
@@ -1098,7 +1112,7 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     }
   } else {
     SweepParams p{};
-    fill_sweep_params(h, method, side, single_k, seed, iteration, out_tau, out_mu, want_mu, proj_y2, proj_ld2, proj_k2, p);
+    fill_sweep_params(h, method, side, single_k, seed, iteration, out_tau, out_mu, want_mu, proj_y2, proj_ld2, proj_k2, p, fold_ok(h));
     if (sd.long_rows) {
       if (h->nmtf || single_k < -2 || p.covA)
         FAIL("a row/column of R has more than 16384 observed entries: the tri-factorisation models do not serve such rows");
@@ -1147,7 +1161,7 @@ static int launch_lambda(bnmtf_nmf_s* h, int method, uint64_t seed, uint32_t ite
   const int K = h->K;
 #define LK(MODE)                                                                                                      \
   lambda_kernel<MODE><<<K, 1024, 0, h->stream>>>(su.km, su.ld, h->I, sv.km, sv.ld, h->J, K, h->hyper, h->colsum,       \
-                                                h->lamstate, h->lamk, seed, iteration, update, h->iter_ptr)
+                                                h->lamstate, h->lamk, seed, iteration, update, h->iter_ptr, h->fold_lam_trace)
   switch (method) {
     case BNMTF_GIBBS: LK(M_GIBBS); break;
     case BNMTF_ICM: LK(M_ICM); break;
@@ -1566,14 +1580,23 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
   const bool use_graph = graph_mode_allowed(h, iterations) && nchunks == 1;
   if (use_graph) {
     const bool lam_tr = h->hyper.ARD && method != BNMTF_NP;
+    // launch-bound models: the sweeps write the gather copies and their trace slots, the lambda kernel its own (4 launches
+    // per iteration instead of 7)
+    const bool fold = fold_ok(h);
+    struct FoldReset { bnmtf_nmf_s* h; ~FoldReset() { h->fold_trace[0] = h->fold_trace[1] = nullptr; h->fold_lam_trace = nullptr; } } fold_reset{h};
+    if (fold) {
+      if (all_U) h->fold_trace[0] = su.trace[0];
+      if (all_V) h->fold_trace[1] = sv.trace[0];
+      if (lam_tr) h->fold_lam_trace = lam_trace;
+    }
     auto one_iteration = [&]() -> int {
       if (launch_lambda(h, method, seed, 0, 1)) return 1;                                  // bnmf_gibbs.py:149-152
       if (launch_sweep(h, method, 0, -1, seed, 0, nullptr, nullptr, want_mu)) return 1;    // :154-158
-      refresh_km(h, 0, method);
+      if (!fold) refresh_km(h, 0, method);
       if (launch_sweep(h, method, 1, -1, seed, 0, nullptr, nullptr, want_mu)) return 1;    // :160-164
-      refresh_km(h, 1, method);
+      if (!fold) refresh_km(h, 1, method);
       if (method == BNMTF_VB && launch_lambda(h, method, seed, 0, 0)) return 1;
-      if (tr || lam_tr) {
+      if ((tr || lam_tr) && !(fold && (!all_U || h->fold_trace[0]) && (!all_V || h->fold_trace[1]))) {
         const int64_t nU = su.n_glob * K, nV = sv.n_glob * K;
         const unsigned grid = (unsigned)std::min<int64_t>((std::max(nU, nV) + 255) / 256, (int64_t)h->num_sms * 4);
         trace_copy_kernel<<<std::max(grid, 1u), 256, 0, h->stream>>>(tr ? su.trace[0] : nullptr, su.val, nU, tr ? sv.trace[0] : nullptr,
@@ -1597,11 +1620,11 @@ int bnmtf_nmf_run(bnmtf_nmf_t h, int method, int iterations, uint64_t seed, doub
       // U sweep                                           bnmf_gibbs.py:154-158
       if (launch_sweep(h, method, 0, -1, seed, (uint32_t)it, nullptr, nullptr, want_mu)) return 1;
       if (allgather_side(h, method, 0, method == BNMTF_VB)) return 1;
-      refresh_km(h, 0, method);
+      if (!fold_ok(h)) refresh_km(h, 0, method);
       // V sweep                                           bnmf_gibbs.py:160-164
       if (launch_sweep(h, method, 1, -1, seed, (uint32_t)it, nullptr, nullptr, want_mu)) return 1;
       if (allgather_side(h, method, 1, true)) return 1;
-      refresh_km(h, 1, method);
+      if (!fold_ok(h)) refresh_km(h, 1, method);
       // tau, statistics                                   bnmf_gibbs.py:166-167,175
       if (method == BNMTF_VB && launch_lambda(h, method, seed, (uint32_t)it, 0)) return 1;
       if (launch_finalize(h, method, h->stats_dev + (size_t)it * BNMTF_NSTATS, seed, (uint32_t)it, 1)) return 1;

@@ -48,6 +48,13 @@ struct SweepParams {
   uint32_t iteration;
   const uint32_t* iter_ptr;              // when set (graph replays) the iteration index is read from the device
   uint32_t purpose;
+  // Small models are launch-bound: a sweep (single_k == -1) can also leave the k-major gather copy of the factor it
+  // updates (what rm_to_km_kernel would write behind it: [K][km_ld][NV], NV == 2 for VB) and its slot of the draw traces
+  // (what trace_copy_kernel would copy), so the iteration needs neither of the two launches.
+  double* km_out;                        // or nullptr
+  int64_t km_ld;
+  double* trace_out;                     // [iterations][n_glob][K] staging buffer of this factor, or nullptr
+  int64_t trace_n;                       // n_glob (rows of the factor)
   int single_k;                          // >=0 one column, no state change; -1 sweep; -2 dry (stats only);
                                          // -3 project: out_mu[row][l] = sum_j e_j Y2[l][j], l < K2 (NMTF S statistics)
                                          // -4 masked sums only (no residual): out_tau = sum y2, out3 = sum y2 - sum y^2
@@ -194,6 +201,10 @@ __device__ __forceinline__ double vb_row_q(const double* xs, const double* xvar,
 // HOLDV: keep the gathered column of the other factor in registers between the
 // accumulation and the rank-1 correction (2 gathers per entry and column instead
 // of 3); switched off for very long rows where the registers are needed for e[].
+// second moment Var + E^2 of a VB factor entry as every gather copy stores it (bnmf_vb.py:254): one expression for all
+// the kernels that write such copies, so that they agree bit for bit
+__device__ __forceinline__ double second_moment(double e, double v) { return fma(e, e, v); }
+
 template <int NPT>
 struct SweepCfg {
   static constexpr int MAXT = NPT < 16 ? 128 : 512;
@@ -462,6 +473,11 @@ __device__ __forceinline__ void sweep_body(const SweepParams& p, const int bid, 
         p.Xval[grow * K + kk] = xs[kk];
         if (MODE == M_VB) p.Xvar[grow * K + kk] = xvar[kk];
         if (p.Xmu != nullptr) { p.Xmu[grow * K + kk] = xmu[kk]; p.Xtau[grow * K + kk] = xtau[kk]; }
+        if (p.km_out != nullptr) {
+          if (MODE == M_VB) reinterpret_cast<double2*>(p.km_out)[(size_t)kk * p.km_ld + grow] = make_double2(xs[kk], second_moment(xs[kk], xvar[kk]));
+          else p.km_out[(size_t)kk * p.km_ld + grow] = xs[kk];
+        }
+        if (p.trace_out != nullptr) p.trace_out[((size_t)iteration * p.trace_n + grow) * K + kk] = xs[kk];
       }
     }
     if (nw == 1) __syncwarp(); else bar_sync(barB, tpr);
@@ -490,10 +506,10 @@ __global__ void rm_to_kmB_kernel(const double* __restrict__ Xval, const double* 
   if (i < n) {
     const int k = 2 * kb;
     e.x = Xval[i * K + k];
-    if (VB) q.x = Xvar[i * K + k] + e.x * e.x;
+    if (VB) q.x = second_moment(e.x, Xvar[i * K + k]);
     if (k + 1 < K) {
       e.y = Xval[i * K + k + 1];
-      if (VB) q.y = Xvar[i * K + k + 1] + e.y * e.y;
+      if (VB) q.y = second_moment(e.y, Xvar[i * K + k + 1]);
     }
   }
   reinterpret_cast<double2*>(YE)[(size_t)kb * ld + i] = e;
@@ -513,10 +529,10 @@ __global__ void rm_to_km_both_kernel(const double* __restrict__ Xval, const doub
   const int k = 2 * kb;
   if (i < n) {
     e.x = Xval[i * K + k];
-    if (VB) q.x = Xvar[i * K + k] + e.x * e.x;
+    if (VB) q.x = second_moment(e.x, Xvar[i * K + k]);
     if (k + 1 < K) {
       e.y = Xval[i * K + k + 1];
-      if (VB) q.y = Xvar[i * K + k + 1] + e.y * e.y;
+      if (VB) q.y = second_moment(e.y, Xvar[i * K + k + 1]);
     }
   }
   reinterpret_cast<double2*>(YE)[(size_t)kb * ld + i] = e;
@@ -543,7 +559,7 @@ __device__ __forceinline__ void rm_to_km_body(const double* __restrict__ Xval, c
     double a = 0.0, b = 0.0;
     if (i < n && k < K) {
       a = Xval[i * K + k];
-      if (NV == 2) { const double vv = Xvar[i * K + k]; b = vv + a * a; }
+      if (NV == 2) b = second_moment(a, Xvar[i * K + k]);
     }
     tile[r][threadIdx.x] = a;
     if (NV == 2) tile2[r][threadIdx.x] = b;
@@ -602,7 +618,8 @@ template <int MODE>
 __device__ __forceinline__ void lambda_body(const double* __restrict__ Ukm, int64_t ldu, int64_t I,
                                             const double* __restrict__ Vkm, int64_t ldv, int64_t J, int K, const Hyper& h,
                                             double* colsum, double* lamstate, double* lamk, uint64_t seed,
-                                            uint32_t iteration, int update, const uint32_t* iter_ptr, const int k) {
+                                            uint32_t iteration, int update, const uint32_t* iter_ptr, const int k,
+                                            double* lam_trace = nullptr) {
   constexpr int NV = (MODE == M_VB) ? 2 : 1;
   __shared__ double sh[32];
   if (iter_ptr) iteration = *iter_ptr;
@@ -635,14 +652,16 @@ __device__ __forceinline__ void lambda_body(const double* __restrict__ Ukm, int6
       lamstate[2 * K + k] = lam;
       lamk[k] = lam;
     }
+    // graph replays: this iteration's slot of all_lambdak (what trace_copy_kernel would copy)
+    if (lam_trace != nullptr && update) lam_trace[(size_t)iteration * K + k] = lamk[k];
   }
 }
 
 template <int MODE>
 __global__ void lambda_kernel(const double* __restrict__ Ukm, int64_t ldu, int64_t I, const double* __restrict__ Vkm,
                               int64_t ldv, int64_t J, int K, Hyper h, double* colsum, double* lamstate, double* lamk,
-                              uint64_t seed, uint32_t iteration, int update, const uint32_t* iter_ptr) {
-  lambda_body<MODE>(Ukm, ldu, I, Vkm, ldv, J, K, h, colsum, lamstate, lamk, seed, iteration, update, iter_ptr, (int)blockIdx.x);
+                              uint64_t seed, uint32_t iteration, int update, const uint32_t* iter_ptr, double* lam_trace) {
+  lambda_body<MODE>(Ukm, ldu, I, Vkm, ldv, J, K, h, colsum, lamstate, lamk, seed, iteration, update, iter_ptr, (int)blockIdx.x, lam_trace);
 }
 
 // -----------------------------------------------------------------------------
