@@ -405,13 +405,6 @@ static __global__ void nmtf_reduce_T_fold_kernel(const double* __restrict__ part
 // The K*L sequential S updates on the small tensors (single CTA).
 //   Gibbs: S_kl ~ TN(muS, tauS)  bnmtf_gibbs.py:200-203      ICM: max(max(0,mu),0.1)  nmtf_icm.py:203-207
 // single_d >= 0: only report (tau, mu) of entry d from the current state.
-// a load the compiler may not sink below the barrier that follows (it is issued where it stands, ahead of the wait)
-__device__ __forceinline__ double ld_now(const double* ptr) {
-  double v;
-  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
-  return v;
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restrict__ c_in, const double* __restrict__ TT, int K, int L, double* S,
                                     const double* __restrict__ lamS, const double* __restrict__ scal, uint64_t seed,
@@ -430,42 +423,11 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restr
   __syncthreads();
   const double tau = scal[0];
   const int d_begin = single_d >= 0 ? single_d : 0, d_end = single_d >= 0 ? single_d + 1 : KL;
-  // The K*L steps are a serial chain (conditional on thread 0 -> barrier -> c -= delta T[:, d] -> barrier).  What a step
-  // reads from global memory does not depend on the moves before it: every thread fetches its entries of column d of T
-  // while thread 0 is busy with the conditional, and thread 0 fetches T_dd and lambda_d of the NEXT step before it
-  // starts -- no L2 round trip is left on the chain (C4: 1.19 -> 0.7 us per step).  Same operands, same order.
-  constexpr int TQ = 8;                                 // entries of a T column per thread: K*L <= 3631 < 8 * 512
-  int pk2[TQ], l2s[TQ];                                 // this thread's entries d2 = tid + 512 q: k2 and l2
-#pragma unroll
-  for (int q = 0; q < TQ; ++q) {
-    const int d2 = threadIdx.x + q * (int)blockDim.x;
-    pk2[q] = d2 < KL ? d2 / L : -1;
-    l2s[q] = d2 < KL ? d2 - (d2 / L) * L : 0;
-  }
-  double tdd_next = 0.0, lam_next = 0.0;
-  if (threadIdx.x == 0) {
-    const int k0 = d_begin / L, l0 = d_begin - k0 * L;
-    tdd_next = TT[(size_t)pair_index(k0, k0, K) * NPL + pair_index(l0, l0, L)];
-    lam_next = lamS[d_begin];
-  }
   for (int d = d_begin; d < d_end; ++d) {
     const int k = d / L, l = d - k * L;
-    double tcol[TQ];
-#pragma unroll
-    for (int q = 0; q < TQ; ++q) {
-      tcol[q] = 0.0;
-      if (pk2[q] >= 0) {
-        const int pk = pair_index(min(k, pk2[q]), max(k, pk2[q]), K), pl = pair_index(min(l, l2s[q]), max(l, l2s[q]), L);
-        tcol[q] = ld_now(TT + (size_t)pk * NPL + pl);
-      }
-    }
     if (threadIdx.x == 0) {
-      const double Tdd = tdd_next, lam_d = lam_next;
-      if (d + 1 < d_end) {
-        const int kn = (d + 1) / L, ln = (d + 1) - kn * L;
-        tdd_next = ld_now(TT + (size_t)pair_index(kn, kn, K) * NPL + pair_index(ln, ln, L));
-        lam_next = ld_now(lamS + d + 1);
-      }
+      const double Tdd = TT[(size_t)pair_index(k, k, K) * NPL + pair_index(l, l, L)];
+      const double lam_d = lamS[d];
       const double ct = tau * Tdd;                                        // bnmtf_gibbs.py:279
       const double cm = (-lam_d + tau * (c[d] + sv[d] * Tdd)) / ct;       // bnmtf_gibbs.py:283
       double x_new;
@@ -488,9 +450,11 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restr
     __syncthreads();
     const double delta = bc[0];
     if (delta != 0.0) {
-#pragma unroll
-      for (int q = 0; q < TQ; ++q)
-        if (pk2[q] >= 0) { const int d2 = threadIdx.x + q * (int)blockDim.x; c[d2] = fma(-delta, tcol[q], c[d2]); }
+      for (int d2 = threadIdx.x; d2 < KL; d2 += blockDim.x) {
+        const int k2 = d2 / L, l2 = d2 - k2 * L;
+        const int pk = pair_index(min(k, k2), max(k, k2), K), pl = pair_index(min(l, l2), max(l, l2), L);
+        c[d2] = fma(-delta, TT[(size_t)pk * NPL + pl], c[d2]);
+      }
     }
     __syncthreads();
   }
