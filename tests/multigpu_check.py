@@ -75,7 +75,8 @@ def main():
             e.close()
     # ---- tri-factorisation engines (Gibbs, ICM, VB, NP): F/G sweeps sharded, S statistics gathered
     from bnmtf_ard_b200._engine import NMTFEngine
-    for (I, J, K, L, dens) in [(301, 223, 4, 3, 0.6), (90, 2600, 3, 5, 0.5)]:
+    # (the last two: F side / G side on the per-row-chain cluster kernel -- projection epilogue, VB covariance term -- sharded)
+    for (I, J, K, L, dens) in [(301, 223, 4, 3, 0.6), (90, 2600, 3, 5, 0.5), (2600, 90, 5, 3, 0.5)]:
         rng = np.random.default_rng(I * 7 + J)
         R = np.abs(rng.exponential(1, (I, K)) @ rng.exponential(1, (K, L)) @ rng.exponential(1, (J, L)).T + rng.normal(0, 1, (I, J))) + 0.05
         M = (rng.random((I, J)) < dens).astype(float)
