@@ -259,7 +259,6 @@ static int pack_block(bnmtf_nmf_s* h, Side& sd, int64_t n, int64_t m, int64_t ld
                       int64_t maxseg) {
   choose_team(maxlen, &sd.tpr, &sd.npt);
   if ((int64_t)sd.tpr * sd.npt < maxlen || sd.tpr > 512) {   // longer than 32 x 512 entries: streamed rows
-    if (h->nmtf) FAIL("a row/column of R has %lld observed entries; the tri-factorisation models support at most 16384 per row", (long long)maxlen);
     sd.long_rows = true; sd.tpr = LONG_T; sd.npt = 0;
   }
   std::vector<int> rowlen(n);
@@ -1005,7 +1004,7 @@ static void fill_sweep_params(bnmtf_nmf_s* h, int method, int side, int single_k
 
 // streamed rows (kernels_long.cuh): one CTA per row
 static int launch_sweep_long(bnmtf_nmf_s* h, int method, const SweepParams& p, Side& sd) {
-  const size_t smem = sizeof(double) * (4 * (size_t)p.K + 3 * (LONG_T / 32) + 2 + (method == BNMTF_GIBBS ? TN_PRE_DOUBLES * (size_t)p.K : 0));
+  const size_t smem = sizeof(double) * (4 * (size_t)p.K + 3 * (LONG_T / 32) + 2 + 2 * (size_t)p.covL + (method == BNMTF_GIBBS ? TN_PRE_DOUBLES * (size_t)p.K : 0));
   if (smem > 200 * 1024) FAIL("too many factors (%d) for the streamed row sweep", p.K);
 #define LONGK(MODE)                                                                                              \
   do {                                                                                                           \
@@ -1114,8 +1113,6 @@ static int launch_sweep(bnmtf_nmf_s* h, int method, int side, int single_k, uint
     SweepParams p{};
     fill_sweep_params(h, method, side, single_k, seed, iteration, out_tau, out_mu, want_mu, proj_y2, proj_ld2, proj_k2, p, fold_ok(h));
     if (sd.long_rows) {
-      if (h->nmtf || single_k < -2 || p.covA)
-        FAIL("a row/column of R has more than 16384 observed entries: the tri-factorisation models do not serve such rows");
       rc = launch_sweep_long(h, method, p, sd);
     } else
     switch (method) {

@@ -95,7 +95,8 @@ def test_icm_trajectory_golden(gold, ard):
 
 # the last two: odd K and L on the per-row-chain cluster sweep (F side with the projection epilogue; G side)
 SHAPES = [(40, 30, 3, 4, 0.7), (150, 220, 5, 3, 0.5), (64, 3000, 4, 6, 0.6), (700, 90, 7, 2, 0.8), (48, 2600, 5, 7, 0.5),
-          (3100, 70, 5, 3, 0.6), (70, 60, 3, 40, 0.8)]      # the last: L = 40, the reference's largest model-selection setting
+          (3100, 70, 5, 3, 0.6), (70, 60, 3, 40, 0.8),      # L = 40, the reference's largest model-selection setting
+          (6, 17500, 3, 4, 0.97)]                           # rows of more than 16384 observed entries: streamed rows (kernels_long.cuh)
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -116,7 +117,7 @@ def test_gibbs_iteration_vs_oracle(shape, monkeypatch):
     assert (F0 >= 0).all() and (S0 >= 0).all() and (G0 >= 0).all() and tau0 > 0
     m.run(1)
     eng = m._engine()
-    if max(I, J) >= 2048:      # the side with >= 2048 columns runs on the per-row-chain cluster sweep (kernels_v5.cuh)
+    if 2048 <= max(I, J) <= 5000:      # the side with >= 2048 columns runs on the per-row-chain cluster sweep (kernels_v5.cuh)
         assert eng.layout_info()["v2_U" if J >= I else "v2_V"] == 5, eng.layout_info()
     lamF, lamG = m.all_lambdaFk[0], m.all_lambdaGl[0]
     F, S, G = F0.copy(), S0.copy(), G0.copy()
@@ -254,10 +255,11 @@ def test_np_golden(gold):
     close(m.all_performances["MSE"], g["tn_MSE"], RTOL_TRAJ); close(m.all_performances["Rp"], g["tn_Rp"], RTOL_TRAJ)
 
 
-def test_np_iterations_vs_oracle():
+@pytest.mark.parametrize("shape", [(120, 2600, 3, 4, 0.5), (6, 17500, 3, 4, 0.97)])
+def test_np_iterations_vs_oracle(shape):
     from bnmtf_ard_b200 import nmtf_np
-    I, J, K, L = 120, 2600, 3, 4
-    R, M, rng = make_problem(77, I, J, K, L, 0.5)
+    I, J, K, L, dens = shape
+    R, M, rng = make_problem(77, I, J, K, L, dens)
     R = np.abs(R) + 0.05
     F0, S0, G0 = rng.random((I, K)) + 0.1, rng.random((K, L)) + 0.1, rng.random((J, L)) + 0.1
     m = nmtf_np(R, M, K, L); m.verbose = False
