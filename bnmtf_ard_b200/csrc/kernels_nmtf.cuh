@@ -405,6 +405,11 @@ static __global__ void nmtf_reduce_T_fold_kernel(const double* __restrict__ part
 // The K*L sequential S updates on the small tensors (single CTA).
 //   Gibbs: S_kl ~ TN(muS, tauS)  bnmtf_gibbs.py:200-203      ICM: max(max(0,mu),0.1)  nmtf_icm.py:203-207
 // single_d >= 0: only report (tau, mu) of entry d from the current state.
+// One barrier per step: c_d is read only at step d, so the move of step d-1 needs to reach the entries > d only.  While
+// thread 0 computes the conditional of step d -- it applies delta_{d-1} to ITS entry c_d itself, the threads having applied
+// delta_0 .. delta_{d-2} to it in the steps before -- the other entries take delta_{d-1}; the barrier at the end of the step
+// publishes delta_d (double buffered) and closes the updates.  Every c_d sees the same FMAs in the same order as in the
+// two-barrier form (conditional -> barrier -> update -> barrier), at about half its step time.
 template <int MODE>
 __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restrict__ c_in, const double* __restrict__ TT, int K, int L, double* S,
                                     const double* __restrict__ lamS, const double* __restrict__ scal, uint64_t seed,
@@ -413,30 +418,37 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restr
   const int KL = K * L, NPL = L * (L + 1) / 2;
   double* c = shs;            // [KL]
   double* sv = c + KL;        // [KL]
-  double* bc = sv + KL;       // [2]
+  double* bc = sv + KL;       // [2] the moves of the last two steps
   double* mat = bc + 2;       // [KL][6] Gibbs: random material of every entry, prepared by all threads up front
   if (iter_ptr) iteration = *iter_ptr;
   for (int d = threadIdx.x; d < KL; d += blockDim.x) {
     c[d] = c_in[d]; sv[d] = S[d];
     if (MODE == M_GIBBS && single_d < 0) tn_pre_material_store(seed, RNG_S, (uint64_t)d, 0u, iteration, mat + TN_PRE_DOUBLES * d);
   }
+  if (threadIdx.x < 2) bc[threadIdx.x] = 0.0;
   __syncthreads();
   const double tau = scal[0];
   const int d_begin = single_d >= 0 ? single_d : 0, d_end = single_d >= 0 ? single_d + 1 : KL;
   for (int d = d_begin; d < d_end; ++d) {
     const int k = d / L, l = d - k * L;
+    // the move of the step before (0 at the first step) and the column of T it goes with
+    const double dprev = bc[(d + 1) & 1];
+    const int kp = d > d_begin ? (d - 1) / L : 0, lp = d > d_begin ? (d - 1) - kp * L : 0;
     if (threadIdx.x == 0) {
+      double cd = c[d];
+      if (dprev != 0.0)
+        cd = fma(-dprev, TT[(size_t)pair_index(min(kp, k), max(kp, k), K) * NPL + pair_index(min(lp, l), max(lp, l), L)], cd);
       const double Tdd = TT[(size_t)pair_index(k, k, K) * NPL + pair_index(l, l, L)];
       const double lam_d = lamS[d];
       const double ct = tau * Tdd;                                        // bnmtf_gibbs.py:279
-      const double cm = (-lam_d + tau * (c[d] + sv[d] * Tdd)) / ct;       // bnmtf_gibbs.py:283
+      const double cm = (-lam_d + tau * (cd + sv[d] * Tdd)) / ct;         // bnmtf_gibbs.py:283
       double x_new;
       if (MODE == M_GIBBS && single_d < 0) {
         Rng rng(seed, RNG_S, (uint64_t)d, 0u, iteration);
         rng.draw = 2;                                   // Philox blocks 0 and 1 made the material
         const TnPre m = tn_pre_load(mat + TN_PRE_DOUBLES * d);
         double cm2;
-        x_new = tn_draw_fast(-lam_d + tau * (c[d] + sv[d] * Tdd), ct, m, rng, cm2);
+        x_new = tn_draw_fast(-lam_d + tau * (cd + sv[d] * Tdd), ct, m, rng, cm2);
       } else if (MODE == M_GIBBS) {
         x_new = sv[d];
       } else {
@@ -444,16 +456,15 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restr
       }
       if (mu_out) { mu_out[d] = cm; tau_out[d] = ct; }
       if (single_d >= 0) x_new = sv[d];
-      bc[0] = x_new - sv[d];
+      bc[d & 1] = x_new - sv[d];
       sv[d] = x_new;
     }
-    __syncthreads();
-    const double delta = bc[0];
-    if (delta != 0.0) {
+    if (dprev != 0.0) {          // entries beyond d take the move of step d - 1 (entry d took it above, the ones before are done)
       for (int d2 = threadIdx.x; d2 < KL; d2 += blockDim.x) {
+        if (d2 <= d) continue;
         const int k2 = d2 / L, l2 = d2 - k2 * L;
-        const int pk = pair_index(min(k, k2), max(k, k2), K), pl = pair_index(min(l, l2), max(l, l2), L);
-        c[d2] = fma(-delta, TT[(size_t)pk * NPL + pl], c[d2]);
+        const int pk = pair_index(min(kp, k2), max(kp, k2), K), pl = pair_index(min(lp, l2), max(lp, l2), L);
+        c[d2] = fma(-dprev, TT[(size_t)pk * NPL + pl], c[d2]);
       }
     }
     __syncthreads();
@@ -462,8 +473,6 @@ __global__ void __launch_bounds__(512) nmtf_s_sweep_kernel(const double* __restr
     for (int d = threadIdx.x; d < KL; d += blockDim.x) S[d] = sv[d];
 }
 
-// lambdaF_k ~ Gamma(alpha0 + I, beta0 + sum_i F_ik), lambdaG_l likewise with J
-// (bnmtf_gibbs.py:187-191,252-266; ICM: modes, nmtf_icm.py:188-192).  One block per column.
 template <int MODE>
 __global__ void nmtf_lambda_kernel(const double* __restrict__ F, int64_t I, int K, const double* __restrict__ G, int64_t J, int L,
                                    Hyper h, double* colsum, double* lamF, double* lamG, uint64_t seed, uint32_t iteration,
@@ -626,7 +635,7 @@ static __global__ void __launch_bounds__(512) nmtf_s_sweep_vb_fast_kernel(const 
   double* tdd = cf + KL;      // [KL]
   double* bs = tdd + KL;      // [KL]
   double* lam = bs + KL;      // [KL]
-  double* bc = lam + KL;      // [1]
+  double* bc = lam + KL;      // [2] the moves of the last two steps
   constexpr int ME = 2;       // entries per thread
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int d = tid; d < KL; d += nt) {
@@ -647,45 +656,43 @@ static __global__ void __launch_bounds__(512) nmtf_s_sweep_vb_fast_kernel(const 
     }
     __syncthreads();
     const int d_begin = mode >= 0 ? mode : 0, d_end = mode >= 0 ? mode + 1 : KL;
+    // One barrier per step (as nmtf_s_sweep_kernel): the running c_d, covG_d, covF_d are read at step d only, so the move of
+    // step d - 1 needs to reach the entries > d; thread 0 applies it to ITS entry d itself and computes the update of step d
+    // while the other entries take it.  Same FMAs in the same order on every entry.
+    if (tid < 2) bc[tid] = 0.0;
+    __syncthreads();
     for (int d = d_begin; d < d_end; ++d) {
       const int k = d / L, l = d - k * L;
-      // what this thread's entries need from global memory for the update of step d
-      double tv[ME], pv[ME];
-#pragma unroll
-      for (int q = 0; q < ME; ++q) {
-        const int d2 = tid + q * nt;
-        tv[q] = 0.0; pv[q] = 0.0;
-        if (d2 < KL && mode < 0) {
-          const int k2 = d2 / L, l2 = d2 - k2 * L;
-          tv[q] = tmat(TT, k, l, k2, l2, K, L, NPL);
-          if (l2 == l && k2 != k) pv[q] = PA[(size_t)pair_index(min(k, k2), max(k, k2), K) * L + l];
-          else if (k2 == k && l2 != l) pv[q] = QC[(size_t)pair_index(min(l, l2), max(l, l2), L) * K + k];
-        }
-      }
+      const double dprev = bc[(d + 1) & 1];
+      const int kp = d > d_begin ? (d - 1) / L : 0, lp = d > d_begin ? (d - 1) - kp * L : 0;
       if (tid == 0) {
+        double cd = c[d], cgd = cg[d], cfd = cf[d];
+        if (dprev != 0.0) {
+          cd = fma(-dprev, tmat(TT, kp, lp, k, l, K, L, NPL), cd);
+          if (l == lp && k != kp) cgd = fma(dprev, PA[(size_t)pair_index(min(kp, k), max(kp, k), K) * L + lp], cgd);
+          else if (k == kp && l != lp) cfd = fma(dprev, QC[(size_t)pair_index(min(lp, l), max(lp, l), L) * K + kp], cfd);
+        }
         const double ct = etau * bs[d];
-        const double cm = (-lam[d] + etau * (c[d] + es[d] * tdd[d]) - etau * cg[d] - etau * cf[d]) / ct;
+        const double cm = (-lam[d] + etau * (cd + es[d] * tdd[d]) - etau * cgd - etau * cfd) / ct;
         double en, vn;
         tn_moments(cm, ct, en, vn);
         if (mode >= 0) {
           out_tau[0] = ct; out_mu[0] = cm;
-          bc[0] = 0.0;
+          bc[d & 1] = 0.0;
         } else {
-          bc[0] = en - es[d];
+          bc[d & 1] = en - es[d];
           Smu[d] = cm; Stau[d] = ct; Svar[d] = vn; es[d] = en;
         }
       }
-      __syncthreads();
-      const double delta = bc[0];
-      if (delta != 0.0) {
+      if (dprev != 0.0 && mode < 0) {   // entries beyond d take the move of step d - 1
 #pragma unroll
         for (int q = 0; q < ME; ++q) {
           const int d2 = tid + q * nt;
-          if (d2 < KL) {
+          if (d2 < KL && d2 > d) {
             const int k2 = d2 / L, l2 = d2 - k2 * L;
-            c[d2] = fma(-delta, tv[q], c[d2]);
-            if (l2 == l && k2 != k) cg[d2] = fma(delta, pv[q], cg[d2]);
-            else if (k2 == k && l2 != l) cf[d2] = fma(delta, pv[q], cf[d2]);
+            c[d2] = fma(-dprev, tmat(TT, kp, lp, k2, l2, K, L, NPL), c[d2]);
+            if (l2 == lp && k2 != kp) cg[d2] = fma(dprev, PA[(size_t)pair_index(min(kp, k2), max(kp, k2), K) * L + lp], cg[d2]);
+            else if (k2 == kp && l2 != lp) cf[d2] = fma(dprev, QC[(size_t)pair_index(min(lp, l2), max(lp, l2), L) * K + kp], cf[d2]);
           }
         }
       }
