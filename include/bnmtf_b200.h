@@ -206,6 +206,7 @@ int bnmtf_nmf_sweep_times(bnmtf_nmf_t h, double* out4);
  * set_factor / get_factor / destroy / launch_count / layout_info apply unchanged.
  * bnmtf_nmtf_run / column_params serve BNMTF_GIBBS (bnmtf_gibbs.py) and BNMTF_ICM (nmtf_icm.py);
  * the VB and NP variants have their own entry points below.
+ * Limits (the reference has none; bnmtf_nmtf_create* fails with a message beyond them): L <= 48, K * L <= 3631.
  * ------------------------------------------------------------------------- */
 int bnmtf_nmtf_create(bnmtf_nmf_t* out, int device, int64_t I, int64_t J, int K, int L,
                       const double* R, const uint8_t* M,
